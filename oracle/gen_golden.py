@@ -1,0 +1,257 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by EXECUTING the unmodified
+reference (dev container only; needs /root/reference).  Run:  python -m oracle.gen_golden
+
+Each fixture records what the reference itself returned; while generating, the numpy/torch
+port (oracle/port.py) is checked bit-for-bit against the reference on the same inputs, so a
+green run pins the oracle to the reference as it executes under the versions written to
+tests/golden/MANIFEST.json.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import port  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REWARD_CODE = {0: 0, 100: 1, -100 / 1000: 2}
+
+
+# ------------------------------------------------------------------ env + solver
+def gen_env_tables(ref):
+    out = {}
+    max_steps = 200
+    for n in (3, 4, 5, 7, 10):
+        env = ref.TowersOfHanoi(N=n, max_steps=max_steps)
+        n_states = 3 ** n
+        variants = (0, 1) if n <= 7 else (0,)
+        shape = (len(variants), n_states, 6)
+        obs_idx = np.zeros(shape, np.uint32)
+        stored_idx = np.zeros(shape, np.uint32)
+        rcode = np.zeros(shape, np.uint8)
+        done = np.zeros(shape, np.uint8)
+        illegal = np.zeros(shape, np.uint8)
+        ctr_after = np.zeros(shape, np.uint16)
+        reset_check = np.zeros(shape, np.uint8)
+        solver = np.zeros(n_states, np.uint16)
+        legal = np.zeros(n_states, np.uint8)
+        for vi, hit_max in enumerate(variants):
+            for si in range(n_states):
+                st = env.states[si]
+                assert port.index_to_state(si, n) == st and port.state_to_index(st) == si
+                for a in range(6):
+                    env.c_state, env.reset_check = st, True
+                    env.step_counter = max_steps - 1 if hit_max else 17
+                    obs, r, d, ill = env.step(a)
+                    obs_state = tuple(int(x) for x in obs.reshape(n, 3).argmax(1))
+                    assert obs.dtype == np.float64 and np.array_equal(obs, port.one_hot(obs_state))
+                    obs_idx[vi, si, a] = port.state_to_index(obs_state)
+                    stored_idx[vi, si, a] = port.state_to_index(env.c_state)
+                    rcode[vi, si, a] = REWARD_CODE[r]
+                    done[vi, si, a], illegal[vi, si, a] = d, ill
+                    ctr_after[vi, si, a], reset_check[vi, si, a] = env.step_counter, env.reset_check
+                    # port == reference
+                    moved, stored, c2, r2, d2, i2, rc2 = port.step_state(
+                        st, max_steps - 1 if hit_max else 17, a, max_steps, env.goal)
+                    assert (moved, stored, c2, d2, i2, rc2) == (obs_state, env.c_state, env.step_counter, d, ill, env.reset_check)
+                    assert r2 == r and type(r2) is type(r)
+                    if vi == 0:
+                        env.c_state = st
+                        if env._move_allowed(env.moves[a]):
+                            legal[si] |= 1 << a
+                if vi == 0:
+                    solver[si] = ref.hanoi_solver(st)
+                    assert port.hanoi_solver(st) == solver[si] and port.legal_mask(st) == legal[si]
+        for k, v in dict(obs_idx=obs_idx, stored_idx=stored_idx, reward_code=rcode, done=done, illegal=illegal,
+                         counter_after=ctr_after, reset_check=reset_check, solver=solver, legal=legal).items():
+            out[f"n{n}_{k}"] = v
+        print(f"env table N={n}: {n_states * 6 * len(variants)} transitions ok")
+    out["max_steps"] = np.int64(max_steps)
+    out["counter_before"] = np.array([17, max_steps - 1])
+    np.savez_compressed(os.path.join(GOLDEN, "env_tables.npz"), **out)
+    # known-answer anchors quoted by the reference (acting_ablations.py:53-60, generate_all_figures.py:78)
+    assert [ref.hanoi_solver(s) for s in ((2, 2, 0), (0, 0, 2), (1, 2, 2), (0, 0, 0))] == [7, 3, 1, 7]
+
+
+# ------------------------------------------------------------------------ search
+SEARCH_CONFIGS = {
+    # name: N, S, alpha, temperature, deterministic, weight seed, lesion heads, n searches
+    "n3_s50_noise_t1": dict(N=3, S=50, alpha=0.25, T=1.0, det=False, wseed=0, lesion=(), K=12),
+    "n3_s25_nonoise_t0": dict(N=3, S=25, alpha=0.0, T=0.0, det=False, wseed=1, lesion=(), K=12),
+    "n3_s25_det": dict(N=3, S=25, alpha=0.25, T=1.0, det=True, wseed=2, lesion=(), K=6),
+    "n4_s200_lesion_t0": dict(N=4, S=200, alpha=0.0, T=0.0, det=False, wseed=3,
+                              lesion=("policy_net", "value_net"), K=6),
+    "n5_s100_noise_t05": dict(N=5, S=100, alpha=0.25, T=0.5, det=False, wseed=4, lesion=(), K=8),
+}
+DISCOUNT = 0.8
+
+
+def gen_search(ref, name, cfg):
+    import torch
+
+    n, S, K = cfg["N"], cfg["S"], cfg["K"]
+    sd = port.make_weights(n, cfg["wseed"])
+    if cfg["lesion"]:
+        sd = port.lesion_weights(sd, cfg["lesion"], seed=100 + cfg["wseed"])
+    net = rh.TracingNet(rh.load_reference_net(ref, n, sd))
+    pnet = port.PortNet(sd)
+    rng = np.random.default_rng(1000 + cfg["wseed"])
+    noises = rng.dirichlet(np.full(6, 0.25), size=K)  # f64[K,6]
+    uniforms = rng.random(K)
+    env = ref.TowersOfHanoi(N=n, max_steps=200)
+    mcts = ref.MCTS(discount=DISCOUNT, root_dirichlet_alpha=cfg["alpha"], n_simulations=S, batch_s=1, device="cpu")
+    pmm = port.MinMax()
+    psearch = port.PortSearch(DISCOUNT, S, pmm)
+    use_noise = (not cfg["det"]) and cfg["alpha"] > 0
+    maxd = S + 1
+    rec = dict(obs=[], state=[], p0=[], v0=[], h0=[], prior=[], depth=[], path=[], r=[], p=[], v=[],
+               child_N=[], pi=[], root_q=[], action=[], mm_min=[], mm_max=[], env_reward=[], env_done=[])
+    obs = env.reset()
+    with rh.HookedSearch(ref, noises=[x for x in noises] if use_noise else [], uniforms=list(uniforms)) as hk:
+        for k in range(K):
+            state = tuple(env.current_state())
+            u_used = None if cfg["det"] else uniforms[k] if not use_noise or True else None
+            action, pi, root_q = mcts.run_mcts(obs, net, cfg["T"], cfg["det"])
+            h0, _, p0, v0 = net.root
+            prior = port.mix_dirichlet(p0, noises[k]) if use_noise else p0
+            depth = np.zeros(S, np.uint16)
+            path = np.full((S, maxd), 255, np.uint8)
+            for s, (pth, _) in enumerate(net.calls):
+                depth[s] = len(pth)
+                path[s, : len(pth)] = pth
+            r = np.array([c[1][1] for c in net.calls], np.float32)
+            p = np.stack([c[1][2] for c in net.calls]).astype(np.float32)
+            v = np.array([c[1][3] for c in net.calls], np.float32)
+            assert all(float(np.float32(c[1][1])) == c[1][1] and float(np.float32(c[1][3])) == c[1][3] for c in net.calls)
+            # --- port vs reference, full (own network) and injected
+            tr = port.SearchTrace()
+            mm_before = (pmm.minimum, pmm.maximum)
+            a2, pi2, q2, visits2, prior2 = port.run_mcts_port(
+                obs, pnet, psearch, cfg["T"], cfg["det"], alpha=cfg["alpha"], noise=noises[k],
+                u=None if cfg["det"] else uniforms[k], trace=tr)
+            assert np.array_equal(prior2, prior) and prior2.dtype == prior.dtype
+            assert a2 == action and np.array_equal(pi2, pi) and q2 == root_q, (name, k)
+            assert (pmm.minimum, pmm.maximum) == (mcts.min_max_stats.minimum, mcts.min_max_stats.maximum)
+            assert [list(x) for x in tr.actions_path] == [c[0] for c in net.calls]
+            assert np.array_equal(np.array(tr.r, np.float32), r) and np.array_equal(np.stack(tr.p), p)
+            inj = port.PortSearch(DISCOUNT, S, port.MinMax(*mm_before))
+            visits3, q3, _ = inj.run(prior, None, None, injected=(r, p, v))
+            assert np.array_equal(visits3, visits2) and q3 == root_q
+            rec["obs"].append(obs.copy()); rec["state"].append(port.state_to_packed(state))
+            rec["p0"].append(p0); rec["v0"].append(np.float32(v0)); rec["h0"].append(h0); rec["prior"].append(np.asarray(prior, np.float64))
+            rec["depth"].append(depth); rec["path"].append(path[:, : int(depth.max())].copy())
+            rec["r"].append(r); rec["p"].append(p); rec["v"].append(v)
+            rec["child_N"].append(visits2); rec["pi"].append(pi); rec["root_q"].append(root_q); rec["action"].append(action)
+            rec["mm_min"].append(pmm.minimum); rec["mm_max"].append(pmm.maximum)
+            obs, rwd, done, _ = env.step(action)
+            rec["env_reward"].append(float(rwd)); rec["env_done"].append(done)
+            if done:
+                obs = env.reset()
+    maxdepth = max(x.shape[1] for x in rec["path"])
+    paths = np.full((K, S, maxdepth), 255, np.uint8)
+    for k, x in enumerate(rec["path"]):
+        paths[k, :, : x.shape[1]] = x
+    out = dict(
+        N=n, S=S, K=K, discount=DISCOUNT, alpha=cfg["alpha"], eps=0.25, temperature=cfg["T"],
+        deterministic=cfg["det"], weight_seed=cfg["wseed"], lesion=np.array(cfg["lesion"], dtype="U16"),
+        lesion_seed=100 + cfg["wseed"], prior_is_f64=use_noise,
+        noise=noises, uniform=uniforms, obs=np.stack(rec["obs"]), state=np.array(rec["state"], np.uint32),
+        p0=np.stack(rec["p0"]), v0=np.array(rec["v0"], np.float32), h0=np.stack(rec["h0"]),
+        prior=np.stack(rec["prior"]), depth=np.stack(rec["depth"]), path=paths,
+        r=np.stack(rec["r"]), p=np.stack(rec["p"]), v=np.stack(rec["v"]),
+        child_N=np.stack(rec["child_N"]).astype(np.int32), pi=np.stack(rec["pi"]),
+        root_q=np.array(rec["root_q"], np.float64), action=np.array(rec["action"], np.int32),
+        mm_min=np.array(rec["mm_min"], np.float64), mm_max=np.array(rec["mm_max"], np.float64),
+        env_reward=np.array(rec["env_reward"]), env_done=np.array(rec["env_done"]),
+    )
+    np.savez_compressed(os.path.join(GOLDEN, f"search_{name}.npz"), **out)
+    print(f"search {name}: {K} searches x {S} sims ok; mean depth {np.mean([d.mean() for d in rec['depth']]):.2f}, "
+          f"max {max(int(d.max()) for d in rec['depth'])}")
+
+
+# ----------------------------------------------------------------------- network
+def gen_net_io(ref):
+    import torch
+
+    out = {}
+    for n, wseed in ((3, 0), (5, 4), (10, 7)):
+        sd = port.make_weights(n, wseed)
+        net = rh.load_reference_net(ref, n, sd)
+        pnet = port.PortNet(sd)
+        rng = np.random.default_rng(50 + n)
+        M = 96
+        h_in = rng.random((M, 64), dtype=np.float32)
+        acts = rng.integers(0, 6, M)
+        states = rng.integers(0, 3 ** n, M)
+        rec = dict(h2=[], r=[], p=[], v=[], h0=[], p0=[], v0=[])
+        for i in range(M):
+            a1 = torch.zeros(6); a1[acts[i]] = 1.0
+            h2, r, p, v = net.recurrent_inference(torch.from_numpy(h_in[i]), a1)
+            q = pnet.recurrent_inference(torch.from_numpy(h_in[i]), a1)
+            assert np.array_equal(q[0], h2) and q[1] == r and np.array_equal(q[2], p) and q[3] == v
+            rec["h2"].append(h2); rec["r"].append(r); rec["p"].append(p); rec["v"].append(v)
+            obs = port.one_hot(port.index_to_state(int(states[i]), n))
+            x = torch.from_numpy(obs).to(dtype=torch.float32)
+            h0, r0, p0, v0 = net.initial_inference(x)
+            q = pnet.initial_inference(x)
+            assert r0 == 0.0 and np.array_equal(q[0], h0) and np.array_equal(q[2], p0) and q[3] == v0
+            rec["h0"].append(h0); rec["p0"].append(p0); rec["v0"].append(v0)
+        out.update({f"n{n}_weight_seed": wseed, f"n{n}_h_in": h_in, f"n{n}_action": acts.astype(np.int32),
+                    f"n{n}_state_idx": states.astype(np.int64),
+                    f"n{n}_h_out": np.stack(rec["h2"]), f"n{n}_r": np.array(rec["r"], np.float32),
+                    f"n{n}_p": np.stack(rec["p"]), f"n{n}_v": np.array(rec["v"], np.float32),
+                    f"n{n}_h0": np.stack(rec["h0"]), f"n{n}_p0": np.stack(rec["p0"]),
+                    f"n{n}_v0": np.array(rec["v0"], np.float32)})
+        print(f"net io N={n}: {M} recurrent + {M} initial inferences ok")
+    # scalar transform anchors
+    net = rh.load_reference_net(ref, 3, port.make_weights(3, 0))
+    xs = torch.tensor([[-16.0], [-1.0], [0.0], [0.5], [16.0]])
+    out["signed_parabolic_in"] = xs.numpy()
+    out["signed_parabolic_out"] = net._signed_parabolic(xs).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "net_io.npz"), **out)
+
+
+def check_choice_hook():
+    """The uniform-as-input restatement of np.random.choice(p=...) equals numpy's legacy path."""
+    rs = np.random.RandomState(7)
+    rs2 = np.random.RandomState(7)
+    for _ in range(2000):
+        p = rs.dirichlet(np.ones(6))
+        rs2.dirichlet(np.ones(6))
+        a = rs.choice(np.arange(6), p=p)
+        assert a == port.sample_action(p, rs2.random_sample())
+
+
+def main():
+    import torch
+
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = rh.import_reference()
+    check_choice_hook()
+    gen_env_tables(ref)
+    for name, cfg in SEARCH_CONFIGS.items():
+        gen_search(ref, name, cfg)
+    gen_net_io(ref)
+    manifest = dict(
+        generated_by="python -m oracle.gen_golden",
+        reference="A-Andrews/Muzero-Hanoi (unmodified, /root/reference)",
+        numpy=np.__version__, torch=torch.__version__, python=sys.version.split()[0],
+        hooks=["lowest-index tie-break (MCTS/node.py:86)", "dirichlet draw as input (MCTS/mcts.py:149)",
+               "sampling uniform as input (MCTS/mcts.py:120)"],
+        search_configs=SEARCH_CONFIGS,
+    )
+    with open(os.path.join(GOLDEN, "MANIFEST.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+    print("golden fixtures written to", GOLDEN)
+
+
+if __name__ == "__main__":
+    main()
