@@ -1,0 +1,218 @@
+/* hmz.h — C ABI of libhmz.so, the B200-native batched MuZero/Hanoi acting engine.
+ *
+ * This header is the drop-in boundary for ONE hot path of A-Andrews/Muzero-Hanoi:
+ *   Hanoi env step -> MCTS select / expand / backup -> dynamics+prediction MLP ->
+ *   root visit histogram -> action sampling.
+ * The reference has no FFI layer (it is pure Python); each entry point below therefore
+ * names the reference *Python function* it replaces (file:line under the reference
+ * repository), and INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - Every pointer is a DEVICE pointer owned by the caller unless the name says `host_`.
+ *   - The library never allocates device memory and never synchronises: kernels are
+ *     enqueued on `stream` (a cudaStream_t passed as void*, NULL = legacy default stream).
+ *   - Every function returns HMZ_OK (0) or a negative HMZ_ERR_* code and never throws;
+ *     hmz_last_error() returns a thread-local message for the last failure.
+ *   - Re-entrant: no global mutable state apart from the thread-local error string.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with HMZ_ERR_CUDA.
+ */
+#ifndef HMZ_H
+#define HMZ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMZ_OK 0
+#define HMZ_ERR_INVALID (-1)     /* bad argument (size, range, null pointer)            */
+#define HMZ_ERR_CUDA (-2)        /* CUDA runtime / launch error                          */
+#define HMZ_ERR_UNSUPPORTED (-3) /* valid request this build cannot serve (e.g. N > 12)  */
+
+#define HMZ_N_ACTIONS 6  /* env/hanoi.py:39-41: permutations(range(3), 2)               */
+#define HMZ_LATENT 64    /* networks.py:22  reprs_output_size                            */
+#define HMZ_HIDDEN 256   /* networks.py:21  h1_s                                         */
+#define HMZ_SUPPORT 33   /* networks.py:34-35 support_size when TD_return=True           */
+#define HMZ_MAX_DISKS 12 /* 2 bits/disk + >= 8 counter bits in one 32-bit env word       */
+#define HMZ_NO_CHILD 0xFFFFu
+
+/* flag bits written by hmz_env_step* (one uint8 per env) */
+#define HMZ_FLAG_DONE 1u    /* env/hanoi.py:68,78  done                                   */
+#define HMZ_FLAG_ILLEGAL 2u /* env/hanoi.py:54     illegal_move                           */
+#define HMZ_FLAG_GOAL 4u    /* env/hanoi.py:65-69  goal reached (reward 100)              */
+#define HMZ_FLAG_TRUNC 8u   /* env/hanoi.py:77-80  step_counter == max_steps              */
+
+const char* hmz_last_error(void);
+int hmz_version(void);
+/* Number of kernels this library has launched from the calling process (for bench.py's
+ * gpu_launches claim). */
+int64_t hmz_launch_count(void);
+int hmz_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ environment ----
+ * Env word (uint32): bits [0, 2N) hold the peg (0..2) of disk d at bits [2d, 2d+2), disk 0
+ * smallest — the tuple of env/hanoi.py:19-25 packed; bits [2N, 32) hold step_counter
+ * (env/hanoi.py:45,56).  Requires N <= HMZ_MAX_DISKS and max_steps < 2^(32-2N).
+ */
+
+/* words[i] = reset_word for all i (TowersOfHanoi.reset, env/hanoi.py:86-96). */
+int hmz_env_reset(uint32_t* words, int64_t n_envs, uint32_t reset_word, void* stream);
+
+/* words[i] = packed state of states[index[i]] where the index is the base-3 number with
+ * disk 0 as most significant digit (itertools.product order, env/hanoi.py:23-25).  Used by
+ * random_reset (env/hanoi.py:98-111) with host-drawn indices in parity mode. */
+int hmz_env_from_index(const uint32_t* index, uint32_t* words, int64_t n_envs, int n_disks, void* stream);
+int hmz_env_to_index(const uint32_t* words, uint32_t* index, int64_t n_envs, int n_disks, void* stream);
+
+/* TowersOfHanoi.random_reset drawn on device: uniform over the 3^N - 1 non-goal states,
+ * Philox4x32-10 keyed by (seed, env id, counter). */
+int hmz_env_random_reset(uint32_t* words, int64_t n_envs, int n_disks, int goal_peg, uint64_t seed,
+                         uint64_t counter, void* stream);
+
+/* TowersOfHanoi.step (env/hanoi.py:47-84) for n_envs envs at once.
+ *   words    in/out  env words (state + counter)
+ *   actions  in      action index 0..5 per env
+ *   rewards  out     0.0f, 100.0f or -0.1f  (env/hanoi.py:62,66,72)
+ *   flags    out     HMZ_FLAG_* bits
+ *   obs_words out, nullable: packed state the returned observation encodes (the GOAL state
+ *            when the goal is reached although the stored state is not updated, :65-69)
+ *   auto_reset != 0: envs that finish are set to reset_word (counter 0) in the same pass.
+ *   auto_reset == 0: finished envs keep the reference's stored state with counter 0; the
+ *            caller must reset them before stepping again (env/hanoi.py:49).
+ */
+int hmz_env_step(uint32_t* words, const uint8_t* actions, float* rewards, uint8_t* flags, uint32_t* obs_words,
+                 int64_t n_envs, int n_disks, int max_steps, int goal_peg, int auto_reset, uint32_t reset_word,
+                 void* stream);
+
+/* Bit a of mask[i] = TowersOfHanoi._move_allowed(moves[a]) (env/hanoi.py:123-139). */
+int hmz_env_legal_mask(const uint32_t* words, uint8_t* mask, int64_t n_envs, int n_disks, void* stream);
+
+/* utils.oneHot_encoding (utils.py:9-25) as float32 [n_envs, 3N], disk-major. */
+int hmz_env_onehot(const uint32_t* words, float* obs, int64_t n_envs, int n_disks, void* stream);
+
+/* env.hanoi_utils.hanoi_solver (env/hanoi_utils.py:4-26): minimal moves to goal_peg. */
+int hmz_env_solver_distance(const uint32_t* words, uint32_t* distance, int64_t n_envs, int n_disks, int goal_peg,
+                            void* stream);
+
+/* One env step with a uniformly random LEGAL move drawn on device (BASELINE.json config 4;
+ * the host equivalent scans _move_allowed over moves as legal_illegal_preds.py:51 does).
+ * Writes the chosen action, reward and flags (13 B / env step of traffic). */
+int hmz_env_step_random(uint32_t* words, uint8_t* actions, float* rewards, uint8_t* flags, int64_t n_envs,
+                        int n_disks, int max_steps, int goal_peg, uint32_t reset_word, uint64_t seed,
+                        uint64_t step_index, void* stream);
+
+/* n_steps random-legal-move steps per env fused in registers (state read and written once).
+ * counters (device, uint64[4], accumulated with atomics): [0] steps taken, [1] goals reached,
+ * [2] truncations, [3] xor-fold checksum of final words.  Auto-resets to reset_word. */
+int hmz_env_rollout_random(uint32_t* words, int64_t n_envs, int n_disks, int max_steps, int goal_peg,
+                           uint32_t reset_word, int n_steps, uint64_t seed, uint64_t step_index,
+                           unsigned long long* counters, void* stream);
+
+/* ------------------------------------------------------------------ tree store -----
+ * One 128-byte record per EXPANDED node; field arrays of 6 (one entry per child action)
+ * inside the record, so a search's whole pUCT decision at a node is one aligned 128-byte
+ * line.  The node expanded by simulation s of a search is record s+1 (root = record 0), so
+ * no allocator is needed.  Fields restate MCTS/node.py:9-28 (prior, N, W, rwd, children).
+ */
+typedef struct hmz_node {
+  double W[6];           /* child.W   (float64 sum of backed-up values, node.py:63)      */
+  float prior[6];        /* child.prior (float32; a noised root keeps float64 in root_prior) */
+  float rwd[6];          /* child.rwd  (float32 value, widened exactly when used)         */
+  uint16_t N[6];         /* child.N                                                       */
+  uint16_t child[6];     /* record index of the expanded child, HMZ_NO_CHILD otherwise    */
+  uint16_t parent;       /* record index of this node's parent (root: 0)                  */
+  uint8_t parent_action; /* action that leads from parent to this node                    */
+  uint8_t pad[5];
+} hmz_node_t;
+
+#define HMZ_LATENT_F32 0
+#define HMZ_LATENT_BF16 1
+
+typedef struct hmz_search {
+  hmz_node_t* nodes;   /* [n_searches][n_records]                                        */
+  void* latents;       /* [n_searches][n_records][64] float32 or bf16 (node.h_state)     */
+  double* root_prior;  /* [n_searches][6] float64 root priors (exact copy of the input)   */
+  double* root_W;      /* [n_searches]   root.W                                           */
+  double* minmax;      /* [n_searches][2] (min, max) of MinMaxStats; PERSISTS across calls */
+  int64_t n_searches;
+  int32_t n_records;   /* >= n_simulations + 1                                           */
+  int32_t latent_dtype;
+  int32_t root_prior_is_f64; /* 1: noised root, U = f32(f64 prior * w) (node.py:122)      */
+  int32_t reserved;
+} hmz_search_t;
+
+/* MinMaxStats() construction (MCTS/utils_mcts.py:4-6): (min, max) = (+inf, -inf). */
+int hmz_search_minmax_reset(double* minmax, int64_t n_searches, void* stream);
+
+/* root_node.expand(prior, h, 0.0) (MCTS/mcts.py:52-69): clears record 0, stores priors.
+ * The root latent must already be in latents[:, 0, :] (written by hmz_net_initial). */
+int hmz_search_begin(const hmz_search_t* s, const double* root_prior, void* stream);
+
+/* Phase 1 of one simulation (MCTS/mcts.py:75-86 -> Node.best_child, node.py:72-123) for all
+ * searches: walk from the root taking arg-max of f32(Q)+f32(U) (lowest index on ties) until an
+ * unexpanded child.  ucb_table[n] = (log((n+19653)/19652)+1.25)*sqrt(n) for n in [0, sim],
+ * float64, computed by the host libm exactly as node.py:114-120 does.
+ *   leaf_parent/leaf_action/leaf_depth out: record of the leaf's parent, its action, path length
+ *   path_out nullable [n_searches][path_cap]: actions root->leaf (0xFF padded), diagnostics. */
+int hmz_search_select(const hmz_search_t* s, int sim, const double* ucb_table, double discount,
+                      uint16_t* leaf_parent, uint8_t* leaf_action, uint16_t* leaf_depth, uint8_t* path_out,
+                      int path_cap, void* stream);
+
+/* Phases 2b+3 (MCTS/mcts.py:106-109 -> Node.expand node.py:30-51, Node.backup :53-70) with the
+ * network outputs of this simulation given per search: creates record sim+1 with priors p,
+ * stores r on the leaf slot, then walks to the root: W += value; N += 1;
+ * minmax.update(rwd + discount*Q); value = rwd + discount*value — all float64. */
+int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, const uint16_t* leaf_parent,
+                             const uint8_t* leaf_action, const float* r, const float* p, const float* v,
+                             void* stream);
+
+/* MCTS/mcts.py:112-126: child_N, generate_play_policy (:154-176), arg-max or sampled action.
+ *   uniforms nullable unless deterministic == 0 (one double in [0,1) per search; the draw of
+ *   np.random.choice at :120 supplied as input);  outputs nullable individually. */
+int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temperature, int deterministic,
+                           const double* uniforms, int32_t* visits, double* pi, double* root_q, int32_t* action,
+                           void* stream);
+
+/* ------------------------------------------------------------------ networks -------
+ * Packed weights: one device blob produced by hmz_weights_pack from the 20 tensors of
+ * MuZeroNet.state_dict() (networks.py:39-67), in the order
+ *   {representation_net, dynamic_net, rwd_net, policy_net, value_net} x {0.weight, 0.bias,
+ *   2.weight, 2.bias}.
+ */
+#define HMZ_MODE_FP32 0 /* FFMA, fp32 accumulate: parity mode (<= 1e-5 vs reference)      */
+#define HMZ_MODE_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 in TMEM: throughput mode (<= 2e-2) */
+
+int64_t hmz_weights_packed_bytes(int n_disks, int mode);
+/* host_tensors: 20 HOST pointers to contiguous float32 tensors; host_out: HOST buffer of
+ * hmz_weights_packed_bytes() bytes that the caller then copies to the device. */
+int hmz_weights_pack(const float* const* host_tensors, int n_disks, int mode, void* host_out);
+
+/* MuZeroNet.initial_inference (networks.py:71-94) for a batch of packed env words:
+ * h0 = normalize(representation_net(onehot(word))), p0 = softmax(policy_net(h0)),
+ * v0 = support_to_scalar(value_net(h0)).  h0 row i is written to
+ * latents_out + (i*out_rows_per_item)*64 elements (so it can target record 0 of a search). */
+int hmz_net_initial(const void* weights, int mode, int n_disks, const uint32_t* words, const float* obs,
+                    void* latents_out, int64_t out_rows_per_item, int latent_dtype, float* p0, float* v0,
+                    int64_t n, void* stream);
+
+/* MuZeroNet.recurrent_inference (networks.py:96-116) for a batch:
+ * input latent of item i  = latents_in  + (i*in_rows_per_item  + in_row[i]) * 64   (in_row nullable = 0)
+ * output latent of item i = latents_out + (i*out_rows_per_item + out_row)   * 64
+ * r, v float32 [n]; p float32 [n,6] (softmax probabilities). */
+int hmz_net_recurrent(const void* weights, int mode, const void* latents_in, int64_t in_rows_per_item,
+                      const uint16_t* in_row, const uint8_t* actions, void* latents_out,
+                      int64_t out_rows_per_item, int64_t out_row, int latent_dtype, float* r, float* p, float* v,
+                      int64_t n, void* stream);
+
+/* Whole search, fused: n_simulations x (select -> g+f MLP -> expand -> backup) for every
+ * search in one launch sequence with no host round trips (MCTS.run_mcts, MCTS/mcts.py:71-109). */
+int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_simulations,
+                   const double* ucb_table, double discount, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMZ_H */

@@ -1,0 +1,65 @@
+"""CPU: libhmz.so loads, exports every symbol include/hmz.h declares, and the ctypes mirror
+matches the header (no compute calls — there is no GPU here)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "hmz.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hmz_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    from muzero_hanoi_b200 import _lib
+
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in hmz.h but not exported by libhmz.so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+
+
+def test_struct_layout():
+    from muzero_hanoi_b200 import _lib
+
+    assert ctypes.sizeof(_lib.NodeRecord) == 128
+    assert _lib.NodeRecord.prior.offset == 48 and _lib.NodeRecord.rwd.offset == 72
+    assert _lib.NodeRecord.N.offset == 96 and _lib.NodeRecord.child.offset == 108
+    assert _lib.NodeRecord.parent.offset == 120 and _lib.NodeRecord.parent_action.offset == 122
+    assert ctypes.sizeof(_lib.SearchDesc) == 64
+
+
+def test_version_and_error_string(lib):
+    assert lib.hmz_version() >= 100
+    assert isinstance(lib.hmz_last_error(), bytes)
+    assert lib.hmz_launch_count() >= 0
+
+
+def test_argument_validation_without_gpu(lib):
+    """Argument errors are reported before any CUDA call, so they are checkable on CPU."""
+    from muzero_hanoi_b200 import _lib
+
+    rc = lib.hmz_env_step(None, None, None, None, None, 4, 3, 200, 2, 0, 0, None)
+    assert rc == _lib.ERR_INVALID
+    buf = (ctypes.c_uint32 * 4)()
+    rc = lib.hmz_env_step(buf, buf, buf, buf, None, 4, 13, 200, 2, 0, 0, None)
+    assert rc == _lib.ERR_UNSUPPORTED and b"n_disks" in lib.hmz_last_error()
+    rc = lib.hmz_env_step(buf, buf, buf, buf, None, 4, 12, 256, 2, 0, 0, None)
+    assert rc == _lib.ERR_UNSUPPORTED and b"max_steps" in lib.hmz_last_error()
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from muzero_hanoi_b200.engine import VecHanoi
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        VecHanoi(3, 200, 16)

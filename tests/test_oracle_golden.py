@@ -1,0 +1,146 @@
+"""CPU: the oracle port (oracle/port.py) against the golden fixtures generated from the
+unmodified reference (tests/golden/, made by oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import port
+
+REWARDS = {0: 0, 1: 100, 2: -100 / 1000}
+SEARCH_FIXTURES = ["n3_s50_noise_t1", "n3_s25_nonoise_t0", "n3_s25_det", "n4_s200_lesion_t0", "n5_s100_noise_t05"]
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 7])
+def test_env_transitions_exhaustive(golden, n):
+    g = golden("env_tables.npz")
+    max_steps = int(g["max_steps"])
+    goal = (2,) * n
+    for vi, c0 in enumerate(g["counter_before"]):
+        for si in range(3 ** n):
+            st = port.index_to_state(si, n)
+            for a in range(6):
+                moved, stored, ctr, r, d, ill, rc = port.step_state(st, int(c0), a, max_steps, goal)
+                assert port.state_to_index(moved) == g[f"n{n}_obs_idx"][vi, si, a]
+                assert port.state_to_index(stored) == g[f"n{n}_stored_idx"][vi, si, a]
+                assert r == REWARDS[int(g[f"n{n}_reward_code"][vi, si, a])]
+                assert (d, ill, ctr, rc) == (bool(g[f"n{n}_done"][vi, si, a]), bool(g[f"n{n}_illegal"][vi, si, a]),
+                                             int(g[f"n{n}_counter_after"][vi, si, a]),
+                                             bool(g[f"n{n}_reset_check"][vi, si, a]))
+
+
+def test_env_transitions_n10_sampled(golden):
+    g = golden("env_tables.npz")
+    rng = np.random.default_rng(0)
+    for si in rng.integers(0, 3 ** 10, 3000):
+        st = port.index_to_state(int(si), 10)
+        assert port.hanoi_solver(st) == g["n10_solver"][si] and port.legal_mask(st) == g["n10_legal"][si]
+        for a in range(6):
+            moved, stored, ctr, r, d, ill, _ = port.step_state(st, 17, a, 200, (2,) * 10)
+            assert port.state_to_index(moved) == g["n10_obs_idx"][0, si, a]
+            assert r == REWARDS[int(g["n10_reward_code"][0, si, a])] and ill == bool(g["n10_illegal"][0, si, a])
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 7])
+def test_solver_and_legal_masks(golden, n):
+    g = golden("env_tables.npz")
+    for si in range(3 ** n):
+        st = port.index_to_state(si, n)
+        assert port.hanoi_solver(st) == g[f"n{n}_solver"][si]
+        assert port.legal_mask(st) == g[f"n{n}_legal"][si]
+        assert port.packed_to_state(port.state_to_packed(st), n) == st
+
+
+def test_known_answers():
+    # acting_ablations.py:53-60 / generate_all_figures.py:78 (OPTIMAL_MOVES) of the reference
+    assert [port.hanoi_solver(s) for s in ((2, 2, 0), (0, 0, 2), (1, 2, 2), (0, 0, 0))] == [7, 3, 1, 7]
+    assert port.MOVES == ((0, 1), (0, 2), (1, 0), (1, 2), (2, 0), (2, 1))
+    # sample rows quoted in SURVEY.md §8c
+    assert port.step_state((0, 2, 2), 0, 1, 200, (2, 2, 2))[3] == 100
+    assert port.step_state((0, 0, 0), 0, 2, 200, (2, 2, 2))[3] == -0.1
+
+
+def test_stateful_env_matches_pure_function():
+    env = port.PortHanoi(3, 5)
+    with pytest.raises(AssertionError):
+        env.step(0)
+    obs = env.reset()
+    assert obs.dtype == np.float64 and obs.tolist() == [1, 0, 0] * 3
+    out = [env.step(a) for a in (2, 2, 2, 2)]
+    assert all(o[3] and not o[2] for o in out)
+    o = env.step(2)  # 5th step: truncation coincides with an illegal move
+    assert o[2] and o[3] and env.step_counter == 0 and not env.reset_check
+
+
+@pytest.mark.parametrize("name", SEARCH_FIXTURES)
+def test_search_injected_matches_reference(golden, name):
+    """Tree arithmetic only (network outputs injected from the reference trace): visit counts,
+    root value and the persistent min/max must equal the reference bit for bit."""
+    g = golden(f"search_{name}.npz")
+    S, K = int(g["S"]), int(g["K"])
+    mm = port.MinMax()
+    for k in range(K):
+        prior = g["prior"][k] if bool(g["prior_is_f64"]) else g["prior"][k].astype(np.float32)
+        tr = port.SearchTrace()
+        search = port.PortSearch(float(g["discount"]), S, mm)
+        visits, q, _ = search.run(prior, None, None, injected=(g["r"][k], g["p"][k], g["v"][k]), trace=tr)
+        assert np.array_equal(visits, g["child_N"][k])
+        assert q == g["root_q"][k]
+        assert (mm.minimum, mm.maximum) == (g["mm_min"][k], g["mm_max"][k])
+        for s in range(S):
+            d = int(g["depth"][k, s])
+            assert tr.actions_path[s] == g["path"][k, s, :d].tolist()
+        pi = port.play_policy(visits, float(g["temperature"]))
+        assert np.array_equal(pi, g["pi"][k])
+        a = int(np.argmax(visits)) if bool(g["deterministic"]) else port.sample_action(pi, g["uniform"][k])
+        assert a == g["action"][k]
+
+
+@pytest.mark.parametrize("name", ["n3_s50_noise_t1", "n5_s100_noise_t05"])
+def test_search_own_network_matches_reference(golden, name):
+    """Whole run_mcts through the port's own float32 torch network.  Bit-exact only when the host
+    BLAS rounds like the one the fixture was made with, so the network outputs are probed first."""
+    import torch
+
+    g = golden(f"search_{name}.npz")
+    n, S = int(g["N"]), int(g["S"])
+    net = port.PortNet(port.make_weights(n, int(g["weight_seed"])))
+    h0, _, p0, v0 = net.initial_inference(torch.from_numpy(g["obs"][0]).to(torch.float32))
+    if not (np.array_equal(h0, g["h0"][0]) and np.array_equal(p0, g["p0"][0])):
+        pytest.skip("host float32 GEMV rounds differently from the fixture's host")
+    mm = port.MinMax()
+    for k in range(min(3, int(g["K"]))):
+        a, pi, q, visits, _ = port.run_mcts_port(
+            g["obs"][k], net, port.PortSearch(float(g["discount"]), S, mm), float(g["temperature"]),
+            bool(g["deterministic"]), alpha=float(g["alpha"]), noise=g["noise"][k], u=g["uniform"][k])
+        assert np.array_equal(visits, g["child_N"][k]) and q == g["root_q"][k] and a == g["action"][k]
+
+
+def test_network_port_close_to_reference(golden):
+    import torch
+
+    g = golden("net_io.npz")
+    for n in (3, 5, 10):
+        net = port.PortNet(port.make_weights(n, int(g[f"n{n}_weight_seed"])))
+        for i in range(0, 96, 8):
+            a1 = torch.zeros(6)
+            a1[int(g[f"n{n}_action"][i])] = 1.0
+            h2, r, p, v = net.recurrent_inference(torch.from_numpy(g[f"n{n}_h_in"][i]), a1)
+            np.testing.assert_allclose(h2, g[f"n{n}_h_out"][i], rtol=0, atol=2e-6)
+            np.testing.assert_allclose(p, g[f"n{n}_p"][i], rtol=1e-5, atol=1e-7)
+            assert abs(r - g[f"n{n}_r"][i]) <= 1e-5 * max(1.0, abs(g[f"n{n}_r"][i]))
+            assert abs(v - g[f"n{n}_v"][i]) <= 1e-5 * max(1.0, abs(g[f"n{n}_v"][i]))
+
+
+def test_ucb_table_and_policy_helpers():
+    t = port.ucb_table(4)
+    assert t[0] == 0.0 and t.dtype == np.float64
+    assert np.array_equal(port.play_policy([1, 2, 1, 0, 0, 0], 0.0), np.array([1, 2, 1, 0, 0, 0]) / 4)
+    assert np.array_equal(port.play_policy([1, 2, 1, 0, 0, 0], 0.5), np.array([1, 4, 1, 0, 0, 0]) / 6)
+    with pytest.raises(ValueError):
+        port.play_policy([1, 1, 1, 1, 1, 1], 1.5)
+    assert port.sample_action(np.array([0.5, 0.5, 0, 0, 0, 0]), 0.5) == 1
+    assert port.sample_action(np.array([0.5, 0.5, 0, 0, 0, 0]), 0.49) == 0
+
+
+def test_n_step_returns():
+    r = port.n_step_returns([0, 0, 100], [1.0, 2.0, 3.0], 2, 0.5)
+    assert r == [0 + 0.5 * 0 + 0.25 * 3.0, 0 + 0.5 * 100 + 0.25 * 0, 100 + 0 + 0]
