@@ -137,12 +137,16 @@ typedef struct hmz_search {
   double* root_prior;  /* [n_searches][6] float64 root priors (exact copy of the input)   */
   double* root_W;      /* [n_searches]   root.W                                           */
   double* minmax;      /* [n_searches][2] (min, max) of MinMaxStats; PERSISTS across calls */
+  void* workspace;     /* hmz_search_workspace_bytes(n_searches) bytes of scratch          */
   int64_t n_searches;
   int32_t n_records;   /* >= n_simulations + 1                                           */
   int32_t latent_dtype;
   int32_t root_prior_is_f64; /* 1: noised root, U = f32(f64 prior * w) (node.py:122)      */
   int32_t reserved;
 } hmz_search_t;
+
+/* Scratch needed by hmz_search_run (per-simulation leaf ids and network outputs). */
+int64_t hmz_search_workspace_bytes(int64_t n_searches);
 
 /* MinMaxStats() construction (MCTS/utils_mcts.py:4-6): (min, max) = (+inf, -inf). */
 int hmz_search_minmax_reset(double* minmax, int64_t n_searches, void* stream);

@@ -33,7 +33,7 @@ class SearchDesc(C.Structure):
     """hmz_search_t."""
 
     _fields_ = [("nodes", C.c_void_p), ("latents", C.c_void_p), ("root_prior", C.c_void_p), ("root_W", C.c_void_p),
-                ("minmax", C.c_void_p), ("n_searches", C.c_int64), ("n_records", C.c_int32),
+                ("minmax", C.c_void_p), ("workspace", C.c_void_p), ("n_searches", C.c_int64), ("n_records", C.c_int32),
                 ("latent_dtype", C.c_int32), ("root_prior_is_f64", C.c_int32), ("reserved", C.c_int32)]
 
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "hmz_env_solver_distance": (_I, [_P, _P, _L, _I, _I, _P]),
     "hmz_env_step_random": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _U32, _U64, _U64, _P]),
     "hmz_env_rollout_random": (_I, [_P, _L, _I, _I, _I, _U32, _I, _U64, _U64, _P, _P]),
+    "hmz_search_workspace_bytes": (_L, [_L]),
     "hmz_search_minmax_reset": (_I, [_P, _L, _P]),
     "hmz_search_begin": (_I, [_SD, _P, _P]),
     "hmz_search_select": (_I, [_SD, _I, _P, _D, _P, _P, _P, _P, _I, _P]),

@@ -1,11 +1,262 @@
-// placeholder — replaced by the tree-store kernels
+// Tree-store kernels: pUCT selection, expansion + discounted backup, root policy (sm_100a).
+//
+// Restates MCTS/mcts.py:34-126 and MCTS/node.py:30-136 of the reference over the 128-byte node
+// records of include/hmz.h.  A search is owned by one 8-lane segment of a warp (lanes 0..5 = the
+// six child actions; 4 searches per warp): a node's whole pUCT decision is one coalesced
+// 128-byte line and the arg-max is three xor-shuffles inside the segment.
+//
+// Arithmetic contract (bit-exact vs the reference):
+//   Q, W, value, min/max  : IEEE float64, every op an explicit __d*_rn so nvcc cannot contract
+//                           the reference's separate multiply and add into an FMA;
+//   f32(Q) + f32(U)       : float32 add after rounding each term (MCTS/node.py:83,103,123);
+//   U = prior * w         : float32 x float32 for a float32 prior (NumPy >= 2 weak scalars),
+//                           float64 product then rounded at a Dirichlet-noised root (:122);
+//   ties                  : lowest action index (the sanctioned replacement of :86).
+// These kernels are HBM/L2-latency bound gathers (one 128 B record per tree level); there is no
+// contraction here and nothing for tensor cores to do.
 #include "hmz_common.cuh"
-using namespace hmz;
-extern "C" {
-int hmz_search_minmax_reset(double*, int64_t, void*) { return fail(HMZ_ERR_UNSUPPORTED, "not built yet"); }
-int hmz_search_begin(const hmz_search_t*, const double*, void*) { return fail(HMZ_ERR_UNSUPPORTED, "not built yet"); }
-int hmz_search_select(const hmz_search_t*, int, const double*, double, uint16_t*, uint8_t*, uint16_t*, uint8_t*, int, void*) { return fail(HMZ_ERR_UNSUPPORTED, "not built yet"); }
-int hmz_search_expand_backup(const hmz_search_t*, int, double, const uint16_t*, const uint8_t*, const float*, const float*, const float*, void*) { return fail(HMZ_ERR_UNSUPPORTED, "not built yet"); }
-int hmz_search_root_policy(const hmz_search_t*, int, double, int, const double*, int32_t*, double*, double*, int32_t*, void*) { return fail(HMZ_ERR_UNSUPPORTED, "not built yet"); }
-int hmz_search_run(const hmz_search_t*, const void*, int, int, const double*, double, void*) { return fail(HMZ_ERR_UNSUPPORTED, "not built yet"); }
+#include "hmz_tree.cuh"
+
+namespace hmz {
+
+constexpr int kSearchesPerBlock = 32;  // 256 threads = 8 warps x 4 searches
+
+__global__ void __launch_bounds__(256) search_minmax_reset(double* __restrict__ minmax, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    minmax[2 * i] = __longlong_as_double(0x7FF0000000000000ll);      // +inf  (MCTS/utils_mcts.py:6)
+    minmax[2 * i + 1] = __longlong_as_double(0xFFF0000000000000ll);  // -inf  (MCTS/utils_mcts.py:5)
+  }
 }
+
+// root_node.expand(prior, h, 0.0): record 0 <- priors, everything else cleared; root.W <- 0.
+__global__ void __launch_bounds__(256) search_begin(hmz_search_t s, const double* __restrict__ root_prior) {
+  const int lane8 = threadIdx.x & 7;
+  for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; b < s.n_searches;
+       b += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    float pr[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double p = root_prior[b * 6 + a];
+      pr[a] = (float)p;
+      if (lane8 == 0 && s.root_prior != root_prior) s.root_prior[b * 6 + a] = p;
+    }
+    write_fresh_record(&s.nodes[b * s.n_records], lane8, pr, 0, 0);
+    if (lane8 == 0) s.root_W[b] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) search_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
+                                                    double discount, uint16_t* __restrict__ leaf_parent,
+                                                    uint8_t* __restrict__ leaf_action,
+                                                    uint16_t* __restrict__ leaf_depth, uint8_t* __restrict__ path_out,
+                                                    int path_cap) {
+  const int lane8 = threadIdx.x & 7;
+  int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+  const bool valid = b < s.n_searches;
+  if (!valid) b = s.n_searches - 1;  // keep whole warps alive for the shuffles
+  const hmz_node_t* nodes = s.nodes + b * s.n_records;
+  const double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
+  const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
+  Leaf leaf = select_leaf(nodes, rp, mn, mx, sim, ucb_table, discount, lane8, valid,
+                          (valid && path_out) ? path_out + b * path_cap : nullptr, path_cap);
+  if (valid && lane8 == 0) {
+    leaf_parent[b] = (uint16_t)leaf.parent;
+    leaf_action[b] = (uint8_t)leaf.action;
+    if (leaf_depth) leaf_depth[b] = (uint16_t)leaf.depth;
+  }
+}
+
+__global__ void __launch_bounds__(256) search_expand_backup(hmz_search_t s, int sim, double discount,
+                                                           const uint16_t* __restrict__ leaf_parent,
+                                                           const uint8_t* __restrict__ leaf_action,
+                                                           const float* __restrict__ r, const float* __restrict__ p,
+                                                           const float* __restrict__ v) {
+  const int lane8 = threadIdx.x & 7;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+  if (b >= s.n_searches) return;
+  hmz_node_t* nodes = s.nodes + b * s.n_records;
+  const int pe = leaf_parent[b], pa = leaf_action[b];
+  float pr[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) pr[a] = p[b * 6 + a];
+  write_fresh_record(&nodes[sim + 1], lane8, pr, pe, pa);
+  if (lane8 == 0) {
+    double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
+    double root_w = s.root_W[b];
+    backup_path(nodes, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
+    s.root_W[b] = root_w;
+    s.minmax[2 * b] = mn;
+    s.minmax[2 * b + 1] = mx;
+  }
+}
+
+// MCTS/mcts.py:112-126 per search (one thread each; 52 bytes in, <= 76 bytes out).
+__global__ void __launch_bounds__(256) search_root_policy(hmz_search_t s, int n_sims, double temperature,
+                                                         int deterministic, const double* __restrict__ uniforms,
+                                                         int32_t* __restrict__ visits, double* __restrict__ pi,
+                                                         double* __restrict__ root_q, int32_t* __restrict__ action) {
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < s.n_searches;
+       b += (int64_t)gridDim.x * blockDim.x) {
+    const hmz_node_t* root = s.nodes + b * s.n_records;
+    int n[6];
+    double w[6];
+    const uint4 nv = *reinterpret_cast<const uint4*>(&root->N[0]);  // N[0..5] + child[0..1], 16-byte aligned
+    n[0] = nv.x & 0xFFFF; n[1] = nv.x >> 16; n[2] = nv.y & 0xFFFF; n[3] = nv.y >> 16; n[4] = nv.z & 0xFFFF; n[5] = nv.z >> 16;
+    // generate_play_policy (:154-176): visits ** clamp(1/T, 1, 5) when T > 0, raw counts when T == 0
+    double ex = 1.0;
+    if (temperature > 0.0) ex = fmax(1.0, fmin(5.0, __ddiv_rn(1.0, temperature)));
+    const int iex = (int)ex;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double x = (double)n[a];
+      if ((double)iex == ex) {  // integer exponents 1..5: exact products while < 2^53
+        double y = x;
+        for (int k = 1; k < iex; ++k) y = __dmul_rn(y, x);
+        w[a] = y;
+      } else {
+        w[a] = pow(x, ex);
+      }
+    }
+    // np.sum of 6 doubles: first element + (0 + the rest, left to right)
+    double rest = 0.0;
+#pragma unroll
+    for (int a = 1; a < 6; ++a) rest = __dadd_rn(rest, w[a]);
+    const double total = __dadd_rn(w[0], rest);
+    double prob[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) prob[a] = __ddiv_rn(w[a], total);
+    int act = 0;
+    if (deterministic) {  // np.argmax(child_visits): first maximum (:117)
+      for (int a = 1; a < 6; ++a)
+        if (n[a] > n[act]) act = a;
+    } else {  // np.random.choice(6, p=pi) with its uniform supplied (:120): cdf / cdf[-1], searchsorted right
+      double cdf[6];
+      cdf[0] = prob[0];
+#pragma unroll
+      for (int a = 1; a < 6; ++a) cdf[a] = __dadd_rn(cdf[a - 1], prob[a]);
+      const double u = uniforms[b], last = cdf[5];
+      act = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) act += (__ddiv_rn(cdf[a], last) <= u) ? 1 : 0;
+      if (act > 5) act = 5;
+    }
+    if (visits) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) visits[b * 6 + a] = n[a];
+    }
+    if (pi) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) pi[b * 6 + a] = prob[a];
+    }
+    if (root_q) root_q[b] = n_sims > 0 ? __ddiv_rn(s.root_W[b], (double)n_sims) : 0.0;  // Node.Q (node.py:125-131)
+    if (action) action[b] = act;
+  }
+}
+
+static int check_search(const hmz_search_t* s, const char* who) {
+  if (!s) return fail(HMZ_ERR_INVALID, "%s: null search descriptor", who);
+  if (s->n_searches < 0 || s->n_records < 1 || s->n_records > 65535)
+    return fail(HMZ_ERR_INVALID, "%s: n_searches=%lld n_records=%d out of range", who, (long long)s->n_searches,
+                s->n_records);
+  if (s->n_searches > 0 && (!s->nodes || !s->root_prior || !s->root_W || !s->minmax))
+    return fail(HMZ_ERR_INVALID, "%s: null buffer in search descriptor", who);
+  if ((reinterpret_cast<uintptr_t>(s->nodes) & 127u) != 0)
+    return fail(HMZ_ERR_INVALID, "%s: nodes must be 128-byte aligned", who);
+  return HMZ_OK;
+}
+
+static unsigned search_grid(int64_t n_searches) {
+  return (unsigned)((n_searches + kSearchesPerBlock - 1) / kSearchesPerBlock);
+}
+
+}  // namespace hmz
+
+using namespace hmz;
+
+extern "C" {
+
+int64_t hmz_search_workspace_bytes(int64_t n_searches) {
+  if (n_searches < 0) return -1;
+  return ((n_searches + 63) / 64) * 64 * 40 + 512;  // p[6] r v (float), leaf_parent (u16), leaf_action (u8) + alignment slack
+}
+
+int hmz_search_minmax_reset(double* minmax, int64_t n, void* stream) {
+  if (n == 0) return HMZ_OK;
+  if (!minmax || n < 0) return fail(HMZ_ERR_INVALID, "hmz_search_minmax_reset: bad arguments");
+  search_minmax_reset<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(minmax, n);
+  return check_launch("search_minmax_reset");
+}
+
+int hmz_search_begin(const hmz_search_t* s, const double* root_prior, void* stream) {
+  if (int rc = check_search(s, "hmz_search_begin")) return rc;
+  if (s->n_searches == 0) return HMZ_OK;
+  if (!root_prior) return fail(HMZ_ERR_INVALID, "hmz_search_begin: null root_prior");
+  search_begin<<<grid_for(s->n_searches, kSearchesPerBlock, 8), 256, 0, (cudaStream_t)stream>>>(*s, root_prior);
+  return check_launch("search_begin");
+}
+
+int hmz_search_select(const hmz_search_t* s, int sim, const double* ucb_table, double discount, uint16_t* leaf_parent,
+                      uint8_t* leaf_action, uint16_t* leaf_depth, uint8_t* path_out, int path_cap, void* stream) {
+  if (int rc = check_search(s, "hmz_search_select")) return rc;
+  if (s->n_searches == 0) return HMZ_OK;
+  if (!ucb_table || !leaf_parent || !leaf_action || sim < 0 || sim + 1 >= s->n_records || (path_out && path_cap < 1))
+    return fail(HMZ_ERR_INVALID, "hmz_search_select: bad arguments (sim=%d, n_records=%d)", sim, s->n_records);
+  search_select<<<search_grid(s->n_searches), 256, 0, (cudaStream_t)stream>>>(*s, sim, ucb_table, discount, leaf_parent,
+                                                                              leaf_action, leaf_depth, path_out,
+                                                                              path_cap);
+  return check_launch("search_select");
+}
+
+int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, const uint16_t* leaf_parent,
+                             const uint8_t* leaf_action, const float* r, const float* p, const float* v,
+                             void* stream) {
+  if (int rc = check_search(s, "hmz_search_expand_backup")) return rc;
+  if (s->n_searches == 0) return HMZ_OK;
+  if (!leaf_parent || !leaf_action || !r || !p || !v || sim < 0 || sim + 1 >= s->n_records)
+    return fail(HMZ_ERR_INVALID, "hmz_search_expand_backup: bad arguments (sim=%d, n_records=%d)", sim, s->n_records);
+  search_expand_backup<<<search_grid(s->n_searches), 256, 0, (cudaStream_t)stream>>>(*s, sim, discount, leaf_parent,
+                                                                                     leaf_action, r, p, v);
+  return check_launch("search_expand_backup");
+}
+
+int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temperature, int deterministic,
+                           const double* uniforms, int32_t* visits, double* pi, double* root_q, int32_t* action,
+                           void* stream) {
+  if (int rc = check_search(s, "hmz_search_root_policy")) return rc;
+  if (!(temperature >= 0.0 && temperature <= 1.0))  // MCTS/mcts.py:163-166 -> ValueError in the Python shim
+    return fail(HMZ_ERR_INVALID, "Expect `temperature` to be in the range [0.0, 1.0], got %g", temperature);
+  if (s->n_searches == 0) return HMZ_OK;
+  if (!deterministic && !uniforms) return fail(HMZ_ERR_INVALID, "hmz_search_root_policy: sampling needs uniforms");
+  search_root_policy<<<grid_for(s->n_searches, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+      *s, n_simulations, temperature, deterministic, uniforms, visits, pi, root_q, action);
+  return check_launch("search_root_policy");
+}
+
+int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_simulations, const double* ucb_table,
+                   double discount, void* stream) {
+  if (int rc = check_search(s, "hmz_search_run")) return rc;
+  if (s->n_searches == 0 || n_simulations == 0) return HMZ_OK;
+  if (!weights || !ucb_table || !s->workspace || !s->latents || n_simulations < 0 ||
+      n_simulations + 1 > s->n_records)
+    return fail(HMZ_ERR_INVALID, "hmz_search_run: bad arguments (n_simulations=%d, n_records=%d)", n_simulations,
+                s->n_records);
+  const int64_t B = s->n_searches;
+  const int64_t Bp = (B + 63) / 64 * 64;
+  char* ws = (char*)s->workspace;
+  ws = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  float* p = (float*)ws;                      // [B][6]
+  float* r = (float*)(ws + Bp * 24);          // [B]
+  float* v = (float*)(ws + Bp * 28);          // [B]
+  uint16_t* lp = (uint16_t*)(ws + Bp * 32);   // [B]
+  uint8_t* la = (uint8_t*)(ws + Bp * 34);     // [B]
+  for (int sim = 0; sim < n_simulations; ++sim) {
+    if (int rc = hmz_search_select(s, sim, ucb_table, discount, lp, la, nullptr, nullptr, 0, stream)) return rc;
+    if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, lp, la, s->latents, s->n_records, sim + 1,
+                                   s->latent_dtype, r, p, v, B, stream))
+      return rc;
+    if (int rc = hmz_search_expand_backup(s, sim, discount, lp, la, r, p, v, stream)) return rc;
+  }
+  return HMZ_OK;
+}
+
+}  // extern "C"

@@ -148,3 +148,126 @@ class VecHanoi:
         w = self.words.cpu().numpy().view(np.uint32)
         shift = 2 * self.discs
         return w & ((1 << shift) - 1), w >> shift
+
+
+# ------------------------------------------------------------------------------- search
+def ucb_table(n_max: int) -> np.ndarray:
+    """TABLE[n] = (log((n + 19652 + 1)/19652) + 1.25) * sqrt(n) for n in [0, n_max], float64 via the
+    host libm in the reference's own evaluation order (MCTS/node.py:114-120); the per-child
+    division by (child.N + 1) happens on the device.  Only the integer parent count enters, so a
+    host table removes any device-vs-glibc log() ulp question from the bit-exact path."""
+    return np.array([(math.log((n + 19652 + 1) / 19652) + 1.25) * math.sqrt(n) for n in range(n_max + 1)],
+                    dtype=np.float64)
+
+
+class SearchStore:
+    """Device buffers of B concurrent searches with room for ``n_records`` expanded nodes each
+    (struct hmz_search_t).  MinMaxStats state persists until ``reset_minmax``."""
+
+    def __init__(self, B, n_records, device="cuda", latent_dtype=_lib.LATENT_F32):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.B, self.n_records, self.latent_dtype = int(B), int(n_records), latent_dtype
+        self.device = torch.device(device)
+        dev = self.device
+        self.nodes = torch.zeros(max(1, self.B * self.n_records * 128), dtype=torch.uint8, device=dev)
+        assert self.nodes.data_ptr() % 128 == 0
+        ldt = torch.float32 if latent_dtype == _lib.LATENT_F32 else torch.bfloat16
+        self.latents = torch.zeros(self.B, self.n_records, _lib.LATENT, dtype=ldt, device=dev)
+        self.root_prior = torch.zeros(self.B, 6, dtype=torch.float64, device=dev)
+        self.root_W = torch.zeros(self.B, dtype=torch.float64, device=dev)
+        self.minmax = torch.zeros(self.B, 2, dtype=torch.float64, device=dev)
+        self.workspace = torch.zeros(int(self.lib.hmz_search_workspace_bytes(self.B)), dtype=torch.uint8, device=dev)
+        self.desc = _lib.SearchDesc(
+            nodes=self.nodes.data_ptr(), latents=self.latents.data_ptr(), root_prior=self.root_prior.data_ptr(),
+            root_W=self.root_W.data_ptr(), minmax=self.minmax.data_ptr(), workspace=self.workspace.data_ptr(),
+            n_searches=self.B, n_records=self.n_records, latent_dtype=latent_dtype, root_prior_is_f64=0, reserved=0)
+        self.reset_minmax()
+
+    def reset_minmax(self):
+        check(self.lib.hmz_search_minmax_reset(ptr(self.minmax), self.B, current_stream()))
+
+    def records(self):
+        """Host copy of the node records as a numpy structured array [B, n_records]."""
+        dt = np.dtype([("W", "<f8", 6), ("prior", "<f4", 6), ("rwd", "<f4", 6), ("N", "<u2", 6), ("child", "<u2", 6),
+                       ("parent", "<u2"), ("parent_action", "u1"), ("pad", "u1", 5)])
+        return self.nodes.cpu().numpy()[: self.B * self.n_records * 128].view(dt).reshape(self.B, self.n_records)
+
+
+class BatchedMCTS:
+    """B independent MCTS searches advanced in lock-step (MCTS.run_mcts, MCTS/mcts.py:34-126)."""
+
+    def __init__(self, discount, root_dirichlet_alpha, n_simulations, B, device="cuda", root_exploration_eps=0.25,
+                 latent_dtype=_lib.LATENT_F32, max_simulations=None):
+        self.discount = float(discount)
+        self.root_dirichlet_alpha = root_dirichlet_alpha
+        self.root_exploration_eps = root_exploration_eps
+        self.n_simulations = int(n_simulations)
+        self.B = int(B)
+        cap = max(self.n_simulations, int(max_simulations or 0))
+        self.store = SearchStore(B, cap + 1, device, latent_dtype)
+        self.lib = self.store.lib
+        self.device = self.store.device
+        self._table_host = ucb_table(cap + 1)
+        self._table = torch.from_numpy(self._table_host).to(self.device)
+        dev = self.device
+        self.leaf_parent = torch.zeros(self.B, dtype=torch.int16, device=dev)
+        self.leaf_action = torch.zeros(self.B, dtype=torch.uint8, device=dev)
+        self.leaf_depth = torch.zeros(self.B, dtype=torch.int16, device=dev)
+        self.visits = torch.zeros(self.B, 6, dtype=torch.int32, device=dev)
+        self.pi = torch.zeros(self.B, 6, dtype=torch.float64, device=dev)
+        self.root_q = torch.zeros(self.B, dtype=torch.float64, device=dev)
+        self.action = torch.zeros(self.B, dtype=torch.int32, device=dev)
+
+    # -- split phases (used by the injected parity path and by tests) ---------------------------
+    def begin(self, root_prior, prior_is_f64):
+        rp = torch.as_tensor(np.asarray(root_prior, dtype=np.float64) if not torch.is_tensor(root_prior) else root_prior,
+                             dtype=torch.float64, device=self.device).contiguous()
+        assert rp.shape == (self.B, 6)
+        self.store.desc.root_prior_is_f64 = int(bool(prior_is_f64))
+        check(self.lib.hmz_search_begin(C.byref(self.store.desc), ptr(rp), current_stream()))
+
+    def select(self, sim, path_out=None):
+        cap = 0 if path_out is None else path_out.shape[1]
+        check(self.lib.hmz_search_select(C.byref(self.store.desc), sim, ptr(self._table), self.discount,
+                                         ptr(self.leaf_parent), ptr(self.leaf_action), ptr(self.leaf_depth),
+                                         ptr(path_out), cap, current_stream()))
+
+    def expand_backup(self, sim, r, p, v):
+        check(self.lib.hmz_search_expand_backup(C.byref(self.store.desc), sim, self.discount, ptr(self.leaf_parent),
+                                                ptr(self.leaf_action), ptr(r), ptr(p), ptr(v), current_stream()))
+
+    def root_policy(self, temperature, deterministic, uniforms=None, n_simulations=None):
+        if not 0.0 <= temperature <= 1.0:  # MCTS/mcts.py:163-166
+            raise ValueError(f"Expect `temperature` to be in the range [0.0, 1.0], got {temperature}")
+        u = None
+        if not deterministic:
+            if uniforms is None:
+                raise ValueError("sampling the action needs one uniform per search (`uniforms`)")
+            u = torch.as_tensor(uniforms, dtype=torch.float64, device=self.device).contiguous()
+        n = self.n_simulations if n_simulations is None else n_simulations
+        check(self.lib.hmz_search_root_policy(C.byref(self.store.desc), n, float(temperature), int(bool(deterministic)),
+                                              ptr(u), ptr(self.visits), ptr(self.pi), ptr(self.root_q),
+                                              ptr(self.action), current_stream()))
+        return self.action, self.pi, self.root_q, self.visits
+
+    def run_injected(self, root_prior, prior_is_f64, r, p, v, want_paths=False):
+        """Search with the network outputs of every simulation supplied (parity mode of
+        BASELINE.json north_star): r, v float32 [S, B]; p float32 [S, B, 6]."""
+        S = self.n_simulations
+        dev = self.device
+        r = torch.as_tensor(r, dtype=torch.float32, device=dev).contiguous()
+        v = torch.as_tensor(v, dtype=torch.float32, device=dev).contiguous()
+        p = torch.as_tensor(p, dtype=torch.float32, device=dev).contiguous()
+        assert r.shape == (S, self.B) and v.shape == (S, self.B) and p.shape == (S, self.B, 6)
+        self.begin(root_prior, prior_is_f64)
+        paths = depths = None
+        if want_paths:
+            paths = torch.full((S, self.B, S + 1), 255, dtype=torch.uint8, device=dev)
+            depths = torch.zeros(S, self.B, dtype=torch.int16, device=dev)
+        for s in range(S):
+            self.select(s, None if paths is None else paths[s])
+            if depths is not None:
+                depths[s].copy_(self.leaf_depth)
+            self.expand_backup(s, r[s], p[s], v[s])
+        return paths, depths

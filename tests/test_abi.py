@@ -31,7 +31,7 @@ def test_struct_layout():
     assert _lib.NodeRecord.prior.offset == 48 and _lib.NodeRecord.rwd.offset == 72
     assert _lib.NodeRecord.N.offset == 96 and _lib.NodeRecord.child.offset == 108
     assert _lib.NodeRecord.parent.offset == 120 and _lib.NodeRecord.parent_action.offset == 122
-    assert ctypes.sizeof(_lib.SearchDesc) == 64
+    assert ctypes.sizeof(_lib.SearchDesc) == 72
 
 
 def test_version_and_error_string(lib):

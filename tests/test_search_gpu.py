@@ -1,0 +1,102 @@
+"""GPU parity: tree-store kernels (select / expand+backup / root policy) vs the golden search
+traces recorded from the unmodified reference.  Network outputs are injected (north_star parity
+mode), noise and sampling uniforms are inputs, ties break to the lowest index.  Bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+FIXTURES = ["n3_s50_noise_t1", "n3_s25_nonoise_t0", "n3_s25_det", "n4_s200_lesion_t0", "n5_s100_noise_t05"]
+INF = float("inf")
+
+
+def _check_against_fixture(g, mcts, ks, paths, depths):
+    S = int(g["S"])
+    act, pi, q, visits = mcts.root_policy(float(g["temperature"]), bool(g["deterministic"]),
+                                          uniforms=g["uniform"][ks])
+    torch.cuda.synchronize()
+    assert np.array_equal(visits.cpu().numpy(), g["child_N"][ks])
+    assert np.array_equal(q.cpu().numpy(), g["root_q"][ks])  # float64, bit for bit
+    assert np.array_equal(pi.cpu().numpy(), g["pi"][ks])
+    assert np.array_equal(act.cpu().numpy(), g["action"][ks])
+    mm = mcts.store.minmax.cpu().numpy()
+    assert np.array_equal(mm[:, 0], g["mm_min"][ks]) and np.array_equal(mm[:, 1], g["mm_max"][ks])
+    if paths is not None:
+        paths, depths = paths.cpu().numpy(), depths.cpu().numpy()
+        for j, k in enumerate(ks):
+            assert np.array_equal(depths[:, j], g["depth"][k])
+            D = g["path"].shape[2]
+            assert np.array_equal(paths[:, j, :D], g["path"][k][:, :D])
+            assert (paths[:, j, D:] == 255).all()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_batched_injected_search_matches_reference(golden, name):
+    """All K recorded searches of a fixture run side by side as one batch, each slot's MinMaxStats
+    preloaded with the state the reference had before that search."""
+    from muzero_hanoi_b200.engine import BatchedMCTS
+
+    g = golden(f"search_{name}.npz")
+    S, K = int(g["S"]), int(g["K"])
+    ks = np.arange(K)
+    mcts = BatchedMCTS(float(g["discount"]), float(g["alpha"]), S, K)
+    mm0 = np.stack([np.concatenate([[INF], g["mm_min"][:-1]]), np.concatenate([[-INF], g["mm_max"][:-1]])], 1)
+    mcts.store.minmax.copy_(torch.from_numpy(mm0))
+    r = np.ascontiguousarray(g["r"].T)
+    v = np.ascontiguousarray(g["v"].T)
+    p = np.ascontiguousarray(g["p"].transpose(1, 0, 2))
+    paths, depths = mcts.run_injected(g["prior"], bool(g["prior_is_f64"]), r, p, v, want_paths=True)
+    _check_against_fixture(g, mcts, ks, paths, depths)
+
+
+@pytest.mark.parametrize("name", ["n3_s50_noise_t1", "n4_s200_lesion_t0"])
+def test_minmax_persists_across_moves(golden, name):
+    """One search slot replays the K consecutive moves of the reference episode: the (min, max) of
+    MinMaxStats must carry over from move to move exactly as on the reference's MCTS object."""
+    from muzero_hanoi_b200.engine import BatchedMCTS
+
+    g = golden(f"search_{name}.npz")
+    S, K = int(g["S"]), int(g["K"])
+    mcts = BatchedMCTS(float(g["discount"]), float(g["alpha"]), S, 1)
+    for k in range(K):
+        mcts.run_injected(g["prior"][k:k + 1], bool(g["prior_is_f64"]), g["r"][k][:, None], g["p"][k][:, None, :],
+                          g["v"][k][:, None])
+        _check_against_fixture(g, mcts, np.array([k]), None, None)
+
+
+def test_ragged_batch_and_record_layout(golden):
+    """Batch sizes that do not fill a warp segment / block, and the node-record layout itself."""
+    from muzero_hanoi_b200.engine import BatchedMCTS
+
+    g = golden("search_n3_s25_nonoise_t0.npz")
+    S = int(g["S"])
+    for B in (1, 3, 5, 33, 67):
+        ks = np.arange(B) % int(g["K"])
+        mcts = BatchedMCTS(float(g["discount"]), 0.0, S, B)
+        mm0 = np.stack([np.concatenate([[INF], g["mm_min"][:-1]]), np.concatenate([[-INF], g["mm_max"][:-1]])], 1)[ks]
+        mcts.store.minmax.copy_(torch.from_numpy(mm0))
+        mcts.run_injected(g["prior"][ks], False, np.ascontiguousarray(g["r"][ks].T),
+                          np.ascontiguousarray(g["p"][ks].transpose(1, 0, 2)), np.ascontiguousarray(g["v"][ks].T))
+        _check_against_fixture(g, mcts, ks, None, None)
+    rec = mcts.store.records()
+    assert (rec["N"][:, 0].sum(1) == S).all()  # sum of root child visits == n_simulations
+    assert (rec["parent"][:, 0] == 0).all()
+    for b in range(3):
+        for e in range(1, S + 1):
+            pe, pa = rec["parent"][b, e], rec["parent_action"][b, e]
+            assert rec["child"][b, pe, pa] == e  # parent/child links are mutual
+            assert np.array_equal(rec["prior"][b, e], g["p"][ks[b]][e - 1])
+            assert rec["rwd"][b, pe, pa] == g["r"][ks[b]][e - 1]
+
+
+def test_empty_batch_and_bad_arguments():
+    from muzero_hanoi_b200 import _lib
+    from muzero_hanoi_b200.engine import BatchedMCTS
+
+    mcts = BatchedMCTS(0.8, 0.0, 4, 2)
+    with pytest.raises(ValueError, match="temperature"):
+        mcts.root_policy(1.5, True)
+    with pytest.raises(_lib.HmzError):
+        mcts.select(10)  # simulation index beyond the record capacity
+    empty = BatchedMCTS(0.8, 0.0, 4, 0)
+    empty.store.reset_minmax()
