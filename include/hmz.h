@@ -155,6 +155,13 @@ int hmz_search_minmax_reset(double* minmax, int64_t n_searches, void* stream);
  * The root latent must already be in latents[:, 0, :] (written by hmz_net_initial). */
 int hmz_search_begin(const hmz_search_t* s, const double* root_prior, void* stream);
 
+/* Same, with the root prior built on the device from the float32 policy p0 [n_searches][6] of
+ * hmz_net_initial: prior = p0 when noise == NULL; otherwise add_dirichlet_noise
+ * (MCTS/mcts.py:132-152) with the Dirichlet draw supplied as noise float64 [n_searches][6]:
+ * prior = float64(float32(1-eps) * p0) + eps * noise.  s->root_prior_is_f64 must be
+ * (noise != NULL). */
+int hmz_search_begin_p0(const hmz_search_t* s, const float* p0, const double* noise, double eps, void* stream);
+
 /* Phase 1 of one simulation (MCTS/mcts.py:75-86 -> Node.best_child, node.py:72-123) for all
  * searches: walk from the root taking arg-max of f32(Q)+f32(U) (lowest index on ties) until an
  * unexpanded child.  ucb_table[n] = (log((n+19653)/19652)+1.25)*sqrt(n) for n in [0, sim],

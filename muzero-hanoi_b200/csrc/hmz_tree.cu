@@ -45,6 +45,28 @@ __global__ void __launch_bounds__(256) search_begin(hmz_search_t s, const double
   }
 }
 
+// Root prior from the network policy (+ optional Dirichlet mix, MCTS/mcts.py:148-150).
+__global__ void __launch_bounds__(256) search_begin_p0(hmz_search_t s, const float* __restrict__ p0,
+                                                      const double* __restrict__ noise, float one_minus_eps,
+                                                      double eps) {
+  const int lane8 = threadIdx.x & 7;
+  for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; b < s.n_searches;
+       b += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    float pr[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const float q = p0[b * 6 + a];
+      double p = (double)q;
+      if (noise != nullptr)  // (1-eps)*prob is a float32 product, the sum with eps*noise is float64
+        p = __dadd_rn((double)__fmul_rn(one_minus_eps, q), __dmul_rn(eps, noise[b * 6 + a]));
+      pr[a] = (float)p;
+      if (lane8 == 0) s.root_prior[b * 6 + a] = p;
+    }
+    write_fresh_record(&s.nodes[b * s.n_records], lane8, pr, 0, 0);
+    if (lane8 == 0) s.root_W[b] = 0.0;
+  }
+}
+
 __global__ void __launch_bounds__(256) search_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
                                                     double discount, uint16_t* __restrict__ leaf_parent,
                                                     uint8_t* __restrict__ leaf_action,
@@ -193,6 +215,17 @@ int hmz_search_begin(const hmz_search_t* s, const double* root_prior, void* stre
   if (!root_prior) return fail(HMZ_ERR_INVALID, "hmz_search_begin: null root_prior");
   search_begin<<<grid_for(s->n_searches, kSearchesPerBlock, 8), 256, 0, (cudaStream_t)stream>>>(*s, root_prior);
   return check_launch("search_begin");
+}
+
+int hmz_search_begin_p0(const hmz_search_t* s, const float* p0, const double* noise, double eps, void* stream) {
+  if (int rc = check_search(s, "hmz_search_begin_p0")) return rc;
+  if (s->n_searches == 0) return HMZ_OK;
+  if (!p0) return fail(HMZ_ERR_INVALID, "hmz_search_begin_p0: null p0");
+  if ((noise != nullptr) != (s->root_prior_is_f64 != 0))
+    return fail(HMZ_ERR_INVALID, "hmz_search_begin_p0: root_prior_is_f64 must be set iff noise is given");
+  search_begin_p0<<<grid_for(s->n_searches, kSearchesPerBlock, 8), 256, 0, (cudaStream_t)stream>>>(
+      *s, p0, noise, (float)(1.0 - eps), eps);
+  return check_launch("search_begin_p0");
 }
 
 int hmz_search_select(const hmz_search_t* s, int sim, const double* ucb_table, double discount, uint16_t* leaf_parent,

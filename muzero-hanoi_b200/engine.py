@@ -271,3 +271,86 @@ class BatchedMCTS:
                 depths[s].copy_(self.leaf_depth)
             self.expand_backup(s, r[s], p[s], v[s])
         return paths, depths
+
+
+# ------------------------------------------------------------------------------ weights
+STATE_DICT_ORDER = [f"{net}.{idx}.{kind}" for net in ("representation_net", "dynamic_net", "rwd_net", "policy_net",
+                                                      "value_net") for idx in ("0", "2") for kind in ("weight", "bias")]
+
+
+class PackedWeights:
+    """Device blob of a MuZeroNet state_dict in kernel layout (hmz_weights_pack).  Accepts a
+    state_dict of torch tensors or numpy arrays with the 20 keys of networks.py:39-67."""
+
+    def __init__(self, state_dict, n_disks, mode=_lib.MODE_FP32, device="cuda"):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.n_disks, self.mode = int(n_disks), int(mode)
+        self.device = torch.device(device)
+        arrays = []
+        for key in STATE_DICT_ORDER:
+            t = state_dict[key]
+            a = t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+            arrays.append(np.ascontiguousarray(a, dtype=np.float32))
+        expect = {"representation_net.0.weight": (256, 3 * n_disks), "dynamic_net.0.weight": (256, 70),
+                  "rwd_net.2.weight": (33, 256), "policy_net.2.weight": (6, 256), "value_net.2.weight": (33, 256)}
+        for key, shape in expect.items():
+            got = arrays[STATE_DICT_ORDER.index(key)].shape
+            if got != shape:
+                raise ValueError(f"{key}: expected shape {shape}, got {got} (TD_return=True nets with h1_s=256, "
+                                 "reprs_output_size=64 are supported)")
+        nbytes = int(self.lib.hmz_weights_packed_bytes(self.n_disks, self.mode))
+        if nbytes <= 0:
+            raise _lib.HmzError(_lib.ERR_UNSUPPORTED, f"no packed layout for n_disks={n_disks}, mode={mode}")
+        host = np.zeros(nbytes, dtype=np.uint8)
+        table = (C.c_void_p * 20)(*[a.ctypes.data for a in arrays])
+        check(self.lib.hmz_weights_pack(table, self.n_disks, self.mode, host.ctypes.data))
+        self.blob = torch.from_numpy(host).to(self.device)
+        self.ptr = C.c_void_p(self.blob.data_ptr())
+
+    def initial(self, n, *, words=None, obs=None, latents_out, out_rows_per_item, latent_dtype, p0, v0):
+        check(self.lib.hmz_net_initial(self.ptr, self.mode, self.n_disks, ptr(words), ptr(obs), ptr(latents_out),
+                                       out_rows_per_item, latent_dtype, ptr(p0), ptr(v0), n, current_stream()))
+
+    def recurrent(self, n, *, latents_in, in_rows_per_item, in_row, actions, latents_out, out_rows_per_item, out_row,
+                  latent_dtype, r, p, v):
+        check(self.lib.hmz_net_recurrent(self.ptr, self.mode, ptr(latents_in), in_rows_per_item, ptr(in_row),
+                                         ptr(actions), ptr(latents_out), out_rows_per_item, out_row, latent_dtype,
+                                         ptr(r), ptr(p), ptr(v), n, current_stream()))
+
+
+def mix_dirichlet(prior_f32: np.ndarray, noise_f64: np.ndarray, eps=0.25) -> np.ndarray:
+    """add_dirichlet_noise arithmetic (MCTS/mcts.py:148-150) with the draw supplied: the
+    (1-eps)*prob product stays float32 (weak python scalar), the sum promotes to float64."""
+    return (1 - eps) * np.asarray(prior_f32, dtype=np.float32) + eps * np.asarray(noise_f64, dtype=np.float64)
+
+
+def _run_mcts(self, weights: PackedWeights, *, words=None, obs=None, temperature=1.0, deterministic=False, noise=None,
+              uniforms=None):
+    """MCTS.run_mcts for B searches (MCTS/mcts.py:34-126): root inference, optional Dirichlet mix
+    (noise float64 [B,6] supplied by the caller), n_simulations fused simulations, root policy.
+    Returns device tensors (action int32 [B], pi float64 [B,6], root_q float64 [B], visits int32 [B,6])."""
+    if not 0.0 <= temperature <= 1.0:
+        raise ValueError(f"Expect `temperature` to be in the range [0.0, 1.0], got {temperature}")
+    st = self.store
+    p0 = torch.empty(self.B, 6, dtype=torch.float32, device=self.device)
+    v0 = torch.empty(self.B, dtype=torch.float32, device=self.device)
+    weights.initial(self.B, words=words, obs=obs, latents_out=st.latents, out_rows_per_item=st.n_records,
+                    latent_dtype=st.latent_dtype, p0=p0, v0=v0)
+    use_noise = (not deterministic) and self.root_dirichlet_alpha > 0.0 and self.root_exploration_eps > 0.0
+    nz = None
+    if use_noise:
+        if noise is None:
+            raise ValueError("Dirichlet noise is an input of the batched engine (`noise`, float64 [B,6])")
+        nz = torch.as_tensor(noise, dtype=torch.float64, device=self.device).contiguous()
+        assert nz.shape == (self.B, 6)
+    self.p0, self.v0 = p0, v0
+    st.desc.root_prior_is_f64 = int(use_noise)
+    check(self.lib.hmz_search_begin_p0(C.byref(st.desc), ptr(p0), ptr(nz), float(self.root_exploration_eps),
+                                       current_stream()))
+    check(self.lib.hmz_search_run(C.byref(st.desc), weights.ptr, weights.mode, self.n_simulations, ptr(self._table),
+                                  self.discount, current_stream()))
+    return self.root_policy(temperature, deterministic, uniforms)
+
+
+BatchedMCTS.run_mcts = _run_mcts

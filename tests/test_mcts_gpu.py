@@ -1,0 +1,144 @@
+"""GPU parity of the whole search (MCTS.run_mcts): BASELINE.json config 2 semantics —
+N=3, 4,096 parallel searches x 50 simulations — plus the drop-in MCTS class.
+
+Bit-exact gate: the device search (own float32 network) records the network outputs of every
+simulation; the C oracle (pinned to the reference, tests/test_oracle_golden.py) replays the tree
+arithmetic with those outputs injected and must reproduce visit counts, root values, leaf depths
+and the persistent min/max bit for bit.  The network outputs themselves are gated separately
+(tests/test_net_gpu.py, <= 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport, port
+
+pytestmark = pytest.mark.gpu
+
+
+def _split_search(mcts, weights, words, noise, record=True):
+    """BatchedMCTS.run_mcts unrolled into its phases so that per-simulation outputs can be recorded."""
+    import ctypes as C
+
+    from muzero_hanoi_b200 import _lib
+
+    st, B, S = mcts.store, mcts.B, mcts.n_simulations
+    dev = mcts.device
+    p0, v0 = torch.empty(B, 6, device=dev), torch.empty(B, device=dev)
+    weights.initial(B, words=words, latents_out=st.latents, out_rows_per_item=st.n_records, latent_dtype=0, p0=p0, v0=v0)
+    nz = None if noise is None else torch.from_numpy(noise).cuda()
+    st.desc.root_prior_is_f64 = int(noise is not None)
+    _lib.check(mcts.lib.hmz_search_begin_p0(C.byref(st.desc), _lib.ptr(p0), _lib.ptr(nz), 0.25, _lib.current_stream()))
+    r, v, p = torch.empty(S, B, device=dev), torch.empty(S, B, device=dev), torch.empty(S, B, 6, device=dev)
+    depth = torch.zeros(S, B, dtype=torch.int16, device=dev)
+    for s in range(S):
+        mcts.select(s)
+        depth[s].copy_(mcts.leaf_depth)
+        weights.recurrent(B, latents_in=st.latents, in_rows_per_item=st.n_records, in_row=mcts.leaf_parent,
+                          actions=mcts.leaf_action, latents_out=st.latents, out_rows_per_item=st.n_records,
+                          out_row=s + 1, latent_dtype=0, r=r[s], p=p[s], v=v[s])
+        mcts.expand_backup(s, r[s], p[s], v[s])
+    return p0, r, p, v, depth
+
+
+@pytest.mark.parametrize("n,B,S,use_noise", [(3, 4096, 50, True), (4, 1024, 200, False), (5, 2048, 100, True)])
+def test_config2_visit_counts_bit_exact_vs_oracle(n, B, S, use_noise):
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    weights = PackedWeights(port.make_weights(n, 0), n)
+    env = VecHanoi(n, 200, B)
+    non_goal = np.array([i for i in range(3 ** n) if i != 3 ** n - 1])
+    env.set_state_indices(non_goal[np.arange(B) % len(non_goal)].astype(np.int32))
+    rng = np.random.default_rng(0)
+    noise = rng.dirichlet(np.full(6, 0.25), size=B) if use_noise else None
+    mcts = BatchedMCTS(0.8, 0.25 if use_noise else 0.0, S, B)
+    for move in range(2):  # second move: MinMaxStats carried over, like a reused MCTS object
+        mm_before = mcts.store.minmax.cpu().numpy().copy()
+        p0, r, p, v, depth = _split_search(mcts, weights, env.words, noise)
+        act, pi, q, visits = mcts.root_policy(1.0, False, uniforms=rng.random(B))
+        torch.cuda.synchronize()
+        prior = mcts.store.root_prior.cpu().numpy()
+        if use_noise:
+            assert np.array_equal(prior, port.mix_dirichlet(p0.cpu().numpy(), noise))
+        else:
+            assert np.array_equal(prior, p0.cpu().numpy().astype(np.float64))
+        mm = mm_before.copy()
+        o_visits, o_q, o_depth = cport.search_injected(prior, use_noise, mm, r.cpu().numpy(), p.cpu().numpy(),
+                                                       v.cpu().numpy(), 0.8, port.ucb_table(S + 1), want_depth=True)
+        assert np.array_equal(visits.cpu().numpy(), o_visits)
+        assert np.array_equal(q.cpu().numpy(), o_q)
+        assert np.array_equal(depth.cpu().numpy().astype(np.uint16), o_depth)
+        assert np.array_equal(mcts.store.minmax.cpu().numpy(), mm)
+        assert (visits.sum(1) == S).all()
+        env.step(act.to(torch.uint8), want_obs=False)
+
+
+def test_fused_run_equals_split_phases():
+    """hmz_search_run (one call) == select / recurrent / expand_backup issued one by one."""
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    n, B, S = 3, 777, 30
+    weights = PackedWeights(port.make_weights(n, 5), n)
+    env = VecHanoi(n, 200, B)
+    env.random_reset(seed=3)
+    noise = np.random.default_rng(1).dirichlet(np.full(6, 0.25), size=B)
+    a, b = BatchedMCTS(0.8, 0.25, S, B), BatchedMCTS(0.8, 0.25, S, B)
+    _split_search(a, weights, env.words, noise)
+    u = np.random.default_rng(2).random(B)
+    ra = [t.clone() for t in a.root_policy(0.5, False, uniforms=u)]
+    rb = b.run_mcts(weights, words=env.words, temperature=0.5, deterministic=False, noise=noise, uniforms=u)
+    for x, y in zip(ra, rb):
+        assert torch.equal(x, y)
+    assert torch.equal(a.store.nodes, b.store.nodes) and torch.equal(a.store.minmax, b.store.minmax)
+
+
+@pytest.mark.parametrize("name", ["n3_s50_noise_t1", "n3_s25_nonoise_t0", "n5_s100_noise_t05"])
+def test_dropin_mcts_close_to_reference_episode(golden, name):
+    """Drop-in MCTS + MuZeroNet + TowersOfHanoi replaying a reference episode with the reference's
+    noise / uniform draws.  The device network is float32-close (not bit-identical) to torch's
+    CPU kernels, so visit counts are compared statistically: root policy within 1e-5 and a mean
+    absolute visit difference under 2% of the simulation budget; exact agreement is reported."""
+    from muzero_hanoi_b200.MCTS.mcts import MCTS
+    from muzero_hanoi_b200.networks import MuZeroNet
+
+    g = golden(f"search_{name}.npz")
+    n, S, K = int(g["N"]), int(g["S"]), int(g["K"])
+    net = MuZeroNet(3 * n, 6, 0.002, "cpu", TD_return=True)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in port.make_weights(n, int(g["weight_seed"])).items()})
+    mcts = MCTS(float(g["discount"]), float(g["alpha"]), S, 1, "cpu")
+
+    class _Feed:  # supplies the reference's recorded draws through the np.random calls run_mcts makes
+        def __init__(self):
+            self.k = 0
+
+        def dirichlet(self, alphas):
+            return g["noise"][self.k]
+
+        def random_sample(self):
+            return g["uniform"][self.k]
+
+    feed = _Feed()
+    import muzero_hanoi_b200.MCTS.mcts as mod
+
+    real = mod.np.random
+    mod.np.random = feed
+    try:
+        diffs, exact = [], 0
+        for k in range(K):
+            feed.k = k
+            action, pi, q = mcts.run_mcts(g["obs"][k], net, float(g["temperature"]), bool(g["deterministic"]))
+            assert isinstance(action, int) and pi.dtype == np.float64 and pi.shape == (6,) and isinstance(q, float)
+            visits = mcts._engine.visits.cpu().numpy()[0]
+            assert visits.sum() == S
+            assert np.abs(mcts._engine.p0.cpu().numpy()[0] - g["p0"][k]).max() <= 1e-5
+            diffs.append(np.abs(visits - g["child_N"][k]).sum() / 2)
+            exact += int(np.array_equal(visits, g["child_N"][k]))
+            # keep the persistent MinMaxStats on the reference trajectory for the next move
+            mcts.min_max_stats.minimum, mcts.min_max_stats.maximum = float(g["mm_min"][k]), float(g["mm_max"][k])
+            la = mcts.return_latent_actions()
+            assert 1 <= len(la) <= S and all(t.dtype == torch.long and t.shape == (1,) for t in la)
+    finally:
+        mod.np.random = real
+    print(f"{name}: {exact}/{K} searches with identical visit counts, mean moved visits {np.mean(diffs):.2f} of {S}")
+    assert np.mean(diffs) <= 0.02 * S + 0.5
+    with pytest.raises(ValueError):
+        mcts.run_mcts(g["obs"][0], net, 1.5, True)

@@ -1,0 +1,123 @@
+"""GPU parity: MuZeroNet inference kernels (through the C ABI) vs outputs recorded from the
+unmodified reference network (tests/golden/net_io.npz).
+
+Tolerances (HMZ_MODE_FP32, north_star: within 1e-5 relative in fp32):
+  latent h and policy p (both in [0, 1]):      |d| <= 1e-5            (relative to their unit scale)
+  reward r and value v (support transform):    |d| <= 1e-5 * |ref| + 2.5e-4
+The absolute term for r/v is the float32 granularity of the reference's OWN signed-parabolic
+evaluation (networks.py:186-189 computes sqrt(..)/2/eps - 1/2/eps ~ 500.x - 500 in float32, i.e.
+its outputs live on a ~1.2e-4 grid near zero), so a 1-ulp difference in the softmax expectation
+moves the reference's result by one grid step; two grid steps are allowed."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+H_TOL, RV_REL, RV_ABS = 1e-5, 1e-5, 2.5e-4
+
+
+def _close_rv(got, ref):
+    return np.all(np.abs(got - ref) <= RV_REL * np.abs(ref) + RV_ABS)
+
+
+def _weights(n, seed, mode=0):
+    from muzero_hanoi_b200.engine import PackedWeights
+
+    return PackedWeights(port.make_weights(n, seed), n, mode)
+
+
+@pytest.mark.parametrize("n", [3, 5, 10])
+@pytest.mark.parametrize("count", [96, 33, 1])
+def test_recurrent_matches_reference(golden, n, count):
+    g = golden("net_io.npz")
+    w = _weights(n, int(g[f"n{n}_weight_seed"]))
+    h_in = torch.from_numpy(g[f"n{n}_h_in"][:count]).cuda()
+    acts = torch.from_numpy(g[f"n{n}_action"][:count].astype(np.uint8)).cuda()
+    h = torch.empty(count, 64, device="cuda")
+    r, v, p = torch.empty(count, device="cuda"), torch.empty(count, device="cuda"), torch.empty(count, 6, device="cuda")
+    w.recurrent(count, latents_in=h_in, in_rows_per_item=1, in_row=None, actions=acts, latents_out=h,
+                out_rows_per_item=1, out_row=0, latent_dtype=0, r=r, p=p, v=v)
+    torch.cuda.synchronize()
+    assert np.abs(h.cpu().numpy() - g[f"n{n}_h_out"][:count]).max() <= H_TOL
+    assert np.abs(p.cpu().numpy() - g[f"n{n}_p"][:count]).max() <= H_TOL
+    assert _close_rv(r.cpu().numpy(), g[f"n{n}_r"][:count]) and _close_rv(v.cpu().numpy(), g[f"n{n}_v"][:count])
+
+
+@pytest.mark.parametrize("n", [3, 5, 10])
+def test_initial_matches_reference_words_and_obs_paths(golden, n):
+    from muzero_hanoi_b200.engine import VecHanoi
+
+    g = golden("net_io.npz")
+    count = 96
+    w = _weights(n, int(g[f"n{n}_weight_seed"]))
+    env = VecHanoi(n, 200, count)
+    env.set_state_indices(g[f"n{n}_state_idx"].astype(np.int32))
+    outs = []
+    for use_words in (True, False):
+        h = torch.empty(count, 64, device="cuda")
+        p0, v0 = torch.empty(count, 6, device="cuda"), torch.empty(count, device="cuda")
+        w.initial(count, words=env.words if use_words else None, obs=None if use_words else env.onehot(),
+                  latents_out=h, out_rows_per_item=1, latent_dtype=0, p0=p0, v0=v0)
+        torch.cuda.synchronize()
+        outs.append((h.cpu().numpy(), p0.cpu().numpy(), v0.cpu().numpy()))
+        assert np.abs(outs[-1][0] - g[f"n{n}_h0"]).max() <= H_TOL
+        assert np.abs(outs[-1][1] - g[f"n{n}_p0"]).max() <= H_TOL
+        assert _close_rv(outs[-1][2], g[f"n{n}_v0"])
+    for a, b in zip(*outs):  # packed-word and float-observation paths add the same terms in the same order
+        assert np.array_equal(a, b)
+
+
+def test_gather_scatter_rows_and_bf16_latent_store(golden):
+    """The search-facing addressing: input row = item*E_in + in_row[item], output row = item*E_out + out_row."""
+    g = golden("net_io.npz")
+    n, count, E = 3, 40, 5
+    w = _weights(n, int(g["n3_weight_seed"]))
+    rows = np.arange(count) % E
+    lat = torch.zeros(count, E, 64, device="cuda")
+    lat[torch.arange(count), torch.from_numpy(rows)] = torch.from_numpy(g["n3_h_in"][:count]).cuda()
+    out = torch.zeros(count, E + 1, 64, device="cuda")
+    acts = torch.from_numpy(g["n3_action"][:count].astype(np.uint8)).cuda()
+    r, v, p = torch.empty(count, device="cuda"), torch.empty(count, device="cuda"), torch.empty(count, 6, device="cuda")
+    w.recurrent(count, latents_in=lat, in_rows_per_item=E, in_row=torch.from_numpy(rows.astype(np.int16)).cuda(),
+                actions=acts, latents_out=out, out_rows_per_item=E + 1, out_row=E, latent_dtype=0, r=r, p=p, v=v)
+    torch.cuda.synchronize()
+    assert np.abs(out[:, E].cpu().numpy() - g["n3_h_out"][:count]).max() <= H_TOL
+    assert float(out[:, :E].abs().max()) == 0.0
+    outb = torch.zeros(count, 64, dtype=torch.bfloat16, device="cuda")
+    w.recurrent(count, latents_in=lat.to(torch.bfloat16), in_rows_per_item=E,
+                in_row=torch.from_numpy(rows.astype(np.int16)).cuda(), actions=acts, latents_out=outb,
+                out_rows_per_item=1, out_row=0, latent_dtype=1, r=r, p=p, v=v)
+    torch.cuda.synchronize()
+    assert np.abs(outb.float().cpu().numpy() - g["n3_h_out"][:count]).max() <= 2e-2
+
+
+def test_dropin_muzeronet_surface(golden):
+    from muzero_hanoi_b200.networks import MuZeroNet
+
+    g = golden("net_io.npz")
+    net = MuZeroNet(rpr_input_s=9, action_s=6, lr=0.002, device="cpu", TD_return=True)
+    want_keys = [f"{m}.{i}.{k}" for m in ("representation_net", "dynamic_net", "rwd_net", "policy_net", "value_net")
+                 for i in (0, 2) for k in ("weight", "bias")]
+    assert list(net.state_dict().keys()) == want_keys
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in port.make_weights(3, 0).items()})
+    a1 = torch.zeros(6)
+    a1[int(g["n3_action"][0])] = 1.0
+    h, r, p, v = net.recurrent_inference(torch.from_numpy(g["n3_h_in"][0]), a1)
+    assert h.dtype == np.float32 and h.shape == (64,) and p.dtype == np.float32 and p.shape == (6,)
+    assert isinstance(r, float) and isinstance(v, float)
+    assert np.abs(h - g["n3_h_out"][0]).max() <= H_TOL and _close_rv(np.float32(r), g["n3_r"][0])
+    obs = port.one_hot(port.index_to_state(int(g["n3_state_idx"][0]), 3))
+    h0, r0, p0, v0 = net.initial_inference(torch.from_numpy(obs).to(torch.float32))
+    assert r0 == 0.0 and np.abs(p0 - g["n3_p0"][0]).max() <= H_TOL
+    h0b, _, _, _ = net.initial_inference(torch.from_numpy(obs).to(torch.float32).reshape(1, 9))  # batched [1, 9] form
+    assert np.array_equal(h0, h0b)
+    # lesion: reset_param changes the weights, the packed blob follows (acting_ablations.py:29-45)
+    torch.manual_seed(0)
+    net.policy_net.apply(net.reset_param)
+    _, _, p1, _ = net.initial_inference(torch.from_numpy(obs).to(torch.float32))
+    assert not np.array_equal(p0, p1)
+    with torch.no_grad():  # differentiable torch forms stay consistent with the kernels
+        hh = net.represent(torch.from_numpy(obs).to(torch.float32))
+    assert np.abs(hh.numpy() - h0).max() <= H_TOL

@@ -144,3 +144,45 @@ def test_ucb_table_and_policy_helpers():
 def test_n_step_returns():
     r = port.n_step_returns([0, 0, 100], [1.0, 2.0, 3.0], 2, 0.5)
     assert r == [0 + 0.5 * 0 + 0.25 * 3.0, 0 + 0.5 * 100 + 0.25 * 0, 100 + 0 + 0]
+
+
+# ------------------------------------------------------------- C oracle (fast checker) pinning
+@pytest.mark.parametrize("name", SEARCH_FIXTURES)
+def test_c_oracle_search_matches_reference(golden, name):
+    from oracle import cport
+
+    g = golden(f"search_{name}.npz")
+    S, K = int(g["S"]), int(g["K"])
+    inf = float("inf")
+    mm = np.stack([np.concatenate([[inf], g["mm_min"][:-1]]), np.concatenate([[-inf], g["mm_max"][:-1]])], 1).copy()
+    visits, q, depth = cport.search_injected(
+        g["prior"], bool(g["prior_is_f64"]), mm, np.ascontiguousarray(g["r"].T), np.ascontiguousarray(g["p"].transpose(1, 0, 2)),
+        np.ascontiguousarray(g["v"].T), float(g["discount"]), port.ucb_table(S + 1), want_depth=True)
+    assert np.array_equal(visits, g["child_N"]) and np.array_equal(q, g["root_q"])
+    assert np.array_equal(mm[:, 0], g["mm_min"]) and np.array_equal(mm[:, 1], g["mm_max"])
+    assert np.array_equal(depth.T, g["depth"])
+
+
+@pytest.mark.parametrize("n", [3, 5, 7, 10])
+def test_c_oracle_env_matches_reference_tables(golden, n):
+    from oracle import cport
+
+    g = golden("env_tables.npz")
+    states = np.array([port.state_to_packed(port.index_to_state(i, n)) for i in range(3 ** n)], dtype=np.uint32)
+    lut = np.zeros(1 << (2 * n), dtype=np.int64)
+    lut[states] = np.arange(3 ** n)
+    for vi in range(g[f"n{n}_obs_idx"].shape[0]):
+        c0 = int(g["counter_before"][vi])
+        words = (np.repeat(states, 6) | np.uint32(c0 << (2 * n))).astype(np.uint32)
+        acts = np.tile(np.arange(6, dtype=np.uint8), 3 ** n)
+        rew, flags, obs = cport.env_step(words, acts, n, int(g["max_steps"]))
+        shape = (3 ** n, 6)
+        assert np.array_equal(lut[obs].reshape(shape), g[f"n{n}_obs_idx"][vi])
+        assert np.array_equal(lut[words & ((1 << (2 * n)) - 1)].reshape(shape), g[f"n{n}_stored_idx"][vi])
+        assert np.array_equal((words >> (2 * n)).reshape(shape), g[f"n{n}_counter_after"][vi])
+        assert np.array_equal((flags & 1).reshape(shape), g[f"n{n}_done"][vi])
+        assert np.array_equal(((flags >> 1) & 1).reshape(shape), g[f"n{n}_illegal"][vi])
+        code = np.where(rew == 100, 1, np.where(rew == 0, 0, 2))
+        assert np.array_equal(code.reshape(shape), g[f"n{n}_reward_code"][vi])
+    assert np.array_equal(cport.legal_mask(states, n), g[f"n{n}_legal"])
+    assert np.array_equal(cport.solver(states, n), g[f"n{n}_solver"])
