@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native MuZero/Hanoi acting engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the config the metric's targets are quoted on): Tower of Hanoi
+with 5 disks, 65,536 parallel self-play games PER GPU x 100 MCTS simulations per move, random-init
+h/g/f networks, Dirichlet root noise, temperature 1.  A "step" is one move of every game:
+root inference -> 100 x (select -> g+f MLP -> expand+backup) -> root policy -> env step.
+`value` = MCTS simulations / s over all GPUs (weak scaling: games per GPU fixed), state resident
+in HBM; `e2e` = the same step with the env words coming from pinned host memory and the move's
+records (state, action, reward, flags, visits, root value) read back to the host every step.
+One JSON line on stdout (rank 0); progress goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_DISKS, GAMES_PER_GPU, N_SIMS, MAX_STEPS = 5, 65536, 100, 200
+DISCOUNT, ALPHA, EPS, TEMPERATURE = 0.8, 0.25, 0.25, 1.0
+FLOP_PER_SIM = 203_776  # 101,888 MAC of g + reward/policy/value heads, un-padded
+ENV_BYTES_PER_STEP = 14  # word r/w 8 + action 1 + reward 4 + flags 1
+METRIC, UNIT = "mcts_simulations_per_second", "sims/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    """One host process of the reference-style CPU path: the oracle port (numpy tree + one-row
+    float32 torch network, oracle/port.py) playing Hanoi self-play moves for `budget_s` seconds
+    or `n_moves` moves."""
+    seed, n_moves, budget_s = args
+    import numpy as np
+    import torch
+
+    from oracle import port
+
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(seed)
+    net = port.PortNet(port.make_weights(N_DISKS, 0))
+    env = port.PortHanoi(N_DISKS, MAX_STEPS)
+    mm = port.MinMax()
+    obs = env.reset()
+    sims = moves = 0
+    t0 = time.perf_counter()
+    while (n_moves is None or moves < n_moves) and (budget_s is None or time.perf_counter() - t0 < budget_s):
+        a, _, _, _, _ = port.run_mcts_port(obs, net, port.PortSearch(DISCOUNT, N_SIMS, mm), TEMPERATURE, False,
+                                           alpha=ALPHA, noise=rng.dirichlet(np.full(6, ALPHA)), u=rng.random())
+        obs, _, done, _ = env.step(a)
+        if done:
+            obs = env.reset()
+        sims += N_SIMS
+        moves += 1
+    return sims, moves, time.perf_counter() - t0
+
+
+def cpu_reference_rate(n_procs, n_moves=None, budget_s=None, pool=None):
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(n_procs)
+    try:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(1000 + i, n_moves, budget_s) for i in range(n_procs)])
+        wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
+    sims = sum(r[0] for r in res)
+    moves = sum(r[1] for r in res)
+    return sims / wall, moves / wall, wall, sims
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure
+    Python and cannot travel to the box) on all host cores, same metric / unit / config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    moves_per_step = 2
+    pool = mp.get_context("fork").Pool(cores)
+    try:
+        for _ in range(args.warmup):
+            cpu_reference_rate(cores, n_moves=1, pool=pool)
+        t0 = time.perf_counter()
+        sims = 0
+        for _ in range(args.steps):
+            _, _, _, s = cpu_reference_rate(cores, n_moves=moves_per_step, pool=pool)
+            sims += s
+        wall = time.perf_counter() - t0
+    finally:
+        pool.close()
+        pool.join()
+    value = sims / wall
+    sample = f"{cores} processes x {moves_per_step} moves x {N_SIMS} sims per step (N={N_DISKS}), oracle port of the reference"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall / max(1, args.steps) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "env_steps_per_second": value / N_SIMS,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ ours
+def workload_config(args, world):
+    return {
+        "workload": f"hanoi{N_DISKS}_selfplay_{GAMES_PER_GPU}games_per_gpu_x{N_SIMS}sims (BASELINE.json configs[2])",
+        "n_disks": N_DISKS, "games_per_gpu": args.games, "global_games": args.games * world, "n_simulations": args.sims,
+        "max_steps": MAX_STEPS, "discount": DISCOUNT, "dirichlet_alpha": ALPHA, "temperature": TEMPERATURE,
+        "mode": args.mode, "parallelism": f"games sharded over {world} GPU(s), NCCL all-gather of move records only",
+        "cache": "working set (tree + latents ~2.5 GB/GPU) is larger than the 126 MB L2; no L2 flush needed",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    # CPU baseline first (rank 0, N=1 only): fork()ing is only safe before CUDA is initialised.
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    cpu_baseline = None
+    if world_env == 1 and args.gpus == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        log(f"[bench] CPU baseline: oracle port on {cores} processes for ~{args.cpu_seconds:.0f} s ...")
+        rate, moves_rate, wall, sims = cpu_reference_rate(cores, budget_s=args.cpu_seconds)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{cores} processes x {wall:.1f} s of N={N_DISKS}, S={N_SIMS} self-play moves "
+                                  f"({sims} simulations) through oracle/port.py (numpy tree + 1-row fp32 torch net)",
+                        "env_steps_per_second": moves_rate}
+        log(f"[bench] CPU baseline: {rate:.1f} sims/s on {cores} cores")
+
+    from muzero_hanoi_b200 import _lib
+    from muzero_hanoi_b200 import dist as hdist
+    from muzero_hanoi_b200.engine import PackedWeights, SelfPlay, VecHanoi
+    from muzero_hanoi_b200.networks import MuZeroNet
+
+    rank, world, local = hdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    mode = _lib.MODE_BF16 if args.mode == "bf16" else _lib.MODE_FP32
+    latent_dtype = _lib.LATENT_BF16 if args.mode == "bf16" else _lib.LATENT_F32
+    torch.manual_seed(0)
+    net = MuZeroNet(3 * N_DISKS, 6, 0.002, "cpu", TD_return=True)  # random-init h / g / f
+    weights = PackedWeights(net.state_dict(), N_DISKS, mode, dev)
+    B, S = args.games, args.sims
+    sp = SelfPlay(N_DISKS, MAX_STEPS, B, S, weights, DISCOUNT, ALPHA, EPS, TEMPERATURE, seed=1234 + rank,
+                  ring_slots=4, device=dev, latent_dtype=latent_dtype)
+    gather_buf = torch.empty(world * B, 26, dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step():
+        t = sp.move()
+        if world > 1:
+            hdist.all_gather_records(sp.slot(t), gather_buf)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    log(f"[bench] rank {rank}/{world}: warm-up {args.warmup} steps (B={B}, S={S}, mode={args.mode})")
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.hmz_launch_count()
+    ms = timed(step, args.steps)
+    launches = lib.hmz_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    sims_per_s = world * B * S * args.steps / (ms * 1e-3)
+    log(f"[bench] {ms / args.steps:.2f} ms/step -> {sims_per_s:.3e} sims/s")
+
+    # ---- per-kernel device time over the same steps (CUDA-event pairs on the launch stream)
+    barrier()
+    _lib.check(lib.hmz_prof_begin())
+    for _ in range(args.steps):
+        step()
+    ms_cls = (C.c_double * 8)()
+    n_cls = (C.c_int64 * 8)()
+    _lib.check(lib.hmz_prof_end(ms_cls, n_cls))
+    names = ["env_step", "select", "net_recurrent", "expand_backup", "net_initial", "root_policy", "other", "-"]
+    kern = {names[i]: {"ms_total": ms_cls[i], "launches": int(n_cls[i]),
+                       "us_per_launch": (ms_cls[i] / n_cls[i] * 1e3) if n_cls[i] else None} for i in range(7)}
+    total_kernel_ms = sum(ms_cls[i] for i in range(7))
+    for k, v in kern.items():
+        v["share"] = v["ms_total"] / total_kernel_ms if total_kernel_ms else None
+    dominant = max(("select", "net_recurrent", "expand_backup"), key=lambda k: kern[k]["ms_total"])
+    peaks = measured_peaks()
+    if dominant == "net_recurrent":
+        per_launch_s = kern[dominant]["us_per_launch"] * 1e-6
+        achieved = FLOP_PER_SIM * B / per_launch_s / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"kernel": "net_recurrent (fused g + reward/policy/value heads)", "bound": "tensor",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peaks["source"] + ", sustained bf16",
+                    "algorithmic": f"{FLOP_PER_SIM} FLOP/sim x {B} sims per launch"}
+    else:
+        # tree kernels: 156*d + 672 B/sim split between select (128 B/level) and expand+backup
+        per_launch_s = kern[dominant]["us_per_launch"] * 1e-6
+        depth = 3.3
+        bytes_per_sim = 128 * depth if dominant == "select" else (28 * (depth + 1) + 32 + 128 + 40)
+        achieved = bytes_per_sim * B / per_launch_s / 1e9
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "algorithmic": f"{bytes_per_sim:.0f} B/sim x {B} sims per launch (mean leaf depth {depth})"}
+
+    # ---- end to end: env words from pinned host memory in, move records back to the host, every step
+    h_words = torch.empty(B, dtype=torch.int32).pin_memory()
+    h_words.copy_(sp.env.words.cpu())
+    h_out = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in sp.slot(0).items()}
+    h_next = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        sp.env.words.copy_(h_words, non_blocking=True)
+        t = sp.move()
+        for k, v in sp.slot(t).items():
+            h_out[k].copy_(v, non_blocking=True)
+        h_next.copy_(sp.env.words, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h_words.copy_(h_next)  # the host owns the env state between steps
+        if world > 1:
+            hdist.all_gather_records(sp.slot(t), gather_buf)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_rate = world * B * S * args.steps / (ms_e2e * 1e-3)
+    d2h = sum(v.numel() * v.element_size() for v in h_out.values()) + 4 * B
+
+    # ---- raw env throughput (BASELINE.json configs[3]: N=10, 2^24 envs, random legal moves)
+    env_line = None
+    if not args.no_env:
+        nenv = 1 << 24
+        env = VecHanoi(10, 200, nenv, dev)
+        env.reset()
+        acts = torch.randint(0, 6, (nenv,), dtype=torch.uint8, device=dev)
+        k_env = [0]
+
+        def env_step_fixed():
+            env.step(acts, want_obs=False)
+
+        def env_step_rand():
+            env.step_random(seed=1, step_index=k_env[0])
+            k_env[0] += 1
+
+        for f in (env_step_fixed, env_step_rand):
+            for _ in range(3):
+                f()
+        ms_env = timed(env_step_fixed, 20) / 20
+        ms_rand = timed(env_step_rand, 20) / 20
+        ms_roll = timed(lambda: env.rollout_random(64, seed=1, step_index=0), 3) / 3
+        gbs = ENV_BYTES_PER_STEP * nenv / (ms_env * 1e-3) / 1e9
+        env_line = {"workload": "hanoi10_2^24envs (BASELINE.json configs[3])", "n_envs_per_gpu": nenv,
+                    "step_given_actions_per_s": world * nenv / (ms_env * 1e-3),
+                    "step_random_legal_per_s": world * nenv / (ms_rand * 1e-3),
+                    "fused_rollout64_random_legal_per_s": world * nenv * 64 / (ms_roll * 1e-3),
+                    "roofline": {"kernel": "env_step_vec4", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                                 "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                 "algorithmic": f"{ENV_BYTES_PER_STEP} B/step x {nenv} steps per launch"}}
+        del env, acts
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": sims_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": e2e_rate, "unit": UNIT, "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline, "kernels": kern,
+            "env_steps_per_second": world * B * args.steps / (ms * 1e-3), "env": env_line,
+            "targets": {"sims_per_s_8gpu": 1e8, "env_steps_per_s_8gpu": 1e9},
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--mode", choices=["bf16", "fp32"], default=os.environ.get("HMZ_BENCH_MODE", "fp32"))
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU, help="games per GPU (default: BASELINE config)")
+    ap.add_argument("--sims", type=int, default=N_SIMS)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-env", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

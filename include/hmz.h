@@ -52,6 +52,21 @@ int hmz_version(void);
 int64_t hmz_launch_count(void);
 int hmz_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Optional per-kernel timing for bench.py's roofline: between hmz_prof_begin() and
+ * hmz_prof_end() every kernel this library launches is bracketed by a CUDA-event pair on its
+ * own stream.  hmz_prof_end synchronises those events and returns, per kernel class, the summed
+ * device time in milliseconds and the number of launches.  Classes: */
+#define HMZ_PROF_ENV 0
+#define HMZ_PROF_SELECT 1
+#define HMZ_PROF_NET_RECURRENT 2
+#define HMZ_PROF_EXPAND_BACKUP 3
+#define HMZ_PROF_NET_INITIAL 4
+#define HMZ_PROF_ROOT_POLICY 5
+#define HMZ_PROF_OTHER 6
+#define HMZ_PROF_CLASSES 8
+int hmz_prof_begin(void);
+int hmz_prof_end(double* ms_by_class, int64_t* launches_by_class);
+
 /* ------------------------------------------------------------------ environment ----
  * Env word (uint32): bits [0, 2N) hold the peg (0..2) of disk d at bits [2d, 2d+2), disk 0
  * smallest — the tuple of env/hanoi.py:19-25 packed; bits [2N, 32) hold step_counter
@@ -222,6 +237,25 @@ int hmz_net_recurrent(const void* weights, int mode, const void* latents_in, int
  * search in one launch sequence with no host round trips (MCTS.run_mcts, MCTS/mcts.py:71-109). */
 int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_simulations,
                    const double* ucb_table, double discount, void* stream);
+
+/* ------------------------------------------------------------------ self-play glue ---
+ * Throughput-mode randomness, drawn on device with Philox4x32-10 keyed by (seed, item,
+ * counter) so results do not depend on how games are sharded over GPUs.  Parity mode passes
+ * the reference's own draws to hmz_search_begin_p0 / hmz_search_root_policy instead.
+ */
+/* np.random.dirichlet(alpha * ones(6)) (MCTS/mcts.py:148-149): out float64 [n][6]. */
+int hmz_rng_dirichlet(double* out, int64_t n, double alpha, uint64_t seed, uint64_t counter, void* stream);
+/* One uniform double in [0, 1) per item (the draw of np.random.choice, MCTS/mcts.py:120). */
+int hmz_rng_uniform(double* out, int64_t n, uint64_t seed, uint64_t counter, void* stream);
+
+/* One trajectory record per game and move — the episode lists of Muzero._play_game
+ * (Muzero.py:179-183) in struct-of-arrays form, slot `t` of a [n_slots][n_games] ring:
+ *   state  uint32  env word BEFORE the move        action  uint8
+ *   visits uint16[6] root child visit counts        root_q  float32 (root_node.Q)
+ * (reward and flags of the move are written by hmz_env_step straight into their ring rows.) */
+int hmz_traj_record(const uint32_t* words, const int32_t* action, const int32_t* visits, const double* root_q,
+                    uint32_t* traj_state, uint8_t* traj_action, uint16_t* traj_visits, float* traj_root_q,
+                    uint8_t* action_u8_out, int64_t n_games, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,8 @@ SIGNATURES = {
     "hmz_version": (_I, []),
     "hmz_launch_count": (_L, []),
     "hmz_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "hmz_prof_begin": (_I, []),
+    "hmz_prof_end": (_I, [_P, _P]),
     "hmz_env_reset": (_I, [_P, _L, _U32, _P]),
     "hmz_env_from_index": (_I, [_P, _P, _L, _I, _P]),
     "hmz_env_to_index": (_I, [_P, _P, _L, _I, _P]),
@@ -70,6 +72,9 @@ SIGNATURES = {
     "hmz_net_initial": (_I, [_P, _I, _I, _P, _P, _P, _L, _I, _P, _P, _L, _P]),
     "hmz_net_recurrent": (_I, [_P, _I, _P, _L, _P, _P, _P, _L, _L, _I, _P, _P, _P, _L, _P]),
     "hmz_search_run": (_I, [_SD, _P, _I, _I, _P, _D, _P]),
+    "hmz_rng_dirichlet": (_I, [_P, _L, _D, _U64, _U64, _P]),
+    "hmz_rng_uniform": (_I, [_P, _L, _U64, _U64, _P]),
+    "hmz_traj_record": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
 }
 
 _lock = threading.Lock()

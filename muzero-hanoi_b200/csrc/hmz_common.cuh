@@ -25,6 +25,21 @@ inline int check_launch(const char* what) {
   return HMZ_OK;
 }
 
+// RAII CUDA-event bracket around the launches of one extern "C" entry point (hmz_prof_*).
+extern std::atomic<int> g_prof_on;
+void prof_push(int cls, cudaStream_t stream, bool start);
+struct ProfScope {
+  int cls;
+  cudaStream_t stream;
+  bool on;
+  ProfScope(int c, void* s) : cls(c), stream((cudaStream_t)s), on(g_prof_on.load(std::memory_order_relaxed) != 0) {
+    if (on) prof_push(cls, stream, true);
+  }
+  ~ProfScope() {
+    if (on) prof_push(cls, stream, false);
+  }
+};
+
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
 
 // Grid for a grid-stride kernel: a whole number of waves of `ctas_per_sm` CTAs on every SM,

@@ -296,6 +296,7 @@ using namespace hmz;
 extern "C" {
 
 int hmz_env_reset(uint32_t* words, int64_t n, uint32_t reset_word, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n == 0) return HMZ_OK;
   if (!words || n < 0) return fail(HMZ_ERR_INVALID, "hmz_env_reset: null pointer or negative size");
   env_fill<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(words, n, reset_word);
@@ -303,6 +304,7 @@ int hmz_env_reset(uint32_t* words, int64_t n, uint32_t reset_word, void* stream)
 }
 
 int hmz_env_from_index(const uint32_t* index, uint32_t* words, int64_t n, int n_disks, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n == 0) return HMZ_OK;
   if (!index || !words || n < 0 || n_disks < 1 || n_disks > HMZ_MAX_DISKS)
     return fail(HMZ_ERR_INVALID, "hmz_env_from_index: bad arguments");
@@ -311,6 +313,7 @@ int hmz_env_from_index(const uint32_t* index, uint32_t* words, int64_t n, int n_
 }
 
 int hmz_env_to_index(const uint32_t* words, uint32_t* index, int64_t n, int n_disks, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n == 0) return HMZ_OK;
   if (!index || !words || n < 0 || n_disks < 1 || n_disks > HMZ_MAX_DISKS)
     return fail(HMZ_ERR_INVALID, "hmz_env_to_index: bad arguments");
@@ -320,6 +323,7 @@ int hmz_env_to_index(const uint32_t* words, uint32_t* index, int64_t n, int n_di
 
 int hmz_env_random_reset(uint32_t* words, int64_t n, int n_disks, int goal_peg, uint64_t seed, uint64_t counter,
                          void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n == 0) return HMZ_OK;
   if (!words || n < 0 || n_disks < 1 || n_disks > HMZ_MAX_DISKS || goal_peg < 0 || goal_peg > 2)
     return fail(HMZ_ERR_INVALID, "hmz_env_random_reset: bad arguments");
@@ -338,6 +342,7 @@ int hmz_env_random_reset(uint32_t* words, int64_t n, int n_disks, int goal_peg, 
 int hmz_env_step(uint32_t* words, const uint8_t* actions, float* rewards, uint8_t* flags, uint32_t* obs_words,
                  int64_t n, int n_disks, int max_steps, int goal_peg, int auto_reset, uint32_t reset_word,
                  void* stream) {
+  ProfScope prof_scope(HMZ_PROF_ENV, stream);
   if (n == 0) return HMZ_OK;
   if (!words || !actions || !rewards || !flags || n < 0) return fail(HMZ_ERR_INVALID, "hmz_env_step: null pointer");
   EnvCfg c;
@@ -366,6 +371,7 @@ int hmz_env_step(uint32_t* words, const uint8_t* actions, float* rewards, uint8_
 }
 
 int hmz_env_legal_mask(const uint32_t* words, uint8_t* mask, int64_t n, int n_disks, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n == 0) return HMZ_OK;
   if (!words || !mask || n < 0 || n_disks < 1 || n_disks > HMZ_MAX_DISKS)
     return fail(HMZ_ERR_INVALID, "hmz_env_legal_mask: bad arguments");
@@ -377,6 +383,7 @@ int hmz_env_legal_mask(const uint32_t* words, uint8_t* mask, int64_t n, int n_di
 }
 
 int hmz_env_onehot(const uint32_t* words, float* obs, int64_t n, int n_disks, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n == 0) return HMZ_OK;
   if (!words || !obs || n < 0 || n_disks < 1 || n_disks > HMZ_MAX_DISKS)
     return fail(HMZ_ERR_INVALID, "hmz_env_onehot: bad arguments");
@@ -386,6 +393,7 @@ int hmz_env_onehot(const uint32_t* words, float* obs, int64_t n, int n_disks, vo
 
 int hmz_env_solver_distance(const uint32_t* words, uint32_t* distance, int64_t n, int n_disks, int goal_peg,
                             void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n == 0) return HMZ_OK;
   if (!words || !distance || n < 0 || n_disks < 1 || n_disks > HMZ_MAX_DISKS || goal_peg < 0 || goal_peg > 2)
     return fail(HMZ_ERR_INVALID, "hmz_env_solver_distance: bad arguments");
@@ -396,6 +404,7 @@ int hmz_env_solver_distance(const uint32_t* words, uint32_t* distance, int64_t n
 int hmz_env_step_random(uint32_t* words, uint8_t* actions, float* rewards, uint8_t* flags, int64_t n, int n_disks,
                         int max_steps, int goal_peg, uint32_t reset_word, uint64_t seed, uint64_t step_index,
                         void* stream) {
+  ProfScope prof_scope(HMZ_PROF_ENV, stream);
   if (n == 0) return HMZ_OK;
   if (!words || !actions || !rewards || !flags || n < 0)
     return fail(HMZ_ERR_INVALID, "hmz_env_step_random: null pointer");
@@ -412,6 +421,7 @@ int hmz_env_step_random(uint32_t* words, uint8_t* actions, float* rewards, uint8
 int hmz_env_rollout_random(uint32_t* words, int64_t n, int n_disks, int max_steps, int goal_peg, uint32_t reset_word,
                            int n_steps, uint64_t seed, uint64_t step_index, unsigned long long* counters,
                            void* stream) {
+  ProfScope prof_scope(HMZ_PROF_ENV, stream);
   if (n == 0) return HMZ_OK;
   if (!words || !counters || n < 0 || n_steps < 0) return fail(HMZ_ERR_INVALID, "hmz_env_rollout_random: bad arguments");
   EnvCfg c;

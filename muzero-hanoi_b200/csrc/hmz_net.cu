@@ -356,6 +356,7 @@ int hmz_weights_pack(const float* const* host_tensors, int n_disks, int mode, vo
 int hmz_net_initial(const void* weights, int mode, int n_disks, const uint32_t* words, const float* obs,
                     void* latents_out, int64_t out_rows_per_item, int latent_dtype, float* p0, float* v0, int64_t n,
                     void* stream) {
+  ProfScope prof_scope(HMZ_PROF_NET_INITIAL, stream);
   if (n == 0) return HMZ_OK;
   if (!weights || (!words && !obs) || !latents_out || !p0 || !v0 || n < 0 || n_disks < 1 || n_disks > HMZ_MAX_DISKS ||
       out_rows_per_item < 1 || (latent_dtype != HMZ_LATENT_F32 && latent_dtype != HMZ_LATENT_BF16))
@@ -373,6 +374,7 @@ int hmz_net_initial(const void* weights, int mode, int n_disks, const uint32_t* 
 int hmz_net_recurrent(const void* weights, int mode, const void* latents_in, int64_t in_rows_per_item,
                       const uint16_t* in_row, const uint8_t* actions, void* latents_out, int64_t out_rows_per_item,
                       int64_t out_row, int latent_dtype, float* r, float* p, float* v, int64_t n, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_NET_RECURRENT, stream);
   if (n == 0) return HMZ_OK;
   if (!weights || !latents_in || !actions || !latents_out || !r || !p || !v || n < 0 || in_rows_per_item < 1 ||
       out_rows_per_item < 1 || out_row < 0 || out_row >= out_rows_per_item ||

@@ -203,6 +203,7 @@ int64_t hmz_search_workspace_bytes(int64_t n_searches) {
 }
 
 int hmz_search_minmax_reset(double* minmax, int64_t n, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n == 0) return HMZ_OK;
   if (!minmax || n < 0) return fail(HMZ_ERR_INVALID, "hmz_search_minmax_reset: bad arguments");
   search_minmax_reset<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(minmax, n);
@@ -210,6 +211,7 @@ int hmz_search_minmax_reset(double* minmax, int64_t n, void* stream) {
 }
 
 int hmz_search_begin(const hmz_search_t* s, const double* root_prior, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (int rc = check_search(s, "hmz_search_begin")) return rc;
   if (s->n_searches == 0) return HMZ_OK;
   if (!root_prior) return fail(HMZ_ERR_INVALID, "hmz_search_begin: null root_prior");
@@ -218,6 +220,7 @@ int hmz_search_begin(const hmz_search_t* s, const double* root_prior, void* stre
 }
 
 int hmz_search_begin_p0(const hmz_search_t* s, const float* p0, const double* noise, double eps, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (int rc = check_search(s, "hmz_search_begin_p0")) return rc;
   if (s->n_searches == 0) return HMZ_OK;
   if (!p0) return fail(HMZ_ERR_INVALID, "hmz_search_begin_p0: null p0");
@@ -230,6 +233,7 @@ int hmz_search_begin_p0(const hmz_search_t* s, const float* p0, const double* no
 
 int hmz_search_select(const hmz_search_t* s, int sim, const double* ucb_table, double discount, uint16_t* leaf_parent,
                       uint8_t* leaf_action, uint16_t* leaf_depth, uint8_t* path_out, int path_cap, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_SELECT, stream);
   if (int rc = check_search(s, "hmz_search_select")) return rc;
   if (s->n_searches == 0) return HMZ_OK;
   if (!ucb_table || !leaf_parent || !leaf_action || sim < 0 || sim + 1 >= s->n_records || (path_out && path_cap < 1))
@@ -243,6 +247,7 @@ int hmz_search_select(const hmz_search_t* s, int sim, const double* ucb_table, d
 int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, const uint16_t* leaf_parent,
                              const uint8_t* leaf_action, const float* r, const float* p, const float* v,
                              void* stream) {
+  ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
   if (int rc = check_search(s, "hmz_search_expand_backup")) return rc;
   if (s->n_searches == 0) return HMZ_OK;
   if (!leaf_parent || !leaf_action || !r || !p || !v || sim < 0 || sim + 1 >= s->n_records)
@@ -255,6 +260,7 @@ int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, co
 int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temperature, int deterministic,
                            const double* uniforms, int32_t* visits, double* pi, double* root_q, int32_t* action,
                            void* stream) {
+  ProfScope prof_scope(HMZ_PROF_ROOT_POLICY, stream);
   if (int rc = check_search(s, "hmz_search_root_policy")) return rc;
   if (!(temperature >= 0.0 && temperature <= 1.0))  // MCTS/mcts.py:163-166 -> ValueError in the Python shim
     return fail(HMZ_ERR_INVALID, "Expect `temperature` to be in the range [0.0, 1.0], got %g", temperature);

@@ -354,3 +354,73 @@ def _run_mcts(self, weights: PackedWeights, *, words=None, obs=None, temperature
 
 
 BatchedMCTS.run_mcts = _run_mcts
+
+
+# ---------------------------------------------------------------------------- self-play
+class SelfPlay:
+    """B games of Muzero._play_game (reference Muzero.py:153-207) advanced one move at a time,
+    entirely on device: root inference -> Dirichlet mix -> n_simulations fused simulations ->
+    root policy + sampled action -> trajectory record -> env step with auto-reset.
+
+    Throughput mode: the Dirichlet draw and the sampling uniform come from on-device Philox
+    streams (parity mode = BatchedMCTS.run_mcts with those supplied as inputs).  Finished-move
+    records land in a [ring_slots, B] struct-of-arrays ring that `gather` all-gathers over NCCL."""
+
+    def __init__(self, N, max_steps, B, n_simulations, weights: PackedWeights, discount=0.8, alpha=0.25, eps=0.25,
+                 temperature=1.0, seed=0, ring_slots=8, device="cuda", latent_dtype=_lib.LATENT_F32):
+        self.env = VecHanoi(N, max_steps, B, device)
+        self.mcts = BatchedMCTS(discount, alpha, n_simulations, B, device, eps, latent_dtype)
+        self.weights, self.temperature, self.seed = weights, float(temperature), int(seed)
+        self.B, self.S, self.T = int(B), int(n_simulations), int(ring_slots)
+        self.lib, self.device = self.env.lib, self.env.device
+        dev = self.device
+        self.p0 = torch.empty(B, 6, dtype=torch.float32, device=dev)
+        self.v0 = torch.empty(B, dtype=torch.float32, device=dev)
+        self.noise = torch.empty(B, 6, dtype=torch.float64, device=dev)
+        self.uniform = torch.empty(B, dtype=torch.float64, device=dev)
+        self.action_u8 = torch.empty(B, dtype=torch.uint8, device=dev)
+        self.traj_state = torch.zeros(self.T, B, dtype=torch.int32, device=dev)
+        self.traj_action = torch.zeros(self.T, B, dtype=torch.uint8, device=dev)
+        self.traj_reward = torch.zeros(self.T, B, dtype=torch.float32, device=dev)
+        self.traj_flags = torch.zeros(self.T, B, dtype=torch.uint8, device=dev)
+        self.traj_visits = torch.zeros(self.T, B, 6, dtype=torch.int16, device=dev)
+        self.traj_root_q = torch.zeros(self.T, B, dtype=torch.float32, device=dev)
+        self.moves_done = 0
+        self.env.reset()
+
+    def move(self):
+        """One move of every game; returns the ring slot that was written.  No host sync."""
+        env, m, st, lib = self.env, self.mcts, self.mcts.store, self.lib
+        stream = current_stream()
+        t, ctr = self.moves_done % self.T, self.moves_done
+        self.weights.initial(self.B, words=env.words, latents_out=st.latents, out_rows_per_item=st.n_records,
+                             latent_dtype=st.latent_dtype, p0=self.p0, v0=self.v0)
+        use_noise = m.root_dirichlet_alpha > 0.0 and m.root_exploration_eps > 0.0
+        if use_noise:
+            check(lib.hmz_rng_dirichlet(ptr(self.noise), self.B, float(m.root_dirichlet_alpha), self.seed, ctr, stream))
+        check(lib.hmz_rng_uniform(ptr(self.uniform), self.B, self.seed, ctr, stream))
+        st.desc.root_prior_is_f64 = int(use_noise)
+        check(lib.hmz_search_begin_p0(C.byref(st.desc), ptr(self.p0), ptr(self.noise) if use_noise else None,
+                                      float(m.root_exploration_eps), stream))
+        check(lib.hmz_search_run(C.byref(st.desc), self.weights.ptr, self.weights.mode, self.S, ptr(m._table),
+                                 m.discount, stream))
+        check(lib.hmz_search_root_policy(C.byref(st.desc), self.S, self.temperature, 0, ptr(self.uniform),
+                                         ptr(m.visits), None, ptr(m.root_q), ptr(m.action), stream))
+        check(lib.hmz_traj_record(ptr(env.words), ptr(m.action), ptr(m.visits), ptr(m.root_q), ptr(self.traj_state[t]),
+                                  ptr(self.traj_action[t]), ptr(self.traj_visits[t]), ptr(self.traj_root_q[t]),
+                                  ptr(self.action_u8), self.B, stream))
+        check(lib.hmz_env_step(ptr(env.words), ptr(self.action_u8), ptr(self.traj_reward[t]), ptr(self.traj_flags[t]),
+                               None, self.B, env.discs, env.max_steps, env.goal_peg, 1, env.reset_word, stream))
+        self.moves_done += 1
+        return t
+
+    def launches_per_move(self):
+        use_noise = self.mcts.root_dirichlet_alpha > 0.0 and self.mcts.root_exploration_eps > 0.0
+        return 3 * self.S + 6 + int(use_noise)
+
+    def record_bytes_per_game(self):
+        return 4 + 1 + 4 + 1 + 12 + 4  # state, action, reward, flags, visits, root_q
+
+    def slot(self, t):
+        return dict(state=self.traj_state[t], action=self.traj_action[t], reward=self.traj_reward[t],
+                    flags=self.traj_flags[t], visits=self.traj_visits[t], root_q=self.traj_root_q[t])
