@@ -366,8 +366,11 @@ int hmz_net_initial(const void* weights, int mode, int n_disks, const uint32_t* 
   if (mode != HMZ_MODE_FP32 && mode != HMZ_MODE_BF16) return fail(HMZ_ERR_INVALID, "hmz_net_initial: unknown mode %d", mode);
   if (int rc = ensure_smem_optin()) return rc;
   const unsigned grid = (unsigned)((n + kRows - 1) / kRows);
+  const float* w32 = mode == HMZ_MODE_BF16
+                         ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(weights) + tc_fp32_offset_bytes())
+                         : reinterpret_cast<const float*>(weights);
   net_initial_fp32<<<grid, kNetThreads, sizeof(NetSmem), (cudaStream_t)stream>>>(
-      (const float*)weights, n_disks, words, obs, latents_out, out_rows_per_item, latent_dtype, p0, v0, n);
+      w32, n_disks, words, obs, latents_out, out_rows_per_item, latent_dtype, p0, v0, n);
   return check_launch("net_initial_fp32");
 }
 

@@ -121,3 +121,59 @@ def test_dropin_muzeronet_surface(golden):
     with torch.no_grad():  # differentiable torch forms stay consistent with the kernels
         hh = net.represent(torch.from_numpy(obs).to(torch.float32))
     assert np.abs(hh.numpy() - h0).max() <= H_TOL
+
+
+# ------------------------------------------------------------- tensor-core (bf16) path
+BF16_TOL = 2e-2  # north_star: network outputs within 2e-2 in bf16 (relative to each output's scale)
+
+
+def _bf16_close(got, ref, scale):
+    return np.abs(got - ref).max() <= BF16_TOL * scale
+
+
+@pytest.mark.parametrize("n", [3, 5])
+@pytest.mark.parametrize("count,latent_dtype", [(96, 0), (1, 0), (300, 1)])
+def test_recurrent_tcgen05_bf16_matches_reference(golden, n, count, latent_dtype):
+    """HMZ_MODE_BF16 (tcgen05 + TMEM + TMA bulk): h, p within 2e-2 absolute (unit scale), r and v
+    within 2e-2 of max(1, |ref|) — bf16 operands, fp32 accumulation."""
+    g = golden("net_io.npz")
+    w = _weights(n, int(g[f"n{n}_weight_seed"]), mode=1)
+    idx = np.arange(count) % 96
+    h_in = torch.from_numpy(g[f"n{n}_h_in"][idx]).cuda()
+    if latent_dtype == 1:
+        h_in = h_in.to(torch.bfloat16)
+    acts = torch.from_numpy(g[f"n{n}_action"][idx].astype(np.uint8)).cuda()
+    h = torch.empty(count, 64, device="cuda", dtype=torch.bfloat16 if latent_dtype else torch.float32)
+    r, v, p = torch.empty(count, device="cuda"), torch.empty(count, device="cuda"), torch.empty(count, 6, device="cuda")
+    w.recurrent(count, latents_in=h_in, in_rows_per_item=1, in_row=None, actions=acts, latents_out=h,
+                out_rows_per_item=1, out_row=0, latent_dtype=latent_dtype, r=r, p=p, v=v)
+    torch.cuda.synchronize()
+    hh, rr, vv, pp = h.float().cpu().numpy(), r.cpu().numpy(), v.cpu().numpy(), p.cpu().numpy()
+    print("max |dh| %.4f |dp| %.4f |dr| %.4f |dv| %.4f" % (
+        np.abs(hh - g[f"n{n}_h_out"][idx]).max(), np.abs(pp - g[f"n{n}_p"][idx]).max(),
+        np.abs(rr - g[f"n{n}_r"][idx]).max(), np.abs(vv - g[f"n{n}_v"][idx]).max()))
+    assert _bf16_close(hh, g[f"n{n}_h_out"][idx], 1.0)
+    assert _bf16_close(pp, g[f"n{n}_p"][idx], 1.0)
+    assert np.all(np.abs(rr - g[f"n{n}_r"][idx]) <= BF16_TOL * np.maximum(1.0, np.abs(g[f"n{n}_r"][idx])))
+    assert np.all(np.abs(vv - g[f"n{n}_v"][idx]) <= BF16_TOL * np.maximum(1.0, np.abs(g[f"n{n}_v"][idx])))
+
+
+def test_bf16_mode_search_runs_and_agrees_with_fp32_mode():
+    """Throughput mode end to end: same searches in bf16 and fp32 modes give visit counts that sum to
+    S and root policies that are close (bf16 rounding moves a few visits, not the search)."""
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    n, B, S = 5, 1000, 50
+    sd = port.make_weights(n, 4)
+    env = VecHanoi(n, 200, B)
+    env.random_reset(seed=9)
+    out = []
+    for mode, ldt in ((0, 0), (1, 1)):
+        m = BatchedMCTS(0.8, 0.0, S, B, latent_dtype=ldt)
+        _, pi, q, visits = m.run_mcts(PackedWeights(sd, n, mode), words=env.words, temperature=1.0, deterministic=True)
+        torch.cuda.synchronize()
+        assert (visits.sum(1) == S).all()
+        out.append((pi.cpu().numpy(), q.cpu().numpy()))
+    moved = np.abs(out[0][0] - out[1][0]).sum(1).mean() / 2
+    print("mean fraction of visits moved by bf16:", moved)
+    assert moved < 0.10
