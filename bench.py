@@ -138,7 +138,7 @@ def workload_config(args, world):
         "workload": f"hanoi{N_DISKS}_selfplay_{GAMES_PER_GPU}games_per_gpu_x{N_SIMS}sims (BASELINE.json configs[2])",
         "n_disks": N_DISKS, "games_per_gpu": args.games, "global_games": args.games * world, "n_simulations": args.sims,
         "max_steps": MAX_STEPS, "discount": DISCOUNT, "dirichlet_alpha": ALPHA, "temperature": TEMPERATURE,
-        "mode": args.mode, "parallelism": f"games sharded over {world} GPU(s), NCCL all-gather of move records only",
+        "mode": args.mode, "search_groups": args.groups, "parallelism": f"games sharded over {world} GPU(s), NCCL all-gather of move records only",
         "cache": "working set (tree + latents ~2.5 GB/GPU) is larger than the 126 MB L2; no L2 flush needed",
     }
 
@@ -151,11 +151,12 @@ class ClockSampler:
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -163,16 +164,25 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.03]
+        if not inside:  # region shorter than one sampling period: take the samples closest to it
+            inside = [r for (_, r) in self.rows[-3:]]
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -221,6 +231,7 @@ def run_ours(args):
     net = MuZeroNet(3 * N_DISKS, 6, 0.002, "cpu", TD_return=True)  # random-init h / g / f
     weights = PackedWeights(net.state_dict(), N_DISKS, mode, dev)
     B, S = args.games, args.sims
+    _lib.check(lib.hmz_search_set_groups(args.groups))
     sp = SelfPlay(N_DISKS, MAX_STEPS, B, S, weights, DISCOUNT, ALPHA, EPS, TEMPERATURE, seed=1234 + rank,
                   ring_slots=4, device=dev, latent_dtype=latent_dtype)
     gather_buf = torch.empty(world * B, 26, dtype=torch.uint8, device=dev) if world > 1 else None
@@ -249,15 +260,17 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # started before the warm-up so that nvidia-smi is already streaming when timing begins
     log(f"[bench] rank {rank}/{world}: warm-up {args.warmup} steps (B={B}, S={S}, mode={args.mode})")
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.hmz_launch_count()
+    sampler.mark_begin()
     ms = timed(step, args.steps)
+    sampler.mark_end()
     launches = lib.hmz_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     sims_per_s = world * B * S * args.steps / (ms * 1e-3)
@@ -265,12 +278,14 @@ def run_ours(args):
 
     # ---- per-kernel device time over the same steps (CUDA-event pairs on the launch stream)
     barrier()
+    _lib.check(lib.hmz_search_set_groups(1))  # serial launches: clean, non-overlapped per-kernel durations
     _lib.check(lib.hmz_prof_begin())
     for _ in range(args.steps):
         step()
     ms_cls = (C.c_double * 8)()
     n_cls = (C.c_int64 * 8)()
     _lib.check(lib.hmz_prof_end(ms_cls, n_cls))
+    _lib.check(lib.hmz_search_set_groups(args.groups))
     names = ["env_step", "select", "net_recurrent", "expand_backup", "net_initial", "root_policy", "other", "-"]
     kern = {names[i]: {"ms_total": ms_cls[i], "launches": int(n_cls[i]),
                        "us_per_launch": (ms_cls[i] / n_cls[i] * 1e3) if n_cls[i] else None} for i in range(7)}
@@ -375,15 +390,16 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--mode", choices=["bf16", "fp32"], default=os.environ.get("HMZ_BENCH_MODE", "fp32"))
+    ap.add_argument("--mode", choices=["bf16", "fp32"], default=os.environ.get("HMZ_BENCH_MODE", "bf16"))
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU, help="games per GPU (default: BASELINE config)")
     ap.add_argument("--sims", type=int, default=N_SIMS)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-env", action="store_true")
+    ap.add_argument("--groups", type=int, default=0, help="concurrent search groups in hmz_search_run (0 = auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

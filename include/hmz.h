@@ -237,6 +237,10 @@ int hmz_net_recurrent(const void* weights, int mode, const void* latents_in, int
  * search in one launch sequence with no host round trips (MCTS.run_mcts, MCTS/mcts.py:71-109). */
 int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_simulations,
                    const double* ucb_table, double discount, void* stream);
+/* Scheduling knob of hmz_search_run: the batch is cut into `groups` independent slices whose
+ * select -> MLP -> backup chains run concurrently on internal streams (forked from and joined back
+ * to `stream`).  0 = automatic, 1 = strictly serial.  Never changes results. */
+int hmz_search_set_groups(int groups);
 
 /* ------------------------------------------------------------------ self-play glue ---
  * Throughput-mode randomness, drawn on device with Philox4x32-10 keyed by (seed, item,

@@ -20,6 +20,7 @@
 namespace hmz {
 
 constexpr int kSearchesPerBlock = 32;  // 256 threads = 8 warps x 4 searches
+constexpr int kLatentWidth = HMZ_LATENT;
 
 __global__ void __launch_bounds__(256) search_minmax_reset(double* __restrict__ minmax, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -271,6 +272,62 @@ int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temp
   return check_launch("search_root_policy");
 }
 
+// Process-wide tuning knob: number of independent search groups hmz_search_run runs concurrently
+// on internal streams (0 = automatic).  Groups only change scheduling, never results.
+static std::atomic<int> g_search_groups{0};
+
+int hmz_search_set_groups(int groups) {
+  if (groups < 0 || groups > 16) return fail(HMZ_ERR_INVALID, "hmz_search_set_groups: %d outside [0, 16]", groups);
+  g_search_groups.store(groups);
+  return HMZ_OK;
+}
+
+namespace {
+struct GroupStreams {
+  int dev = -1;
+  cudaStream_t stream[16] = {};
+  cudaEvent_t done[16] = {};
+  cudaEvent_t fork = nullptr;
+  int n = 0;
+};
+// Lazily created, per host thread and device; lives for the life of the process.
+int get_group_streams(int want, GroupStreams** out) {
+  static thread_local GroupStreams gs;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed");
+  if (gs.dev != dev) {
+    gs = GroupStreams();
+    gs.dev = dev;
+  }
+  if (!gs.fork && cudaEventCreateWithFlags(&gs.fork, cudaEventDisableTiming) != cudaSuccess)
+    return fail(HMZ_ERR_CUDA, "cudaEventCreate failed");
+  while (gs.n < want) {
+    if (cudaStreamCreateWithFlags(&gs.stream[gs.n], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&gs.done[gs.n], cudaEventDisableTiming) != cudaSuccess)
+      return fail(HMZ_ERR_CUDA, "cudaStreamCreate failed");
+    ++gs.n;
+  }
+  *out = &gs;
+  return HMZ_OK;
+}
+
+struct SimScratch {
+  float *p, *r, *v;
+  uint16_t* lp;
+  uint8_t* la;
+};
+SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  SimScratch sc;
+  sc.p = (float*)ws + lo * 6;
+  sc.r = (float*)(ws + padded_total * 24) + lo;
+  sc.v = (float*)(ws + padded_total * 28) + lo;
+  sc.lp = (uint16_t*)(ws + padded_total * 32) + lo;
+  sc.la = (uint8_t*)(ws + padded_total * 34) + lo;
+  return sc;
+}
+}  // namespace
+
 int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_simulations, const double* ucb_table,
                    double discount, void* stream) {
   if (int rc = check_search(s, "hmz_search_run")) return rc;
@@ -281,21 +338,58 @@ int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_s
                 s->n_records);
   const int64_t B = s->n_searches;
   const int64_t Bp = (B + 63) / 64 * 64;
-  char* ws = (char*)s->workspace;
-  ws = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-  float* p = (float*)ws;                      // [B][6]
-  float* r = (float*)(ws + Bp * 24);          // [B]
-  float* v = (float*)(ws + Bp * 28);          // [B]
-  uint16_t* lp = (uint16_t*)(ws + Bp * 32);   // [B]
-  uint8_t* la = (uint8_t*)(ws + Bp * 34);     // [B]
-  for (int sim = 0; sim < n_simulations; ++sim) {
-    if (int rc = hmz_search_select(s, sim, ucb_table, discount, lp, la, nullptr, nullptr, 0, stream)) return rc;
-    if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, lp, la, s->latents, s->n_records, sim + 1,
-                                   s->latent_dtype, r, p, v, B, stream))
-      return rc;
-    if (int rc = hmz_search_expand_backup(s, sim, discount, lp, la, r, p, v, stream)) return rc;
+  // Searches never interact, so the batch is cut into groups whose select -> MLP -> backup chains
+  // run on separate streams: the latency-bound tree kernels of one group fill the issue slots the
+  // tensor-core kernel of another leaves idle.  Group boundaries are multiples of 128 searches.
+  int groups = g_search_groups.load();
+  if (groups == 0) groups = B >= 32768 ? 4 : (B >= 8192 ? 2 : 1);
+  const int64_t per = ((B + groups - 1) / groups + 127) / 128 * 128;
+  groups = (int)((B + per - 1) / per);
+  if (groups <= 1) {
+    SimScratch sc = carve_scratch(s->workspace, Bp, 0);
+    for (int sim = 0; sim < n_simulations; ++sim) {
+      if (int rc = hmz_search_select(s, sim, ucb_table, discount, sc.lp, sc.la, nullptr, nullptr, 0, stream)) return rc;
+      if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, sc.lp, sc.la, s->latents, s->n_records,
+                                     sim + 1, s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
+        return rc;
+      if (int rc = hmz_search_expand_backup(s, sim, discount, sc.lp, sc.la, sc.r, sc.p, sc.v, stream)) return rc;
+    }
+    return HMZ_OK;
   }
-  return HMZ_OK;
+  GroupStreams* gs = nullptr;
+  if (int rc = get_group_streams(groups, &gs)) return rc;
+  cudaStream_t main_stream = (cudaStream_t)stream;
+  if (cudaEventRecord(gs->fork, main_stream) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaEventRecord(fork) failed");
+  hmz_search_t sub[16];
+  SimScratch sc[16];
+  const size_t lat_elem = s->latent_dtype == HMZ_LATENT_F32 ? 4 : 2;
+  for (int g = 0; g < groups; ++g) {
+    const int64_t lo = g * per, hi = (lo + per < B) ? lo + per : B;
+    sub[g] = *s;
+    sub[g].nodes = s->nodes + lo * s->n_records;
+    sub[g].latents = (char*)s->latents + (size_t)lo * s->n_records * kLatentWidth * lat_elem;
+    sub[g].root_prior = s->root_prior + lo * 6;
+    sub[g].root_W = s->root_W + lo;
+    sub[g].minmax = s->minmax + 2 * lo;
+    sub[g].n_searches = hi - lo;
+    sc[g] = carve_scratch(s->workspace, Bp, lo);
+    if (cudaStreamWaitEvent(gs->stream[g], gs->fork, 0) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaStreamWaitEvent failed");
+  }
+  int rc = HMZ_OK;
+  for (int sim = 0; sim < n_simulations && rc == HMZ_OK; ++sim)
+    for (int g = 0; g < groups && rc == HMZ_OK; ++g) {
+      void* st = (void*)gs->stream[g];
+      rc = hmz_search_select(&sub[g], sim, ucb_table, discount, sc[g].lp, sc[g].la, nullptr, nullptr, 0, st);
+      if (rc == HMZ_OK)
+        rc = hmz_net_recurrent(weights, mode, sub[g].latents, s->n_records, sc[g].lp, sc[g].la, sub[g].latents,
+                               s->n_records, sim + 1, s->latent_dtype, sc[g].r, sc[g].p, sc[g].v, sub[g].n_searches, st);
+      if (rc == HMZ_OK) rc = hmz_search_expand_backup(&sub[g], sim, discount, sc[g].lp, sc[g].la, sc[g].r, sc[g].p, sc[g].v, st);
+    }
+  for (int g = 0; g < groups; ++g) {  // always join, even after an error, so the caller's stream stays ordered
+    cudaEventRecord(gs->done[g], gs->stream[g]);
+    cudaStreamWaitEvent(main_stream, gs->done[g], 0);
+  }
+  return rc;
 }
 
 }  // extern "C"
