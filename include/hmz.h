@@ -242,6 +242,10 @@ int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_s
  * to `stream`).  0 = automatic, 1 = strictly serial.  Never changes results. */
 int hmz_search_set_groups(int groups);
 
+/* Tooling only: with HMZ_TC_TIMELINE=1 in the environment, CTA 0 of the tensor-core kernel records
+ * clock64() at its phase boundaries; this copies the 96 marks of the last launch to the host. */
+int hmz_debug_tc_timeline(unsigned long long* host_out);
+
 /* ------------------------------------------------------------------ self-play glue ---
  * Throughput-mode randomness, drawn on device with Philox4x32-10 keyed by (seed, item,
  * counter) so results do not depend on how games are sharded over GPUs.  Parity mode passes

@@ -44,6 +44,7 @@ void pack_fp32(const float* const* tensors, int n_disks, float* out);
 // tensor-core path (hmz_net_tc.cu)
 int64_t tc_packed_bytes(int n_disks);
 int64_t tc_fp32_offset_bytes();
+int tc_debug_read_timeline(unsigned long long* host_out);
 void tc_pack(const float* const* tensors, int n_disks, void* out);
 int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
                      const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row,

@@ -14,6 +14,8 @@
 //   ties                  : lowest action index (the sanctioned replacement of :86).
 // These kernels are HBM/L2-latency bound gathers (one 128 B record per tree level); there is no
 // contraction here and nothing for tensor cores to do.
+#include <cstdlib>
+
 #include "hmz_common.cuh"
 #include "hmz_tree.cuh"
 
@@ -68,20 +70,22 @@ __global__ void __launch_bounds__(256) search_begin_p0(hmz_search_t s, const flo
   }
 }
 
+template <bool kPrefetch>
 __global__ void __launch_bounds__(256) search_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
                                                     double discount, uint16_t* __restrict__ leaf_parent,
                                                     uint8_t* __restrict__ leaf_action,
                                                     uint16_t* __restrict__ leaf_depth, uint8_t* __restrict__ path_out,
-                                                    int path_cap) {
+                                                    int path_cap, uint32_t* __restrict__ path_ent) {
   const int lane8 = threadIdx.x & 7;
-  int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
   const bool valid = b < s.n_searches;
-  if (!valid) b = s.n_searches - 1;  // keep whole warps alive for the shuffles
+  if (!valid) return;  // whole segments leave together: shuffles are segment-masked
   const hmz_node_t* nodes = s.nodes + b * s.n_records;
   const double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
-  Leaf leaf = select_leaf(nodes, rp, mn, mx, sim, ucb_table, discount, lane8, valid,
-                          (valid && path_out) ? path_out + b * path_cap : nullptr, path_cap);
+  Leaf leaf = select_leaf<kPrefetch>(nodes, rp, mn, mx, sim, ucb_table, discount, lane8, valid,
+                          path_out ? path_out + b * path_cap : nullptr, path_cap,
+                          path_ent ? path_ent + b * kPathCap : nullptr);
   if (valid && lane8 == 0) {
     leaf_parent[b] = (uint16_t)leaf.parent;
     leaf_action[b] = (uint8_t)leaf.action;
@@ -111,6 +115,100 @@ __global__ void __launch_bounds__(256) search_expand_backup(hmz_search_t s, int 
     s.minmax[2 * b] = mn;
     s.minmax[2 * b + 1] = mx;
   }
+}
+
+// Fused hot-loop kernel: expansion + backup of simulation `sim` (lane-parallel over the recorded
+// path) followed at once by the selection of simulation `sim + 1` — the path just updated is still in
+// this SM's L1, and the next walk usually shares its prefix.
+template <bool kPrefetch>
+__global__ void __launch_bounds__(256, 4) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
+                                                           double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
+                                                           uint16_t* leaf_depth, uint32_t* path_ent,
+                                                           const float* __restrict__ r, const float* __restrict__ p,
+                                                           const float* __restrict__ v, int do_select) {
+  const int lane8 = threadIdx.x & 7;
+  const int seg_base = (threadIdx.x & 31) & ~7;
+  const unsigned seg = 0xFFu << seg_base;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+  if (b >= s.n_searches) return;
+  hmz_node_t* nodes = s.nodes + b * s.n_records;
+  uint32_t* path = path_ent + b * kPathCap;
+  const int pe = leaf_parent[b], pa = leaf_action[b], depth = leaf_depth[b];
+  float pr[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) pr[a] = p[b * 6 + a];
+  write_fresh_record(&nodes[sim + 1], lane8, pr, pe, pa);
+  double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1], root_w = s.root_W[b];
+  if (depth <= kPathCap) {
+    backup_levels(nodes, path, depth, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx, lane8);
+  } else {  // very deep path: walk the parent links on one lane, then share the result
+    if (lane8 == 0) backup_path(nodes, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
+    mn = __shfl_sync(seg, mn, seg_base);
+    mx = __shfl_sync(seg, mx, seg_base);
+    root_w = __shfl_sync(seg, root_w, seg_base);
+  }
+  if (lane8 == 0) {
+    s.root_W[b] = root_w;
+    s.minmax[2 * b] = mn;
+    s.minmax[2 * b + 1] = mx;
+  }
+  if (!do_select) return;
+  __syncwarp(seg);  // the segment's record updates are ordered before its next walk
+  const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
+  Leaf leaf = select_leaf<kPrefetch>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, lane8, true, nullptr, 0, path);
+  if (lane8 == 0) {
+    leaf_parent[b] = (uint16_t)leaf.parent;
+    leaf_action[b] = (uint8_t)leaf.action;
+    leaf_depth[b] = (uint16_t)leaf.depth;
+  }
+}
+
+// Thread-per-search hot-loop kernels (see hmz_tree.cuh): selection only (first simulation) and the
+// fused expansion + backup of simulation `sim` followed by the selection of simulation `sim + 1`.
+constexpr int kTpsThreads = 64;
+
+__global__ void __launch_bounds__(kTpsThreads) search_select_tps(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
+                                                                double discount, uint16_t* __restrict__ leaf_parent,
+                                                                uint8_t* __restrict__ leaf_action,
+                                                                uint16_t* __restrict__ leaf_depth, uint32_t* __restrict__ path_ent) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= s.n_searches) return;
+  const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
+  const Leaf leaf = select_leaf_thread(s.nodes + b * s.n_records, rp, s.minmax[2 * b], s.minmax[2 * b + 1], sim, ucb_table,
+                                       discount, path_ent + b * kPathCap);
+  leaf_parent[b] = (uint16_t)leaf.parent;
+  leaf_action[b] = (uint8_t)leaf.action;
+  leaf_depth[b] = (uint16_t)leaf.depth;
+}
+
+__global__ void __launch_bounds__(kTpsThreads) search_backup_select_tps(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
+                                                                       double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
+                                                                       uint16_t* leaf_depth, uint32_t* path_ent,
+                                                                       const float* __restrict__ r, const float* __restrict__ p,
+                                                                       const float* __restrict__ v, int do_select) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= s.n_searches) return;
+  hmz_node_t* nodes = s.nodes + b * s.n_records;
+  uint32_t* path = path_ent + b * kPathCap;
+  const int pe = leaf_parent[b], pa = leaf_action[b], depth = leaf_depth[b];
+  float pr[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) pr[a] = p[b * 6 + a];
+  write_fresh_record_thread(&nodes[sim + 1], pr, pe, pa);
+  double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1], root_w = s.root_W[b];
+  if (depth <= 8)
+    backup_thread8(nodes, path, depth, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
+  else
+    backup_path(nodes, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
+  s.root_W[b] = root_w;
+  s.minmax[2 * b] = mn;
+  s.minmax[2 * b + 1] = mx;
+  if (!do_select) return;
+  const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
+  const Leaf leaf = select_leaf_thread(nodes, rp, mn, mx, sim + 1, ucb_table, discount, path);
+  leaf_parent[b] = (uint16_t)leaf.parent;
+  leaf_action[b] = (uint8_t)leaf.action;
+  leaf_depth[b] = (uint16_t)leaf.depth;
 }
 
 // MCTS/mcts.py:112-126 per search (one thread each; 52 bytes in, <= 76 bytes out).
@@ -200,7 +298,7 @@ extern "C" {
 
 int64_t hmz_search_workspace_bytes(int64_t n_searches) {
   if (n_searches < 0) return -1;
-  return ((n_searches + 63) / 64) * 64 * 40 + 512;  // p[6] r v (float), leaf_parent (u16), leaf_action (u8) + alignment slack
+  return ((n_searches + 63) / 64) * 64 * 168 + 512;  // p[6] r v, leaf_parent/action/depth, 32 path words per search
 }
 
 int hmz_search_minmax_reset(double* minmax, int64_t n, void* stream) {
@@ -239,9 +337,9 @@ int hmz_search_select(const hmz_search_t* s, int sim, const double* ucb_table, d
   if (s->n_searches == 0) return HMZ_OK;
   if (!ucb_table || !leaf_parent || !leaf_action || sim < 0 || sim + 1 >= s->n_records || (path_out && path_cap < 1))
     return fail(HMZ_ERR_INVALID, "hmz_search_select: bad arguments (sim=%d, n_records=%d)", sim, s->n_records);
-  search_select<<<search_grid(s->n_searches), 256, 0, (cudaStream_t)stream>>>(*s, sim, ucb_table, discount, leaf_parent,
+  search_select<false><<<search_grid(s->n_searches), 256, 0, (cudaStream_t)stream>>>(*s, sim, ucb_table, discount, leaf_parent,
                                                                               leaf_action, leaf_depth, path_out,
-                                                                              path_cap);
+                                                                              path_cap, nullptr);
   return check_launch("search_select");
 }
 
@@ -313,8 +411,9 @@ int get_group_streams(int want, GroupStreams** out) {
 
 struct SimScratch {
   float *p, *r, *v;
-  uint16_t* lp;
+  uint16_t *lp, *depth;
   uint8_t* la;
+  uint32_t* path;
 };
 SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -324,9 +423,62 @@ SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
   sc.v = (float*)(ws + padded_total * 28) + lo;
   sc.lp = (uint16_t*)(ws + padded_total * 32) + lo;
   sc.la = (uint8_t*)(ws + padded_total * 34) + lo;
+  sc.depth = (uint16_t*)(ws + padded_total * 36) + lo;
+  sc.path = (uint32_t*)(ws + padded_total * 40) + lo * kPathCap;
   return sc;
 }
 }  // namespace
+
+
+// Experiment switches (environment, read once): HMZ_FUSED=0 keeps select and backup as separate
+// launches, HMZ_PREFETCH=1 prefetches the most-visited child's record during the score arithmetic.
+static int env_flag(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// One simulation of one group: [select (first simulation only)] -> g+f MLP -> fused backup + next select.
+static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* weights, int mode, int sim,
+                       int n_simulations, const double* ucb_table, double discount, void* stream) {
+  static const int fused = env_flag("HMZ_FUSED", 1), prefetch = env_flag("HMZ_PREFETCH", 0), tps = env_flag("HMZ_TPS", 1);
+  const int64_t B = s->n_searches;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tps) {  // thread-per-search hot loop
+    const unsigned grid = (unsigned)((B + kTpsThreads - 1) / kTpsThreads);
+    if (sim == 0) {
+      ProfScope prof_scope(HMZ_PROF_SELECT, stream);
+      search_select_tps<<<grid, kTpsThreads, 0, st>>>(*s, 0, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path);
+      if (int rc = check_launch("search_select_tps")) return rc;
+    }
+    if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, sc.lp, sc.la, s->latents, s->n_records,
+                                   sim + 1, s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
+      return rc;
+    ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
+    search_backup_select_tps<<<grid, kTpsThreads, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
+                                                          sc.r, sc.p, sc.v, sim + 1 < n_simulations ? 1 : 0);
+    return check_launch("search_backup_select_tps");
+  }
+  if (sim == 0 || !fused) {
+    ProfScope prof_scope(HMZ_PROF_SELECT, stream);
+    if (prefetch)
+      search_select<true><<<search_grid(B), 256, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, nullptr, 0, sc.path);
+    else
+      search_select<false><<<search_grid(B), 256, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, nullptr, 0, sc.path);
+    if (int rc = check_launch("search_select")) return rc;
+  }
+  if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, sc.lp, sc.la, s->latents, s->n_records, sim + 1,
+                                 s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
+    return rc;
+  ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
+  const int do_select = (fused && sim + 1 < n_simulations) ? 1 : 0;
+  if (prefetch)
+    search_backup_select<true><<<search_grid(B), 256, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
+                                                             sc.r, sc.p, sc.v, do_select);
+  else
+    search_backup_select<false><<<search_grid(B), 256, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
+                                                              sc.r, sc.p, sc.v, do_select);
+  return check_launch("search_backup_select");
+}
 
 int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_simulations, const double* ucb_table,
                    double discount, void* stream) {
@@ -347,13 +499,8 @@ int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_s
   groups = (int)((B + per - 1) / per);
   if (groups <= 1) {
     SimScratch sc = carve_scratch(s->workspace, Bp, 0);
-    for (int sim = 0; sim < n_simulations; ++sim) {
-      if (int rc = hmz_search_select(s, sim, ucb_table, discount, sc.lp, sc.la, nullptr, nullptr, 0, stream)) return rc;
-      if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, sc.lp, sc.la, s->latents, s->n_records,
-                                     sim + 1, s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
-        return rc;
-      if (int rc = hmz_search_expand_backup(s, sim, discount, sc.lp, sc.la, sc.r, sc.p, sc.v, stream)) return rc;
-    }
+    for (int sim = 0; sim < n_simulations; ++sim)
+      if (int rc = run_one_sim(s, sc, weights, mode, sim, n_simulations, ucb_table, discount, stream)) return rc;
     return HMZ_OK;
   }
   GroupStreams* gs = nullptr;
@@ -377,14 +524,8 @@ int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_s
   }
   int rc = HMZ_OK;
   for (int sim = 0; sim < n_simulations && rc == HMZ_OK; ++sim)
-    for (int g = 0; g < groups && rc == HMZ_OK; ++g) {
-      void* st = (void*)gs->stream[g];
-      rc = hmz_search_select(&sub[g], sim, ucb_table, discount, sc[g].lp, sc[g].la, nullptr, nullptr, 0, st);
-      if (rc == HMZ_OK)
-        rc = hmz_net_recurrent(weights, mode, sub[g].latents, s->n_records, sc[g].lp, sc[g].la, sub[g].latents,
-                               s->n_records, sim + 1, s->latent_dtype, sc[g].r, sc[g].p, sc[g].v, sub[g].n_searches, st);
-      if (rc == HMZ_OK) rc = hmz_search_expand_backup(&sub[g], sim, discount, sc[g].lp, sc[g].la, sc[g].r, sc[g].p, sc[g].v, st);
-    }
+    for (int g = 0; g < groups && rc == HMZ_OK; ++g)
+      rc = run_one_sim(&sub[g], sc[g], weights, mode, sim, n_simulations, ucb_table, discount, (void*)gs->stream[g]);
   for (int g = 0; g < groups; ++g) {  // always join, even after an error, so the caller's stream stays ordered
     cudaEventRecord(gs->done[g], gs->stream[g]);
     cudaStreamWaitEvent(main_stream, gs->done[g], 0);
