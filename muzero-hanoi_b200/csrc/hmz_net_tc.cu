@@ -4,20 +4,23 @@
 // networks.py:96-116 (dynamics :129-138, prediction :140-150, support transform :152-189,
 // normalize_h_state :191-196) runs inside the CTA:
 //
-//   gather parent latents -> smem A0 (bf16, K-major, SWIZZLE_128B)
-//   D[0:256)   = A0  x Wg1^T      tcgen05.mma kind::f16, accumulators in TMEM
-//   A1         = relu(D + b1 + W1[:,64+a])  (tcgen05.ld -> regs -> bf16 -> smem)
-//   D[256:320) = A1  x Wg2^T  -> raw latent, min-max normalised -> A_raw, A_hn (smem) + HBM
-//   reward / policy / value heads: D[0:256) = A_{raw|hn} x W1^T -> relu -> A1 -> D[256:..) = A1 x W2^T
+//   gather parent latents -> smem A0 (bf16, K-major, SWIZZLE_128B); AX = [onehot(action), 1, 0..] (K = 16)
+//   D[0:256)   = [A0 | AX] x [Wg1 | Wg1_action, b1]^T   tcgen05.mma kind::f16, accumulators in TMEM
+//   A1         = relu(D)  (tcgen05.ld -> regs -> packed bf16 relu -> smem)
+//   D[256:320) = [A1 | AX] x [Wg2 | b2]^T  -> raw latent, min-max normalised -> A_raw, A_hn (smem) + HBM
+//   reward / policy / value heads: D[0:256) = [A_{raw|hn} | AX] x W1'^T -> relu -> A1 -> D[256:..) = [A1 | AX] x W2'^T
 //   softmax-expectation + signed-parabolic epilogues in registers
+// Every bias (and the one-hot action columns of dynamic_net.0) rides in the extra K = 16 step, so the
+// epilogues do no bias arithmetic at all.
 //
 // Weights (216 KB bf16, pre-swizzled into the exact shared-memory image by hmz_weights_pack) are
 // streamed from L2 per layer with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
 // into two 32 KB buffers; every copy is issued as soon as the MMAs that read the buffer's previous
 // content have committed, so it overlaps the epilogue of the current layer.
 //
-// 256 threads: thread t owns row (t & 127) — TMEM lane — and column half (t >> 7) of the wide
-// epilogues.  One elected thread issues TMA and tcgen05.mma.
+// 13 warps: 8 hidden-epilogue warps (thread -> row t & 127, column half t >> 7), 4 small-epilogue
+// warps (latent normalisation and the head outputs) and one control warp whose elected lane issues
+// every TMA copy and every tcgen05.mma; all hand-offs are mbarriers.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -28,25 +31,29 @@ namespace hmz {
 
 namespace tc {
 constexpr int kM = 128;          // rows per CTA / UMMA M
-constexpr int kThreads = 288;  // 8 epilogue warps + 1 control warp
+constexpr int kHiddenThreads = 256, kSmallThreads = 128;
+constexpr int kThreads = kHiddenThreads + kSmallThreads + 32;  // + control warp
 constexpr uint32_t kAtomA = kM * 128;  // one K-atom (64 bf16) of a 128-row A tile: 16 KB
 
+// A weight matrix [n_out][K] is stored as K/64 SWIZZLE_128B K-atoms of [n_out][128 B] followed by the
+// "extra" K = 16 slice [n_out][32 B] in the un-swizzled core-matrix layout (8 rows x 16 B contiguous,
+// the two K-chunks 128 B apart, 8-row groups 256 B apart) carrying the bias at k = 6 (and, for
+// dynamic_net.0, the six one-hot action columns at k = 0..5).
+constexpr uint32_t w_bytes(uint32_t n_out, uint32_t k_atoms) { return n_out * 128 * k_atoms + n_out * 32; }
+constexpr uint32_t kBytesW1 = w_bytes(256, 1);   // 40960
+constexpr uint32_t kBytesWg2 = w_bytes(64, 4);   // 34816
+constexpr uint32_t kBytesW48 = w_bytes(48, 4);   // 26112
+constexpr uint32_t kBytesW16 = w_bytes(16, 4);   // 8704
 // byte offsets inside the tensor-core section of the weight blob (all multiples of 1024)
-constexpr uint32_t kWg1 = 0, kWg2 = 32768, kWr1 = 65536, kWr2 = 98304, kWp1 = 122880, kWp2 = 155648, kWv1 = 163840,
-                   kWv2 = 196608, kTables = 221184;
-constexpr uint32_t kBytesW1 = 32768;                      // [256 out][64 in] bf16
-constexpr uint32_t kBytesWg2 = 32768;                     // [64 out][256 in]
-constexpr uint32_t kBytesW48 = 48 * 256 * 2, kBytesW16 = 16 * 256 * 2;
-// float tables (element offsets from kTables)
-constexpr int kBiasARow = 260;     // row pitch of the per-action bias table: 4-bank skew -> conflict-free LDS.128
-constexpr int tBiasA = 0;          // [8][260]: b_g1[n] + W_g1[n][64 + a]  (the one-hot action column folded in)
-constexpr int tBg2 = 2080;         // [64]
-constexpr int tBr1 = 2144, tBr2 = 2400;  // [256], [48]
-constexpr int tBp1 = 2448, tBp2 = 2704;  // [256], [16]
-constexpr int tBv1 = 2720, tBv2 = 2976;  // [256], [48]
-constexpr int kTableFloats = 3024;
-constexpr uint32_t kTableBytes = kTableFloats * 4;  // 12096, multiple of 16
-constexpr uint32_t kSectionBytes = kTables + kTableBytes;
+constexpr uint32_t kWg1 = 0, kWg2 = 40960, kWr1 = 75776, kWr2 = 116736, kWp1 = 142848 + 1024 - 512, kWp2 = kWp1 + 40960,
+                   kWv1 = kWp2 + 9216, kWv2 = kWv1 + 40960, kSectionBytes = kWv2 + 26112 + 512;
+static_assert(kWg2 % 1024 == 0 && kWr1 % 1024 == 0 && kWr2 % 1024 == 0 && kWp1 % 1024 == 0 && kWp2 % 1024 == 0 &&
+                  kWv1 % 1024 == 0 && kWv2 % 1024 == 0,
+              "weight blocks must be 1024-byte aligned for SWIZZLE_128B");
+static_assert(kWr1 >= kWg2 + kBytesWg2 && kWr2 >= kWr1 + kBytesW1 && kWp1 >= kWr2 + kBytesW48 && kWp2 >= kWp1 + kBytesW1 &&
+                  kWv1 >= kWp2 + kBytesW16 && kWv2 >= kWv1 + kBytesW1,
+              "weight blocks overlap");
+constexpr int kBiasK = 6;  // column of the extra slice that multiplies the constant 1
 
 // Debug timeline: block 0 records clock64() at phase boundaries when HMZ_TC_TIMELINE=1 (tools only).
 __device__ unsigned long long g_timeline[96];
@@ -56,17 +63,18 @@ struct __align__(1024) Smem {
   uint8_t a0[kAtomA];       // input latent tile, later the raw (un-normalised) new latent
   uint8_t ahn[kAtomA];      // normalised new latent
   uint8_t a1[4 * kAtomA];   // hidden activations, 4 K-atoms
-  uint8_t wf[32768];        // first-layer weights of the running MLP
-  uint8_t ws[32768];        // second-layer weights of the running MLP
-  float tables[kTableFloats];
-  uint64_t bar_wf, bar_ws, bar_tab;  // TMA landed (tx-count barriers)
-  uint64_t bar_a[2];                 // column-half h of the next A operand written (128 arrivals)
-  uint64_t bar_d[2];                 // hidden accumulator columns [128h, 128h+128) complete (tcgen05.commit)
-  uint64_t bar_s;                    // second-layer (small) accumulator complete
-  uint64_t bar_lat;                  // raw + normalised latent tiles written (128 arrivals)
-  uint64_t bar_fin;                  // small accumulator consumed by its epilogue (128 arrivals)
+  uint8_t wf[kBytesW1];     // first-layer weights of the running MLP (+ extra slice)
+  uint8_t ws[35840];        // second-layer weights of the running MLP (+ extra slice)
+  uint8_t ax[kM * 32];      // extra A slice: [onehot(action) (6), 1, 0 x 9] per row, core-matrix layout
+  uint64_t bar_wf, bar_ws;  // TMA landed (tx-count barriers)
+  uint64_t bar_g;           // gather done: A0 and AX written (384 arrivals)
+  uint64_t bar_a[2];        // column half h of the next A1 written by the hidden warps (128 arrivals)
+  uint64_t bar_d[2];        // hidden accumulator columns [128h, 128h+128) complete (tcgen05.commit)
+  uint64_t bar_s;           // second-layer (small) accumulator complete
+  uint64_t bar_lat;         // raw + normalised latent tiles written by the hidden warps (256 arrivals)
+  uint64_t bar_fin;         // small accumulator consumed by its epilogue (128 arrivals)
   uint32_t tmem_base;
-  int action[kM];
+  float2 row_minmax[2][kM];  // per-row (min, max) of each 32-column half of the raw latent
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,16 +109,39 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// One lane of a fully converged warp (the control warp runs warp-uniform code and elects a lane only
+// around the instructions that must be issued once: descriptors then stay in uniform registers
+// instead of being moved there with R2UR before every tcgen05.mma).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
-// start>>4 | LBO=1 (unused for swizzled K-major) | SBO = 1024 B between 8-row groups | version 1 | SW128
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor, sm100; version field = 1).
+// K-major SWIZZLE_128B: LBO unused (1), SBO = 1024 B between 8-row groups, layout type 2.
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr) {
   const uint64_t hi = 64ull | (1ull << 14) | (2ull << 29);
   return (uint64_t)(((smem_addr >> 4) & 0x3FFFu) | (1u << 16)) | (hi << 32);
 }
+// K-major, no swizzle (core matrices of 8 rows x 16 B): LBO = 128 B between the two K-chunks,
+// SBO = 256 B between 8-row groups, layout type 0.
+__device__ __forceinline__ uint64_t desc_plain(uint32_t smem_addr) {
+  const uint64_t hi = 16ull | (1ull << 14);
+  return (uint64_t)(((smem_addr >> 4) & 0x3FFFu) | (8u << 16)) | (hi << 32);
+}
+// byte offset of (row, 16-byte chunk c in {0, 1}) inside a core-matrix-layout K = 16 slice
+__device__ __host__ __forceinline__ uint32_t plain_off(int row, int c) { return (uint32_t)((row >> 3) * 256 + c * 128 + (row & 7) * 16); }
+
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
@@ -128,21 +159,51 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a_desc, uint64_t 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem_d .. +n) (+)= A[128 x 64 per atom] x B[n x 64 per atom]^T over K-atoms [ka0, ka1);
-// A atoms are 16 KB apart, B atoms b_atom_stride bytes apart.  `first` clears the accumulator.
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a, const uint8_t* b, int ka0, int ka1,
-                                           uint32_t b_atom_stride, uint32_t n, bool first) {
-  const uint32_t idesc = umma_idesc(n);
-  const uint32_t a0 = smem_u32(a), b0 = smem_u32(b);
-  for (int ka = ka0; ka < ka1; ++ka)
+// D[tmem_d .. +n) (+)= A x B^T over the SWIZZLE_128B K-atoms [KA0, KA1): A atoms 16 KB apart, B atoms
+// b_atom_stride bytes apart.  The descriptors of successive K-steps differ only in the 14-bit start
+// address field, so each step is one 32-bit add per operand on a base descriptor (the control lane is
+// a single thread: every instruction it executes sits on the critical path).
+template <int KA0, int KA1>
+__device__ __forceinline__ void issue_atoms(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t b_atom_stride,
+                                            uint32_t idesc, bool clear_first) {
+  const uint64_t a_base = desc_sw128(a_addr), b_base = desc_sw128(b_addr);
+#pragma unroll
+  for (int ka = KA0; ka < KA1; ++ka)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk)  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
-      umma(tmem_d, umma_desc(a0 + ka * kAtomA + kk * 32), umma_desc(b0 + ka * b_atom_stride + kk * 32), idesc,
-           (first && ka == ka0 && kk == 0) ? 0u : 1u);
+      umma(tmem_d, a_base + (uint64_t)((ka * kAtomA + kk * 32) >> 4), b_base + (uint64_t)((ka * b_atom_stride + kk * 32) >> 4),
+           idesc, (clear_first && ka == KA0 && kk == 0) ? 0u : 1u);
+}
+// First layer of an MLP as two N = 128 halves, half 0 first: its epilogue then runs while the tensor
+// core produces half 1 (issuing the halves interleaved was measured slower — both epilogues then
+// start together and fight for the same ALU pipes).
+__device__ __forceinline__ void issue_first_layer(uint32_t tmem, uint32_t a_addr, uint32_t ax_addr, uint32_t wf_addr,
+                                                  uint32_t idesc128, uint64_t* bar_d0, uint64_t* bar_d1) {
+  const uint64_t a_base = desc_sw128(a_addr), b0 = desc_sw128(wf_addr), b1 = desc_sw128(wf_addr + 128 * 128);
+  const uint64_t ax = desc_plain(ax_addr), bx0 = desc_plain(wf_addr + 256 * 128),
+                 bx1 = desc_plain(wf_addr + 256 * 128 + 4096);  // rows 128.. of the extra slice: (128 / 8) * 256 B
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) umma(tmem, a_base + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc128, kk ? 1u : 0u);
+  umma(tmem, ax, bx0, idesc128, 1u);
+  umma_commit(bar_d0);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) umma(tmem + 128, a_base + (uint64_t)(kk * 2), b1 + (uint64_t)(kk * 2), idesc128, kk ? 1u : 0u);
+  umma(tmem + 128, ax, bx1, idesc128, 1u);
+  umma_commit(bar_d1);
+}
+
+// the extra K = 16 step: [onehot, 1] x [action columns, bias]
+__device__ __forceinline__ void issue_extra(uint32_t tmem_d, uint32_t ax_addr, uint32_t bx_addr, uint32_t idesc) {
+  umma(tmem_d, desc_plain(ax_addr), desc_plain(bx_addr), idesc, 1u);
+}
+
+__device__ __forceinline__ void issue_extra_first(uint32_t tmem_d, uint32_t ax_addr, uint32_t bx_addr, uint32_t idesc) {
+  umma(tmem_d, desc_plain(ax_addr), desc_plain(bx_addr), idesc, 0u);  // clears the accumulator
 }
 
 // 32 lanes x 32 consecutive columns of TMEM -> 32 registers per thread (thread = lane = row).
-// Issue and wait are separate so that the next chunk's load overlaps the current chunk's math.
+// Issue and wait are separate so that the next chunk's load overlaps the current chunk's math; the
+// wait names the destination registers as in/out operands so no use can be scheduled above it.
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -155,9 +216,6 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// Same wait, but naming the destination registers as in/out operands so that the compiler cannot
-// schedule any use of them above the wait.
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
@@ -183,7 +241,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  tmem_ld_wait();
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -193,18 +255,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// relu on two packed bf16 (rounding to bf16 preserves sign and zero, so relu commutes with it)
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
+  return r;
+}
 // 16-byte chunk `chunk` (8 bf16) of row `row` inside a [rows][128 B] SWIZZLE_128B K-atom
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
-// bias + ReLU + bf16 of 32 accumulator columns starting at hidden column n0, stored into A1
-__device__ __forceinline__ void hidden_chunk(Smem& s, const uint32_t (&acc)[32], int row, int n0, const float* bias) {
+// ReLU + bf16 of 32 accumulator columns starting at hidden column n0, stored into A1 (bias already in D)
+__device__ __forceinline__ void hidden_chunk(Smem& s, const uint32_t (&acc)[32], int row, int n0) {
   uint32_t pk[16];
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + n0 + j);  // 16-byte aligned: n0, j multiples of 4
-    pk[(j >> 1)] = pack_bf16(fmaxf(__uint_as_float(acc[j]) + b.x, 0.f), fmaxf(__uint_as_float(acc[j + 1]) + b.y, 0.f));
-    pk[(j >> 1) + 1] = pack_bf16(fmaxf(__uint_as_float(acc[j + 2]) + b.z, 0.f), fmaxf(__uint_as_float(acc[j + 3]) + b.w, 0.f));
-  }
+  for (int j = 0; j < 16; ++j) pk[j] = relu_bf16x2(pack_bf16(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])));
   uint8_t* atom = s.a1 + (n0 >> 6) * kAtomA;
   const int c0 = (n0 & 63) >> 3;
 #pragma unroll
@@ -212,38 +276,33 @@ __device__ __forceinline__ void hidden_chunk(Smem& s, const uint32_t (&acc)[32],
     *reinterpret_cast<uint4*>(atom + sw128(row, c0 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
 
-// Hidden-layer epilogue: D[128*half .. +128) -> relu(D + bias) -> bf16 -> A1 atoms 2*half, 2*half+1.
+// Hidden-layer epilogue: D[128*half .. +128) -> relu -> bf16 -> A1 atoms 2*half, 2*half+1.
 // The TMEM load of chunk c+1 is in flight while chunk c is converted.
-__device__ __forceinline__ void hidden_epilogue(Smem& s, uint32_t tmem_row, int row, int half, const float* bias) {
+__device__ __forceinline__ void hidden_epilogue(Smem& s, uint32_t tmem_row, int row, int half) {
   uint32_t va[32], vb[32];
   const int n0 = half * 128;
   tmem_ld32_issue(tmem_row + n0, va);
   tmem_ld_wait(va);
   tmem_ld32_issue(tmem_row + n0 + 32, vb);
-  hidden_chunk(s, va, row, n0, bias);
+  hidden_chunk(s, va, row, n0);
   tmem_ld_wait(vb);
   tmem_ld32_issue(tmem_row + n0 + 64, va);
-  hidden_chunk(s, vb, row, n0 + 32, bias);
+  hidden_chunk(s, vb, row, n0 + 32);
   tmem_ld_wait(va);
   tmem_ld32_issue(tmem_row + n0 + 96, vb);
-  hidden_chunk(s, va, row, n0 + 64, bias);
+  hidden_chunk(s, va, row, n0 + 64);
   tmem_ld_wait(vb);
-  hidden_chunk(s, vb, row, n0 + 96, bias);
+  hidden_chunk(s, vb, row, n0 + 96);
 }
 
 // softmax expectation over the 33 support logits in D[256:304) + signed parabolic (networks.py:152-189)
-__device__ __forceinline__ float support_epilogue(uint32_t tmem_row, const float* bias) {
+__device__ __forceinline__ float support_epilogue(uint32_t tmem_row) {
   float a[32], b[16];
   tmem_ld32(tmem_row + 256, a);
   tmem_ld16(tmem_row + 288, b);
-  float mx = -INFINITY;
+  float mx = b[0];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    a[i] += bias[i];
-    mx = fmaxf(mx, a[i]);
-  }
-  b[0] += bias[32];
-  mx = fmaxf(mx, b[0]);
+  for (int i = 0; i < 32; ++i) mx = fmaxf(mx, a[i]);
   float den = 0.f, num = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -257,15 +316,15 @@ __device__ __forceinline__ float support_epilogue(uint32_t tmem_row, const float
   return signed_parabolic(__fdividef(num, den));
 }
 
-// Warp roles: warps 0-7 = epilogue (thread -> row tid & 127, column half tid >> 7), warp 8 = control
-// (one lane issues every TMA copy and every tcgen05.mma).  All hand-offs go through mbarriers:
-//   bar_a[h]  epilogue -> control : column half h of the next A operand is in shared memory
-//   bar_d[h]  control  -> epilogue: hidden accumulator columns [128h, 128h+128) are complete
-//   bar_s     control  -> epilogue: the second-layer accumulator D[256:..) is complete
-//   bar_lat / bar_fin  epilogue -> control: latent tiles written / small accumulator consumed
-// so the MMA of one column half overlaps the epilogue of the other, the second-layer MMA starts as
-// soon as its first two K-atoms exist, and the next head's first-layer MMA runs under the current
-// head's final epilogue.
+// Hand-offs (all mbarriers):
+//   bar_g     epilogue -> control : A0 and AX are in shared memory
+//   bar_d[h]  control  -> hidden  : hidden accumulator columns [128h, 128h+128) are complete
+//   bar_a[h]  hidden   -> control : A1 atoms 2h, 2h+1 written (and D[128h..) drained)
+//   bar_s     control  -> small + hidden: the second-layer accumulator D[256:..) is complete / A1 is free
+//   bar_lat / bar_fin   small -> control: latent tiles written / small accumulator drained
+// The MMA of one column half overlaps the epilogue of the other, the second-layer MMA starts as soon
+// as its first two K-atoms exist, and a head's outputs are reduced by the small warps while the
+// tensor core and the hidden warps already work on the next head.
 __global__ void __launch_bounds__(kThreads, 1)
 net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_t in_rows_per_item,
                  const uint16_t* __restrict__ in_row, const uint8_t* __restrict__ actions, void* lat_out,
@@ -276,17 +335,44 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
   const int tid = threadIdx.x, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * kM;
 
+  // The parent-latent gather is the longest single latency of the tile (HBM round trip): issue its
+  // loads first, let barrier init / TMEM allocation / the first weight copies run underneath.
+  // Coalescing: 8 consecutive lanes fetch the 8 16-byte chunks of one latent row, so a warp-wide
+  // load touches 4 rows = 4 lines (one thread per row would touch 32 lines per instruction and the
+  // L1 tag stage serves one line per cycle).
+  uint4 gathered[4];
+  int act_early = 0;
+  if (tid < kHiddenThreads) {
+    const int chunk = tid & 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = (tid >> 3) + 32 * i;
+      const int64_t it = (row0 + row) < n ? (row0 + row) : n - 1;
+      const int64_t irow = it * in_rows_per_item + (in_row ? (int64_t)in_row[it] : 0);
+      if (latent_dtype == HMZ_LATENT_F32) {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(lat_in) + irow * kLatent + chunk * 8);
+        const float4 t0 = __ldcs(src), t1 = __ldcs(src + 1);  // streaming: do not displace the tree records in L2
+        gathered[i] = make_uint4(pack_bf16(t0.x, t0.y), pack_bf16(t0.z, t0.w), pack_bf16(t1.x, t1.y), pack_bf16(t1.z, t1.w));
+      } else {
+        gathered[i] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(lat_in) + irow * kLatent + chunk * 8));
+      }
+    }
+  } else if (tid < kHiddenThreads + kSmallThreads) {
+    const int64_t it = (row0 + tid - kHiddenThreads) < n ? (row0 + tid - kHiddenThreads) : n - 1;
+    act_early = actions[it];
+  }
+
   if (tid == 0) {
     mbar_init(&s.bar_wf, 1);
     mbar_init(&s.bar_ws, 1);
-    mbar_init(&s.bar_tab, 1);
+    mbar_init(&s.bar_g, kHiddenThreads + kSmallThreads);
     mbar_init(&s.bar_a[0], 128);
     mbar_init(&s.bar_a[1], 128);
     mbar_init(&s.bar_d[0], 1);
     mbar_init(&s.bar_d[1], 1);
     mbar_init(&s.bar_s, 1);
-    mbar_init(&s.bar_lat, 128);
-    mbar_init(&s.bar_fin, 128);
+    mbar_init(&s.bar_lat, kHiddenThreads);
+    mbar_init(&s.bar_fin, kSmallThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {  // TMEM: all 512 columns (one CTA per SM)
@@ -299,242 +385,246 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
 
-  if (warp == 8) {
+  if (warp == (kHiddenThreads + kSmallThreads) / 32) {
     // ================================= control warp =================================
-    if ((tid & 31) == 0) {
+    {
       uint32_t ph_wf = 0, ph_ws = 0, ph_a = 0, ph_d = 0, ph_s = 0, ph_fin = 0;
-      TL(0);
-      tma_load(s.tables, wsec + kTables, kTableBytes, &s.bar_tab);
-      tma_load(s.wf, wsec + kWg1, kBytesW1, &s.bar_wf);
-      tma_load(s.ws, wsec + kWg2, kBytesWg2, &s.bar_ws);
-      // dynamics layer 1: D[0:256) = A0 x Wg1^T, issued as two N = 128 halves
-      mbar_wait(&s.bar_a[0], ph_a);
-      mbar_wait(&s.bar_a[1], ph_a);
-      ph_a ^= 1;
-      TL(1);  // A0 gathered
+      const uint32_t a0 = smem_u32(s.a0), ahn = smem_u32(s.ahn), a1 = smem_u32(s.a1), ax = smem_u32(s.ax);
+      const uint32_t wf = smem_u32(s.wf), ws = smem_u32(s.ws);
+      const uint32_t id128 = umma_idesc(128), id64 = umma_idesc(64);
+      if (timeline && elect_one()) TL(0);
+      if (elect_one()) tma_load(s.wf, wsec + kWg1, kBytesW1, &s.bar_wf);
+      if (elect_one()) tma_load(s.ws, wsec + kWg2, kBytesWg2, &s.bar_ws);
+      // dynamics layer 1: D[0:256) = [A0 | AX] x Wg1'^T, issued as two N = 128 halves
+      mbar_wait(&s.bar_g, 0);
+      if (timeline && elect_one()) TL(1);
       mbar_wait(&s.bar_wf, ph_wf);
       ph_wf ^= 1;
-      TL(2);  // Wg1 landed
+      if (timeline && elect_one()) TL(2);
       tc_fence_after();
-      issue_gemm(tmem, s.a0, s.wf, 0, 1, 0, 128, true);
-      umma_commit(&s.bar_d[0]);
-      issue_gemm(tmem + 128, s.a0, s.wf + 16384, 0, 1, 0, 128, true);
-      umma_commit(&s.bar_d[1]);
-      TL(3);  // L1 issued
+      if (elect_one()) {
+        issue_first_layer(tmem, a0, ax, wf, id128, &s.bar_d[0], &s.bar_d[1]);
+      }
+      __syncwarp();
+      if (timeline && elect_one()) TL(3);
       mbar_wait(&s.bar_d[1], ph_d);
       ph_d ^= 1;
-      TL(4);  // L1 complete
-      tma_load(s.wf, wsec + kWr1, kBytesW1, &s.bar_wf);  // wf is free again: prefetch the reward head
-      // dynamics layer 2: D[256:320) = A1 x Wg2^T, K-atoms consumed as the epilogue halves deliver them
+      if (timeline && elect_one()) TL(4);
+      if (elect_one()) tma_load(s.wf, wsec + kWr1, kBytesW1, &s.bar_wf);  // wf is free again: prefetch the reward head
+      // dynamics layer 2: D[256:320) = [A1 | AX] x Wg2'^T, K-atoms consumed as the hidden halves deliver them
       mbar_wait(&s.bar_ws, ph_ws);
       ph_ws ^= 1;
-      TL(5);  // Wg2 landed
+      if (timeline && elect_one()) TL(5);
       mbar_wait(&s.bar_a[0], ph_a);
-      TL(6);  // g-hidden half 0 written
+      if (timeline && elect_one()) TL(6);
       tc_fence_after();
-      issue_gemm(tmem + 256, s.a1, s.ws, 0, 2, 64 * 128, 64, true);
+      if (elect_one()) {
+        issue_extra_first(tmem + 256, ax, ws + 64 * 128 * 4, id64);
+        issue_atoms<0, 2>(tmem + 256, a1, ws, 64 * 128, id64, false);
+      }
+      __syncwarp();
       mbar_wait(&s.bar_a[1], ph_a);
       ph_a ^= 1;
-      TL(7);  // g-hidden half 1 written
+      if (timeline && elect_one()) TL(7);
       tc_fence_after();
-      issue_gemm(tmem + 256, s.a1, s.ws, 2, 4, 64 * 128, 64, false);
-      umma_commit(&s.bar_s);
+      if (elect_one()) {
+        issue_atoms<2, 4>(tmem + 256, a1, ws, 64 * 128, id64, false);
+        umma_commit(&s.bar_s);
+      }
+      __syncwarp();
       mbar_wait(&s.bar_s, ph_s);
       ph_s ^= 1;
-      TL(8);  // L2 complete
-      tma_load(s.ws, wsec + kWr2, kBytesW48, &s.bar_ws);
-      mbar_wait(&s.bar_lat, 0);  // raw + normalised latent tiles are in shared memory
-      TL(9);  // E2 done
+      if (timeline && elect_one()) TL(8);
+      if (elect_one()) tma_load(s.ws, wsec + kWr2, kBytesW48, &s.bar_ws);
+      mbar_wait(&s.bar_lat, 0);  // raw + normalised latent tiles are in shared memory, D[256:320) drained
+      if (timeline && elect_one()) TL(9);
 #pragma unroll 1
       for (int head = 0; head < 3; ++head) {
-        const uint8_t* a_in = head == 0 ? s.a0 : s.ahn;
+        const uint32_t a_in = head == 0 ? a0 : ahn;
         const uint32_t n2 = head == 1 ? 16u : 48u;
+        const uint32_t id2 = umma_idesc(n2);
         mbar_wait(&s.bar_wf, ph_wf);
         ph_wf ^= 1;
-        TL(10 + head * 6);  // head first-layer weights landed
+        if (timeline && elect_one()) TL(10 + head * 6);
         tc_fence_after();
-        issue_gemm(tmem, a_in, s.wf, 0, 1, 0, 128, true);
-        umma_commit(&s.bar_d[0]);
-        issue_gemm(tmem + 128, a_in, s.wf + 16384, 0, 1, 0, 128, true);
-        umma_commit(&s.bar_d[1]);
+        if (elect_one()) {
+          issue_first_layer(tmem, a_in, ax, wf, id128, &s.bar_d[0], &s.bar_d[1]);
+        }
+        __syncwarp();
         mbar_wait(&s.bar_d[1], ph_d);
         ph_d ^= 1;
-        TL(11 + head * 6);  // head first-layer MMA complete
-        if (head < 2) tma_load(s.wf, wsec + (head == 0 ? kWp1 : kWv1), kBytesW1, &s.bar_wf);
+        if (timeline && elect_one()) TL(11 + head * 6);
+        if (head < 2 && elect_one()) tma_load(s.wf, wsec + (head == 0 ? kWp1 : kWv1), kBytesW1, &s.bar_wf);
         mbar_wait(&s.bar_ws, ph_ws);
         ph_ws ^= 1;
-        TL(12 + head * 6);  // head second-layer weights landed
-        if (head > 0) {  // D[256:..) must have been drained by the previous head's final epilogue
+        if (timeline && elect_one()) TL(12 + head * 6);
+        if (head > 0) {  // D[256:..) must have been drained by the previous head's output epilogue
           mbar_wait(&s.bar_fin, ph_fin);
           ph_fin ^= 1;
         }
         mbar_wait(&s.bar_a[0], ph_a);
-        TL(13 + head * 6);  // head hidden half 0 written
+        if (timeline && elect_one()) TL(13 + head * 6);
         tc_fence_after();
-        issue_gemm(tmem + 256, s.a1, s.ws, 0, 2, n2 * 128, n2, true);
+        if (elect_one()) {
+          issue_extra_first(tmem + 256, ax, ws + n2 * 128 * 4, id2);
+          issue_atoms<0, 2>(tmem + 256, a1, ws, n2 * 128, id2, false);
+        }
+        __syncwarp();
         mbar_wait(&s.bar_a[1], ph_a);
         ph_a ^= 1;
-        TL(14 + head * 6);  // head hidden half 1 written
+        if (timeline && elect_one()) TL(14 + head * 6);
         tc_fence_after();
-        issue_gemm(tmem + 256, s.a1, s.ws, 2, 4, n2 * 128, n2, false);
-        umma_commit(&s.bar_s);
+        if (elect_one()) {
+          issue_atoms<2, 4>(tmem + 256, a1, ws, n2 * 128, id2, false);
+          umma_commit(&s.bar_s);
+        }
+        __syncwarp();
         mbar_wait(&s.bar_s, ph_s);
         ph_s ^= 1;
-        TL(15 + head * 6);  // head second-layer MMA complete
-        if (head < 2) tma_load(s.ws, wsec + (head == 0 ? kWp2 : kWv2), head == 0 ? kBytesW16 : kBytesW48, &s.bar_ws);
+        if (timeline && elect_one()) TL(15 + head * 6);
+        if (head < 2 && elect_one()) tma_load(s.ws, wsec + (head == 0 ? kWp2 : kWv2), head == 0 ? kBytesW16 : kBytesW48, &s.bar_ws);
       }
     }
-  } else {
-    // ================================ epilogue warps ================================
+  } else if (tid < kHiddenThreads) {
+    // ============================== hidden-epilogue warps ==============================
     const int row = tid & 127, half = tid >> 7;
     const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lane quarter
     const int64_t item = row0 + row;
     uint32_t ph_d = 0, ph_s = 0;
-    {  // gather the parent latent: thread (row, half) moves 32 of the row's 64 values
-      const int64_t it = item < n ? item : n - 1;
-      const int64_t irow = it * in_rows_per_item + (in_row ? (int64_t)in_row[it] : 0);
-      uint32_t pk[16];
-      if (latent_dtype == HMZ_LATENT_F32) {
-        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(lat_in) + irow * kLatent + half * 32);
+    {  // parent latent (loaded at kernel entry) -> swizzled A0 tile
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = __ldcs(src + q);  // streaming: do not displace the tree records in L2
-          pk[2 * q] = pack_bf16(t.x, t.y);
-          pk[2 * q + 1] = pack_bf16(t.z, t.w);
-        }
-      } else {
-        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(lat_in) + irow * kLatent + half * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 t = __ldcs(src + q);
-          pk[4 * q] = t.x; pk[4 * q + 1] = t.y; pk[4 * q + 2] = t.z; pk[4 * q + 3] = t.w;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(s.a0 + sw128(row, half * 4 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(s.a0 + sw128((tid >> 3) + 32 * i, tid & 7)) = gathered[i];
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(&s.bar_a[half]);
-      if (tid == 0) TL(32);  // gather done
+      mbar_arrive(&s.bar_g);
+      if (tid == 0) TL(32);
     }
-    int act = actions[item < n ? item : n - 1];
-    act = act < kActions ? act : kActions - 1;
-    mbar_wait(&s.bar_tab, 0);
-
-    // ---- dynamics hidden layer: relu(D + b1 + W1[:, 64 + a]) -> A1
-    mbar_wait(&s.bar_d[half], ph_d);
-    ph_d ^= 1;
-    tc_fence_after();
-    if (tid == 0) TL(33);  // saw L1 half 0
-    hidden_epilogue(s, tmem_row, row, half, s.tables + tBiasA + act * kBiasARow);
-    if (tid == 0) TL(34);  // hidden epilogue math done
-    fence_proxy_async();
-    tc_fence_before();
-    mbar_arrive(&s.bar_a[half]);
-    if (tid == 0) TL(35);  // fenced + arrived
-
-    // ---- new latent: normalize_h_state (networks.py:191-196) and its three copies
-    mbar_wait(&s.bar_s, ph_s);
-    ph_s ^= 1;
-    tc_fence_after();
-    if (tid == 0) TL(36);  // saw L2
-    if (half == 0) {
-      float raw[64];
-      {
-        float t[32];
-        tmem_ld32(tmem_row + 256, t);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) raw[i] = t[i] + s.tables[tBg2 + i];
-        tmem_ld32(tmem_row + 288, t);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) raw[32 + i] = t[i] + s.tables[tBg2 + 32 + i];
-      }
-      float mn = raw[0], mx = raw[0];
-#pragma unroll
-      for (int i = 1; i < 64; ++i) {
-        mn = fminf(mn, raw[i]);
-        mx = fmaxf(mx, raw[i]);
-      }
-      const float inv = 1.0f / ((mx - mn) + 1e-8f);
-      const int64_t orow = item * out_rows_per_item + out_row;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float hn[8];
-        uint32_t pr[4], ph[4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hn[j] = (raw[c * 8 + j] - mn) * inv;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          pr[j] = pack_bf16(raw[c * 8 + 2 * j], raw[c * 8 + 2 * j + 1]);
-          ph[j] = pack_bf16(hn[2 * j], hn[2 * j + 1]);
-        }
-        *reinterpret_cast<uint4*>(s.a0 + sw128(row, c)) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-        *reinterpret_cast<uint4*>(s.ahn + sw128(row, c)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-        if (item < n) {
-          if (latent_dtype == HMZ_LATENT_F32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(lat_out) + orow * kLatent + c * 8);
-            __stcs(dst, make_float4(hn[0], hn[1], hn[2], hn[3]));
-            __stcs(dst + 1, make_float4(hn[4], hn[5], hn[6], hn[7]));
-          } else {
-            __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(lat_out) + orow * kLatent + c * 8),
-                   make_uint4(ph[0], ph[1], ph[2], ph[3]));
-          }
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&s.bar_lat);
-      if (tid == 0) TL(37);  // E2 done
-    }
-
-    // ---- the three heads: {reward on the raw latent, policy and value on the normalised latent}
 #pragma unroll 1
-    for (int head = 0; head < 3; ++head) {
-      const float* b1 = s.tables + (head == 0 ? tBr1 : (head == 1 ? tBp1 : tBv1));
-      const float* b2 = s.tables + (head == 0 ? tBr2 : (head == 1 ? tBp2 : tBv2));
+    for (int layer = 0; layer < 4; ++layer) {  // dynamics, reward, policy, value hidden layers
       mbar_wait(&s.bar_d[half], ph_d);
       ph_d ^= 1;
       tc_fence_after();
-      if (tid == 0) TL(38 + head * 4);  // saw head first layer
-      // A1 is rewritten here: the previous second-layer MMA (the last reader of A1) has completed —
-      // both halves observed bar_s for it (dynamics: above; heads: at the end of the previous iteration).
-      hidden_epilogue(s, tmem_row, row, half, b1);
+      if (tid == 0) TL(33 + layer * 3);
+      // A1 is rewritten here: its last reader (the previous second-layer MMA) has completed — this
+      // thread observed bar_s for it at the end of the previous iteration.
+      hidden_epilogue(s, tmem_row, row, half);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&s.bar_a[half]);
-      if (tid == 0) TL(39 + head * 4);  // head hidden epilogue done
+      if (tid == 0) TL(34 + layer * 3);
+      mbar_wait(&s.bar_s, ph_s);
+      ph_s ^= 1;
+      if (tid == 0) TL(35 + layer * 3);
+      if (layer == 0) {
+        // ---- new latent: normalize_h_state (networks.py:191-196) and its three copies; thread
+        // (row, half) owns latent columns [32*half, 32*half + 32), the row's two threads exchange
+        // their partial (min, max) through shared memory and a 64-thread named barrier per lane quarter.
+        tc_fence_after();
+        float raw[32];
+        tmem_ld32(tmem_row + 256 + half * 32, raw);
+        if (tid == 0) TL(56);
+        float mn4[4], mx4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mn4[i] = mx4[i] = raw[i];
+#pragma unroll
+        for (int i = 4; i < 32; ++i) {
+          mn4[i & 3] = fminf(mn4[i & 3], raw[i]);
+          mx4[i & 3] = fmaxf(mx4[i & 3], raw[i]);
+        }
+        s.row_minmax[half][row] = make_float2(fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3])),
+                                              fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+        if (tid == 0) TL(57);
+        const float2 m0 = s.row_minmax[0][row], m1 = s.row_minmax[1][row];
+        const float mn = fminf(m0.x, m1.x), mx = fmaxf(m0.y, m1.y);
+        const float inv = 1.0f / ((mx - mn) + 1e-8f);
+        const int64_t orow = item * out_rows_per_item + out_row;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float hn[8];
+          uint32_t pr[4], ph[4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hn[j] = (raw[c * 8 + j] - mn) * inv;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pr[j] = pack_bf16(raw[c * 8 + 2 * j], raw[c * 8 + 2 * j + 1]);
+            ph[j] = pack_bf16(hn[2 * j], hn[2 * j + 1]);
+          }
+          *reinterpret_cast<uint4*>(s.a0 + sw128(row, half * 4 + c)) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+          *reinterpret_cast<uint4*>(s.ahn + sw128(row, half * 4 + c)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          if (latent_dtype == HMZ_LATENT_F32 && item < n) {  // float32 store keeps the per-row form (parity-mode stores)
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(lat_out) + orow * kLatent + half * 32 + c * 8);
+            __stcs(dst, make_float4(hn[0], hn[1], hn[2], hn[3]));
+            __stcs(dst + 1, make_float4(hn[4], hn[5], hn[6], hn[7]));
+          }
+        }
+        if (latent_dtype != HMZ_LATENT_F32) {
+          // bf16 rows leave through the normalised tile in shared memory so that 8 consecutive lanes
+          // write one 128-byte row: the two warps of a lane quarter copy out 16 rows each.
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+          const int lane = tid & 31, chunk = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r2 = (warp & 3) * 32 + half * 16 + i * 4 + (lane >> 3);
+            const int64_t it2 = row0 + r2;
+            const uint4 val = *reinterpret_cast<const uint4*>(s.ahn + sw128(r2, chunk));
+            if (it2 < n)
+              __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(lat_out) + (it2 * out_rows_per_item + out_row) * kLatent + chunk * 8), val);
+          }
+        }
+        if (tid == 0) TL(58);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&s.bar_lat);
+        if (tid == 0) TL(49);
+      }
+    }
+  } else {
+    // ============================== small-epilogue warps ==============================
+    const int row = tid - kHiddenThreads;
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int64_t item = row0 + row;
+    uint32_t ph_s = 0;
+    {  // the extra A slice of this row: one-hot(action) at k = 0..5, the constant 1 at k = 6
+      const int act = act_early < kActions ? act_early : kActions - 1;
+      uint32_t w[4] = {0u, 0u, 0u, 0x3F80u};  // k = 6 -> 1.0 (bf16 0x3F80), k = 7 -> 0
+      w[act >> 1] |= 0x3F80u << ((act & 1) * 16);
+      *reinterpret_cast<uint4*>(s.ax + plain_off(row, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(s.ax + plain_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async();
+      mbar_arrive(&s.bar_g);
+    }
+    mbar_wait(&s.bar_s, ph_s);  // dynamics layer 2: consumed by the hidden warps (latent epilogue)
+    ph_s ^= 1;
+    // ---- head outputs
+#pragma unroll 1
+    for (int head = 0; head < 3; ++head) {
       mbar_wait(&s.bar_s, ph_s);
       ph_s ^= 1;
       tc_fence_after();
-      if (tid == 0) TL(40 + head * 4);  // saw head second layer
-      if (half == 0) {
-        if (head == 1) {  // F.softmax(pi_logits) (networks.py:109)
-          float lg[16];
-          tmem_ld16(tmem_row + 256, lg);
-          float mx = -INFINITY, den = 0.f;
+      if (row == 0) TL(50 + head * 2);
+      if (head == 1) {  // F.softmax(pi_logits) (networks.py:109)
+        float lg[16];
+        tmem_ld16(tmem_row + 256, lg);
+        float mx = lg[0], den = 0.f;
 #pragma unroll
-          for (int a = 0; a < kActions; ++a) {
-            lg[a] += b2[a];
-            mx = fmaxf(mx, lg[a]);
-          }
+        for (int a = 1; a < kActions; ++a) mx = fmaxf(mx, lg[a]);
 #pragma unroll
-          for (int a = 0; a < kActions; ++a) {
-            lg[a] = exp2f((lg[a] - mx) * 1.4426950408889634f);
-            den += lg[a];
-          }
-          const float inv = 1.0f / den;
-          if (item < n) {
-#pragma unroll
-            for (int a = 0; a < kActions; ++a) p_out[item * kActions + a] = lg[a] * inv;
-          }
-        } else {
-          const float x = support_epilogue(tmem_row, b2);
-          if (item < n) (head == 0 ? r_out : v_out)[item] = x;
+        for (int a = 0; a < kActions; ++a) {
+          lg[a] = exp2f((lg[a] - mx) * 1.4426950408889634f);
+          den += lg[a];
         }
-        tc_fence_before();
-        if (head < 2) mbar_arrive(&s.bar_fin);
-        if (tid == 0) TL(41 + head * 4);  // head final epilogue done
+        const float inv = 1.0f / den;
+        if (item < n) {
+#pragma unroll
+          for (int a = 0; a < kActions; ++a) p_out[item * kActions + a] = lg[a] * inv;
+        }
+      } else {
+        const float x = support_epilogue(tmem_row);
+        if (item < n) (head == 0 ? r_out : v_out)[item] = x;
       }
+      tc_fence_before();
+      if (head < 2) mbar_arrive(&s.bar_fin);
+      if (row == 0) TL(51 + head * 2);
     }
   }
 
@@ -576,6 +666,25 @@ int64_t tc_fp32_offset_bytes() { return ((int64_t)tc::kSectionBytes + 1023) / 10
 
 int64_t tc_packed_bytes(int n_disks) { return tc_fp32_offset_bytes() + (int64_t)Fp32Layout::total(n_disks) * 4; }
 
+// extra K = 16 slice of a weight block in the core-matrix layout: column kBiasK carries the bias,
+// columns 0..n_extra-1 carry w[:, extra_col0 + j] (the one-hot action columns of dynamic_net.0).
+static void pack_extra(uint8_t* dst, const float* w, const float* bias, int out, int in, int out_pad, int extra_col0,
+                       int n_extra) {
+  for (int n = 0; n < out_pad; ++n)
+    for (int c = 0; c < 2; ++c) {
+      uint16_t* chunk = reinterpret_cast<uint16_t*>(dst + tc::plain_off(n, c));
+      for (int j = 0; j < 8; ++j) {
+        const int k = c * 8 + j;
+        float v = 0.f;
+        if (n < out) {
+          if (k < n_extra) v = w[(size_t)n * in + extra_col0 + k];
+          else if (k == tc::kBiasK) v = bias[n];
+        }
+        chunk[j] = tc::f2bf(v);
+      }
+    }
+}
+
 void tc_pack(const float* const* t, int n_disks, void* out) {
   using namespace tc;
   std::memset(out, 0, (size_t)tc_packed_bytes(n_disks));
@@ -583,30 +692,19 @@ void tc_pack(const float* const* t, int n_disks, void* out) {
   pack_fp32(t, n_disks, (float*)((uint8_t*)out + tc_fp32_offset_bytes()));
   uint8_t* sec = (uint8_t*)out;
   // state_dict order: rep(0-3) dyn(4-7) rwd(8-11) pol(12-15) val(16-19); each {w1, b1, w2, b2}
-  pack_kmajor_sw128(sec + kWg1, t[4], kHidden, kLatent + kActions, 256, 0, 1);
-  pack_kmajor_sw128(sec + kWg2, t[6], kLatent, kHidden, 64, 0, 4);
-  pack_kmajor_sw128(sec + kWr1, t[8], kHidden, kLatent, 256, 0, 1);
-  pack_kmajor_sw128(sec + kWr2, t[10], kSupport, kHidden, 48, 0, 4);
-  pack_kmajor_sw128(sec + kWp1, t[12], kHidden, kLatent, 256, 0, 1);
-  pack_kmajor_sw128(sec + kWp2, t[14], kActions, kHidden, 16, 0, 4);
-  pack_kmajor_sw128(sec + kWv1, t[16], kHidden, kLatent, 256, 0, 1);
-  pack_kmajor_sw128(sec + kWv2, t[18], kSupport, kHidden, 48, 0, 4);
-  float* tab = reinterpret_cast<float*>(sec + kTables);
   const int in_g1 = kLatent + kActions;
-  for (int a = 0; a < 8; ++a)
-    for (int n = 0; n < kHidden; ++n)
-      tab[tBiasA + a * kBiasARow + n] = t[5][n] + (a < kActions ? t[4][(size_t)n * in_g1 + kLatent + a] : 0.f);
-  for (int i = 0; i < kLatent; ++i) tab[tBg2 + i] = t[7][i];
-  for (int i = 0; i < kHidden; ++i) {
-    tab[tBr1 + i] = t[9][i];
-    tab[tBp1 + i] = t[13][i];
-    tab[tBv1 + i] = t[17][i];
+  pack_kmajor_sw128(sec + kWg1, t[4], kHidden, in_g1, 256, 0, 1);
+  pack_extra(sec + kWg1 + 256 * 128, t[4], t[5], kHidden, in_g1, 256, kLatent, kActions);
+  pack_kmajor_sw128(sec + kWg2, t[6], kLatent, kHidden, 64, 0, 4);
+  pack_extra(sec + kWg2 + 64 * 128 * 4, t[6], t[7], kLatent, kHidden, 64, 0, 0);
+  const struct { uint32_t w1, w2; int i; int out2, pad2; } heads[3] = {
+      {kWr1, kWr2, 8, kSupport, 48}, {kWp1, kWp2, 12, kActions, 16}, {kWv1, kWv2, 16, kSupport, 48}};
+  for (const auto& h : heads) {
+    pack_kmajor_sw128(sec + h.w1, t[h.i], kHidden, kLatent, 256, 0, 1);
+    pack_extra(sec + h.w1 + 256 * 128, t[h.i], t[h.i + 1], kHidden, kLatent, 256, 0, 0);
+    pack_kmajor_sw128(sec + h.w2, t[h.i + 2], h.out2, kHidden, h.pad2, 0, 4);
+    pack_extra(sec + h.w2 + h.pad2 * 128 * 4, t[h.i + 2], t[h.i + 3], h.out2, kHidden, h.pad2, 0, 0);
   }
-  for (int i = 0; i < kSupport; ++i) {
-    tab[tBr2 + i] = t[11][i];
-    tab[tBv2 + i] = t[19][i];
-  }
-  for (int i = 0; i < kActions; ++i) tab[tBp2 + i] = t[15][i];
 }
 
 static int tc_timeline_enabled() {

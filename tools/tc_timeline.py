@@ -21,15 +21,18 @@ torch.cuda.synchronize()
 buf = (C.c_ulonglong * 96)()
 _lib.check(_lib.load().hmz_debug_tc_timeline(buf))
 t = np.array(list(buf), dtype=np.int64)
-names = {0: "ctl start", 1: "ctl A0 gathered", 2: "ctl Wg1 landed", 3: "ctl L1 issued", 4: "ctl L1 complete", 5: "ctl Wg2 landed",
-         6: "ctl g-hid h0 written", 7: "ctl g-hid h1 written", 8: "ctl L2 complete", 9: "ctl E2 done"}
+names = {0: "ctl start", 1: "ctl gather seen", 2: "ctl Wg1 landed", 3: "ctl L1 issued", 4: "ctl L1 complete", 5: "ctl Wg2 landed",
+         6: "ctl g-hid h0 written", 7: "ctl g-hid h1 written", 8: "ctl L2 complete", 9: "ctl latent tiles written", 32: "hid gather done", 63: "end",
+         48: "small saw L2", 49: "hid latent done (arrived)", 56: "hid latent: tmem loaded", 57: "hid latent: minmax exchanged", 58: "hid latent: stores issued"}
 for hd, nm in enumerate("rpv"):
     for j, what in enumerate(["W1 landed", "first MMA complete", "W2 landed", "hid h0 written", "hid h1 written", "second MMA complete"]):
         names[10 + hd * 6 + j] = f"ctl {nm}: {what}"
-names.update({32: "epi gather done", 33: "epi saw L1", 34: "epi g-hid math done", 35: "epi fenced+arrived", 36: "epi saw L2", 37: "epi E2 done", 63: "end"})
-for hd, nm in enumerate("rpv"):
-    for j, what in enumerate(["saw first layer", "hidden epilogue done", "saw second layer", "final epilogue done"]):
-        names[38 + hd * 4 + j] = f"epi {nm}: {what}"
+    names[50 + hd * 2] = f"small {nm}: saw second layer"
+    names[51 + hd * 2] = f"small {nm}: output done"
+for ly, nm in enumerate("grpv"):
+    names[33 + ly * 3] = f"hid {nm}: saw first layer"
+    names[34 + ly * 3] = f"hid {nm}: epilogue done"
+    names[35 + ly * 3] = f"hid {nm}: saw second layer"
 t0 = t[0]
 ev = sorted((int(t[k] - t0), names[k]) for k in names if t[k] != 0)
 prev = 0
