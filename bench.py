@@ -286,13 +286,14 @@ def run_ours(args):
     n_cls = (C.c_int64 * 8)()
     _lib.check(lib.hmz_prof_end(ms_cls, n_cls))
     _lib.check(lib.hmz_search_set_groups(args.groups))
-    names = ["env_step", "select", "net_recurrent", "expand_backup", "net_initial", "root_policy", "other", "-"]
+    # "backup_select" = the fused expansion + backup(sim) + selection(sim+1) kernel; "select" = the first selection of a move
+    names = ["env_step", "select", "net_recurrent", "backup_select", "net_initial", "root_policy", "other", "-"]
     kern = {names[i]: {"ms_total": ms_cls[i], "launches": int(n_cls[i]),
                        "us_per_launch": (ms_cls[i] / n_cls[i] * 1e3) if n_cls[i] else None} for i in range(7)}
     total_kernel_ms = sum(ms_cls[i] for i in range(7))
     for k, v in kern.items():
         v["share"] = v["ms_total"] / total_kernel_ms if total_kernel_ms else None
-    dominant = max(("select", "net_recurrent", "expand_backup"), key=lambda k: kern[k]["ms_total"])
+    dominant = max(("net_recurrent", "backup_select"), key=lambda k: kern[k]["ms_total"])
     peaks = measured_peaks()
     if dominant == "net_recurrent":
         per_launch_s = kern[dominant]["us_per_launch"] * 1e-6
@@ -303,15 +304,17 @@ def run_ours(args):
                     "peak_source": peaks["source"] + ", sustained bf16",
                     "algorithmic": f"{FLOP_PER_SIM} FLOP/sim x {B} sims per launch"}
     else:
-        # tree kernels: 156*d + 672 B/sim split between select (128 B/level) and expand+backup
+        # fused tree kernel, algorithmic bytes per simulation: selection reads one 128 B record per
+        # level, backup reads + writes one 16 B slot per level, the expansion writes one 128 B record, plus the
+        # per-search scalars (leaf ids 5 B r/w, p 24 B, r/v 8 B, min/max + root W 24 B r/w, path 4 B/level r/w)
         per_launch_s = kern[dominant]["us_per_launch"] * 1e-6
-        depth = 3.3
-        bytes_per_sim = 128 * depth if dominant == "select" else (28 * (depth + 1) + 32 + 128 + 40)
+        depth = 3.4
+        bytes_per_sim = 128 * depth + 32 * depth + 128 + 8 * depth + 10 + 32 + 48
         achieved = bytes_per_sim * B / per_launch_s / 1e9
-        roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+        roofline = {"kernel": "search_backup_select (expand + backup + next select)", "bound": "hbm", "achieved": achieved,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                    "peak_source": peaks["source"],
                     "algorithmic": f"{bytes_per_sim:.0f} B/sim x {B} sims per launch (mean leaf depth {depth})"}
-
     # ---- end to end: env words from pinned host memory in, move records back to the host, every step
     h_words = torch.empty(B, dtype=torch.int32).pin_memory()
     h_words.copy_(sp.env.words.cpu())

@@ -127,20 +127,30 @@ int hmz_env_rollout_random(uint32_t* words, int64_t n_envs, int n_disks, int max
                            unsigned long long* counters, void* stream);
 
 /* ------------------------------------------------------------------ tree store -----
- * One 128-byte record per EXPANDED node; field arrays of 6 (one entry per child action)
- * inside the record, so a search's whole pUCT decision at a node is one aligned 128-byte
- * line.  The node expanded by simulation s of a search is record s+1 (root = record 0), so
- * no allocator is needed.  Fields restate MCTS/node.py:9-28 (prior, N, W, rwd, children).
+ * One 128-byte record per EXPANDED node = two 64-byte halves, each holding three child slots
+ * (one 16-byte slot per child action: W, rwd, N, child record) followed by those children's
+ * priors.  A search is owned by a pair of lanes; each lane's whole share of a pUCT decision is
+ * its 64-byte half (four 128-bit loads), and a backup step is one 16-byte slot read + write.
+ * The node expanded by simulation s of a search is record s+1 (root = record 0), so no
+ * allocator is needed.  Fields restate MCTS/node.py:9-28 (prior, N, W, rwd, children).
  */
+typedef struct hmz_child {
+  double W;       /* child.W   (float64 sum of backed-up values, node.py:63)              */
+  float rwd;      /* child.rwd  (float32 value, widened exactly when used)                */
+  uint16_t N;     /* child.N                                                              */
+  uint16_t child; /* record index of the expanded child, HMZ_NO_CHILD otherwise           */
+} hmz_child_t;
+
+typedef struct hmz_half {
+  hmz_child_t c[3];      /* children 3h .. 3h+2 of the node                               */
+  float prior[3];        /* their priors (float32; a noised root keeps float64 in root_prior) */
+  uint16_t parent;       /* half 0 only: record index of this node's parent (root: 0)     */
+  uint8_t parent_action; /* half 0 only: action that leads from the parent to this node   */
+  uint8_t pad;
+} hmz_half_t;
+
 typedef struct hmz_node {
-  double W[6];           /* child.W   (float64 sum of backed-up values, node.py:63)      */
-  float prior[6];        /* child.prior (float32; a noised root keeps float64 in root_prior) */
-  float rwd[6];          /* child.rwd  (float32 value, widened exactly when used)         */
-  uint16_t N[6];         /* child.N                                                       */
-  uint16_t child[6];     /* record index of the expanded child, HMZ_NO_CHILD otherwise    */
-  uint16_t parent;       /* record index of this node's parent (root: 0)                  */
-  uint8_t parent_action; /* action that leads from parent to this node                    */
-  uint8_t pad[5];
+  hmz_half_t h[2]; /* child a lives in h[a / 3].c[a % 3], its prior in h[a / 3].prior[a % 3] */
 } hmz_node_t;
 
 #define HMZ_LATENT_F32 0

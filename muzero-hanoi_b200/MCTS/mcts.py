@@ -59,11 +59,11 @@ class MCTS:
         eng = self._engine
         if eng is None or eng.n_simulations == 0:
             return []
-        rec = eng.store.records()[0]
+        rec = eng.store.records()
         e, path = eng.n_simulations, []  # the last simulation expanded record n_simulations
         while e != 0:
-            path.append(int(rec["parent_action"][e]))
-            e = int(rec["parent"][e])
+            path.append(int(rec["parent_action"][0, e]))
+            e = int(rec["parent"][0, e])
         self.latent_actions = [torch.tensor([a], dtype=torch.long, device=self.dev) for a in reversed(path)]
         return self.latent_actions
 

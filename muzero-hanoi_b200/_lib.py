@@ -22,11 +22,23 @@ class HmzError(RuntimeError):
         self.code = code
 
 
+class ChildSlot(C.Structure):
+    """hmz_child_t — 16 bytes."""
+
+    _fields_ = [("W", C.c_double), ("rwd", C.c_float), ("N", C.c_uint16), ("child", C.c_uint16)]
+
+
+class NodeHalf(C.Structure):
+    """hmz_half_t — 64 bytes."""
+
+    _fields_ = [("c", ChildSlot * 3), ("prior", C.c_float * 3), ("parent", C.c_uint16), ("parent_action", C.c_uint8),
+                ("pad", C.c_uint8)]
+
+
 class NodeRecord(C.Structure):
     """hmz_node_t — 128 bytes."""
 
-    _fields_ = [("W", C.c_double * 6), ("prior", C.c_float * 6), ("rwd", C.c_float * 6), ("N", C.c_uint16 * 6),
-                ("child", C.c_uint16 * 6), ("parent", C.c_uint16), ("parent_action", C.c_uint8), ("pad", C.c_uint8 * 5)]
+    _fields_ = [("h", NodeHalf * 2)]
 
 
 class SearchDesc(C.Structure):

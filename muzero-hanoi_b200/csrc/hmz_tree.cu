@@ -1,19 +1,9 @@
 // Tree-store kernels: pUCT selection, expansion + discounted backup, root policy (sm_100a).
 //
 // Restates MCTS/mcts.py:34-126 and MCTS/node.py:30-136 of the reference over the 128-byte node
-// records of include/hmz.h.  A search is owned by one 8-lane segment of a warp (lanes 0..5 = the
-// six child actions; 4 searches per warp): a node's whole pUCT decision is one coalesced
-// 128-byte line and the arg-max is three xor-shuffles inside the segment.
-//
-// Arithmetic contract (bit-exact vs the reference):
-//   Q, W, value, min/max  : IEEE float64, every op an explicit __d*_rn so nvcc cannot contract
-//                           the reference's separate multiply and add into an FMA;
-//   f32(Q) + f32(U)       : float32 add after rounding each term (MCTS/node.py:83,103,123);
-//   U = prior * w         : float32 x float32 for a float32 prior (NumPy >= 2 weak scalars),
-//                           float64 product then rounded at a Dirichlet-noised root (:122);
-//   ties                  : lowest action index (the sanctioned replacement of :86).
-// These kernels are HBM/L2-latency bound gathers (one 128 B record per tree level); there is no
-// contraction here and nothing for tensor cores to do.
+// records of include/hmz.h; device-side building blocks and the arithmetic contract are in
+// hmz_tree.cuh.  These kernels are latency-bound gathers (one 128-byte record per tree level, one
+// 16-byte slot per backup step); there is no contraction here and nothing for tensor cores to do.
 #include <cstdlib>
 
 #include "hmz_common.cuh"
@@ -21,7 +11,8 @@
 
 namespace hmz {
 
-constexpr int kSearchesPerBlock = 32;  // 256 threads = 8 warps x 4 searches
+constexpr int kTreeThreads = 128;                    // 4 warps x 16 searches
+constexpr int kSearchesPerBlock = kTreeThreads / 2;  // one lane pair per search
 constexpr int kLatentWidth = HMZ_LATENT;
 
 __global__ void __launch_bounds__(256) search_minmax_reset(double* __restrict__ minmax, int64_t n) {
@@ -31,184 +22,93 @@ __global__ void __launch_bounds__(256) search_minmax_reset(double* __restrict__ 
   }
 }
 
-// root_node.expand(prior, h, 0.0): record 0 <- priors, everything else cleared; root.W <- 0.
-__global__ void __launch_bounds__(256) search_begin(hmz_search_t s, const double* __restrict__ root_prior) {
-  const int lane8 = threadIdx.x & 7;
-  for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; b < s.n_searches;
-       b += ((int64_t)gridDim.x * blockDim.x) >> 3) {
-    float pr[6];
+// root_node.expand(prior, h, 0.0) (MCTS/mcts.py:52-69): record 0 <- priors, everything else cleared;
+// root.W <- 0.  The prior is either given (float64) or built from the network policy p0 with the
+// optional Dirichlet mix of add_dirichlet_noise (MCTS/mcts.py:148-150).
+__global__ void __launch_bounds__(kTreeThreads) search_begin(hmz_search_t s, const double* __restrict__ root_prior,
+                                                             const float* __restrict__ p0, const double* __restrict__ noise,
+                                                             float one_minus_eps, double eps) {
+  const int half = threadIdx.x & 1;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
+  if (b >= s.n_searches) return;
+  float pr[6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double p = root_prior[b * 6 + a];
-      pr[a] = (float)p;
-      if (lane8 == 0 && s.root_prior != root_prior) s.root_prior[b * 6 + a] = p;
-    }
-    write_fresh_record(&s.nodes[b * s.n_records], lane8, pr, 0, 0);
-    if (lane8 == 0) s.root_W[b] = 0.0;
-  }
-}
-
-// Root prior from the network policy (+ optional Dirichlet mix, MCTS/mcts.py:148-150).
-__global__ void __launch_bounds__(256) search_begin_p0(hmz_search_t s, const float* __restrict__ p0,
-                                                      const double* __restrict__ noise, float one_minus_eps,
-                                                      double eps) {
-  const int lane8 = threadIdx.x & 7;
-  for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; b < s.n_searches;
-       b += ((int64_t)gridDim.x * blockDim.x) >> 3) {
-    float pr[6];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
+  for (int a = 0; a < 6; ++a) {
+    double p;
+    if (p0 != nullptr) {
       const float q = p0[b * 6 + a];
-      double p = (double)q;
+      p = (double)q;
       if (noise != nullptr)  // (1-eps)*prob is a float32 product, the sum with eps*noise is float64
         p = __dadd_rn((double)__fmul_rn(one_minus_eps, q), __dmul_rn(eps, noise[b * 6 + a]));
-      pr[a] = (float)p;
-      if (lane8 == 0) s.root_prior[b * 6 + a] = p;
+    } else {
+      p = root_prior[b * 6 + a];
     }
-    write_fresh_record(&s.nodes[b * s.n_records], lane8, pr, 0, 0);
-    if (lane8 == 0) s.root_W[b] = 0.0;
+    pr[a] = (float)p;
+    if (half == 0 && (p0 != nullptr || s.root_prior != root_prior)) s.root_prior[b * 6 + a] = p;
   }
+  write_fresh_half(&s.nodes[b * s.n_records], half, pr, 0, 0);
+  if (half == 0) s.root_W[b] = 0.0;
 }
 
-template <bool kPrefetch>
-__global__ void __launch_bounds__(256) search_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
-                                                    double discount, uint16_t* __restrict__ leaf_parent,
-                                                    uint8_t* __restrict__ leaf_action,
-                                                    uint16_t* __restrict__ leaf_depth, uint8_t* __restrict__ path_out,
-                                                    int path_cap, uint32_t* __restrict__ path_ent) {
-  const int lane8 = threadIdx.x & 7;
-  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
-  const bool valid = b < s.n_searches;
-  if (!valid) return;  // whole segments leave together: shuffles are segment-masked
-  const hmz_node_t* nodes = s.nodes + b * s.n_records;
-  const double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
+// Phase 1 of one simulation for every search (one lane pair each).
+__global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
+                                                              double discount, uint16_t* __restrict__ leaf_parent,
+                                                              uint8_t* __restrict__ leaf_action,
+                                                              uint16_t* __restrict__ leaf_depth, uint8_t* __restrict__ path_out,
+                                                              int path_cap, uint32_t* __restrict__ path_ent) {
+  const int half = threadIdx.x & 1;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
+  if (b >= s.n_searches) return;  // whole pairs leave together: shuffles are pair-masked
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
-  Leaf leaf = select_leaf<kPrefetch>(nodes, rp, mn, mx, sim, ucb_table, discount, lane8, valid,
-                          path_out ? path_out + b * path_cap : nullptr, path_cap,
-                          path_ent ? path_ent + b * kPathCap : nullptr);
-  if (valid && lane8 == 0) {
+  const Leaf leaf = select_leaf(s.nodes + b * s.n_records, rp, s.minmax[2 * b], s.minmax[2 * b + 1], sim, ucb_table,
+                                discount, half, path_out ? path_out + b * path_cap : nullptr, path_cap,
+                                path_ent ? path_ent + b * kPathCap : nullptr);
+  if (half == 0) {
     leaf_parent[b] = (uint16_t)leaf.parent;
     leaf_action[b] = (uint8_t)leaf.action;
     if (leaf_depth) leaf_depth[b] = (uint16_t)leaf.depth;
   }
 }
 
-__global__ void __launch_bounds__(256) search_expand_backup(hmz_search_t s, int sim, double discount,
-                                                           const uint16_t* __restrict__ leaf_parent,
-                                                           const uint8_t* __restrict__ leaf_action,
-                                                           const float* __restrict__ r, const float* __restrict__ p,
-                                                           const float* __restrict__ v) {
-  const int lane8 = threadIdx.x & 7;
-  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+// Phases 2b + 3 of simulation `sim` (expansion with the network outputs, backup), optionally followed
+// at once by the selection of simulation `sim + 1` — the fused hot-loop form: the path just updated
+// is still in this SM's L1 and the next walk usually shares its prefix.  With path_ent the backup
+// loads all path slots up front; without it (split-phase API) it walks the parent links.
+__global__ void __launch_bounds__(kTreeThreads) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
+                                                                     double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
+                                                                     uint16_t* leaf_depth, uint32_t* path_ent,
+                                                                     const float* __restrict__ r, const float* __restrict__ p,
+                                                                     const float* __restrict__ v, int do_select) {
+  const int half = threadIdx.x & 1;
+  const unsigned pair = 3u << ((threadIdx.x & 31) & ~1);
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
   if (b >= s.n_searches) return;
   hmz_node_t* nodes = s.nodes + b * s.n_records;
+  uint32_t* path = path_ent ? path_ent + b * kPathCap : nullptr;
   const int pe = leaf_parent[b], pa = leaf_action[b];
-  float pr[6];
-#pragma unroll
-  for (int a = 0; a < 6; ++a) pr[a] = p[b * 6 + a];
-  write_fresh_record(&nodes[sim + 1], lane8, pr, pe, pa);
-  if (lane8 == 0) {
-    double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
+  write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
+  double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
+  if (half == 0) {
     double root_w = s.root_W[b];
-    backup_path(nodes, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
-    s.root_W[b] = root_w;
-    s.minmax[2 * b] = mn;
-    s.minmax[2 * b + 1] = mx;
-  }
-}
-
-// Fused hot-loop kernel: expansion + backup of simulation `sim` (lane-parallel over the recorded
-// path) followed at once by the selection of simulation `sim + 1` — the path just updated is still in
-// this SM's L1, and the next walk usually shares its prefix.
-template <bool kPrefetch>
-__global__ void __launch_bounds__(256, 4) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
-                                                           double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
-                                                           uint16_t* leaf_depth, uint32_t* path_ent,
-                                                           const float* __restrict__ r, const float* __restrict__ p,
-                                                           const float* __restrict__ v, int do_select) {
-  const int lane8 = threadIdx.x & 7;
-  const int seg_base = (threadIdx.x & 31) & ~7;
-  const unsigned seg = 0xFFu << seg_base;
-  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
-  if (b >= s.n_searches) return;
-  hmz_node_t* nodes = s.nodes + b * s.n_records;
-  uint32_t* path = path_ent + b * kPathCap;
-  const int pe = leaf_parent[b], pa = leaf_action[b], depth = leaf_depth[b];
-  float pr[6];
-#pragma unroll
-  for (int a = 0; a < 6; ++a) pr[a] = p[b * 6 + a];
-  write_fresh_record(&nodes[sim + 1], lane8, pr, pe, pa);
-  double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1], root_w = s.root_W[b];
-  if (depth <= kPathCap) {
-    backup_levels(nodes, path, depth, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx, lane8);
-  } else {  // very deep path: walk the parent links on one lane, then share the result
-    if (lane8 == 0) backup_path(nodes, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
-    mn = __shfl_sync(seg, mn, seg_base);
-    mx = __shfl_sync(seg, mx, seg_base);
-    root_w = __shfl_sync(seg, root_w, seg_base);
-  }
-  if (lane8 == 0) {
+    const int depth = (path != nullptr && leaf_depth != nullptr) ? (int)leaf_depth[b] : kPathCap + 1;
+    if (depth <= 8)
+      backup_path8(nodes, path, depth, sim, r[b], (double)v[b], discount, root_w, mn, mx);
+    else
+      backup_walk(nodes, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
     s.root_W[b] = root_w;
     s.minmax[2 * b] = mn;
     s.minmax[2 * b + 1] = mx;
   }
   if (!do_select) return;
-  __syncwarp(seg);  // the segment's record updates are ordered before its next walk
+  mn = __shfl_sync(pair, mn, (threadIdx.x & 31) & ~1);  // also orders lane 0's record updates before the pair's next walk
+  mx = __shfl_sync(pair, mx, (threadIdx.x & 31) & ~1);
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
-  Leaf leaf = select_leaf<kPrefetch>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, lane8, true, nullptr, 0, path);
-  if (lane8 == 0) {
+  const Leaf leaf = select_leaf(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path);
+  if (half == 0) {
     leaf_parent[b] = (uint16_t)leaf.parent;
     leaf_action[b] = (uint8_t)leaf.action;
     leaf_depth[b] = (uint16_t)leaf.depth;
   }
-}
-
-// Thread-per-search hot-loop kernels (see hmz_tree.cuh): selection only (first simulation) and the
-// fused expansion + backup of simulation `sim` followed by the selection of simulation `sim + 1`.
-constexpr int kTpsThreads = 64;
-
-__global__ void __launch_bounds__(kTpsThreads) search_select_tps(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
-                                                                double discount, uint16_t* __restrict__ leaf_parent,
-                                                                uint8_t* __restrict__ leaf_action,
-                                                                uint16_t* __restrict__ leaf_depth, uint32_t* __restrict__ path_ent) {
-  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (b >= s.n_searches) return;
-  const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
-  const Leaf leaf = select_leaf_thread(s.nodes + b * s.n_records, rp, s.minmax[2 * b], s.minmax[2 * b + 1], sim, ucb_table,
-                                       discount, path_ent + b * kPathCap);
-  leaf_parent[b] = (uint16_t)leaf.parent;
-  leaf_action[b] = (uint8_t)leaf.action;
-  leaf_depth[b] = (uint16_t)leaf.depth;
-}
-
-__global__ void __launch_bounds__(kTpsThreads) search_backup_select_tps(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
-                                                                       double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
-                                                                       uint16_t* leaf_depth, uint32_t* path_ent,
-                                                                       const float* __restrict__ r, const float* __restrict__ p,
-                                                                       const float* __restrict__ v, int do_select) {
-  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (b >= s.n_searches) return;
-  hmz_node_t* nodes = s.nodes + b * s.n_records;
-  uint32_t* path = path_ent + b * kPathCap;
-  const int pe = leaf_parent[b], pa = leaf_action[b], depth = leaf_depth[b];
-  float pr[6];
-#pragma unroll
-  for (int a = 0; a < 6; ++a) pr[a] = p[b * 6 + a];
-  write_fresh_record_thread(&nodes[sim + 1], pr, pe, pa);
-  double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1], root_w = s.root_W[b];
-  if (depth <= 8)
-    backup_thread8(nodes, path, depth, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
-  else
-    backup_path(nodes, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
-  s.root_W[b] = root_w;
-  s.minmax[2 * b] = mn;
-  s.minmax[2 * b + 1] = mx;
-  if (!do_select) return;
-  const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
-  const Leaf leaf = select_leaf_thread(nodes, rp, mn, mx, sim + 1, ucb_table, discount, path);
-  leaf_parent[b] = (uint16_t)leaf.parent;
-  leaf_action[b] = (uint8_t)leaf.action;
-  leaf_depth[b] = (uint16_t)leaf.depth;
 }
 
 // MCTS/mcts.py:112-126 per search (one thread each; 52 bytes in, <= 76 bytes out).
@@ -221,8 +121,8 @@ __global__ void __launch_bounds__(256) search_root_policy(hmz_search_t s, int n_
     const hmz_node_t* root = s.nodes + b * s.n_records;
     int n[6];
     double w[6];
-    const uint4 nv = *reinterpret_cast<const uint4*>(&root->N[0]);  // N[0..5] + child[0..1], 16-byte aligned
-    n[0] = nv.x & 0xFFFF; n[1] = nv.x >> 16; n[2] = nv.y & 0xFFFF; n[3] = nv.y >> 16; n[4] = nv.z & 0xFFFF; n[5] = nv.z >> 16;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) n[a] = root->h[a / 3].c[a % 3].N;
     // generate_play_policy (:154-176): visits ** clamp(1/T, 1, 5) when T > 0, raw counts when T == 0
     double ex = 1.0;
     if (temperature > 0.0) ex = fmax(1.0, fmin(5.0, __ddiv_rn(1.0, temperature)));
@@ -314,7 +214,7 @@ int hmz_search_begin(const hmz_search_t* s, const double* root_prior, void* stre
   if (int rc = check_search(s, "hmz_search_begin")) return rc;
   if (s->n_searches == 0) return HMZ_OK;
   if (!root_prior) return fail(HMZ_ERR_INVALID, "hmz_search_begin: null root_prior");
-  search_begin<<<grid_for(s->n_searches, kSearchesPerBlock, 8), 256, 0, (cudaStream_t)stream>>>(*s, root_prior);
+  search_begin<<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(*s, root_prior, nullptr, nullptr, 0.f, 0.0);
   return check_launch("search_begin");
 }
 
@@ -325,8 +225,8 @@ int hmz_search_begin_p0(const hmz_search_t* s, const float* p0, const double* no
   if (!p0) return fail(HMZ_ERR_INVALID, "hmz_search_begin_p0: null p0");
   if ((noise != nullptr) != (s->root_prior_is_f64 != 0))
     return fail(HMZ_ERR_INVALID, "hmz_search_begin_p0: root_prior_is_f64 must be set iff noise is given");
-  search_begin_p0<<<grid_for(s->n_searches, kSearchesPerBlock, 8), 256, 0, (cudaStream_t)stream>>>(
-      *s, p0, noise, (float)(1.0 - eps), eps);
+  search_begin<<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(*s, nullptr, p0, noise,
+                                                                                   (float)(1.0 - eps), eps);
   return check_launch("search_begin_p0");
 }
 
@@ -337,9 +237,8 @@ int hmz_search_select(const hmz_search_t* s, int sim, const double* ucb_table, d
   if (s->n_searches == 0) return HMZ_OK;
   if (!ucb_table || !leaf_parent || !leaf_action || sim < 0 || sim + 1 >= s->n_records || (path_out && path_cap < 1))
     return fail(HMZ_ERR_INVALID, "hmz_search_select: bad arguments (sim=%d, n_records=%d)", sim, s->n_records);
-  search_select<false><<<search_grid(s->n_searches), 256, 0, (cudaStream_t)stream>>>(*s, sim, ucb_table, discount, leaf_parent,
-                                                                              leaf_action, leaf_depth, path_out,
-                                                                              path_cap, nullptr);
+  search_select<<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(
+      *s, sim, ucb_table, discount, leaf_parent, leaf_action, leaf_depth, path_out, path_cap, nullptr);
   return check_launch("search_select");
 }
 
@@ -351,8 +250,10 @@ int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, co
   if (s->n_searches == 0) return HMZ_OK;
   if (!leaf_parent || !leaf_action || !r || !p || !v || sim < 0 || sim + 1 >= s->n_records)
     return fail(HMZ_ERR_INVALID, "hmz_search_expand_backup: bad arguments (sim=%d, n_records=%d)", sim, s->n_records);
-  search_expand_backup<<<search_grid(s->n_searches), 256, 0, (cudaStream_t)stream>>>(*s, sim, discount, leaf_parent,
-                                                                                     leaf_action, r, p, v);
+  // split-phase form: no recorded path, the backup walks the parent links
+  search_backup_select<<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(
+      *s, sim, nullptr, discount, const_cast<uint16_t*>(leaf_parent), const_cast<uint8_t*>(leaf_action), nullptr, nullptr,
+      r, p, v, 0);
   return check_launch("search_expand_backup");
 }
 
@@ -430,53 +331,23 @@ SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
 }  // namespace
 
 
-// Experiment switches (environment, read once): HMZ_FUSED=0 keeps select and backup as separate
-// launches, HMZ_PREFETCH=1 prefetches the most-visited child's record during the score arithmetic.
-static int env_flag(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
 // One simulation of one group: [select (first simulation only)] -> g+f MLP -> fused backup + next select.
 static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* weights, int mode, int sim,
                        int n_simulations, const double* ucb_table, double discount, void* stream) {
-  static const int fused = env_flag("HMZ_FUSED", 1), prefetch = env_flag("HMZ_PREFETCH", 0), tps = env_flag("HMZ_TPS", 1);
   const int64_t B = s->n_searches;
   cudaStream_t st = (cudaStream_t)stream;
-  if (tps) {  // thread-per-search hot loop
-    const unsigned grid = (unsigned)((B + kTpsThreads - 1) / kTpsThreads);
-    if (sim == 0) {
-      ProfScope prof_scope(HMZ_PROF_SELECT, stream);
-      search_select_tps<<<grid, kTpsThreads, 0, st>>>(*s, 0, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path);
-      if (int rc = check_launch("search_select_tps")) return rc;
-    }
-    if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, sc.lp, sc.la, s->latents, s->n_records,
-                                   sim + 1, s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
-      return rc;
-    ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
-    search_backup_select_tps<<<grid, kTpsThreads, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
-                                                          sc.r, sc.p, sc.v, sim + 1 < n_simulations ? 1 : 0);
-    return check_launch("search_backup_select_tps");
-  }
-  if (sim == 0 || !fused) {
+  if (sim == 0) {
     ProfScope prof_scope(HMZ_PROF_SELECT, stream);
-    if (prefetch)
-      search_select<true><<<search_grid(B), 256, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, nullptr, 0, sc.path);
-    else
-      search_select<false><<<search_grid(B), 256, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, nullptr, 0, sc.path);
+    search_select<<<search_grid(B), kTreeThreads, 0, st>>>(*s, 0, ucb_table, discount, sc.lp, sc.la, sc.depth, nullptr, 0,
+                                                          sc.path);
     if (int rc = check_launch("search_select")) return rc;
   }
   if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, sc.lp, sc.la, s->latents, s->n_records, sim + 1,
                                  s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
     return rc;
   ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
-  const int do_select = (fused && sim + 1 < n_simulations) ? 1 : 0;
-  if (prefetch)
-    search_backup_select<true><<<search_grid(B), 256, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
-                                                             sc.r, sc.p, sc.v, do_select);
-  else
-    search_backup_select<false><<<search_grid(B), 256, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
-                                                              sc.r, sc.p, sc.v, do_select);
+  search_backup_select<<<search_grid(B), kTreeThreads, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
+                                                               sc.r, sc.p, sc.v, sim + 1 < n_simulations ? 1 : 0);
   return check_launch("search_backup_select");
 }
 

@@ -188,10 +188,15 @@ class SearchStore:
         check(self.lib.hmz_search_minmax_reset(ptr(self.minmax), self.B, current_stream()))
 
     def records(self):
-        """Host copy of the node records as a numpy structured array [B, n_records]."""
-        dt = np.dtype([("W", "<f8", 6), ("prior", "<f4", 6), ("rwd", "<f4", 6), ("N", "<u2", 6), ("child", "<u2", 6),
-                       ("parent", "<u2"), ("parent_action", "u1"), ("pad", "u1", 5)])
-        return self.nodes.cpu().numpy()[: self.B * self.n_records * 128].view(dt).reshape(self.B, self.n_records)
+        """Host copy of the node records as a dict of numpy arrays indexed [search, record, action]
+        (W, rwd, N, child, prior) and [search, record] (parent, parent_action)."""
+        slot = np.dtype([("W", "<f8"), ("rwd", "<f4"), ("N", "<u2"), ("child", "<u2")])
+        half = np.dtype([("c", slot, 3), ("prior", "<f4", 3), ("parent", "<u2"), ("parent_action", "u1"), ("pad", "u1")])
+        raw = self.nodes.cpu().numpy()[: self.B * self.n_records * 128].view(half).reshape(self.B, self.n_records, 2)
+        out = {k: raw["c"][k].reshape(self.B, self.n_records, 6) for k in ("W", "rwd", "N", "child")}
+        out["prior"] = raw["prior"].reshape(self.B, self.n_records, 6)
+        out["parent"], out["parent_action"] = raw["parent"][:, :, 0], raw["parent_action"][:, :, 0]
+        return out
 
 
 class BatchedMCTS:

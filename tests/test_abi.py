@@ -27,10 +27,9 @@ def test_header_symbols_exported(lib):
 def test_struct_layout():
     from muzero_hanoi_b200 import _lib
 
-    assert ctypes.sizeof(_lib.NodeRecord) == 128
-    assert _lib.NodeRecord.prior.offset == 48 and _lib.NodeRecord.rwd.offset == 72
-    assert _lib.NodeRecord.N.offset == 96 and _lib.NodeRecord.child.offset == 108
-    assert _lib.NodeRecord.parent.offset == 120 and _lib.NodeRecord.parent_action.offset == 122
+    assert ctypes.sizeof(_lib.NodeRecord) == 128 and ctypes.sizeof(_lib.NodeHalf) == 64 and ctypes.sizeof(_lib.ChildSlot) == 16
+    assert _lib.ChildSlot.rwd.offset == 8 and _lib.ChildSlot.N.offset == 12 and _lib.ChildSlot.child.offset == 14
+    assert _lib.NodeHalf.prior.offset == 48 and _lib.NodeHalf.parent.offset == 60 and _lib.NodeHalf.parent_action.offset == 62
     assert ctypes.sizeof(_lib.SearchDesc) == 72
 
 

@@ -87,6 +87,7 @@ def test_ragged_batch_and_record_layout(golden):
             assert rec["child"][b, pe, pa] == e  # parent/child links are mutual
             assert np.array_equal(rec["prior"][b, e], g["p"][ks[b]][e - 1])
             assert rec["rwd"][b, pe, pa] == g["r"][ks[b]][e - 1]
+            assert rec["N"][b, e].sum() <= rec["N"][b, pe, pa]  # a node's visits bound its children's
 
 
 def test_empty_batch_and_bad_arguments():
