@@ -197,6 +197,13 @@ int hmz_search_select(const hmz_search_t* s, int sim, const double* ucb_table, d
                       uint16_t* leaf_parent, uint8_t* leaf_action, uint16_t* leaf_depth, uint8_t* path_out,
                       int path_cap, void* stream);
 
+/* Node.child_Q and Node.child_U (MCTS/node.py:90-123) of one expanded node per search, for
+ * inspection through the Node view: record[i] names the node, node_n[i] is that node's own visit
+ * count (the N that enters the exploration factor).  q_out, u_out float32 [n_searches][6];
+ * best_out (nullable) = Node.best_child's arg-max of q+u with lowest-index tie-break. */
+int hmz_search_child_scores(const hmz_search_t* s, const uint16_t* record, const int32_t* node_n, const double* ucb_table,
+                            double discount, float* q_out, float* u_out, int32_t* best_out, void* stream);
+
 /* Phases 2b+3 (MCTS/mcts.py:106-109 -> Node.expand node.py:30-51, Node.backup :53-70) with the
  * network outputs of this simulation given per search: creates record sim+1 with priors p,
  * stores r on the leaf slot, then walks to the root: W += value; N += 1;

@@ -54,6 +54,12 @@ class MCTS:
         self._last_records = None
         return int(action.cpu().item()), pi[0].cpu().numpy(), float(root_q.cpu().item())
 
+    def root_node(self):
+        """Node view of the last search's root (the reference keeps `root_node` local to run_mcts)."""
+        from .node import Node
+
+        return Node.root_of(self._engine)
+
     def return_latent_actions(self):
         """:128-130 — actions along the path of the LAST simulation, as LongTensor[1] each."""
         eng = self._engine

@@ -77,6 +77,7 @@ SIGNATURES = {
     "hmz_search_begin": (_I, [_SD, _P, _P]),
     "hmz_search_begin_p0": (_I, [_SD, _P, _P, _D, _P]),
     "hmz_search_select": (_I, [_SD, _I, _P, _D, _P, _P, _P, _P, _I, _P]),
+    "hmz_search_child_scores": (_I, [_SD, _P, _P, _P, _D, _P, _P, _P, _P]),
     "hmz_search_expand_backup": (_I, [_SD, _I, _D, _P, _P, _P, _P, _P, _P]),
     "hmz_search_root_policy": (_I, [_SD, _I, _D, _I, _P, _P, _P, _P, _P, _P]),
     "hmz_weights_packed_bytes": (_L, [_I, _I]),

@@ -111,6 +111,42 @@ __global__ void __launch_bounds__(kTreeThreads) search_backup_select(hmz_search_
   }
 }
 
+// Node.child_Q / child_U of one node per search (inspection; same arithmetic as select_leaf).
+__global__ void __launch_bounds__(128) search_child_scores(hmz_search_t s, const uint16_t* __restrict__ record,
+                                                          const int32_t* __restrict__ node_n, const double* __restrict__ ucb_table,
+                                                          double discount, float* __restrict__ q_out, float* __restrict__ u_out,
+                                                          int32_t* __restrict__ best_out) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= s.n_searches) return;
+  const int e = record[b];
+  const hmz_node_t* rec = s.nodes + b * s.n_records + e;
+  const double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
+  const bool normalise = mx > mn;
+  const double range = __dsub_rn(mx, mn), tn = ucb_table[node_n[b]];
+  float best_score = 0.f;
+  int best = 0;
+  for (int a = 0; a < 6; ++a) {
+    const hmz_child_t c = rec->h[a / 3].c[a % 3];
+    float qf = 0.0f;
+    if (c.N > 0) {
+      double q = __dadd_rn((double)c.rwd, __dmul_rn(discount, __ddiv_rn(c.W, (double)c.N)));
+      if (normalise) q = __ddiv_rn(__dsub_rn(q, mn), range);
+      qf = __double2float_rn(q);
+    }
+    const double w = __ddiv_rn(tn, (double)(c.N + 1));
+    const float u = (e == 0 && s.root_prior_is_f64) ? __double2float_rn(__dmul_rn(s.root_prior[b * 6 + a], w))
+                                                    : __fmul_rn(rec->h[a / 3].prior[a % 3], __double2float_rn(w));
+    q_out[b * 6 + a] = qf;
+    u_out[b * 6 + a] = u;
+    const float score = __fadd_rn(qf, u);
+    if (a == 0 || score > best_score) {
+      best_score = score;
+      best = a;
+    }
+  }
+  if (best_out) best_out[b] = best;
+}
+
 // MCTS/mcts.py:112-126 per search (one thread each; 52 bytes in, <= 76 bytes out).
 __global__ void __launch_bounds__(256) search_root_policy(hmz_search_t s, int n_sims, double temperature,
                                                          int deterministic, const double* __restrict__ uniforms,
@@ -240,6 +276,18 @@ int hmz_search_select(const hmz_search_t* s, int sim, const double* ucb_table, d
   search_select<<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(
       *s, sim, ucb_table, discount, leaf_parent, leaf_action, leaf_depth, path_out, path_cap, nullptr);
   return check_launch("search_select");
+}
+
+int hmz_search_child_scores(const hmz_search_t* s, const uint16_t* record, const int32_t* node_n, const double* ucb_table,
+                            double discount, float* q_out, float* u_out, int32_t* best_out, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
+  if (int rc = check_search(s, "hmz_search_child_scores")) return rc;
+  if (s->n_searches == 0) return HMZ_OK;
+  if (!record || !node_n || !ucb_table || !q_out || !u_out)
+    return fail(HMZ_ERR_INVALID, "hmz_search_child_scores: null pointer");
+  search_child_scores<<<(unsigned)((s->n_searches + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      *s, record, node_n, ucb_table, discount, q_out, u_out, best_out);
+  return check_launch("search_child_scores");
 }
 
 int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, const uint16_t* leaf_parent,

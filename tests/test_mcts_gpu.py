@@ -142,3 +142,73 @@ def test_dropin_mcts_close_to_reference_episode(golden, name):
     assert np.mean(diffs) <= 0.02 * S + 0.5
     with pytest.raises(ValueError):
         mcts.run_mcts(g["obs"][0], net, 1.5, True)
+
+
+def test_config5_lesion_mode_bit_exact_vs_oracle():
+    """BASELINE.json config 5 semantics (acting_ablations.py lesion mode): N=4, random non-goal starts,
+    policy and value heads re-initialised U(-1/8, 1/8) (networks.py:201-205), no root noise, S=200,
+    temperature 0 with sampling (deterministic=False) — 16,384 searches replayed by the C oracle."""
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    n, B, S = 4, 16384, 200
+    sd = port.lesion_weights(port.make_weights(n, 3), ("policy_net", "value_net"), seed=103)
+    weights = PackedWeights(sd, n)
+    env = VecHanoi(n, 200, B)
+    env.random_reset(seed=5)
+    mcts = BatchedMCTS(0.8, 0.0, S, B)
+    p0, r, p, v, depth = _split_search(mcts, weights, env.words, None)
+    u = np.random.default_rng(1).random(B)
+    act, pi, q, visits = mcts.root_policy(0.0, False, uniforms=u)
+    torch.cuda.synchronize()
+    mm = np.tile(np.array([[np.inf, -np.inf]]), (B, 1))
+    o_visits, o_q, o_depth = cport.search_injected(p0.cpu().numpy().astype(np.float64), False, mm, r.cpu().numpy(),
+                                                   p.cpu().numpy(), v.cpu().numpy(), 0.8, port.ucb_table(S + 1), want_depth=True)
+    assert np.array_equal(visits.cpu().numpy(), o_visits) and np.array_equal(q.cpu().numpy(), o_q)
+    assert np.array_equal(depth.cpu().numpy().astype(np.uint16), o_depth)
+    assert int(depth.max()) > 8  # lesioned searches go deep: the parent-link backup path is exercised too
+    pi_o = np.stack([port.play_policy(o_visits[i], 0.0) for i in range(256)])
+    assert np.array_equal(pi.cpu().numpy()[:256], pi_o)
+    assert [port.sample_action(pi_o[i], u[i]) for i in range(256)] == act.cpu().numpy()[:256].tolist()
+
+
+def test_node_view_matches_tree_store(golden):
+    """MCTS/node.py drop-in: Node views over the device tree expose the reference's fields / methods."""
+    from muzero_hanoi_b200.MCTS.mcts import MCTS
+    from muzero_hanoi_b200.MCTS.node import Node
+    from muzero_hanoi_b200.networks import MuZeroNet
+
+    g = golden("search_n3_s25_nonoise_t0.npz")
+    net = MuZeroNet(9, 6, 0.002, "cpu", TD_return=True)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in port.make_weights(3, 1).items()})
+    mcts = MCTS(0.8, 0.0, 25, 1, "cpu")
+    mcts.run_mcts(g["obs"][0], net, 0.0, True)
+    root = mcts.root_node()
+    assert isinstance(root, Node) and root.is_expanded and not root.has_parent and root.prior == 0.0
+    assert root.N == 25 and np.array_equal(root.child_N, g["child_N"][0]) and root.child_N.dtype == np.int32
+    assert root.Q == g["root_q"][0] and root.rwd == 0.0 and root.h_state.shape == (64,)
+    kids = root.children
+    assert len(kids) == 6 and all(k.has_parent and k.parent is root and k.move == a for a, k in enumerate(kids))
+    assert np.array_equal(np.array([k.prior for k in kids], np.float32), g["p0"][0])
+    q, u = root.child_Q(mcts, mcts.min_max_stats), root.child_U(mcts)
+    assert q.dtype == np.float32 and u.dtype == np.float32 and q.shape == (6,)
+    # the reference formulas (node.py:90-123) on the same statistics
+    mm = mcts.min_max_stats
+    for a, k in enumerate(kids):
+        want_q = np.float32(mm.normalize(k.rwd + 0.8 * k.Q)) if k.N > 0 else np.float32(0)
+        w = (np.log((root.N + 19652 + 1) / 19652) + 1.25) * np.sqrt(root.N) / (k.N + 1)
+        assert q[a] == want_q and u[a] == np.float32(np.float32(k.prior) * np.float32(w))
+    best = root.best_child(mcts, mm)
+    assert best.move == int(np.argmax(q + u))
+    deep = best
+    while deep.is_expanded and deep.children:
+        nxt = deep.best_child(mcts, mm)
+        if not nxt.is_expanded:
+            break
+        deep = nxt
+    assert deep.N >= 1 and sum(c.N for c in deep.children) <= deep.N
+    with pytest.raises(RuntimeError, match="already been expanded"):
+        root.expand(g["p0"][0], None, 0.0)
+    leaf = next(c for c in deep.children if not c.is_expanded)
+    with pytest.raises(ValueError, match="Expand leaf node first"):
+        leaf.best_child(mcts, mm)
+    assert leaf.N == 0 and leaf.Q == 0.0 and leaf.h_state is None and leaf.children == []
