@@ -188,7 +188,8 @@ def test_node_view_matches_tree_store(golden):
     assert root.Q == g["root_q"][0] and root.rwd == 0.0 and root.h_state.shape == (64,)
     kids = root.children
     assert len(kids) == 6 and all(k.has_parent and k.parent is root and k.move == a for a, k in enumerate(kids))
-    assert np.array_equal(np.array([k.prior for k in kids], np.float32), g["p0"][0])
+    assert np.array_equal(np.array([k.prior for k in kids], np.float32), mcts._engine.p0.cpu().numpy()[0])
+    assert np.abs(np.array([k.prior for k in kids], np.float32) - g["p0"][0]).max() <= 1e-5
     q, u = root.child_Q(mcts, mcts.min_max_stats), root.child_U(mcts)
     assert q.dtype == np.float32 and u.dtype == np.float32 and q.shape == (6,)
     # the reference formulas (node.py:90-123) on the same statistics
