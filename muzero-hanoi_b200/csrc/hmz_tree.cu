@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
 // at once by the selection of simulation `sim + 1` — the fused hot-loop form: the path just updated
 // is still in this SM's L1 and the next walk usually shares its prefix.  With path_ent the backup
 // loads all path slots up front; without it (split-phase API) it walks the parent links.
-__global__ void __launch_bounds__(kTreeThreads) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
+__global__ void __launch_bounds__(kTreeThreads, 6) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
                                                                      double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
                                                                      uint16_t* leaf_depth, uint32_t* path_ent,
                                                                      const float* __restrict__ r, const float* __restrict__ p,

@@ -178,36 +178,40 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
   minmax_update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_w, (double)(sim + 1)))), mn, mx);
 }
 
-// Same backup for a path of depth <= 8 recorded by select_leaf: the slots of all levels are loaded
-// up front (independent 16-byte loads: one memory round trip instead of `depth` dependent ones), then
-// the leaf-to-root float64 recurrence runs in registers.  Operation for operation identical to
+// Same backup for a path of depth <= 8 recorded by select_leaf: the slots are loaded four levels at a
+// time up front (independent 16-byte loads: one memory round trip per batch instead of one per level),
+// then the leaf-to-root float64 recurrence runs in registers.  Operation for operation identical to
 // backup_walk, so results are bit-identical.
-__device__ __forceinline__ void backup_path8(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, int depth, int sim,
-                                             float r, double value, double discount, double& root_w, double& mn,
-                                             double& mx) {
-  const uint4 p0 = *reinterpret_cast<const uint4*>(path_ent);
-  const uint4 p1 = depth > 4 ? *reinterpret_cast<const uint4*>(path_ent + 4) : make_uint4(0u, 0u, 0u, 0u);
-  const uint32_t ent[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-  uint4 raw[8];
+__device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& ent4, int k0, int depth, int sim, float r,
+                                              double& value, double discount, double& mn, double& mx) {
+  const uint32_t ent[4] = {ent4.x, ent4.y, ent4.z, ent4.w};
+  uint4 raw[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    if (k < depth) raw[k] = *slot_ptr(nodes, (int)(ent[k] & 0xFFFFu), (int)(ent[k] >> 16));
+  for (int j = 0; j < 4; ++j)
+    if (k0 + j < depth) raw[j] = *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16));
 #pragma unroll
-  for (int k = 7; k >= 0; --k) {
-    if (k < depth) {
-      Slot c = Slot::unpack(raw[k]);
-      if (k == depth - 1) {
+  for (int j = 3; j >= 0; --j) {
+    if (k0 + j < depth) {
+      Slot c = Slot::unpack(raw[j]);
+      if (k0 + j == depth - 1) {  // the leaf slot: Node.expand bookkeeping on the parent (node.py:44-49)
         c.rwd = r;
         c.child = sim + 1;
       }
-      c.W = __dadd_rn(c.W, value);
-      c.n += 1;
-      *slot_ptr(nodes, (int)(ent[k] & 0xFFFFu), (int)(ent[k] >> 16)) = c.pack();
+      c.W = __dadd_rn(c.W, value);  // current.W += value
+      c.n += 1;                     // current.N += 1
+      *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16)) = c.pack();
       const double rwd = (double)c.rwd;
       minmax_update(__dadd_rn(rwd, __dmul_rn(discount, __ddiv_rn(c.W, (double)c.n))), mn, mx);
-      value = __dadd_rn(rwd, __dmul_rn(discount, value));
+      value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
     }
   }
+}
+
+__device__ __forceinline__ void backup_path8(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, int depth, int sim,
+                                             float r, double value, double discount, double& root_w, double& mn,
+                                             double& mx) {
+  if (depth > 4) backup_batch4(nodes, *reinterpret_cast<const uint4*>(path_ent + 4), 4, depth, sim, r, value, discount, mn, mx);
+  backup_batch4(nodes, *reinterpret_cast<const uint4*>(path_ent), 0, depth, sim, r, value, discount, mn, mx);
   root_w = __dadd_rn(root_w, value);
   minmax_update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_w, (double)(sim + 1)))), mn, mx);
 }
