@@ -219,6 +219,48 @@ def gen_net_io(ref):
     np.savez_compressed(os.path.join(GOLDEN, "net_io.npz"), **out)
 
 
+def gen_episode_post(ref):
+    """Episode post-processing of Muzero._play_game (Muzero.py:189-205): n-step returns, priorities,
+    organise_transitions — reference functions on random synthetic episodes."""
+    import types
+
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    import Muzero as ref_muzero  # noqa: E402  (imports cleanly behind the plotting stubs)
+
+    rng = np.random.default_rng(77)
+    out, n_step, discount, unroll = {}, 10, 0.8, 5
+    lengths = [1, 2, 5, 7, 11, 24, 60, 200]
+    for k, T in enumerate(lengths):
+        codes = rng.choice(3, size=T, p=[0.75, 0.0, 0.25])  # 0: legal (0), 2: illegal (-0.1)
+        if k % 2 == 0:
+            codes[-1] = 1  # solved episode: reward 100 on the last move
+        rw = [{0: 0, 1: 100, 2: -100 / 1000}[int(c)] for c in codes]
+        visits = rng.multinomial(100, rng.dirichlet(np.ones(6)), size=T)
+        pis = [port.play_policy(v, 1.0) for v in visits]
+        root_q = [float(x) for x in rng.normal(0, 20, T)]
+        actions = [int(a) for a in rng.integers(0, 6, T)]
+        states = [port.one_hot(port.index_to_state(int(i), 5)) for i in rng.integers(0, 242, T)]
+        returns = ref.compute_n_step_returns(rw, root_q, n_step, discount)
+        assert returns == port.n_step_returns(rw, root_q, n_step, discount), "port n-step returns != reference"
+        prio = np.abs(np.array(returns, dtype=np.float32) - np.array(root_q, dtype=np.float32))
+        assert np.array_equal(prio, port.priorities(returns, root_q))
+        dummy = types.SimpleNamespace(unroll_n_steps=unroll, n_action=6)
+        np.random.seed(100 + k)
+        st, o_r, o_a, o_p, o_g = ref_muzero.Muzero.organise_transitions(dummy, list(states), list(rw), list(actions), list(pis),
+                                                                      list(returns))
+        np.random.seed(100 + k)
+        absorbing = np.random.randint(0, 6)
+        mine = port.organise_transitions(states, rw, actions, pis, returns, unroll, 6, absorbing)
+        for a, b in zip((st, o_r, o_a, o_p, o_g), mine):
+            assert a.dtype == b.dtype and np.array_equal(a, b), "port organise_transitions != reference"
+        out.update({f"e{k}_reward_code": codes.astype(np.uint8), f"e{k}_visits": visits.astype(np.int32), f"e{k}_root_q": np.array(root_q),
+                    f"e{k}_action": np.array(actions, np.int32), f"e{k}_returns": np.array(returns, np.float64), f"e{k}_priority": prio,
+                    f"e{k}_absorbing": np.int64(absorbing), f"e{k}_o_r": o_r, f"e{k}_o_a": o_a, f"e{k}_o_p": o_p, f"e{k}_o_g": o_g})
+    out.update(n_episodes=len(lengths), n_step=n_step, discount=discount, unroll=unroll)
+    np.savez_compressed(os.path.join(GOLDEN, "episode_post.npz"), **out)
+    print(f"episode post-processing: {len(lengths)} episodes ok (returns, priorities, transitions)")
+
+
 def check_choice_hook():
     """The uniform-as-input restatement of np.random.choice(p=...) equals numpy's legacy path."""
     rs = np.random.RandomState(7)
@@ -240,6 +282,7 @@ def main():
     for name, cfg in SEARCH_CONFIGS.items():
         gen_search(ref, name, cfg)
     gen_net_io(ref)
+    gen_episode_post(ref)
     manifest = dict(
         generated_by="python -m oracle.gen_golden",
         reference="A-Andrews/Muzero-Hanoi (unmodified, /root/reference)",

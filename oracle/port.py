@@ -451,13 +451,60 @@ def run_mcts_port(obs, net: PortNet, search: PortSearch, temperature, determinis
 
 
 # ------------------------------------------------------- trajectory post-processing (§8f row 1)
+def py312_sum(terms):
+    """Python >= 3.12 ``sum()`` over floats: the first add goes through the generic int + float path,
+    the rest through Neumaier compensated summation (CPython Python/bltinmodule.c) — the reference's
+    ``sum([...])`` at utils.py:64-66 therefore is NOT a plain left-to-right float64 sum."""
+    if not terms:
+        return 0
+    f, c = 0 + float(terms[0]), 0.0
+    for x in terms[1:]:
+        x = float(x)
+        t = f + x
+        if abs(f) >= abs(x):
+            c += (f - t) + x
+        else:
+            c += (x - t) + f
+        f = t
+    if c and math.isfinite(c):
+        f += c
+    return f
+
+
 def n_step_returns(rwds, root_values, n_step, discount):
-    """utils.py:28-72."""
+    """utils.py:28-72 (n-step TD targets; zeros beyond the end of the episode)."""
     T = len(rwds)
     r = list(rwds) + [0] * n_step
     q = list(root_values) + [0] * n_step
     out = []
     for t in range(T):
-        acc = sum([discount ** i * x for i, x in enumerate(r[t:t + n_step])])
+        acc = py312_sum([discount ** i * x for i, x in enumerate(r[t:t + n_step])])
         out.append(acc + discount ** n_step * q[t + n_step])
     return out
+
+
+def priorities(returns, root_values):
+    """Muzero.py:197-200: |float32(return) - float32(root value)|."""
+    return np.abs(np.array(returns, dtype=np.float32) - np.array(root_values, dtype=np.float32))
+
+
+def organise_transitions(states, rwds, actions, pi_probs, returns, unroll, n_action, absorbing_action):
+    """Muzero.organise_transitions (Muzero.py:276-323): every step gets its next `unroll` rewards /
+    actions / policies / returns; beyond the end of the episode the padding is reward 0, return 0,
+    the uniform policy and ONE absorbing action (drawn once per call by the caller, :300-303)."""
+    n = len(states)
+    rwds = list(rwds) + [0] * unroll
+    actions = list(actions) + [absorbing_action] * unroll
+    returns = list(returns) + [0] * unroll
+    uniform = np.ones_like(pi_probs[-1]) / len(pi_probs[-1])
+    pi_probs = list(pi_probs) + [uniform] * unroll
+    o_r = np.zeros((n, unroll), np.float32)
+    o_a = np.zeros((n, unroll), np.int64)
+    o_p = np.zeros((n, unroll, n_action), np.float32)
+    o_g = np.zeros((n, unroll), np.float32)
+    for i in range(n):
+        o_r[i] = rwds[i:i + unroll]
+        o_a[i] = actions[i:i + unroll]
+        o_p[i] = pi_probs[i:i + unroll]
+        o_g[i] = returns[i:i + unroll]
+    return np.array(states), o_r, o_a, o_p, o_g

@@ -186,3 +186,26 @@ def test_c_oracle_env_matches_reference_tables(golden, n):
         assert np.array_equal(code.reshape(shape), g[f"n{n}_reward_code"][vi])
     assert np.array_equal(cport.legal_mask(states, n), g[f"n{n}_legal"])
     assert np.array_equal(cport.solver(states, n), g[f"n{n}_solver"])
+
+
+# ------------------------------------------------- episode post-processing (§8f row 1) pinning
+def _episode(g, k):
+    rw = [{0: 0, 1: 100, 2: -100 / 1000}[int(c)] for c in g[f"e{k}_reward_code"]]
+    pis = [port.play_policy(v, 1.0) for v in g[f"e{k}_visits"]]
+    return rw, [float(x) for x in g[f"e{k}_root_q"]], [int(a) for a in g[f"e{k}_action"]], pis
+
+
+def test_episode_post_matches_reference(golden):
+    """n-step returns (utils.py:28-72), priorities (Muzero.py:197-200) and organise_transitions
+    (Muzero.py:276-323) of the port against outputs of the reference's own functions."""
+    g = golden("episode_post.npz")
+    n_step, discount, unroll = int(g["n_step"]), float(g["discount"]), int(g["unroll"])
+    for k in range(int(g["n_episodes"])):
+        rw, root_q, actions, pis = _episode(g, k)
+        returns = port.n_step_returns(rw, root_q, n_step, discount)
+        assert np.array_equal(np.array(returns, np.float64), g[f"e{k}_returns"])
+        assert np.array_equal(port.priorities(returns, root_q), g[f"e{k}_priority"])
+        states = [np.zeros(15)] * len(rw)
+        _, o_r, o_a, o_p, o_g = port.organise_transitions(states, rw, actions, pis, returns, unroll, 6, int(g[f"e{k}_absorbing"]))
+        for name, arr in (("o_r", o_r), ("o_a", o_a), ("o_p", o_p), ("o_g", o_g)):
+            assert arr.dtype == g[f"e{k}_{name}"].dtype and np.array_equal(arr, g[f"e{k}_{name}"]), (k, name)
