@@ -326,7 +326,7 @@ __device__ __forceinline__ float support_epilogue(uint32_t tmem_row) {
 // as its first two K-atoms exist, and a head's outputs are reduced by the small warps while the
 // tensor core and the hidden warps already work on the next head.
 __global__ void __launch_bounds__(kThreads, 1)
-net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_t in_rows_per_item,
+net_recurrent_tc_v3(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_t in_rows_per_item,
                  const uint16_t* __restrict__ in_row, const uint8_t* __restrict__ actions, void* lat_out,
                  int64_t out_rows_per_item, int64_t out_row, int latent_dtype, float* __restrict__ r_out,
                  float* __restrict__ p_out, float* __restrict__ v_out, int64_t n, int timeline) {
@@ -637,6 +637,449 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
   }
 }
 
+// =====================================================================================
+// net_recurrent_tc (v4): two 128-search tiles per CTA pass, ping-ponged.
+//
+//   * Both tiles consume every weight block from the same shared-memory copy (double-buffered
+//     per layer kind, streamed by a dedicated loader warp), which halves the L2 -> SM weight
+//     traffic per search, and the tensor core works on one tile while the other tile's epilogue
+//     warps drain TMEM.
+//   * Hidden activations never touch shared memory: the epilogue reads the float32 accumulator
+//     with tcgen05.ld, applies relu + bf16 and writes the packed row back IN PLACE with
+//     tcgen05.st; the second-layer MMA takes its A operand from TMEM (the .ts form of
+//     tcgen05.mma).  TMEM columns of tile t (base 256 t):
+//         [0,128)   H0: first-layer accumulator, hidden units 0..127  -> A1 k 0..127 in [0,64)
+//         [64,128)  O : second-layer accumulator (free once H0 is drained)
+//         [128,256) H1: hidden units 128..255                         -> A1 k 128..255 in [128,192)
+//   * The kernel is persistent over tile pairs (grid = min(pairs, SMs)).
+//
+// 23 warps: 2 x 8 hidden-epilogue warps (warp -> TMEM lane quarter w & 3, column half (w >> 2) & 1),
+// 4 output warps shared by both tiles, one MMA-issuing warp per tile, one loader warp.
+namespace v4 {
+constexpr int kHidThreadsPerTile = 256;
+constexpr int kSmallWarp0 = 16, kMmaWarp0 = 20, kLoaderWarp = 22;
+constexpr int kThreads = 23 * 32;
+constexpr uint32_t kColsPerTile = 256, kColH1 = 128, kColO = 64;
+
+struct __align__(1024) Tile {
+  uint8_t a0[kAtomA];   // input latent tile, later the raw (un-normalised) new latent
+  uint8_t ahn[kAtomA];  // normalised new latent
+  uint8_t ax[kM * 32];  // extra A slice [onehot(action) (6), 1, 0 x 9] per row, core-matrix layout
+};
+struct __align__(1024) Smem {
+  Tile t[2];
+  uint8_t wf[2][kBytesW1];   // first-layer weight blocks (+ extra slice), double-buffered
+  uint8_t ws[2][kBytesWg2];  // second-layer weight blocks (+ extra slice), double-buffered
+  float2 row_minmax[2][2][kM];
+  uint64_t bar_wfull[2][2];  // [kind][slot] TMA landed
+  uint64_t bar_wfree[2][2];  // [kind][slot] both tiles' MMAs reading the slot have completed (2 commits)
+  uint64_t bar_g[2];         // gather done: A0 and AX of the tile written (384 arrivals)
+  uint64_t bar_d[2][2];      // [tile][half] first-layer accumulator half complete
+  uint64_t bar_a[2][2];      // [tile][half] A1 half written back to TMEM (128 arrivals)
+  uint64_t bar_o[2];         // dynamics second layer complete (raw latent in O)
+  uint64_t bar_s[2];         // head second layer complete (logits in O)
+  uint64_t bar_lat[2];       // raw + normalised latent tiles written, O drained (256 arrivals)
+  uint64_t bar_fin[2];       // head logits copied out of O (128 arrivals)
+  uint64_t bar_end[2];       // every MMA of the tile's issuing thread has completed
+  uint32_t tmem_base;
+};
+
+__constant__ uint32_t c_block_off[8] = {kWg1, kWg2, kWr1, kWr2, kWp1, kWp2, kWv1, kWv2};
+__constant__ uint32_t c_block_bytes[8] = {kBytesW1, kBytesWg2, kBytesW1, kBytesW48, kBytesW1, kBytesW16, kBytesW1, kBytesW48};
+
+// D = A x B^T with A in TMEM (lane = row, one 32-bit column = two consecutive k)
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// relu + bf16 of 16 accumulator columns, written back as 8 packed columns
+__device__ __forceinline__ void hidden_chunk_tmem(uint32_t dst, const uint32_t (&acc)[16]) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pk[j] = relu_bf16x2(pack_bf16(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])));
+  tmem_st8(dst, pk);
+}
+// Hidden-layer epilogue of one column half: H[0:128) float32 -> relu -> bf16 -> A1 in H[0:64), in place.
+// Chunk c (columns 16c..16c+15) lands in columns 8c..8c+7, always behind the read pointer; the TMEM
+// load of chunk c+1 is in flight while chunk c is converted.
+__device__ __forceinline__ void hidden_epilogue_tmem(uint32_t h) {
+  uint32_t va[16], vb[16];
+  tmem_ld16_issue(h, va);
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    tmem_ld16_wait(va);
+    tmem_ld16_issue(h + 16 * (c + 1), vb);
+    hidden_chunk_tmem(h + 8 * c, va);
+    tmem_ld16_wait(vb);
+    if (c + 2 < 8) tmem_ld16_issue(h + 16 * (c + 2), va);
+    hidden_chunk_tmem(h + 8 * (c + 1), vb);
+  }
+  tmem_st_wait();
+}
+
+#define TL4(slot) do { if (timeline && blockIdx.x == 0 && pass == 0) g_timeline[slot] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(kThreads, 1)
+net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_t in_rows_per_item,
+                 const uint16_t* __restrict__ in_row, const uint8_t* __restrict__ actions, void* lat_out,
+                 int64_t out_rows_per_item, int64_t out_row, int latent_dtype, float* __restrict__ r_out,
+                 float* __restrict__ p_out, float* __restrict__ v_out, int64_t n, int n_pairs, int timeline) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int k = 0; k < 2; ++k)
+      for (int j = 0; j < 2; ++j) {
+        mbar_init(&s.bar_wfull[k][j], 1);
+        mbar_init(&s.bar_wfree[k][j], 2);
+        mbar_init(&s.bar_d[k][j], 1);
+        mbar_init(&s.bar_a[k][j], 128);
+      }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s.bar_g[t], kHidThreadsPerTile + 128);
+      mbar_init(&s.bar_o[t], 1);
+      mbar_init(&s.bar_s[t], 1);
+      mbar_init(&s.bar_lat[t], kHidThreadsPerTile);
+      mbar_init(&s.bar_fin[t], 128);
+      mbar_init(&s.bar_end[t], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {  // TMEM: all 512 columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+
+  if (warp == kLoaderWarp) {
+    // ================================= loader warp =================================
+    uint32_t use[2] = {0u, 0u};
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        const int kind = i & 1;
+        const uint32_t u = use[kind], slot = u & 1u;
+        if (u >= 2u) mbar_wait(&s.bar_wfree[kind][slot], ((u >> 1) - 1u) & 1u);
+        if (elect_one()) tma_load(kind ? s.ws[slot] : s.wf[slot], wsec + c_block_off[i], c_block_bytes[i], &s.bar_wfull[kind][slot]);
+        __syncwarp();
+        use[kind] = u + 1u;
+      }
+    }
+  } else if (warp >= kMmaWarp0) {
+    // ============================ MMA-issuing warp of tile t ============================
+    const int t = warp - kMmaWarp0;
+    const uint32_t T = tmem + kColsPerTile * t;
+    const uint32_t a0 = smem_u32(s.t[t].a0), ahn = smem_u32(s.t[t].ahn), ax = smem_u32(s.t[t].ax);
+    const uint32_t id128 = umma_idesc(128);
+    uint32_t use_f = 0, use_s = 0, ph_g = 0, ph_a = 0, ph_lat = 0, ph_fin = 0;
+    bool first = true;
+    int ev = 0;
+    for (int pass = 0, pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pass) {
+#pragma unroll 1
+      for (int net = 0; net < 4; ++net) {  // dynamics, reward, policy, value
+        // ---- first layer: H = [A | AX] x W1'^T, half 1 first (half 0 hosts O, drained later)
+        const uint32_t a_in = net == 0 ? a0 : (net == 1 ? a0 : ahn);
+        if (net == 0) {
+          mbar_wait(&s.bar_g[t], ph_g);
+          ph_g ^= 1;
+        }
+        {
+          const uint32_t slot = use_f & 1u;
+          mbar_wait(&s.bar_wfull[0][slot], (use_f >> 1) & 1u);
+          if (elect_one()) TL4(t * 40 + ev);
+          ++ev;
+          tc_fence_after();
+          const uint32_t wf = smem_u32(s.wf[slot]);
+          const uint64_t a_base = desc_sw128(a_in), axd = desc_plain(ax);
+          if (elect_one()) {
+            const uint64_t b1 = desc_sw128(wf + 128 * 128), bx1 = desc_plain(wf + 256 * 128 + 4096);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma(T + kColH1, a_base + (uint64_t)(kk * 2), b1 + (uint64_t)(kk * 2), id128, kk ? 1u : 0u);
+            umma(T + kColH1, axd, bx1, id128, 1u);
+            umma_commit(&s.bar_d[t][1]);
+          }
+          __syncwarp();
+          if (!(first && net == 0)) {  // O (inside H0) must have been copied out by its previous reader
+            if (net == 1) {
+              // drained by the latent epilogue: bar_lat was observed below
+            } else {
+              mbar_wait(&s.bar_fin[t], ph_fin);
+              ph_fin ^= 1;
+            }
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            const uint64_t b0 = desc_sw128(wf), bx0 = desc_plain(wf + 256 * 128);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma(T, a_base + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), id128, kk ? 1u : 0u);
+            umma(T, axd, bx0, id128, 1u);
+            umma_commit(&s.bar_d[t][0]);
+            umma_commit(&s.bar_wfree[0][slot]);
+          }
+          __syncwarp();
+          ++use_f;
+          if (elect_one()) TL4(t * 40 + ev);
+          ++ev;
+        }
+        // ---- second layer: O = [A1 | AX] x W2'^T, A1 from TMEM
+        {
+          const uint32_t n2 = net == 0 ? 64u : (net == 2 ? 16u : 48u);
+          const uint32_t id2 = umma_idesc(n2);
+          const uint32_t slot = use_s & 1u;
+          mbar_wait(&s.bar_wfull[1][slot], (use_s >> 1) & 1u);
+          const uint32_t ws = smem_u32(s.ws[slot]);
+          mbar_wait(&s.bar_a[t][1], ph_a);
+          mbar_wait(&s.bar_a[t][0], ph_a);
+          ph_a ^= 1;
+          if (elect_one()) TL4(t * 40 + ev);
+          ++ev;
+          tc_fence_after();
+          if (elect_one()) {
+            umma(T + kColO, desc_plain(ax), desc_plain(ws + n2 * 128 * 4), id2, 0u);  // bias step clears O
+            const uint64_t b_base = desc_sw128(ws);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              umma_ts(T + kColO, T + (j >> 3) * kColH1 + (j & 7) * 8,
+                      b_base + (uint64_t)(((j >> 2) * n2 * 128 + (j & 3) * 32) >> 4), id2, 1u);
+            umma_commit(net == 0 ? &s.bar_o[t] : &s.bar_s[t]);
+            umma_commit(&s.bar_wfree[1][slot]);
+          }
+          __syncwarp();
+          ++use_s;
+        }
+        if (net == 0) {  // raw + normalised latent tiles must be in shared memory before the heads start
+          mbar_wait(&s.bar_lat[t], ph_lat);
+          ph_lat ^= 1;
+          if (elect_one()) TL4(t * 40 + ev);
+          ++ev;
+        }
+      }
+      first = false;
+    }
+    if (elect_one()) umma_commit(&s.bar_end[t]);
+    __syncwarp();
+    mbar_wait(&s.bar_end[t], 0);
+  } else if (warp < kSmallWarp0) {
+    // ============================== hidden-epilogue warps ==============================
+    const int t = warp >> 3, ltid = tid & 255;
+    const int row = ltid & 127, half = ltid >> 7, quarter = warp & 3;
+    Tile& tile = s.t[t];
+    const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
+    const uint32_t T = tmem + kColsPerTile * t + lane_bits;
+    uint32_t ph_d = 0, ph_o = 0;
+    for (int pass = 0, pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pass) {
+      const int64_t row0 = ((int64_t)pair * 2 + t) * kM;
+      const int64_t item = row0 + row;
+      {  // parent latents -> swizzled A0 tile; 8 consecutive lanes fetch the 8 16-byte chunks of one row
+        const int chunk = ltid & 7;
+        uint4 gathered[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int grow = (ltid >> 3) + 32 * i;
+          const int64_t it = (row0 + grow) < n ? (row0 + grow) : n - 1;
+          const int64_t irow = it * in_rows_per_item + (in_row ? (int64_t)in_row[it] : 0);
+          if (latent_dtype == HMZ_LATENT_F32) {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(lat_in) + irow * kLatent + chunk * 8);
+            const float4 t0 = __ldcs(src), t1 = __ldcs(src + 1);
+            gathered[i] = make_uint4(pack_bf16(t0.x, t0.y), pack_bf16(t0.z, t0.w), pack_bf16(t1.x, t1.y), pack_bf16(t1.z, t1.w));
+          } else {
+            gathered[i] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(lat_in) + irow * kLatent + chunk * 8));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(tile.a0 + sw128((ltid >> 3) + 32 * i, chunk)) = gathered[i];
+        fence_proxy_async();
+        mbar_arrive(&s.bar_g[t]);
+        if (ltid == 0) TL4(80 + t * 8);
+      }
+#pragma unroll 1
+      for (int layer = 0; layer < 4; ++layer) {
+        mbar_wait(&s.bar_d[t][half], ph_d);
+        ph_d ^= 1;
+        tc_fence_after();
+        hidden_epilogue_tmem(T + half * kColH1);
+        tc_fence_before();
+        mbar_arrive(&s.bar_a[t][half]);
+        if (ltid == 0) TL4(81 + t * 8 + layer);
+        if (layer == 0) {
+          // ---- new latent: normalize_h_state (networks.py:191-196) and its copies; thread (row, half)
+          // owns latent columns [32*half, 32*half + 32)
+          mbar_wait(&s.bar_o[t], ph_o);
+          ph_o ^= 1;
+          tc_fence_after();
+          float raw[32];
+          tmem_ld32(T + kColO + half * 32, raw);
+          float mn4[4], mx4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mn4[i] = mx4[i] = raw[i];
+#pragma unroll
+          for (int i = 4; i < 32; ++i) {
+            mn4[i & 3] = fminf(mn4[i & 3], raw[i]);
+            mx4[i & 3] = fmaxf(mx4[i & 3], raw[i]);
+          }
+          s.row_minmax[t][half][row] = make_float2(fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3])),
+                                                   fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + quarter) : "memory");
+          const float2 m0 = s.row_minmax[t][0][row], m1 = s.row_minmax[t][1][row];
+          const float mn = fminf(m0.x, m1.x), mx = fmaxf(m0.y, m1.y);
+          const float inv = 1.0f / ((mx - mn) + 1e-8f);
+          const int64_t orow = item * out_rows_per_item + out_row;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float hn[8];
+            uint32_t pr[4], ph[4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hn[j] = (raw[c * 8 + j] - mn) * inv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              pr[j] = pack_bf16(raw[c * 8 + 2 * j], raw[c * 8 + 2 * j + 1]);
+              ph[j] = pack_bf16(hn[2 * j], hn[2 * j + 1]);
+            }
+            *reinterpret_cast<uint4*>(tile.a0 + sw128(row, half * 4 + c)) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+            *reinterpret_cast<uint4*>(tile.ahn + sw128(row, half * 4 + c)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            if (latent_dtype == HMZ_LATENT_F32 && item < n) {  // parity-mode stores keep the per-row form
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(lat_out) + orow * kLatent + half * 32 + c * 8);
+              __stcs(dst, make_float4(hn[0], hn[1], hn[2], hn[3]));
+              __stcs(dst + 1, make_float4(hn[4], hn[5], hn[6], hn[7]));
+            }
+          }
+          if (latent_dtype != HMZ_LATENT_F32) {
+            // bf16 rows leave through the normalised tile so that 8 consecutive lanes write one 128-byte
+            // row: the two warps of a lane quarter copy out 16 rows each.
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + quarter) : "memory");
+            const int lane = tid & 31, chunk = lane & 7;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r2 = quarter * 32 + half * 16 + i * 4 + (lane >> 3);
+              const int64_t it2 = row0 + r2;
+              const uint4 val = *reinterpret_cast<const uint4*>(tile.ahn + sw128(r2, chunk));
+              if (it2 < n)
+                __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(lat_out) + (it2 * out_rows_per_item + out_row) * kLatent + chunk * 8), val);
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&s.bar_lat[t]);
+          if (ltid == 0) TL4(85 + t * 8);
+        }
+      }
+    }
+  } else {
+    // ============================== output warps (both tiles) ==============================
+    const int row = tid - kSmallWarp0 * 32;
+    const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ph_s[2] = {0u, 0u};
+    for (int pass = 0, pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pass) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {  // the extra A slice of this row: one-hot(action) at k = 0..5, the constant 1 at k = 6
+        const int64_t item = ((int64_t)pair * 2 + t) * kM + row;
+        int act = actions[item < n ? item : n - 1];
+        act = act < kActions ? act : kActions - 1;
+        uint32_t w[4] = {0u, 0u, 0u, 0x3F80u};  // k = 6 -> 1.0 (bf16 0x3F80), k = 7 -> 0
+        w[act >> 1] |= 0x3F80u << ((act & 1) * 16);
+        *reinterpret_cast<uint4*>(s.t[t].ax + plain_off(row, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(s.t[t].ax + plain_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+        mbar_arrive(&s.bar_g[t]);
+      }
+#pragma unroll 1
+      for (int head = 0; head < 3; ++head) {
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const int64_t item = ((int64_t)pair * 2 + t) * kM + row;
+          const uint32_t O = tmem + kColsPerTile * t + kColO + lane_bits;
+          mbar_wait(&s.bar_s[t], ph_s[t]);
+          ph_s[t] ^= 1;
+          tc_fence_after();
+          if (head == 1) {  // F.softmax(pi_logits) (networks.py:109)
+            float lg[16];
+            tmem_ld16(O, lg);
+            tc_fence_before();
+            mbar_arrive(&s.bar_fin[t]);
+            float mx = lg[0], den = 0.f;
+#pragma unroll
+            for (int a = 1; a < kActions; ++a) mx = fmaxf(mx, lg[a]);
+#pragma unroll
+            for (int a = 0; a < kActions; ++a) {
+              lg[a] = exp2f((lg[a] - mx) * 1.4426950408889634f);
+              den += lg[a];
+            }
+            const float inv = 1.0f / den;
+            if (item < n) {
+#pragma unroll
+              for (int a = 0; a < kActions; ++a) p_out[item * kActions + a] = lg[a] * inv;
+            }
+          } else {  // softmax expectation over the 33 support logits + signed parabolic (networks.py:152-189)
+            float a[32], b[16];
+            tmem_ld32(O, a);
+            tmem_ld16(O + 32, b);
+            tc_fence_before();
+            mbar_arrive(&s.bar_fin[t]);
+            float mx = b[0];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, a[i]);
+            float den = 0.f, num = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float e = exp2f((a[i] - mx) * 1.4426950408889634f);
+              den += e;
+              num = fmaf(e, (float)(i - 16), num);
+            }
+            const float e = exp2f((b[0] - mx) * 1.4426950408889634f);
+            den += e;
+            num = fmaf(e, 16.f, num);
+            const float x = signed_parabolic(__fdividef(num, den));
+            if (item < n) (head == 0 ? r_out : v_out)[item] = x;
+          }
+          if (row == 0) TL4(70 + head * 2 + t);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+}  // namespace v4
+
 // ---- host-side packing ----------------------------------------------------------------
 static uint16_t f2bf(float f) {
   uint32_t u;
@@ -716,22 +1159,38 @@ int tc_debug_read_timeline(unsigned long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, tc::g_timeline, sizeof(unsigned long long) * 96) == cudaSuccess ? HMZ_OK : HMZ_ERR_CUDA;
 }
 
+static int tc_use_v3() {
+  static const int on = getenv("HMZ_TC_V3") ? atoi(getenv("HMZ_TC_V3")) : 0;
+  return on;
+}
+
 int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
                      const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row,
                      int latent_dtype, float* r, float* p, float* v, int64_t n, cudaStream_t stream) {
   static thread_local int done_dev = -1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)");
-  const int smem_bytes = (int)sizeof(tc::Smem) + 1024;
+  const int smem_v3 = (int)sizeof(tc::Smem) + 1024, smem_v4 = (int)sizeof(tc::v4::Smem) + 1024;
   if (done_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(tc::net_recurrent_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(tc::net_recurrent_tc_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v3);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::v4::net_recurrent_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v4);
     if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaFuncSetAttribute(net_recurrent_tc): %s", cudaGetErrorString(e));
     done_dev = dev;
   }
-  const unsigned grid = (unsigned)((n + tc::kM - 1) / tc::kM);
-  tc::net_recurrent_tc<<<grid, tc::kThreads, smem_bytes, stream>>>((const uint8_t*)weights, lat_in, in_rows_per_item, in_row,
-                                                                   actions, lat_out, out_rows_per_item, out_row,
-                                                                   latent_dtype, r, p, v, n, tc_timeline_enabled());
+  if (tc_use_v3()) {
+    const unsigned grid = (unsigned)((n + tc::kM - 1) / tc::kM);
+    tc::net_recurrent_tc_v3<<<grid, tc::kThreads, smem_v3, stream>>>((const uint8_t*)weights, lat_in, in_rows_per_item, in_row,
+                                                                     actions, lat_out, out_rows_per_item, out_row,
+                                                                     latent_dtype, r, p, v, n, tc_timeline_enabled());
+    return check_launch("net_recurrent_tc_v3");
+  }
+  const int64_t n_pairs = (n + 2 * tc::kM - 1) / (2 * tc::kM);
+  const int sms = sm_count();
+  const unsigned grid = (unsigned)(n_pairs < sms ? n_pairs : sms);
+  tc::v4::net_recurrent_tc<<<grid, tc::v4::kThreads, smem_v4, stream>>>((const uint8_t*)weights, lat_in, in_rows_per_item, in_row,
+                                                                        actions, lat_out, out_rows_per_item, out_row,
+                                                                        latent_dtype, r, p, v, n, (int)n_pairs,
+                                                                        tc_timeline_enabled());
   return check_launch("net_recurrent_tc");
 }
 
