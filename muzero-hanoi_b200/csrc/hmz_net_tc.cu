@@ -255,6 +255,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// relu + round-to-nearest-even bf16 of two floats in one conversion
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // relu on two packed bf16 (rounding to bf16 preserves sign and zero, so relu commutes with it)
 __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
   uint32_t r;
@@ -653,12 +659,12 @@ net_recurrent_tc_v3(const uint8_t* __restrict__ wsec, const void* __restrict__ l
 //         [128,256) H1: hidden units 128..255                         -> A1 k 128..255 in [128,192)
 //   * The kernel is persistent over tile pairs (grid = min(pairs, SMs)).
 //
-// 23 warps: 2 x 8 hidden-epilogue warps (warp -> TMEM lane quarter w & 3, column half (w >> 2) & 1),
-// 4 output warps shared by both tiles, one MMA-issuing warp per tile, one loader warp.
+// 22 warps: 2 x 8 hidden-epilogue warps (warp -> TMEM lane quarter w & 3, column half (w >> 2) & 1),
+// 4 output warps shared by both tiles, one MMA-issuing warp, one loader warp.
 namespace v4 {
 constexpr int kHidThreadsPerTile = 256;
-constexpr int kSmallWarp0 = 16, kMmaWarp0 = 20, kLoaderWarp = 22;
-constexpr int kThreads = 23 * 32;
+constexpr int kSmallWarp0 = 16, kMmaWarp = 20, kLoaderWarp = 21;
+constexpr int kThreads = 22 * 32;
 constexpr uint32_t kColsPerTile = 256, kColH1 = 128, kColO = 64;
 
 struct __align__(1024) Tile {
@@ -672,15 +678,16 @@ struct __align__(1024) Smem {
   uint8_t ws[2][kBytesWg2];  // second-layer weight blocks (+ extra slice), double-buffered
   float2 row_minmax[2][2][kM];
   uint64_t bar_wfull[2][2];  // [kind][slot] TMA landed
-  uint64_t bar_wfree[2][2];  // [kind][slot] both tiles' MMAs reading the slot have completed (2 commits)
+  uint64_t bar_wfree[2][2];  // [kind][slot] both tiles' MMAs reading the slot have completed
   uint64_t bar_g[2];         // gather done: A0 and AX of the tile written (384 arrivals)
-  uint64_t bar_d[2][2];      // [tile][half] first-layer accumulator half complete
-  uint64_t bar_a[2][2];      // [tile][half] A1 half written back to TMEM (128 arrivals)
+  uint64_t bar_d[2];         // [tile] first-layer accumulator complete
+  uint64_t bar_a[2];         // [tile] A1 written back to TMEM (256 arrivals)
   uint64_t bar_o[2];         // dynamics second layer complete (raw latent in O)
   uint64_t bar_s[2];         // head second layer complete (logits in O)
-  uint64_t bar_lat[2];       // raw + normalised latent tiles written, O drained (256 arrivals)
+  uint64_t bar_raw[2];       // raw latent tile written, O copied out (256 arrivals)
+  uint64_t bar_hn[2];        // normalised latent tile written (256 arrivals)
   uint64_t bar_fin[2];       // head logits copied out of O (128 arrivals)
-  uint64_t bar_end[2];       // every MMA of the tile's issuing thread has completed
+  uint64_t bar_end;          // every MMA has completed
   uint32_t tmem_base;
 };
 
@@ -725,7 +732,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void hidden_chunk_tmem(uint32_t dst, const uint32_t (&acc)[16]) {
   uint32_t pk[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) pk[j] = relu_bf16x2(pack_bf16(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])));
+  for (int j = 0; j < 8; ++j) pk[j] = pack_relu_bf16(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
   tmem_st8(dst, pk);
 }
 // Hidden-layer epilogue of one column half: H[0:128) float32 -> relu -> bf16 -> A1 in H[0:64), in place.
@@ -761,18 +768,19 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
     for (int k = 0; k < 2; ++k)
       for (int j = 0; j < 2; ++j) {
         mbar_init(&s.bar_wfull[k][j], 1);
-        mbar_init(&s.bar_wfree[k][j], 2);
-        mbar_init(&s.bar_d[k][j], 1);
-        mbar_init(&s.bar_a[k][j], 128);
+        mbar_init(&s.bar_wfree[k][j], 1);
       }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s.bar_g[t], kHidThreadsPerTile + 128);
+      mbar_init(&s.bar_d[t], 1);
+      mbar_init(&s.bar_a[t], kHidThreadsPerTile);
       mbar_init(&s.bar_o[t], 1);
       mbar_init(&s.bar_s[t], 1);
-      mbar_init(&s.bar_lat[t], kHidThreadsPerTile);
+      mbar_init(&s.bar_raw[t], kHidThreadsPerTile);
+      mbar_init(&s.bar_hn[t], kHidThreadsPerTile);
       mbar_init(&s.bar_fin[t], 128);
-      mbar_init(&s.bar_end[t], 1);
     }
+    mbar_init(&s.bar_end, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {  // TMEM: all 512 columns (one CTA per SM)
@@ -799,61 +807,55 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
         use[kind] = u + 1u;
       }
     }
-  } else if (warp >= kMmaWarp0) {
-    // ============================ MMA-issuing warp of tile t ============================
-    const int t = warp - kMmaWarp0;
-    const uint32_t T = tmem + kColsPerTile * t;
-    const uint32_t a0 = smem_u32(s.t[t].a0), ahn = smem_u32(s.t[t].ahn), ax = smem_u32(s.t[t].ax);
-    const uint32_t id128 = umma_idesc(128);
-    uint32_t use_f = 0, use_s = 0, ph_g = 0, ph_a = 0, ph_lat = 0, ph_fin = 0;
+  } else if (warp == kMmaWarp) {
+    // ================================= MMA-issuing warp =================================
+    // One elected lane issues every tcgen05.mma of both tiles in the static ping-pong order
+    //   L1(T0) L1(T1) L2(T0) L2(T1)   per network,
+    // so that the tensor core always has the other tile's layer to run while one tile's epilogue
+    // warps drain TMEM.
+    const uint32_t id256 = umma_idesc(256);
+    uint32_t use_f = 0, use_s = 0, ph_g = 0, ph_a = 0, ph_raw = 0, ph_hn = 0, ph_fin[2] = {0u, 0u};
     bool first = true;
     int ev = 0;
     for (int pass = 0, pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pass) {
 #pragma unroll 1
       for (int net = 0; net < 4; ++net) {  // dynamics, reward, policy, value
-        // ---- first layer: H = [A | AX] x W1'^T, half 1 first (half 0 hosts O, drained later)
-        const uint32_t a_in = net == 0 ? a0 : (net == 1 ? a0 : ahn);
-        if (net == 0) {
-          mbar_wait(&s.bar_g[t], ph_g);
-          ph_g ^= 1;
-        }
+        // ---- first layer: H[0:256) = [A | AX] x W1'^T
         {
           const uint32_t slot = use_f & 1u;
           mbar_wait(&s.bar_wfull[0][slot], (use_f >> 1) & 1u);
-          if (elect_one()) TL4(t * 40 + ev);
-          ++ev;
-          tc_fence_after();
           const uint32_t wf = smem_u32(s.wf[slot]);
-          const uint64_t a_base = desc_sw128(a_in), axd = desc_plain(ax);
-          if (elect_one()) {
-            const uint64_t b1 = desc_sw128(wf + 128 * 128), bx1 = desc_plain(wf + 256 * 128 + 4096);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma(T + kColH1, a_base + (uint64_t)(kk * 2), b1 + (uint64_t)(kk * 2), id128, kk ? 1u : 0u);
-            umma(T + kColH1, axd, bx1, id128, 1u);
-            umma_commit(&s.bar_d[t][1]);
-          }
-          __syncwarp();
-          if (!(first && net == 0)) {  // O (inside H0) must have been copied out by its previous reader
-            if (net == 1) {
-              // drained by the latent epilogue: bar_lat was observed below
-            } else {
-              mbar_wait(&s.bar_fin[t], ph_fin);
-              ph_fin ^= 1;
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t T = tmem + kColsPerTile * t;
+            const uint32_t ax = smem_u32(s.t[t].ax);
+            const uint32_t a_in = net <= 1 ? smem_u32(s.t[t].a0) : smem_u32(s.t[t].ahn);
+            if (net == 0) mbar_wait(&s.bar_g[t], ph_g);
+            if (net == 1) mbar_wait(&s.bar_raw[t], ph_raw);  // raw latent tile written, O copied out
+            if (net == 2) mbar_wait(&s.bar_hn[t], ph_hn);    // normalised latent tile written
+            if (net != 1 && !(first && net == 0)) {  // O (inside H) must have been copied out by the output warps
+              mbar_wait(&s.bar_fin[t], ph_fin[t]);
+              ph_fin[t] ^= 1;
             }
+            if (elect_one()) TL4(ev);
+            ++ev;
             tc_fence_after();
-          }
-          if (elect_one()) {
-            const uint64_t b0 = desc_sw128(wf), bx0 = desc_plain(wf + 256 * 128);
+            if (elect_one()) {
+              // one N = 256 instruction per k-step: A is fetched from shared memory once for both column
+              // halves (two N = 128 instructions read it twice and saturate the shared-memory port)
+              const uint64_t a_base = desc_sw128(a_in), b_base = desc_sw128(wf);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma(T, a_base + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), id128, kk ? 1u : 0u);
-            umma(T, axd, bx0, id128, 1u);
-            umma_commit(&s.bar_d[t][0]);
-            umma_commit(&s.bar_wfree[0][slot]);
+              for (int kk = 0; kk < 4; ++kk) umma(T, a_base + (uint64_t)(kk * 2), b_base + (uint64_t)(kk * 2), id256, kk ? 1u : 0u);
+              umma(T, desc_plain(ax), desc_plain(wf + 256 * 128), id256, 1u);
+              umma_commit(&s.bar_d[t]);
+              if (t == 1) umma_commit(&s.bar_wfree[0][slot]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
+          if (net == 0) ph_g ^= 1;
+          if (net == 1) ph_raw ^= 1;
+          if (net == 2) ph_hn ^= 1;
           ++use_f;
-          if (elect_one()) TL4(t * 40 + ev);
-          ++ev;
         }
         // ---- second layer: O = [A1 | AX] x W2'^T, A1 from TMEM
         {
@@ -862,37 +864,35 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
           const uint32_t slot = use_s & 1u;
           mbar_wait(&s.bar_wfull[1][slot], (use_s >> 1) & 1u);
           const uint32_t ws = smem_u32(s.ws[slot]);
-          mbar_wait(&s.bar_a[t][1], ph_a);
-          mbar_wait(&s.bar_a[t][0], ph_a);
-          ph_a ^= 1;
-          if (elect_one()) TL4(t * 40 + ev);
-          ++ev;
-          tc_fence_after();
-          if (elect_one()) {
-            umma(T + kColO, desc_plain(ax), desc_plain(ws + n2 * 128 * 4), id2, 0u);  // bias step clears O
-            const uint64_t b_base = desc_sw128(ws);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              umma_ts(T + kColO, T + (j >> 3) * kColH1 + (j & 7) * 8,
-                      b_base + (uint64_t)(((j >> 2) * n2 * 128 + (j & 3) * 32) >> 4), id2, 1u);
-            umma_commit(net == 0 ? &s.bar_o[t] : &s.bar_s[t]);
-            umma_commit(&s.bar_wfree[1][slot]);
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t T = tmem + kColsPerTile * t;
+            const uint32_t ax = smem_u32(s.t[t].ax);
+            mbar_wait(&s.bar_a[t], ph_a);
+            if (elect_one()) TL4(ev);
+            ++ev;
+            tc_fence_after();
+            if (elect_one()) {
+              umma(T + kColO, desc_plain(ax), desc_plain(ws + n2 * 128 * 4), id2, 0u);  // bias step clears O
+              const uint64_t b_base = desc_sw128(ws);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                umma_ts(T + kColO, T + (j >> 3) * kColH1 + (j & 7) * 8,
+                        b_base + (uint64_t)(((j >> 2) * n2 * 128 + (j & 3) * 32) >> 4), id2, 1u);
+              umma_commit(net == 0 ? &s.bar_o[t] : &s.bar_s[t]);
+              if (t == 1) umma_commit(&s.bar_wfree[1][slot]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
+          ph_a ^= 1;
           ++use_s;
-        }
-        if (net == 0) {  // raw + normalised latent tiles must be in shared memory before the heads start
-          mbar_wait(&s.bar_lat[t], ph_lat);
-          ph_lat ^= 1;
-          if (elect_one()) TL4(t * 40 + ev);
-          ++ev;
         }
       }
       first = false;
     }
-    if (elect_one()) umma_commit(&s.bar_end[t]);
+    if (elect_one()) umma_commit(&s.bar_end);
     __syncwarp();
-    mbar_wait(&s.bar_end[t], 0);
+    mbar_wait(&s.bar_end, 0);
   } else if (warp < kSmallWarp0) {
     // ============================== hidden-epilogue warps ==============================
     const int t = warp >> 3, ltid = tid & 255;
@@ -928,12 +928,12 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
       }
 #pragma unroll 1
       for (int layer = 0; layer < 4; ++layer) {
-        mbar_wait(&s.bar_d[t][half], ph_d);
+        mbar_wait(&s.bar_d[t], ph_d);
         ph_d ^= 1;
         tc_fence_after();
         hidden_epilogue_tmem(T + half * kColH1);
         tc_fence_before();
-        mbar_arrive(&s.bar_a[t][half]);
+        mbar_arrive(&s.bar_a[t]);
         if (ltid == 0) TL4(81 + t * 8 + layer);
         if (layer == 0) {
           // ---- new latent: normalize_h_state (networks.py:191-196) and its copies; thread (row, half)
@@ -941,8 +941,21 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
           mbar_wait(&s.bar_o[t], ph_o);
           ph_o ^= 1;
           tc_fence_after();
+          if (ltid == 0) TL4(44 + t * 8);
           float raw[32];
           tmem_ld32(T + kColO + half * 32, raw);
+          // the raw latent feeds the reward head: publish it first so that head's MMA overlaps the rest
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pr[j] = pack_bf16(raw[c * 8 + 2 * j], raw[c * 8 + 2 * j + 1]);
+            *reinterpret_cast<uint4*>(tile.a0 + sw128(row, half * 4 + c)) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&s.bar_raw[t]);
+          if (ltid == 0) TL4(86 + t * 8);
           float mn4[4], mx4[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) mn4[i] = mx4[i] = raw[i];
@@ -954,6 +967,7 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
           s.row_minmax[t][half][row] = make_float2(fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3])),
                                                    fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
           asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + quarter) : "memory");
+          if (ltid == 0) TL4(40 + t * 8);
           const float2 m0 = s.row_minmax[t][0][row], m1 = s.row_minmax[t][1][row];
           const float mn = fminf(m0.x, m1.x), mx = fmaxf(m0.y, m1.y);
           const float inv = 1.0f / ((mx - mn) + 1e-8f);
@@ -961,15 +975,11 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float hn[8];
-            uint32_t pr[4], ph[4];
+            uint32_t ph[4];
 #pragma unroll
             for (int j = 0; j < 8; ++j) hn[j] = (raw[c * 8 + j] - mn) * inv;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              pr[j] = pack_bf16(raw[c * 8 + 2 * j], raw[c * 8 + 2 * j + 1]);
-              ph[j] = pack_bf16(hn[2 * j], hn[2 * j + 1]);
-            }
-            *reinterpret_cast<uint4*>(tile.a0 + sw128(row, half * 4 + c)) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+            for (int j = 0; j < 4; ++j) ph[j] = pack_bf16(hn[2 * j], hn[2 * j + 1]);
             *reinterpret_cast<uint4*>(tile.ahn + sw128(row, half * 4 + c)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
             if (latent_dtype == HMZ_LATENT_F32 && item < n) {  // parity-mode stores keep the per-row form
               float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(lat_out) + orow * kLatent + half * 32 + c * 8);
@@ -977,11 +987,17 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
               __stcs(dst + 1, make_float4(hn[4], hn[5], hn[6], hn[7]));
             }
           }
+          if (ltid == 0) TL4(41 + t * 8);
+          fence_proxy_async();
+          mbar_arrive(&s.bar_hn[t]);
+          if (ltid == 0) TL4(42 + t * 8);
           if (latent_dtype != HMZ_LATENT_F32) {
             // bf16 rows leave through the normalised tile so that 8 consecutive lanes write one 128-byte
-            // row: the two warps of a lane quarter copy out 16 rows each.
+            // row: the two warps of a lane quarter copy out 16 rows each (off the critical path: the heads
+            // are already running).
             asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + quarter) : "memory");
             const int lane = tid & 31, chunk = lane & 7;
+            if (ltid == 0) TL4(43 + t * 8);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int r2 = quarter * 32 + half * 16 + i * 4 + (lane >> 3);
@@ -991,9 +1007,6 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
                 __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(lat_out) + (it2 * out_rows_per_item + out_row) * kLatent + chunk * 8), val);
             }
           }
-          fence_proxy_async();
-          tc_fence_before();
-          mbar_arrive(&s.bar_lat[t]);
           if (ltid == 0) TL4(85 + t * 8);
         }
       }
@@ -1002,7 +1015,7 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
     // ============================== output warps (both tiles) ==============================
     const int row = tid - kSmallWarp0 * 32;
     const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t ph_s[2] = {0u, 0u};
+    uint32_t ph_s = 0;
     for (int pass = 0, pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pass) {
 #pragma unroll
       for (int t = 0; t < 2; ++t) {  // the extra A slice of this row: one-hot(action) at k = 0..5, the constant 1 at k = 6
@@ -1022,8 +1035,7 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
         for (int t = 0; t < 2; ++t) {
           const int64_t item = ((int64_t)pair * 2 + t) * kM + row;
           const uint32_t O = tmem + kColsPerTile * t + kColO + lane_bits;
-          mbar_wait(&s.bar_s[t], ph_s[t]);
-          ph_s[t] ^= 1;
+          mbar_wait(&s.bar_s[t], ph_s);
           tc_fence_after();
           if (head == 1) {  // F.softmax(pi_logits) (networks.py:109)
             float lg[16];
@@ -1049,24 +1061,27 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
             tmem_ld16(O + 32, b);
             tc_fence_before();
             mbar_arrive(&s.bar_fin[t]);
-            float mx = b[0];
+            float m4[4] = {a[0], a[1], a[2], a[3]};
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, a[i]);
-            float den = 0.f, num = 0.f;
+            for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], a[i]);
+            const float mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), b[0]);
+            const float ms = mx * 1.4426950408889634f;
+            float den4[4] = {0.f, 0.f, 0.f, 0.f}, num4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float e = exp2f((a[i] - mx) * 1.4426950408889634f);
-              den += e;
-              num = fmaf(e, (float)(i - 16), num);
+              const float e = exp2f(fmaf(a[i], 1.4426950408889634f, -ms));
+              den4[i & 3] += e;
+              num4[i & 3] = fmaf(e, (float)(i - 16), num4[i & 3]);
             }
-            const float e = exp2f((b[0] - mx) * 1.4426950408889634f);
-            den += e;
-            num = fmaf(e, 16.f, num);
+            const float e = exp2f(fmaf(b[0], 1.4426950408889634f, -ms));
+            const float den = ((den4[0] + den4[1]) + (den4[2] + den4[3])) + e;
+            const float num = fmaf(e, 16.f, (num4[0] + num4[1]) + (num4[2] + num4[3]));
             const float x = signed_parabolic(__fdividef(num, den));
             if (item < n) (head == 0 ? r_out : v_out)[item] = x;
           }
           if (row == 0) TL4(70 + head * 2 + t);
         }
+        ph_s ^= 1;
       }
     }
   }
