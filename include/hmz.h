@@ -262,6 +262,14 @@ int hmz_search_set_groups(int groups);
 /* Tooling only: with HMZ_TC_TIMELINE=1 in the environment, CTA 0 of the tensor-core kernel records
  * clock64() at its phase boundaries; this copies the 96 marks of the last launch to the host. */
 int hmz_debug_tc_timeline(unsigned long long* host_out);
+/* Tooling only: key = search | (simulation << 32) >= 0 switches hmz_search_run to the instrumented fused
+ * backup + select kernel, whose lane pair `search` records clock64() at its phase boundaries in that
+ * simulation (-1 switches it off); host_out (nullable, 64 values) receives the marks. */
+int hmz_debug_tree_timeline(long long search, unsigned long long* host_out);
+/* Tests only: compares the search kernels' exact-division shortcuts (table / precomputed reciprocal + two
+ * FMA corrections) with IEEE division bit for bit on n_samples random operand pairs; adds the number of
+ * mismatches to counters[0] (division by a visit count) and counters[1] (division by the min-max range). */
+int hmz_debug_div_check(uint64_t n_samples, uint64_t seed, unsigned long long* counters, void* stream);
 
 /* ------------------------------------------------------------------ self-play glue ---
  * Throughput-mode randomness, drawn on device with Philox4x32-10 keyed by (seed, item,

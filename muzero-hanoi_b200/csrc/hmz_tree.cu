@@ -74,7 +74,11 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
 // at once by the selection of simulation `sim + 1` — the fused hot-loop form: the path just updated
 // is still in this SM's L1 and the next walk usually shares its prefix.  With path_ent the backup
 // loads all path slots up front; without it (split-phase API) it walks the parent links.
-__global__ void __launch_bounds__(kTreeThreads, 6) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
+#ifndef HMZ_TREE_MIN_BLOCKS
+#define HMZ_TREE_MIN_BLOCKS 6
+#endif
+template <bool kTL>
+__global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
                                                                      double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
                                                                      uint16_t* leaf_depth, uint32_t* path_ent,
                                                                      const float* __restrict__ r, const float* __restrict__ p,
@@ -83,31 +87,54 @@ __global__ void __launch_bounds__(kTreeThreads, 6) search_backup_select(hmz_sear
   const unsigned pair = 3u << ((threadIdx.x & 31) & ~1);
   const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
   if (b >= s.n_searches) return;
+  const bool tl = kTL && b == (g_tree_timeline_search & 0xFFFFFFFFll) && sim == (int)(g_tree_timeline_search >> 32) && half == 0;
+  tree_mark<kTL>(0, tl);
   hmz_node_t* nodes = s.nodes + b * s.n_records;
   uint32_t* path = path_ent ? path_ent + b * kPathCap : nullptr;
   const int pe = leaf_parent[b], pa = leaf_action[b];
-  write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
+  tree_mark<kTL>(1, tl, (uint32_t)(pe + pa));
+  const int depth = (path != nullptr && leaf_depth != nullptr) ? (int)leaf_depth[b] : kPathCap + 1;
+  // everything the backup needs that depends only on the search index is requested up front, in one
+  // memory round trip: leaf scalars, network outputs, min/max, and the recorded path (levels 0..15)
+  uint4 ent0 = make_uint4(0u, 0u, 0u, 0u), ent1 = ent0, ent2 = ent0, ent3 = ent0;
+  if (half == 0 && path != nullptr) {
+    const uint4* p4 = reinterpret_cast<const uint4*>(path);
+    ent0 = p4[0];
+    ent1 = p4[1];
+    ent2 = p4[2];
+    ent3 = p4[3];
+  }
   double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
+  const float r_leaf = r[b];
+  const double v_leaf = (double)v[b];
+  write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
   if (half == 0) {
     double root_w = s.root_W[b];
-    const int depth = (path != nullptr && leaf_depth != nullptr) ? (int)leaf_depth[b] : kPathCap + 1;
-    if (depth <= 8)
-      backup_path8(nodes, path, depth, sim, r[b], (double)v[b], discount, root_w, mn, mx);
+    if (depth <= kPathCap)
+      backup_path(nodes, path, ent0, ent1, ent2, ent3, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
     else
-      backup_walk(nodes, pe, pa, sim, r[b], (double)v[b], discount, root_w, mn, mx);
+      backup_walk(nodes, pe, pa, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
     s.root_W[b] = root_w;
     s.minmax[2 * b] = mn;
     s.minmax[2 * b + 1] = mx;
+    if (tl) {
+      g_tree_timeline[2] = (unsigned long long)depth;
+      tree_mark<kTL>(3, tl, (uint32_t)__double2loint(mn));
+    }
   }
   if (!do_select) return;
   mn = __shfl_sync(pair, mn, (threadIdx.x & 31) & ~1);  // also orders lane 0's record updates before the pair's next walk
   mx = __shfl_sync(pair, mx, (threadIdx.x & 31) & ~1);
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
-  const Leaf leaf = select_leaf(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path);
+  const Leaf leaf = select_leaf<kTL>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path, tl);
   if (half == 0) {
     leaf_parent[b] = (uint16_t)leaf.parent;
     leaf_action[b] = (uint8_t)leaf.action;
     leaf_depth[b] = (uint16_t)leaf.depth;
+    if (tl) {
+      g_tree_timeline[4] = (unsigned long long)leaf.depth;
+      tree_mark<kTL>(5, tl);
+    }
   }
 }
 
@@ -129,7 +156,7 @@ __global__ void __launch_bounds__(128) search_child_scores(hmz_search_t s, const
     const hmz_child_t c = rec->h[a / 3].c[a % 3];
     float qf = 0.0f;
     if (c.N > 0) {
-      double q = __dadd_rn((double)c.rwd, __dmul_rn(discount, __ddiv_rn(c.W, (double)c.N)));
+      double q = __dadd_rn((double)c.rwd, __dmul_rn(discount, div_by_count(c.W, (int)c.N)));
       if (normalise) q = __ddiv_rn(__dsub_rn(q, mn), range);
       qf = __double2float_rn(q);
     }
@@ -210,6 +237,35 @@ __global__ void __launch_bounds__(256) search_root_policy(hmz_search_t s, int n_
   }
 }
 
+// Tooling / tests: the exact-division shortcuts of hmz_tree.cuh against __ddiv_rn, bit for bit, on random
+// operands shaped like the search's (sums of float32-derived values over small counts, ranges of such).
+__global__ void __launch_bounds__(256) div_check(uint64_t n_samples, uint64_t seed, unsigned long long* __restrict__ counters) {
+  unsigned long long bad_count = 0, bad_known = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_samples; i += (uint64_t)gridDim.x * blockDim.x) {
+    const Philox4 x = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x1234u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const Philox4 y = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x5678u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    // a: full random significand, exponent in [-60, 60) around 1, random sign; every 4th sample a float32 value,
+    // every 16th an integer-valued double
+    const unsigned long long mant = ((unsigned long long)(x.x & 0xFFFFFu) << 32) | x.y;
+    const int ex = 1023 - 60 + (int)(x.z % 120u);
+    double a = __longlong_as_double((long long)(((unsigned long long)(x.w & 1u) << 63) | ((unsigned long long)ex << 52) | mant));
+    if ((i & 3u) == 1u) a = (double)(float)a;
+    if ((i & 15u) == 2u) a = (double)(long long)(a * 1024.0);
+    const int n = (i & 1u) ? 1 + (int)(y.x % 256u) : 1 + (int)(y.x % (unsigned)kRcpTable);
+    if (__double_as_longlong(div_by_count(a, n)) != __double_as_longlong(__ddiv_rn(a, (double)n))) ++bad_count;
+    // b: positive, exponent in [-30, 30), random significand; every 8th sample an all-ones significand
+    unsigned long long bm = ((unsigned long long)(y.y & 0xFFFFFu) << 32) | y.z;
+    if ((i & 7u) == 3u) bm = 0xFFFFFFFFFFFFFull;
+    const double b = __longlong_as_double((long long)(((unsigned long long)(1023 - 30 + (int)(y.w % 60u)) << 52) | bm));
+    const bool ok = rcp_usable(b);
+    if (__double_as_longlong(div_by_known(a, b, ok ? __drcp_rn(b) : 0.0, ok)) != __double_as_longlong(__ddiv_rn(a, b))) ++bad_known;
+  }
+  if (bad_count) atomicAdd(&counters[0], bad_count);
+  if (bad_known) atomicAdd(&counters[1], bad_known);
+}
+
+static int ensure_rcp_table();
+
 static int check_search(const hmz_search_t* s, const char* who) {
   if (!s) return fail(HMZ_ERR_INVALID, "%s: null search descriptor", who);
   if (s->n_searches < 0 || s->n_records < 1 || s->n_records > 65535)
@@ -219,6 +275,21 @@ static int check_search(const hmz_search_t* s, const char* who) {
     return fail(HMZ_ERR_INVALID, "%s: null buffer in search descriptor", who);
   if ((reinterpret_cast<uintptr_t>(s->nodes) & 127u) != 0)
     return fail(HMZ_ERR_INVALID, "%s: nodes must be 128-byte aligned", who);
+  return s->n_searches > 0 ? ensure_rcp_table() : HMZ_OK;
+}
+
+// g_rcp[k] = 1.0 / k by the host's IEEE division, uploaded once per device and host thread.
+static int ensure_rcp_table() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)");
+  if (done_dev == dev) return HMZ_OK;
+  static double host[kRcpTable + 1];
+  host[0] = 0.0;
+  for (int k = 1; k <= kRcpTable; ++k) host[k] = 1.0 / (double)k;
+  if (cudaMemcpyToSymbol(g_rcp, host, sizeof(host)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+    return fail(HMZ_ERR_CUDA, "reciprocal table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  done_dev = dev;
   return HMZ_OK;
 }
 
@@ -230,7 +301,28 @@ static unsigned search_grid(int64_t n_searches) {
 
 using namespace hmz;
 
+static long long g_tree_tl_search = -1;  // host copy of g_tree_timeline_search (tooling)
+
 extern "C" {
+
+// Tooling only: search >= 0 makes hmz_search_run launch the instrumented instantiation of the fused
+// backup + select kernel, whose lane pair `search` records clock64() at its phase boundaries; host_out
+// (nullable) receives the 64 marks of the last launch.
+int hmz_debug_div_check(uint64_t n_samples, uint64_t seed, unsigned long long* counters, void* stream) {
+  if (!counters) return fail(HMZ_ERR_INVALID, "hmz_debug_div_check: null counters");
+  if (int rc = ensure_rcp_table()) return rc;
+  div_check<<<grid_for((int64_t)n_samples, 256 * 64, 8), 256, 0, (cudaStream_t)stream>>>(n_samples, seed, counters);
+  return check_launch("div_check");
+}
+
+int hmz_debug_tree_timeline(long long search, unsigned long long* host_out) {
+  if (host_out && cudaMemcpyFromSymbol(host_out, g_tree_timeline, sizeof(unsigned long long) * 64) != cudaSuccess)
+    return fail(HMZ_ERR_CUDA, "hmz_debug_tree_timeline: cudaMemcpyFromSymbol failed");
+  if (cudaMemcpyToSymbol(g_tree_timeline_search, &search, sizeof(search)) != cudaSuccess)
+    return fail(HMZ_ERR_CUDA, "hmz_debug_tree_timeline: cudaMemcpyToSymbol failed");
+  g_tree_tl_search = search;
+  return HMZ_OK;
+}
 
 int64_t hmz_search_workspace_bytes(int64_t n_searches) {
   if (n_searches < 0) return -1;
@@ -299,7 +391,7 @@ int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, co
   if (!leaf_parent || !leaf_action || !r || !p || !v || sim < 0 || sim + 1 >= s->n_records)
     return fail(HMZ_ERR_INVALID, "hmz_search_expand_backup: bad arguments (sim=%d, n_records=%d)", sim, s->n_records);
   // split-phase form: no recorded path, the backup walks the parent links
-  search_backup_select<<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(
+  search_backup_select<false><<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(
       *s, sim, nullptr, discount, const_cast<uint16_t*>(leaf_parent), const_cast<uint8_t*>(leaf_action), nullptr, nullptr,
       r, p, v, 0);
   return check_launch("search_expand_backup");
@@ -394,8 +486,12 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
                                  s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
     return rc;
   ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
-  search_backup_select<<<search_grid(B), kTreeThreads, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
-                                                               sc.r, sc.p, sc.v, sim + 1 < n_simulations ? 1 : 0);
+  if (g_tree_tl_search >= 0)
+    search_backup_select<true><<<search_grid(B), kTreeThreads, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
+                                                                      sc.r, sc.p, sc.v, sim + 1 < n_simulations ? 1 : 0);
+  else
+    search_backup_select<false><<<search_grid(B), kTreeThreads, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
+                                                                       sc.r, sc.p, sc.v, sim + 1 < n_simulations ? 1 : 0);
   return check_launch("search_backup_select");
 }
 

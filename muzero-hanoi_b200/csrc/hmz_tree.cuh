@@ -28,6 +28,15 @@ static_assert(sizeof(hmz_child_t) == 16 && sizeof(hmz_half_t) == 64 && sizeof(hm
 
 constexpr int kPathCap = 32;  // path levels recorded for the backup (deeper paths walk parent links)
 
+// Tooling: clock64() marks of one lane pair (hmz_debug_tree_timeline), compiled only into the kTL = true
+// instantiations.  `dep` makes the clock read wait for a loaded value.
+static __device__ unsigned long long g_tree_timeline[64];
+static __device__ long long g_tree_timeline_search = -1;
+template <bool kTL>
+__device__ __forceinline__ void tree_mark(int slot, bool on, uint32_t dep = 0u) {
+  if (kTL && on && dep != 0xFFFFFFF1u) g_tree_timeline[slot] = clock64();
+}
+
 struct Leaf {
   int parent;  // record of the leaf's parent
   int action;  // action from that parent to the (unexpanded) leaf
@@ -70,9 +79,79 @@ __device__ __forceinline__ void write_fresh_half(hmz_node_t* rec, int half, cons
                       half == 0 ? ((uint32_t)parent | ((uint32_t)parent_action << 16)) : 0u);
 }
 
+// ---- exact float64 division without the generic division routine ---------------------------------
+// The reference divides by small integers (visit counts, N + 1) and by the min-max range.  For a
+// positive divisor b whose correctly rounded reciprocal y = RN(1/b) is known — a host-computed table for
+// integers, one __drcp_rn per search and launch for the range — two Markstein corrections
+//     q0 = RN(a y);  r0 = a - b q0 (exact, one FMA);  q1 = RN(q0 + r0 y);  r1 = a - b q1;  q = RN(q1 + r1 y)
+// give the correctly rounded quotient RN(a / b): q1 is within half an ulp (+ 2^-53 ulp) of a / b, i.e.
+// faithful, and Markstein's theorem (Markstein 1990; Cornea, Harrison, Tang 2002, thm. on FMA-based
+// division) then makes the second correction exact for every b whose significand is not all ones.
+// Operands outside the comfortably normal range (and b with an all-ones significand) take __ddiv_rn.
+// tests/test_div_gpu.py compares this bit for bit with __ddiv_rn on ~10^9 operand pairs.
+constexpr int kRcpTable = 4096;
+static __device__ double g_rcp[kRcpTable + 1];  // g_rcp[k] = RN(1 / k) for k >= 1 (filled by the host, IEEE division)
+
+__device__ __forceinline__ bool div_fast_ok(double a) {
+  const double m = fabs(a);
+  return m > 1e-250 && m < 1e250;
+}
+__device__ __forceinline__ double div_refine(double a, double b, double y) {
+  double q = __dmul_rn(a, y);
+  double r = __fma_rn(-b, q, a);
+  q = __fma_rn(r, y, q);
+  r = __fma_rn(-b, q, a);
+  return __fma_rn(r, y, q);
+}
+// a / n for a visit count n >= 1
+__device__ __forceinline__ double div_by_count(double a, int n) {
+  if (a == 0.0) return a;  // +-0 / n
+  if (n <= kRcpTable && div_fast_ok(a)) return div_refine(a, (double)n, __ldg(&g_rcp[n]));
+  return __ddiv_rn(a, (double)n);
+}
+// a / b with y = __drcp_rn(b) precomputed; y_ok = b is positive, comfortably normal and its significand is not all ones
+__device__ __forceinline__ double div_by_known(double a, double b, double y, bool y_ok) {
+  if (y_ok && div_fast_ok(a)) return div_refine(a, b, y);
+  return __ddiv_rn(a, b);
+}
+__device__ __forceinline__ bool rcp_usable(double b) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(b);
+  return b > 1e-250 && b < 1e250 && (bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull;
+}
+
 __device__ __forceinline__ void minmax_update(double x, double& mn, double& mx) {
   if (x > mx) mx = x;  // python max(maximum, value): value only when strictly greater
   if (x < mn) mn = x;
+}
+
+#ifndef HMZ_PREFETCH_SECTORS
+#define HMZ_PREFETCH_SECTORS 4
+#endif
+// Request a 128-byte node record into L1 without a destination register.
+__device__ __forceinline__ void prefetch_record(const void* rec) {
+#pragma unroll
+  for (int k = 0; k < HMZ_PREFETCH_SECTORS; ++k)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec) + 32 * k * (4 / HMZ_PREFETCH_SECTORS)));
+}
+
+// An operand the two-correction division handles exactly: +0 or comfortably normal.
+__device__ __forceinline__ bool div_operand_ok(double a) {
+  return __double_as_longlong(a) == 0ll || div_fast_ok(a);
+}
+
+// Reference-order evaluation of one child (the slow, always-exact form): used when an operand falls
+// outside the range the straight-line form below is proven for.
+__device__ __noinline__ float child_score_exact(double W, float rwd, int n, float prior, double prior64, bool use64, double tn,
+                                                double discount, double mn, double range, bool normalise) {
+  float qf = 0.0f;  // child_Q: 0 for unvisited children (node.py:98-102)
+  if (n > 0) {
+    double q = __dadd_rn((double)rwd, __dmul_rn(discount, __ddiv_rn(W, (double)n)));
+    if (normalise) q = __ddiv_rn(__dsub_rn(q, mn), range);
+    qf = __double2float_rn(q);
+  }
+  const double w = __ddiv_rn(tn, (double)(n + 1));
+  const float u = use64 ? __double2float_rn(__dmul_rn(prior64, w)) : __fmul_rn(prior, __double2float_rn(w));
+  return __fadd_rn(qf, u);
 }
 
 // Node.best_child repeated from the root until an unexpanded child (MCTS/mcts.py:80-86,
@@ -81,62 +160,98 @@ __device__ __forceinline__ void minmax_update(double x, double& mn, double& mx) 
 //   root_prior64  float64 root priors when the root was Dirichlet-noised, else nullptr
 //   path_out      nullable [path_cap] bytes: chosen action per level (diagnostics)
 //   path_ent      nullable [kPathCap] words: (record | action << 16) per level, for the backup
+// The three children of a lane are evaluated as ONE straight-line block (no data-dependent branch
+// between them), so their float64 chains interleave: every division is the two-correction form of
+// div_refine on reciprocals fetched up front, unvisited children are computed and discarded, and the
+// rare operand outside the proven range re-evaluates the lane's children with child_score_exact.
+template <bool kTL = false>
 __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const double* __restrict__ root_prior64, double mn,
                                             double mx, int root_n, const double* __restrict__ ucb_table,
                                             double discount, int half, uint8_t* __restrict__ path_out, int path_cap,
-                                            uint32_t* __restrict__ path_ent) {
+                                            uint32_t* __restrict__ path_ent, bool tl_on = false) {
   const int lane = threadIdx.x & 31;
   const unsigned pair = 3u << (lane & ~1);
   const bool normalise = mx > mn;  // MinMaxStats.normalize (MCTS/utils_mcts.py:12-16)
   const double range = __dsub_rn(mx, mn);
+  const bool range_ok = normalise && rcp_usable(range);
+  const double range_rcp = range_ok ? __drcp_rn(range) : 0.0;
+  double rp64[3] = {0.0, 0.0, 0.0};
+  if (root_prior64 != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) rp64[j] = root_prior64[3 * half + j];
+  }
   int e = 0, n_parent = root_n, depth = 0;
   Leaf leaf{0, 0, 0};
   while (true) {
     const uint4* hp = reinterpret_cast<const uint4*>(&nodes[e].h[half]);
     const uint4 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3];
     const double tn = ucb_table[n_parent];
-    float best_score = 0.f;
-    int best = 0, best_child = 0, best_n = 0;
+    if (depth < 8) tree_mark<kTL>(8 + 2 * depth, tl_on, q0.w ^ q1.w ^ q2.w ^ q3.w);
+    const bool use64 = e == 0 && root_prior64 != nullptr;
+    Slot c[3] = {Slot::unpack(q0), Slot::unpack(q1), Slot::unpack(q2)};
+#if HMZ_PREFETCH_SECTORS > 0
+    // The walk continues in one of the expanded children: request their records now, so that the fetch
+    // overlaps the float64 evaluation below instead of following it (one dependent memory round trip per
+    // level otherwise).  Costs extra record reads; the kernel is latency-bound, not bandwidth-bound.
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (c[j].child != (int)HMZ_NO_CHILD) prefetch_record(&nodes[c[j].child]);
+#endif
+    const float prior[3] = {__uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z)};
+    double y[3], yw[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {  // reciprocals first: six independent L1 hits
+      y[j] = __ldg(&g_rcp[min(max(c[j].n, 1), kRcpTable)]);
+      yw[j] = __ldg(&g_rcp[min(c[j].n + 1, kRcpTable)]);
+    }
+    float score[3];
+    bool exact_needed = !div_operand_ok(tn);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const Slot c = Slot::unpack(j == 0 ? q0 : (j == 1 ? q1 : q2));
-      const float prior = __uint_as_float(j == 0 ? q3.x : (j == 1 ? q3.y : q3.z));
-      float qf = 0.0f;  // child_Q: 0 for unvisited children (node.py:98-102)
-      if (c.n > 0) {
-        double q = __dadd_rn((double)c.rwd, __dmul_rn(discount, __ddiv_rn(c.W, (double)c.n)));
-        if (normalise) q = __ddiv_rn(__dsub_rn(q, mn), range);
-        qf = __double2float_rn(q);
-      }
+      const int n = c[j].n;
+      const double t1 = div_refine(c[j].W, (double)max(n, 1), y[j]);
+      const double q = __dadd_rn((double)c[j].rwd, __dmul_rn(discount, t1));
+      const double num = __dsub_rn(q, mn);
+      const double qn = normalise ? div_refine(num, range, range_rcp) : q;
+      const float qf = n > 0 ? __double2float_rn(qn) : 0.0f;  // child_Q: 0 for unvisited children (node.py:98-102)
       // child_U: w = (log((N+c_base+1)/c_base) + c_init) * sqrt(N) / (child.N + 1)  (node.py:114-121)
-      const double w = __ddiv_rn(tn, (double)(c.n + 1));
-      float u;
-      if (e == 0 && root_prior64 != nullptr)
-        u = __double2float_rn(__dmul_rn(root_prior64[3 * half + j], w));  // float64 prior: product in float64
-      else
-        u = __fmul_rn(prior, __double2float_rn(w));  // float32 prior: weak scalar -> float32 product
-      const float score = __fadd_rn(qf, u);          // node.py:83 on float32 arrays
-      if (j == 0 || score > best_score) {             // first maximum wins inside the half
-        best_score = score;
-        best = 3 * half + j;
-        best_child = c.child;
-        best_n = c.n;
-      }
+      const double w = div_refine(tn, (double)(n + 1), yw[j]);
+      // float64 prior (noised root): product in float64; float32 prior: weak scalar -> float32 product (node.py:122)
+      const float u = use64 ? __double2float_rn(__dmul_rn(rp64[j], w)) : __fmul_rn(prior[j], __double2float_rn(w));
+      score[j] = __fadd_rn(qf, u);  // node.py:83 on float32 arrays
+      exact_needed |= n + 1 > kRcpTable;
+      exact_needed |= n > 0 && (!div_operand_ok(c[j].W) || (normalise && (!range_ok || !div_operand_ok(num))));
     }
+    if (exact_needed) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        score[j] = child_score_exact(c[j].W, c[j].rwd, c[j].n, prior[j], rp64[j], use64, tn, discount, mn, range, normalise);
+    }
+    float best_score = score[0];
+    int best = 3 * half, best_child = c[0].child, best_n = c[0].n;
+#pragma unroll
+    for (int j = 1; j < 3; ++j)
+      if (score[j] > best_score) {  // first maximum wins inside the half
+        best_score = score[j];
+        best = 3 * half + j;
+        best_child = c[j].child;
+        best_n = c[j].n;
+      }
     // merge the two halves: actions 0..2 (lane 0) beat 3..5 (lane 1) on equal scores
     const float other_score = __shfl_xor_sync(pair, best_score, 1);
-    const int other_best = __shfl_xor_sync(pair, best, 1);
-    const int other_child = __shfl_xor_sync(pair, best_child, 1);
+    const int other_pack = __shfl_xor_sync(pair, best | (best_child << 16), 1);
     const int other_n = __shfl_xor_sync(pair, best_n, 1);
     const bool take_other = half == 0 ? (other_score > best_score) : !(best_score > other_score);
     if (take_other) {
-      best = other_best;
-      best_child = other_child;
+      best = other_pack & 7;
+      best_child = (int)((unsigned)other_pack >> 16);
       best_n = other_n;
     }
     if (half == 0) {
       if (path_out != nullptr && depth < path_cap) path_out[depth] = (uint8_t)best;
       if (path_ent != nullptr && depth < kPathCap) path_ent[depth] = (uint32_t)e | ((uint32_t)best << 16);
     }
+    if (depth < 8) tree_mark<kTL>(9 + 2 * depth, tl_on, (uint32_t)best_child);
     ++depth;
     if (best_child == (int)HMZ_NO_CHILD) {
       leaf.parent = e;
@@ -167,7 +282,7 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
     c.n += 1;                     // current.N += 1
     *sp = c.pack();
     const double rwd = (double)c.rwd;
-    minmax_update(__dadd_rn(rwd, __dmul_rn(discount, __ddiv_rn(c.W, (double)c.n))), mn, mx);
+    minmax_update(__dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n))), mn, mx);
     value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
     if (e == 0) break;
     a = nodes[e].h[0].parent_action;
@@ -175,22 +290,24 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
   }
   // the root itself: rwd = 0.0 (MCTS/mcts.py:69), N = sim + 1 after this backup
   root_w = __dadd_rn(root_w, value);
-  minmax_update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_w, (double)(sim + 1)))), mn, mx);
+  minmax_update(__dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1))), mn, mx);
 }
 
-// Same backup for a path of depth <= 8 recorded by select_leaf: the slots are loaded four levels at a
-// time up front (independent 16-byte loads: one memory round trip per batch instead of one per level),
-// then the leaf-to-root float64 recurrence runs in registers.  Operation for operation identical to
-// backup_walk, so results are bit-identical.
-__device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& ent4, int k0, int depth, int sim, float r,
-                                              double& value, double discount, double& mn, double& mx) {
-  const uint32_t ent[4] = {ent4.x, ent4.y, ent4.z, ent4.w};
-  uint4 raw[4];
+// Same backup for a path of depth <= kPathCap recorded by select_leaf, eight levels per batch (leaf-side
+// batch first): the batch's slots are loaded together (one memory round trip), then the leaf-to-root
+// float64 recurrence runs in registers as straight-line predicated code — the per-level divisions W / N
+// are independent of each other, only value = rwd + discount * value and the min/max compares chain.
+// Operation for operation identical to backup_walk, so results are bit-identical.
+__device__ __forceinline__ void backup_batch8(hmz_node_t* nodes, const uint4& ent_lo, const uint4& ent_hi, int k0, int depth,
+                                              int sim, float r, double& value, double discount, double& mn, double& mx) {
+  const uint32_t ent[8] = {ent_lo.x, ent_lo.y, ent_lo.z, ent_lo.w, ent_hi.x, ent_hi.y, ent_hi.z, ent_hi.w};
+  uint4 raw[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < 8; ++j)
     if (k0 + j < depth) raw[j] = *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16));
+  double q[8];
 #pragma unroll
-  for (int j = 3; j >= 0; --j) {
+  for (int j = 7; j >= 0; --j) {
     if (k0 + j < depth) {
       Slot c = Slot::unpack(raw[j]);
       if (k0 + j == depth - 1) {  // the leaf slot: Node.expand bookkeeping on the parent (node.py:44-49)
@@ -201,19 +318,26 @@ __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& en
       c.n += 1;                     // current.N += 1
       *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16)) = c.pack();
       const double rwd = (double)c.rwd;
-      minmax_update(__dadd_rn(rwd, __dmul_rn(discount, __ddiv_rn(c.W, (double)c.n))), mn, mx);
+      q[j] = __dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n)));
       value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
     }
   }
+#pragma unroll
+  for (int j = 7; j >= 0; --j)
+    if (k0 + j < depth) minmax_update(q[j], mn, mx);  // min_max_stats.update(rwd + discount * Q), leaf to root
 }
 
-__device__ __forceinline__ void backup_path8(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, int depth, int sim,
-                                             float r, double value, double discount, double& root_w, double& mn,
-                                             double& mx) {
-  if (depth > 4) backup_batch4(nodes, *reinterpret_cast<const uint4*>(path_ent + 4), 4, depth, sim, r, value, discount, mn, mx);
-  backup_batch4(nodes, *reinterpret_cast<const uint4*>(path_ent), 0, depth, sim, r, value, discount, mn, mx);
+// ent0..ent3: path entries of levels 0..15, loaded by the caller together with the leaf scalars.
+__device__ __forceinline__ void backup_path(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, const uint4& ent0,
+                                            const uint4& ent1, const uint4& ent2, const uint4& ent3, int depth, int sim,
+                                            float r, double value, double discount, double& root_w, double& mn, double& mx) {
+  for (int k0 = (depth - 1) & ~7; k0 >= 16; k0 -= 8)
+    backup_batch8(nodes, *reinterpret_cast<const uint4*>(path_ent + k0), *reinterpret_cast<const uint4*>(path_ent + k0 + 4), k0,
+                  depth, sim, r, value, discount, mn, mx);
+  if (depth > 8) backup_batch8(nodes, ent2, ent3, 8, depth, sim, r, value, discount, mn, mx);
+  backup_batch8(nodes, ent0, ent1, 0, depth, sim, r, value, discount, mn, mx);
   root_w = __dadd_rn(root_w, value);
-  minmax_update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_w, (double)(sim + 1)))), mn, mx);
+  minmax_update(__dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1))), mn, mx);
 }
 
 }  // namespace hmz
