@@ -792,6 +792,10 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
+  // Programmatic dependent launch: barrier init, TMEM allocation and (loader warp) the first weight
+  // blocks do not depend on the preceding tree kernel; everything that reads its outputs does.
+  pdl_launch_dependents();
+  if (warp != kLoaderWarp && warp != kMmaWarp) pdl_wait();
 
   if (warp == kLoaderWarp) {
     // ================================= loader warp =================================
@@ -1202,10 +1206,10 @@ int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_pe
   const int64_t n_pairs = (n + 2 * tc::kM - 1) / (2 * tc::kM);
   const int sms = sm_count();
   const unsigned grid = (unsigned)(n_pairs < sms ? n_pairs : sms);
-  tc::v4::net_recurrent_tc<<<grid, tc::v4::kThreads, smem_v4, stream>>>((const uint8_t*)weights, lat_in, in_rows_per_item, in_row,
-                                                                        actions, lat_out, out_rows_per_item, out_row,
-                                                                        latent_dtype, r, p, v, n, (int)n_pairs,
-                                                                        tc_timeline_enabled());
+  cudaError_t e = launch_pdl(tc::v4::net_recurrent_tc, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem_v4, stream,
+                             (const uint8_t*)weights, lat_in, in_rows_per_item, in_row, actions, lat_out, out_rows_per_item, out_row,
+                             latent_dtype, r, p, v, n, (int)n_pairs, tc_timeline_enabled());
+  if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_recurrent_tc launch: %s", cudaGetErrorString(e));
   return check_launch("net_recurrent_tc");
 }
 

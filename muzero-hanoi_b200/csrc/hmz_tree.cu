@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
   const int half = threadIdx.x & 1;
   const unsigned pair = 3u << ((threadIdx.x & 31) & ~1);
   const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
+  pdl_launch_dependents();
+  pdl_wait();  // everything below reads what the network kernel wrote
   if (b >= s.n_searches) return;
   const bool tl = kTL && b == (g_tree_timeline_search & 0xFFFFFFFFll) && sim == (int)(g_tree_timeline_search >> 32) && half == 0;
   tree_mark<kTL>(0, tl);
@@ -95,15 +97,9 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
   tree_mark<kTL>(1, tl, (uint32_t)(pe + pa));
   const int depth = (path != nullptr && leaf_depth != nullptr) ? (int)leaf_depth[b] : kPathCap + 1;
   // everything the backup needs that depends only on the search index is requested up front, in one
-  // memory round trip: leaf scalars, network outputs, min/max, and the recorded path (levels 0..15)
-  uint4 ent0 = make_uint4(0u, 0u, 0u, 0u), ent1 = ent0, ent2 = ent0, ent3 = ent0;
-  if (half == 0 && path != nullptr) {
-    const uint4* p4 = reinterpret_cast<const uint4*>(path);
-    ent0 = p4[0];
-    ent1 = p4[1];
-    ent2 = p4[2];
-    ent3 = p4[3];
-  }
+  // memory round trip: leaf scalars, network outputs, min/max (the leaf-side path entries follow the depth)
+  uint4 ent4 = make_uint4(0u, 0u, 0u, 0u);
+  if (half == 0 && path != nullptr && depth <= kPathCap) ent4 = *reinterpret_cast<const uint4*>(path + ((depth - 1) & ~3));
   double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
   const float r_leaf = r[b];
   const double v_leaf = (double)v[b];
@@ -111,7 +107,7 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
   if (half == 0) {
     double root_w = s.root_W[b];
     if (depth <= kPathCap)
-      backup_path(nodes, path, ent0, ent1, ent2, ent3, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
+      backup_path(nodes, path, ent4, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
     else
       backup_walk(nodes, pe, pa, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
     s.root_W[b] = root_w;
@@ -486,12 +482,12 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
                                  s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
     return rc;
   ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
-  if (g_tree_tl_search >= 0)
-    search_backup_select<true><<<search_grid(B), kTreeThreads, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
-                                                                      sc.r, sc.p, sc.v, sim + 1 < n_simulations ? 1 : 0);
-  else
-    search_backup_select<false><<<search_grid(B), kTreeThreads, 0, st>>>(*s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path,
-                                                                       sc.r, sc.p, sc.v, sim + 1 < n_simulations ? 1 : 0);
+  const int do_select = sim + 1 < n_simulations ? 1 : 0;
+  const float *cr = sc.r, *cp = sc.p, *cv = sc.v;
+  cudaError_t e = launch_pdl(g_tree_tl_search >= 0 ? search_backup_select<true> : search_backup_select<false>, dim3(search_grid(B)),
+                             dim3(kTreeThreads), 0, st, *s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path, cr, cp, cv,
+                             do_select);
+  if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "search_backup_select launch: %s", cudaGetErrorString(e));
   return check_launch("search_backup_select");
 }
 

@@ -175,11 +175,6 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
   const double range = __dsub_rn(mx, mn);
   const bool range_ok = normalise && rcp_usable(range);
   const double range_rcp = range_ok ? __drcp_rn(range) : 0.0;
-  double rp64[3] = {0.0, 0.0, 0.0};
-  if (root_prior64 != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) rp64[j] = root_prior64[3 * half + j];
-  }
   int e = 0, n_parent = root_n, depth = 0;
   Leaf leaf{0, 0, 0};
   while (true) {
@@ -188,6 +183,11 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
     const double tn = ucb_table[n_parent];
     if (depth < 8) tree_mark<kTL>(8 + 2 * depth, tl_on, q0.w ^ q1.w ^ q2.w ^ q3.w);
     const bool use64 = e == 0 && root_prior64 != nullptr;
+    double rp64[3] = {0.0, 0.0, 0.0};
+    if (use64) {  // only the (noised) root has float64 priors; requested together with the record
+#pragma unroll
+      for (int j = 0; j < 3; ++j) rp64[j] = root_prior64[3 * half + j];
+    }
     Slot c[3] = {Slot::unpack(q0), Slot::unpack(q1), Slot::unpack(q2)};
 #if HMZ_PREFETCH_SECTORS > 0
     // The walk continues in one of the expanded children: request their records now, so that the fetch
@@ -293,21 +293,20 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
   minmax_update(__dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1))), mn, mx);
 }
 
-// Same backup for a path of depth <= kPathCap recorded by select_leaf, eight levels per batch (leaf-side
+// Same backup for a path of depth <= kPathCap recorded by select_leaf, four levels per batch (leaf-side
 // batch first): the batch's slots are loaded together (one memory round trip), then the leaf-to-root
-// float64 recurrence runs in registers as straight-line predicated code — the per-level divisions W / N
-// are independent of each other, only value = rwd + discount * value and the min/max compares chain.
-// Operation for operation identical to backup_walk, so results are bit-identical.
-__device__ __forceinline__ void backup_batch8(hmz_node_t* nodes, const uint4& ent_lo, const uint4& ent_hi, int k0, int depth,
-                                              int sim, float r, double& value, double discount, double& mn, double& mx) {
-  const uint32_t ent[8] = {ent_lo.x, ent_lo.y, ent_lo.z, ent_lo.w, ent_hi.x, ent_hi.y, ent_hi.z, ent_hi.w};
-  uint4 raw[8];
+// float64 recurrence runs in registers.  Operation for operation identical to backup_walk, so results
+// are bit-identical.  The batch loop is deliberately not unrolled: registers (occupancy) matter more
+// to this latency-bound kernel than the second batch's instruction-level parallelism.
+__device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& ent4, int k0, int depth, int sim, float r,
+                                              double& value, double discount, double& mn, double& mx) {
+  const uint32_t ent[4] = {ent4.x, ent4.y, ent4.z, ent4.w};
+  uint4 raw[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < 4; ++j)
     if (k0 + j < depth) raw[j] = *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16));
-  double q[8];
 #pragma unroll
-  for (int j = 7; j >= 0; --j) {
+  for (int j = 3; j >= 0; --j) {
     if (k0 + j < depth) {
       Slot c = Slot::unpack(raw[j]);
       if (k0 + j == depth - 1) {  // the leaf slot: Node.expand bookkeeping on the parent (node.py:44-49)
@@ -318,24 +317,21 @@ __device__ __forceinline__ void backup_batch8(hmz_node_t* nodes, const uint4& en
       c.n += 1;                     // current.N += 1
       *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16)) = c.pack();
       const double rwd = (double)c.rwd;
-      q[j] = __dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n)));
+      minmax_update(__dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n))), mn, mx);
       value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
     }
   }
-#pragma unroll
-  for (int j = 7; j >= 0; --j)
-    if (k0 + j < depth) minmax_update(q[j], mn, mx);  // min_max_stats.update(rwd + discount * Q), leaf to root
 }
 
-// ent0..ent3: path entries of levels 0..15, loaded by the caller together with the leaf scalars.
-__device__ __forceinline__ void backup_path(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, const uint4& ent0,
-                                            const uint4& ent1, const uint4& ent2, const uint4& ent3, int depth, int sim,
-                                            float r, double value, double discount, double& root_w, double& mn, double& mx) {
-  for (int k0 = (depth - 1) & ~7; k0 >= 16; k0 -= 8)
-    backup_batch8(nodes, *reinterpret_cast<const uint4*>(path_ent + k0), *reinterpret_cast<const uint4*>(path_ent + k0 + 4), k0,
-                  depth, sim, r, value, discount, mn, mx);
-  if (depth > 8) backup_batch8(nodes, ent2, ent3, 8, depth, sim, r, value, discount, mn, mx);
-  backup_batch8(nodes, ent0, ent1, 0, depth, sim, r, value, discount, mn, mx);
+// ent_first: path entries of the leaf-side batch, loaded by the caller together with the leaf scalars.
+__device__ __forceinline__ void backup_path(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, uint4 ent4, int depth,
+                                            int sim, float r, double value, double discount, double& root_w, double& mn,
+                                            double& mx) {
+#pragma unroll 1
+  for (int k0 = (depth - 1) & ~3; k0 >= 0; k0 -= 4) {
+    backup_batch4(nodes, ent4, k0, depth, sim, r, value, discount, mn, mx);
+    if (k0 >= 4) ent4 = *reinterpret_cast<const uint4*>(path_ent + k0 - 4);
+  }
   root_w = __dadd_rn(root_w, value);
   minmax_update(__dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1))), mn, mx);
 }
