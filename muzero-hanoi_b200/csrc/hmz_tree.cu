@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
 // is still in this SM's L1 and the next walk usually shares its prefix.  With path_ent the backup
 // loads all path slots up front; without it (split-phase API) it walks the parent links.
 #ifndef HMZ_TREE_MIN_BLOCKS
-#define HMZ_TREE_MIN_BLOCKS 6
+#define HMZ_TREE_MIN_BLOCKS 5
 #endif
 template <bool kTL>
 __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
@@ -106,7 +106,11 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
   write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
   if (half == 0) {
     double root_w = s.root_W[b];
+#if defined(HMZ_ABLATE) && (HMZ_ABLATE & 2)  // timing experiment only: no backup
+    if (depth < 0)
+#else
     if (depth <= kPathCap)
+#endif
       backup_path(nodes, path, ent4, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
     else
       backup_walk(nodes, pe, pa, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
@@ -118,6 +122,9 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
       tree_mark<kTL>(3, tl, (uint32_t)__double2loint(mn));
     }
   }
+#if defined(HMZ_ABLATE) && (HMZ_ABLATE & 4)  // timing experiment only: no selection
+  if (sim >= 0) return;
+#endif
   if (!do_select) return;
   mn = __shfl_sync(pair, mn, (threadIdx.x & 31) & ~1);  // also orders lane 0's record updates before the pair's next walk
   mx = __shfl_sync(pair, mx, (threadIdx.x & 31) & ~1);

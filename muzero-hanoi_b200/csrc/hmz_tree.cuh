@@ -62,6 +62,19 @@ struct Slot {
   }
 };
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): half a node record in two instructions
+__device__ __forceinline__ void ld256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st256(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
 __device__ __forceinline__ uint4* slot_ptr(hmz_node_t* nodes, int e, int a) {
   return reinterpret_cast<uint4*>(&nodes[e].h[a / 3].c[a % 3]);
 }
@@ -72,11 +85,10 @@ __device__ __forceinline__ void write_fresh_half(hmz_node_t* rec, int half, cons
                                                  int parent_action) {
   uint4* dst = reinterpret_cast<uint4*>(&rec->h[half]);
   const uint4 empty = make_uint4(0u, 0u, 0u, 0xFFFF0000u);  // W = 0, rwd = 0, N = 0, child = HMZ_NO_CHILD
-  dst[0] = empty;
-  dst[1] = empty;
-  dst[2] = empty;
-  dst[3] = make_uint4(__float_as_uint(pr[3 * half]), __float_as_uint(pr[3 * half + 1]), __float_as_uint(pr[3 * half + 2]),
-                      half == 0 ? ((uint32_t)parent | ((uint32_t)parent_action << 16)) : 0u);
+  st256(dst, empty, empty);
+  st256(dst + 2, empty,
+        make_uint4(__float_as_uint(pr[3 * half]), __float_as_uint(pr[3 * half + 1]), __float_as_uint(pr[3 * half + 2]),
+                   half == 0 ? ((uint32_t)parent | ((uint32_t)parent_action << 16)) : 0u));
 }
 
 // ---- exact float64 division without the generic division routine ---------------------------------
@@ -125,7 +137,7 @@ __device__ __forceinline__ void minmax_update(double x, double& mn, double& mx) 
 }
 
 #ifndef HMZ_PREFETCH_SECTORS
-#define HMZ_PREFETCH_SECTORS 4
+#define HMZ_PREFETCH_SECTORS 0
 #endif
 // Request a 128-byte node record into L1 without a destination register.
 __device__ __forceinline__ void prefetch_record(const void* rec) {
@@ -179,7 +191,9 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
   Leaf leaf{0, 0, 0};
   while (true) {
     const uint4* hp = reinterpret_cast<const uint4*>(&nodes[e].h[half]);
-    const uint4 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3];
+    uint4 q0, q1, q2, q3;
+    ld256(hp, q0, q1);
+    ld256(hp + 2, q2, q3);
     const double tn = ucb_table[n_parent];
     if (depth < 8) tree_mark<kTL>(8 + 2 * depth, tl_on, q0.w ^ q1.w ^ q2.w ^ q3.w);
     const bool use64 = e == 0 && root_prior64 != nullptr;
@@ -206,6 +220,11 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
     }
     float score[3];
     bool exact_needed = !div_operand_ok(tn);
+#if defined(HMZ_ABLATE) && (HMZ_ABLATE & 1)  // timing experiment only: no float64 evaluation
+#pragma unroll
+    for (int j = 0; j < 3; ++j) score[j] = prior[j] + (float)c[j].n * 1e-3f + __double2float_rn(y[j] + yw[j]) * 1e-9f;
+    exact_needed = false;
+#else
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int n = c[j].n;
@@ -222,6 +241,7 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
       exact_needed |= n + 1 > kRcpTable;
       exact_needed |= n > 0 && (!div_operand_ok(c[j].W) || (normalise && (!range_ok || !div_operand_ok(num))));
     }
+#endif
     if (exact_needed) {
 #pragma unroll
       for (int j = 0; j < 3; ++j)
