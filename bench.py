@@ -315,26 +315,29 @@ def run_ours(args):
         v["share"] = v["ms_total"] / total_kernel_ms if total_kernel_ms else None
     dominant = max(("net_recurrent", "backup_select"), key=lambda k: kern[k]["ms_total"])
     peaks = measured_peaks()
-    if dominant == "net_recurrent":
-        per_launch_s = kern[dominant]["us_per_launch"] * 1e-6
-        achieved = FLOP_PER_SIM * B / per_launch_s / 1e12
-        peak = peaks["bf16_tflops_sustained"]
-        roofline = {"kernel": "net_recurrent (fused g + reward/policy/value heads)", "bound": "tensor",
+
+    def roofline_of(name):
+        per_launch_s = kern[name]["us_per_launch"] * 1e-6
+        if name == "net_recurrent":
+            achieved = FLOP_PER_SIM * B / per_launch_s / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            return {"kernel": "net_recurrent_tc (fused g + reward/policy/value heads, tcgen05)", "bound": "tensor",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peaks["source"] + ", sustained bf16",
                     "algorithmic": f"{FLOP_PER_SIM} FLOP/sim x {B} sims per launch"}
-    else:
         # fused tree kernel, algorithmic bytes per simulation: selection reads one 128 B record per
         # level, backup reads + writes one 16 B slot per level, the expansion writes one 128 B record, plus the
         # per-search scalars (leaf ids 5 B r/w, p 24 B, r/v 8 B, min/max + root W 24 B r/w, path 4 B/level r/w)
-        per_launch_s = kern[dominant]["us_per_launch"] * 1e-6
         depth = 3.4
         bytes_per_sim = 128 * depth + 32 * depth + 128 + 8 * depth + 10 + 32 + 48
         achieved = bytes_per_sim * B / per_launch_s / 1e9
-        roofline = {"kernel": "search_backup_select (expand + backup + next select)", "bound": "hbm", "achieved": achieved,
-                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                    "peak_source": peaks["source"],
-                    "algorithmic": f"{bytes_per_sim:.0f} B/sim x {B} sims per launch (mean leaf depth {depth})"}
+        return {"kernel": "search_backup_select (expand + backup + next select)", "bound": "hbm", "achieved": achieved,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peaks["source"],
+                "algorithmic": f"{bytes_per_sim:.0f} B/sim x {B} sims per launch (mean leaf depth {depth})"}
+
+    roofline = roofline_of(dominant)
+    roofline_other = roofline_of("backup_select" if dominant == "net_recurrent" else "net_recurrent")
     # ---- end to end: env words from pinned host memory in, move records back to the host, every step
     h_words = torch.empty(B, dtype=torch.int32).pin_memory()
     h_words.copy_(sp.env.words.cpu())
@@ -398,7 +401,7 @@ def run_ours(args):
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_rate, "unit": UNIT, "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline, "kernels": kern,
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_second_kernel": roofline_other, "kernels": kern,
             "env_steps_per_second": world * B * args.steps / (ms * 1e-3), "env": env_line,
             "targets": {"sims_per_s_8gpu": 1e8, "env_steps_per_s_8gpu": 1e9},
         }

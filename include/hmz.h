@@ -290,6 +290,43 @@ int hmz_traj_record(const uint32_t* words, const int32_t* action, const int32_t*
                     uint32_t* traj_state, uint8_t* traj_action, uint16_t* traj_visits, float* traj_root_q,
                     uint8_t* action_u8_out, int64_t n_games, void* stream);
 
+/* ------------------------------------------------------------------ episode post-processing ---
+ * The tail of Muzero._play_game (Muzero.py:189-205) and Buffer.add (buffer.py:47-83) on the device.
+ * Episode store: struct-of-arrays [t_max][n_games], slot = the game's own step counter (the counter
+ * bits of its env word before the move), so slots [0, ep_len[g]) hold game g's current episode:
+ *   ep_state u32 env word before the move | ep_action u8 | ep_flags u8 HMZ_FLAG_* of the move (the
+ *   reward 0 / 100 / -0.1 is a function of them) | ep_visits u16[6] | ep_root_q f64 (root_node.Q).
+ */
+/* The episode lists of one move (Muzero.py:179-183) for every game; cur_slot[g] <- slot written. */
+int hmz_episode_record(const uint32_t* words, const int32_t* action, const int32_t* visits, const double* root_q, int n_disks,
+                       int t_max, int64_t n_games, uint32_t* ep_state, uint8_t* ep_action, uint16_t* ep_visits,
+                       double* ep_root_q, int32_t* cur_slot, uint8_t* action_u8_out, void* stream);
+/* After hmz_env_step: the move's flags join its slot; ep_len[g] = episode length if the game just
+ * finished (HMZ_FLAG_DONE), else 0. */
+int hmz_episode_close(const uint8_t* flags, const int32_t* cur_slot, int64_t n_games, uint8_t* ep_flags, int32_t* ep_len,
+                      void* stream);
+/* compute_n_step_returns (utils.py:28-72) and the priorities |f32(return) - f32(rootQ)|
+ * (Muzero.py:197-200) of every finished episode (ep_len[g] > 0): returns float64 / priority float32
+ * [t_max][n_games].  discount_pow[i] = discount ** i for i in [0, n_step], computed by the HOST libm
+ * as the reference does; the discounted reward sum reproduces CPython's compensated float sum(). */
+int hmz_episode_returns(const uint8_t* ep_flags, const double* ep_root_q, const int32_t* ep_len, int64_t n_games, int t_max,
+                        const double* discount_pow, int n_step, double* returns, float* priority, void* stream);
+/* Replay rows of the finished episodes: row_base[g] = ptr + exclusive prefix sum of the stored lengths
+ * (or -1), *total_out = rows to add.  only_solved != 0 keeps an episode only if returns[-1] > 0
+ * (training_loop, Muzero.py:98). */
+int hmz_episode_rows(const int32_t* ep_len, const double* returns, int64_t n_games, int64_t ptr, int only_solved,
+                     int64_t* row_base, int64_t* total_out, void* stream);
+/* organise_transitions (Muzero.py:276-323) written as Buffer.add (buffer.py:47-83) into a replay ring
+ * of `capacity` rows with buffer.py's arrays (:29-39): states f32[3N], rwds f32[unroll], actions
+ * i64[unroll], pi f32[unroll][6], returns f32[unroll], priority f32.  Step t of game g lands in row
+ * (row_base[g] + t) % capacity; beyond the episode end the padding is reward 0, return 0, the uniform
+ * policy and absorbing_action[g] (the reference draws ONE np.random.randint per episode, :300-303). */
+int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const uint8_t* ep_flags, const uint16_t* ep_visits,
+                       const double* returns, const float* priority, const int32_t* ep_len, const int64_t* row_base,
+                       const uint8_t* absorbing_action, int64_t n_games, int t_max, int n_disks, int unroll, double temperature,
+                       int64_t capacity, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
+                       float* buf_returns, float* buf_priority, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

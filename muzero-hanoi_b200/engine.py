@@ -372,7 +372,7 @@ class SelfPlay:
     records land in a [ring_slots, B] struct-of-arrays ring that `gather` all-gathers over NCCL."""
 
     def __init__(self, N, max_steps, B, n_simulations, weights: PackedWeights, discount=0.8, alpha=0.25, eps=0.25,
-                 temperature=1.0, seed=0, ring_slots=8, device="cuda", latent_dtype=_lib.LATENT_F32):
+                 temperature=1.0, seed=0, ring_slots=8, device="cuda", latent_dtype=_lib.LATENT_F32, episodes=False):
         self.env = VecHanoi(N, max_steps, B, device)
         self.mcts = BatchedMCTS(discount, alpha, n_simulations, B, device, eps, latent_dtype)
         self.weights, self.temperature, self.seed = weights, float(temperature), int(seed)
@@ -391,6 +391,13 @@ class SelfPlay:
         self.traj_visits = torch.zeros(self.T, B, 6, dtype=torch.int16, device=dev)
         self.traj_root_q = torch.zeros(self.T, B, dtype=torch.float32, device=dev)
         self.moves_done = 0
+        # episodes=True additionally keeps whole episodes (slot = the game's own step counter) for the
+        # device-side post-processing of replay.EpisodeStore / ReplayRing
+        self.episodes = None
+        if episodes:
+            from .replay import EpisodeStore
+
+            self.episodes = EpisodeStore(B, max_steps, N, device)
         self.env.reset()
 
     def move(self):
@@ -414,14 +421,18 @@ class SelfPlay:
         check(lib.hmz_traj_record(ptr(env.words), ptr(m.action), ptr(m.visits), ptr(m.root_q), ptr(self.traj_state[t]),
                                   ptr(self.traj_action[t]), ptr(self.traj_visits[t]), ptr(self.traj_root_q[t]),
                                   ptr(self.action_u8), self.B, stream))
+        if self.episodes is not None:
+            self.episodes.record(env.words, m.action, m.visits, m.root_q)
         check(lib.hmz_env_step(ptr(env.words), ptr(self.action_u8), ptr(self.traj_reward[t]), ptr(self.traj_flags[t]),
                                None, self.B, env.discs, env.max_steps, env.goal_peg, 1, env.reset_word, stream))
+        if self.episodes is not None:
+            self.episodes.close(self.traj_flags[t])
         self.moves_done += 1
         return t
 
     def launches_per_move(self):
         use_noise = self.mcts.root_dirichlet_alpha > 0.0 and self.mcts.root_exploration_eps > 0.0
-        return 3 * self.S + 6 + int(use_noise)
+        return 3 * self.S + 6 + int(use_noise) + (2 if self.episodes is not None else 0)
 
     def record_bytes_per_game(self):
         return 4 + 1 + 4 + 1 + 12 + 4  # state, action, reward, flags, visits, root_q
