@@ -327,6 +327,15 @@ int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const
                        int64_t capacity, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
                        float* buf_returns, float* buf_priority, void* stream);
 
+/* ------------------------------------------------------------------ acting evaluation ------
+ * acting_ablations.get_results (acting_experiments/acting_ablations.py:72-128) for parallel episodes.
+ * hmz_eval_track, after the env step of move `move_index`: steps[g] <- move_index + 1 when game g's
+ * FIRST episode finishes (0 while it runs), illegal_moves[g] counts its illegal moves
+ * (illegal_move_rate_comparison.py:27-50).  hmz_eval_errors: errors[g] = steps[g] - min_moves[g]
+ * (the hanoi_solver distance of the start state, :96-123), -1 for unfinished games. */
+int hmz_eval_track(const uint8_t* flags, int move_index, int64_t n_games, int32_t* steps, int32_t* illegal_moves, void* stream);
+int hmz_eval_errors(const int32_t* steps, const uint32_t* min_moves, int64_t n_games, int32_t* errors, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -274,3 +274,46 @@ int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const
 }
 
 }  // extern "C"
+
+// ---- acting evaluation (acting_experiments/acting_ablations.py:72-128) --------------------------
+// Per game: the length of its FIRST episode (`step` when `done` first turns true, :104-123) and the
+// number of illegal moves in it (illegal_move_rate_comparison.py:27-50).  steps[g] == 0 means the
+// first episode is still running.
+namespace hmz {
+__global__ void __launch_bounds__(256) eval_track(const uint8_t* __restrict__ flags, int move_index, int64_t n,
+                                                 int32_t* __restrict__ steps, int32_t* __restrict__ illegal_moves) {
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
+    if (steps[g] != 0) continue;
+    const uint8_t f = flags[g];
+    if (f & HMZ_FLAG_ILLEGAL) illegal_moves[g] += 1;
+    if (f & HMZ_FLAG_DONE) steps[g] = move_index + 1;
+  }
+}
+// errors[g] = steps[g] - hanoi_solver(start state) (acting_ablations.py:96-123); -1 while unfinished
+__global__ void __launch_bounds__(256) eval_errors(const int32_t* __restrict__ steps, const uint32_t* __restrict__ min_moves,
+                                                  int64_t n, int32_t* __restrict__ errors) {
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x)
+    errors[g] = steps[g] > 0 ? steps[g] - (int32_t)min_moves[g] : -1;
+}
+}  // namespace hmz
+
+extern "C" {
+
+int hmz_eval_track(const uint8_t* flags, int move_index, int64_t n_games, int32_t* steps, int32_t* illegal_moves, void* stream) {
+  hmz::ProfScope prof_scope(HMZ_PROF_OTHER, stream);
+  if (n_games == 0) return HMZ_OK;
+  if (!flags || !steps || !illegal_moves || n_games < 0 || move_index < 0)
+    return hmz::fail(HMZ_ERR_INVALID, "hmz_eval_track: bad arguments");
+  hmz::eval_track<<<hmz::grid_for(n_games, 256, 8), 256, 0, (cudaStream_t)stream>>>(flags, move_index, n_games, steps, illegal_moves);
+  return hmz::check_launch("eval_track");
+}
+
+int hmz_eval_errors(const int32_t* steps, const uint32_t* min_moves, int64_t n_games, int32_t* errors, void* stream) {
+  hmz::ProfScope prof_scope(HMZ_PROF_OTHER, stream);
+  if (n_games == 0) return HMZ_OK;
+  if (!steps || !min_moves || !errors || n_games < 0) return hmz::fail(HMZ_ERR_INVALID, "hmz_eval_errors: bad arguments");
+  hmz::eval_errors<<<hmz::grid_for(n_games, 256, 8), 256, 0, (cudaStream_t)stream>>>(steps, min_moves, n_games, errors);
+  return hmz::check_launch("eval_errors");
+}
+
+}  // extern "C"
