@@ -363,9 +363,12 @@ int hmz_net_initial(const void* weights, int mode, int n_disks, const uint32_t* 
   if (!weights || (!words && !obs) || !latents_out || !p0 || !v0 || n < 0 || n_disks < 1 || n_disks > HMZ_MAX_DISKS ||
       out_rows_per_item < 1 || (latent_dtype != HMZ_LATENT_F32 && latent_dtype != HMZ_LATENT_BF16))
     return fail(HMZ_ERR_INVALID, "hmz_net_initial: bad arguments");
-  // The root inference runs once per move (1/S of the work): both modes use the float32 blob
-  // section for it; HMZ_MODE_BF16 blobs embed a float32 copy at their head.
+  // HMZ_MODE_BF16 blobs embed a float32 copy of the weights behind the tensor-core section.
   if (mode != HMZ_MODE_FP32 && mode != HMZ_MODE_BF16) return fail(HMZ_ERR_INVALID, "hmz_net_initial: unknown mode %d", mode);
+  // throughput mode with packed env words: the tcgen05 kernel (bf16 representation + policy + value);
+  // float observations (drop-in B = 1 views, arbitrary input vectors) keep the float32 kernel below
+  if (mode == HMZ_MODE_BF16 && words != nullptr)
+    return tc_net_initial(weights, n_disks, words, latents_out, out_rows_per_item, latent_dtype, p0, v0, n, (cudaStream_t)stream);
   if (int rc = ensure_smem_optin()) return rc;
   const unsigned grid = (unsigned)((n + kRows - 1) / kRows);
   const float* w32 = mode == HMZ_MODE_BF16

@@ -46,6 +46,8 @@ int64_t tc_packed_bytes(int n_disks);
 int64_t tc_fp32_offset_bytes();
 int tc_debug_read_timeline(unsigned long long* host_out);
 void tc_pack(const float* const* tensors, int n_disks, void* out);
+int tc_net_initial(const void* weights, int n_disks, const uint32_t* words, void* lat_out, int64_t out_rows_per_item,
+                   int latent_dtype, float* p0, float* v0, int64_t n, cudaStream_t stream);
 int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
                      const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row,
                      int latent_dtype, float* r, float* p, float* v, int64_t n, cudaStream_t stream);

@@ -1,26 +1,22 @@
-// MuZeroNet recurrent inference on the 5th-generation tensor cores (HMZ_MODE_BF16).
+// MuZeroNet inference on the 5th-generation tensor cores (HMZ_MODE_BF16): recurrent_inference
+// (networks.py:96-116: dynamics :129-138, prediction :140-150) and initial_inference (:71-94:
+// represent :124-127, prediction), both with the support transform (:152-189) and normalize_h_state
+// (:191-196), as ONE persistent kernel template.
 //
-// One CTA = 128 searches = one UMMA M=128 tile (cta_group::1).  The whole g + f chain of
-// networks.py:96-116 (dynamics :129-138, prediction :140-150, support transform :152-189,
-// normalize_h_state :191-196) runs inside the CTA:
+// One CTA pass = two tiles of 128 rows (UMMA M = 128, cta_group::1), ping-ponged; per tile and network
+//   first layer   H[0:256) = [A | AX] x [W1 | W1_action, b1]^T    tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM)
+//                 A  = input latent / one-hot observation / new latent tile in shared memory (K-major, SWIZZLE_128B)
+//                 AX = [onehot(action) (6), 1, 0 x 9] per row (K = 16): every bias and the one-hot action columns
+//                      of dynamic_net.0 ride in this extra MMA step, so no epilogue does bias arithmetic
+//   epilogue      tcgen05.ld -> relu + bf16 (one cvt.rn.relu.bf16x2 per pair) -> tcgen05.st IN PLACE: the hidden
+//                 activations never leave TMEM
+//   second layer  O = [A1 | AX] x [W2 | b2]^T with A1 taken from TMEM (the .ts form of tcgen05.mma)
+//   latent        min-max normalised in registers -> raw / normalised bf16 tiles (the heads' A operands) + HBM
+//   heads         softmax expectation over the 33-bin support + signed parabolic, policy softmax, in registers
 //
-//   gather parent latents -> smem A0 (bf16, K-major, SWIZZLE_128B); AX = [onehot(action), 1, 0..] (K = 16)
-//   D[0:256)   = [A0 | AX] x [Wg1 | Wg1_action, b1]^T   tcgen05.mma kind::f16, accumulators in TMEM
-//   A1         = relu(D)  (tcgen05.ld -> regs -> packed bf16 relu -> smem)
-//   D[256:320) = [A1 | AX] x [Wg2 | b2]^T  -> raw latent, min-max normalised -> A_raw, A_hn (smem) + HBM
-//   reward / policy / value heads: D[0:256) = [A_{raw|hn} | AX] x W1'^T -> relu -> A1 -> D[256:..) = [A1 | AX] x W2'^T
-//   softmax-expectation + signed-parabolic epilogues in registers
-// Every bias (and the one-hot action columns of dynamic_net.0) rides in the extra K = 16 step, so the
-// epilogues do no bias arithmetic at all.
-//
-// Weights (216 KB bf16, pre-swizzled into the exact shared-memory image by hmz_weights_pack) are
-// streamed from L2 per layer with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
-// into two 32 KB buffers; every copy is issued as soon as the MMAs that read the buffer's previous
-// content have committed, so it overlaps the epilogue of the current layer.
-//
-// 13 warps: 8 hidden-epilogue warps (thread -> row t & 127, column half t >> 7), 4 small-epilogue
-// warps (latent normalisation and the head outputs) and one control warp whose elected lane issues
-// every TMA copy and every tcgen05.mma; all hand-offs are mbarriers.
+// Weights (pre-swizzled by hmz_weights_pack into the exact shared-memory image, with the extra slice
+// appended) are streamed from L2 per layer with 1-D TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx) by a loader warp into double-buffered slots that BOTH tiles consume.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -31,8 +27,6 @@ namespace hmz {
 
 namespace tc {
 constexpr int kM = 128;          // rows per CTA / UMMA M
-constexpr int kHiddenThreads = 256, kSmallThreads = 128;
-constexpr int kThreads = kHiddenThreads + kSmallThreads + 32;  // + control warp
 constexpr uint32_t kAtomA = kM * 128;  // one K-atom (64 bf16) of a 128-row A tile: 16 KB
 
 // A weight matrix [n_out][K] is stored as K/64 SWIZZLE_128B K-atoms of [n_out][128 B] followed by the
@@ -46,9 +40,10 @@ constexpr uint32_t kBytesW48 = w_bytes(48, 4);   // 26112
 constexpr uint32_t kBytesW16 = w_bytes(16, 4);   // 8704
 // byte offsets inside the tensor-core section of the weight blob (all multiples of 1024)
 constexpr uint32_t kWg1 = 0, kWg2 = 40960, kWr1 = 75776, kWr2 = 116736, kWp1 = 142848 + 1024 - 512, kWp2 = kWp1 + 40960,
-                   kWv1 = kWp2 + 9216, kWv2 = kWv1 + 40960, kSectionBytes = kWv2 + 26112 + 512;
+                   kWv1 = kWp2 + 9216, kWv2 = kWv1 + 40960, kWh1 = kWv2 + 26112 + 512, kWh2 = kWh1 + 40960,
+                   kSectionBytes = kWh2 + 34816;  // kWh*: representation_net (root inference)
 static_assert(kWg2 % 1024 == 0 && kWr1 % 1024 == 0 && kWr2 % 1024 == 0 && kWp1 % 1024 == 0 && kWp2 % 1024 == 0 &&
-                  kWv1 % 1024 == 0 && kWv2 % 1024 == 0,
+                  kWv1 % 1024 == 0 && kWv2 % 1024 == 0 && kWh1 % 1024 == 0 && kWh2 % 1024 == 0,
               "weight blocks must be 1024-byte aligned for SWIZZLE_128B");
 static_assert(kWr1 >= kWg2 + kBytesWg2 && kWr2 >= kWr1 + kBytesW1 && kWp1 >= kWr2 + kBytesW48 && kWp2 >= kWp1 + kBytesW1 &&
                   kWv1 >= kWp2 + kBytesW16 && kWv2 >= kWv1 + kBytesW1,
@@ -57,25 +52,6 @@ constexpr int kBiasK = 6;  // column of the extra slice that multiplies the cons
 
 // Debug timeline: block 0 records clock64() at phase boundaries when HMZ_TC_TIMELINE=1 (tools only).
 __device__ unsigned long long g_timeline[96];
-#define TL(slot) do { if (timeline && blockIdx.x == 0) g_timeline[slot] = clock64(); } while (0)
-
-struct __align__(1024) Smem {
-  uint8_t a0[kAtomA];       // input latent tile, later the raw (un-normalised) new latent
-  uint8_t ahn[kAtomA];      // normalised new latent
-  uint8_t a1[4 * kAtomA];   // hidden activations, 4 K-atoms
-  uint8_t wf[kBytesW1];     // first-layer weights of the running MLP (+ extra slice)
-  uint8_t ws[35840];        // second-layer weights of the running MLP (+ extra slice)
-  uint8_t ax[kM * 32];      // extra A slice: [onehot(action) (6), 1, 0 x 9] per row, core-matrix layout
-  uint64_t bar_wf, bar_ws;  // TMA landed (tx-count barriers)
-  uint64_t bar_g;           // gather done: A0 and AX written (384 arrivals)
-  uint64_t bar_a[2];        // column half h of the next A1 written by the hidden warps (128 arrivals)
-  uint64_t bar_d[2];        // hidden accumulator columns [128h, 128h+128) complete (tcgen05.commit)
-  uint64_t bar_s;           // second-layer (small) accumulator complete
-  uint64_t bar_lat;         // raw + normalised latent tiles written by the hidden warps (256 arrivals)
-  uint64_t bar_fin;         // small accumulator consumed by its epilogue (128 arrivals)
-  uint32_t tmem_base;
-  float2 row_minmax[2][kM];  // per-row (min, max) of each 32-column half of the raw latent
-};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -159,48 +135,6 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a_desc, uint64_t 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem_d .. +n) (+)= A x B^T over the SWIZZLE_128B K-atoms [KA0, KA1): A atoms 16 KB apart, B atoms
-// b_atom_stride bytes apart.  The descriptors of successive K-steps differ only in the 14-bit start
-// address field, so each step is one 32-bit add per operand on a base descriptor (the control lane is
-// a single thread: every instruction it executes sits on the critical path).
-template <int KA0, int KA1>
-__device__ __forceinline__ void issue_atoms(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t b_atom_stride,
-                                            uint32_t idesc, bool clear_first) {
-  const uint64_t a_base = desc_sw128(a_addr), b_base = desc_sw128(b_addr);
-#pragma unroll
-  for (int ka = KA0; ka < KA1; ++ka)
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
-      umma(tmem_d, a_base + (uint64_t)((ka * kAtomA + kk * 32) >> 4), b_base + (uint64_t)((ka * b_atom_stride + kk * 32) >> 4),
-           idesc, (clear_first && ka == KA0 && kk == 0) ? 0u : 1u);
-}
-// First layer of an MLP as two N = 128 halves, half 0 first: its epilogue then runs while the tensor
-// core produces half 1 (issuing the halves interleaved was measured slower — both epilogues then
-// start together and fight for the same ALU pipes).
-__device__ __forceinline__ void issue_first_layer(uint32_t tmem, uint32_t a_addr, uint32_t ax_addr, uint32_t wf_addr,
-                                                  uint32_t idesc128, uint64_t* bar_d0, uint64_t* bar_d1) {
-  const uint64_t a_base = desc_sw128(a_addr), b0 = desc_sw128(wf_addr), b1 = desc_sw128(wf_addr + 128 * 128);
-  const uint64_t ax = desc_plain(ax_addr), bx0 = desc_plain(wf_addr + 256 * 128),
-                 bx1 = desc_plain(wf_addr + 256 * 128 + 4096);  // rows 128.. of the extra slice: (128 / 8) * 256 B
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) umma(tmem, a_base + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc128, kk ? 1u : 0u);
-  umma(tmem, ax, bx0, idesc128, 1u);
-  umma_commit(bar_d0);
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) umma(tmem + 128, a_base + (uint64_t)(kk * 2), b1 + (uint64_t)(kk * 2), idesc128, kk ? 1u : 0u);
-  umma(tmem + 128, ax, bx1, idesc128, 1u);
-  umma_commit(bar_d1);
-}
-
-// the extra K = 16 step: [onehot, 1] x [action columns, bias]
-__device__ __forceinline__ void issue_extra(uint32_t tmem_d, uint32_t ax_addr, uint32_t bx_addr, uint32_t idesc) {
-  umma(tmem_d, desc_plain(ax_addr), desc_plain(bx_addr), idesc, 1u);
-}
-
-__device__ __forceinline__ void issue_extra_first(uint32_t tmem_d, uint32_t ax_addr, uint32_t bx_addr, uint32_t idesc) {
-  umma(tmem_d, desc_plain(ax_addr), desc_plain(bx_addr), idesc, 0u);  // clears the accumulator
-}
-
 // 32 lanes x 32 consecutive columns of TMEM -> 32 registers per thread (thread = lane = row).
 // Issue and wait are separate so that the next chunk's load overlaps the current chunk's math; the
 // wait names the destination registers as in/out operands so no use can be scheduled above it.
@@ -269,379 +203,6 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
 }
 // 16-byte chunk `chunk` (8 bf16) of row `row` inside a [rows][128 B] SWIZZLE_128B K-atom
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
-
-// ReLU + bf16 of 32 accumulator columns starting at hidden column n0, stored into A1 (bias already in D)
-__device__ __forceinline__ void hidden_chunk(Smem& s, const uint32_t (&acc)[32], int row, int n0) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) pk[j] = relu_bf16x2(pack_bf16(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])));
-  uint8_t* atom = s.a1 + (n0 >> 6) * kAtomA;
-  const int c0 = (n0 & 63) >> 3;
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    *reinterpret_cast<uint4*>(atom + sw128(row, c0 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-}
-
-// Hidden-layer epilogue: D[128*half .. +128) -> relu -> bf16 -> A1 atoms 2*half, 2*half+1.
-// The TMEM load of chunk c+1 is in flight while chunk c is converted.
-__device__ __forceinline__ void hidden_epilogue(Smem& s, uint32_t tmem_row, int row, int half) {
-  uint32_t va[32], vb[32];
-  const int n0 = half * 128;
-  tmem_ld32_issue(tmem_row + n0, va);
-  tmem_ld_wait(va);
-  tmem_ld32_issue(tmem_row + n0 + 32, vb);
-  hidden_chunk(s, va, row, n0);
-  tmem_ld_wait(vb);
-  tmem_ld32_issue(tmem_row + n0 + 64, va);
-  hidden_chunk(s, vb, row, n0 + 32);
-  tmem_ld_wait(va);
-  tmem_ld32_issue(tmem_row + n0 + 96, vb);
-  hidden_chunk(s, va, row, n0 + 64);
-  tmem_ld_wait(vb);
-  hidden_chunk(s, vb, row, n0 + 96);
-}
-
-// softmax expectation over the 33 support logits in D[256:304) + signed parabolic (networks.py:152-189)
-__device__ __forceinline__ float support_epilogue(uint32_t tmem_row) {
-  float a[32], b[16];
-  tmem_ld32(tmem_row + 256, a);
-  tmem_ld16(tmem_row + 288, b);
-  float mx = b[0];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) mx = fmaxf(mx, a[i]);
-  float den = 0.f, num = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float e = exp2f((a[i] - mx) * 1.4426950408889634f);
-    den += e;
-    num = fmaf(e, (float)(i - 16), num);
-  }
-  const float e = exp2f((b[0] - mx) * 1.4426950408889634f);
-  den += e;
-  num = fmaf(e, 16.f, num);
-  return signed_parabolic(__fdividef(num, den));
-}
-
-// Hand-offs (all mbarriers):
-//   bar_g     epilogue -> control : A0 and AX are in shared memory
-//   bar_d[h]  control  -> hidden  : hidden accumulator columns [128h, 128h+128) are complete
-//   bar_a[h]  hidden   -> control : A1 atoms 2h, 2h+1 written (and D[128h..) drained)
-//   bar_s     control  -> small + hidden: the second-layer accumulator D[256:..) is complete / A1 is free
-//   bar_lat / bar_fin   small -> control: latent tiles written / small accumulator drained
-// The MMA of one column half overlaps the epilogue of the other, the second-layer MMA starts as soon
-// as its first two K-atoms exist, and a head's outputs are reduced by the small warps while the
-// tensor core and the hidden warps already work on the next head.
-__global__ void __launch_bounds__(kThreads, 1)
-net_recurrent_tc_v3(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_t in_rows_per_item,
-                 const uint16_t* __restrict__ in_row, const uint8_t* __restrict__ actions, void* lat_out,
-                 int64_t out_rows_per_item, int64_t out_row, int latent_dtype, float* __restrict__ r_out,
-                 float* __restrict__ p_out, float* __restrict__ v_out, int64_t n, int timeline) {
-  extern __shared__ uint8_t smem_raw[];
-  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int64_t row0 = (int64_t)blockIdx.x * kM;
-
-  // The parent-latent gather is the longest single latency of the tile (HBM round trip): issue its
-  // loads first, let barrier init / TMEM allocation / the first weight copies run underneath.
-  // Coalescing: 8 consecutive lanes fetch the 8 16-byte chunks of one latent row, so a warp-wide
-  // load touches 4 rows = 4 lines (one thread per row would touch 32 lines per instruction and the
-  // L1 tag stage serves one line per cycle).
-  uint4 gathered[4];
-  int act_early = 0;
-  if (tid < kHiddenThreads) {
-    const int chunk = tid & 7;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = (tid >> 3) + 32 * i;
-      const int64_t it = (row0 + row) < n ? (row0 + row) : n - 1;
-      const int64_t irow = it * in_rows_per_item + (in_row ? (int64_t)in_row[it] : 0);
-      if (latent_dtype == HMZ_LATENT_F32) {
-        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(lat_in) + irow * kLatent + chunk * 8);
-        const float4 t0 = __ldcs(src), t1 = __ldcs(src + 1);  // streaming: do not displace the tree records in L2
-        gathered[i] = make_uint4(pack_bf16(t0.x, t0.y), pack_bf16(t0.z, t0.w), pack_bf16(t1.x, t1.y), pack_bf16(t1.z, t1.w));
-      } else {
-        gathered[i] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(lat_in) + irow * kLatent + chunk * 8));
-      }
-    }
-  } else if (tid < kHiddenThreads + kSmallThreads) {
-    const int64_t it = (row0 + tid - kHiddenThreads) < n ? (row0 + tid - kHiddenThreads) : n - 1;
-    act_early = actions[it];
-  }
-
-  if (tid == 0) {
-    mbar_init(&s.bar_wf, 1);
-    mbar_init(&s.bar_ws, 1);
-    mbar_init(&s.bar_g, kHiddenThreads + kSmallThreads);
-    mbar_init(&s.bar_a[0], 128);
-    mbar_init(&s.bar_a[1], 128);
-    mbar_init(&s.bar_d[0], 1);
-    mbar_init(&s.bar_d[1], 1);
-    mbar_init(&s.bar_s, 1);
-    mbar_init(&s.bar_lat, kHiddenThreads);
-    mbar_init(&s.bar_fin, kSmallThreads);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {  // TMEM: all 512 columns (one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = s.tmem_base;
-
-  if (warp == (kHiddenThreads + kSmallThreads) / 32) {
-    // ================================= control warp =================================
-    {
-      uint32_t ph_wf = 0, ph_ws = 0, ph_a = 0, ph_d = 0, ph_s = 0, ph_fin = 0;
-      const uint32_t a0 = smem_u32(s.a0), ahn = smem_u32(s.ahn), a1 = smem_u32(s.a1), ax = smem_u32(s.ax);
-      const uint32_t wf = smem_u32(s.wf), ws = smem_u32(s.ws);
-      const uint32_t id128 = umma_idesc(128), id64 = umma_idesc(64);
-      if (timeline && elect_one()) TL(0);
-      if (elect_one()) tma_load(s.wf, wsec + kWg1, kBytesW1, &s.bar_wf);
-      if (elect_one()) tma_load(s.ws, wsec + kWg2, kBytesWg2, &s.bar_ws);
-      // dynamics layer 1: D[0:256) = [A0 | AX] x Wg1'^T, issued as two N = 128 halves
-      mbar_wait(&s.bar_g, 0);
-      if (timeline && elect_one()) TL(1);
-      mbar_wait(&s.bar_wf, ph_wf);
-      ph_wf ^= 1;
-      if (timeline && elect_one()) TL(2);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_first_layer(tmem, a0, ax, wf, id128, &s.bar_d[0], &s.bar_d[1]);
-      }
-      __syncwarp();
-      if (timeline && elect_one()) TL(3);
-      mbar_wait(&s.bar_d[1], ph_d);
-      ph_d ^= 1;
-      if (timeline && elect_one()) TL(4);
-      if (elect_one()) tma_load(s.wf, wsec + kWr1, kBytesW1, &s.bar_wf);  // wf is free again: prefetch the reward head
-      // dynamics layer 2: D[256:320) = [A1 | AX] x Wg2'^T, K-atoms consumed as the hidden halves deliver them
-      mbar_wait(&s.bar_ws, ph_ws);
-      ph_ws ^= 1;
-      if (timeline && elect_one()) TL(5);
-      mbar_wait(&s.bar_a[0], ph_a);
-      if (timeline && elect_one()) TL(6);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_extra_first(tmem + 256, ax, ws + 64 * 128 * 4, id64);
-        issue_atoms<0, 2>(tmem + 256, a1, ws, 64 * 128, id64, false);
-      }
-      __syncwarp();
-      mbar_wait(&s.bar_a[1], ph_a);
-      ph_a ^= 1;
-      if (timeline && elect_one()) TL(7);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_atoms<2, 4>(tmem + 256, a1, ws, 64 * 128, id64, false);
-        umma_commit(&s.bar_s);
-      }
-      __syncwarp();
-      mbar_wait(&s.bar_s, ph_s);
-      ph_s ^= 1;
-      if (timeline && elect_one()) TL(8);
-      if (elect_one()) tma_load(s.ws, wsec + kWr2, kBytesW48, &s.bar_ws);
-      mbar_wait(&s.bar_lat, 0);  // raw + normalised latent tiles are in shared memory, D[256:320) drained
-      if (timeline && elect_one()) TL(9);
-#pragma unroll 1
-      for (int head = 0; head < 3; ++head) {
-        const uint32_t a_in = head == 0 ? a0 : ahn;
-        const uint32_t n2 = head == 1 ? 16u : 48u;
-        const uint32_t id2 = umma_idesc(n2);
-        mbar_wait(&s.bar_wf, ph_wf);
-        ph_wf ^= 1;
-        if (timeline && elect_one()) TL(10 + head * 6);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_first_layer(tmem, a_in, ax, wf, id128, &s.bar_d[0], &s.bar_d[1]);
-        }
-        __syncwarp();
-        mbar_wait(&s.bar_d[1], ph_d);
-        ph_d ^= 1;
-        if (timeline && elect_one()) TL(11 + head * 6);
-        if (head < 2 && elect_one()) tma_load(s.wf, wsec + (head == 0 ? kWp1 : kWv1), kBytesW1, &s.bar_wf);
-        mbar_wait(&s.bar_ws, ph_ws);
-        ph_ws ^= 1;
-        if (timeline && elect_one()) TL(12 + head * 6);
-        if (head > 0) {  // D[256:..) must have been drained by the previous head's output epilogue
-          mbar_wait(&s.bar_fin, ph_fin);
-          ph_fin ^= 1;
-        }
-        mbar_wait(&s.bar_a[0], ph_a);
-        if (timeline && elect_one()) TL(13 + head * 6);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_extra_first(tmem + 256, ax, ws + n2 * 128 * 4, id2);
-          issue_atoms<0, 2>(tmem + 256, a1, ws, n2 * 128, id2, false);
-        }
-        __syncwarp();
-        mbar_wait(&s.bar_a[1], ph_a);
-        ph_a ^= 1;
-        if (timeline && elect_one()) TL(14 + head * 6);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_atoms<2, 4>(tmem + 256, a1, ws, n2 * 128, id2, false);
-          umma_commit(&s.bar_s);
-        }
-        __syncwarp();
-        mbar_wait(&s.bar_s, ph_s);
-        ph_s ^= 1;
-        if (timeline && elect_one()) TL(15 + head * 6);
-        if (head < 2 && elect_one()) tma_load(s.ws, wsec + (head == 0 ? kWp2 : kWv2), head == 0 ? kBytesW16 : kBytesW48, &s.bar_ws);
-      }
-    }
-  } else if (tid < kHiddenThreads) {
-    // ============================== hidden-epilogue warps ==============================
-    const int row = tid & 127, half = tid >> 7;
-    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lane quarter
-    const int64_t item = row0 + row;
-    uint32_t ph_d = 0, ph_s = 0;
-    {  // parent latent (loaded at kernel entry) -> swizzled A0 tile
-#pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(s.a0 + sw128((tid >> 3) + 32 * i, tid & 7)) = gathered[i];
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(&s.bar_g);
-      if (tid == 0) TL(32);
-    }
-#pragma unroll 1
-    for (int layer = 0; layer < 4; ++layer) {  // dynamics, reward, policy, value hidden layers
-      mbar_wait(&s.bar_d[half], ph_d);
-      ph_d ^= 1;
-      tc_fence_after();
-      if (tid == 0) TL(33 + layer * 3);
-      // A1 is rewritten here: its last reader (the previous second-layer MMA) has completed — this
-      // thread observed bar_s for it at the end of the previous iteration.
-      hidden_epilogue(s, tmem_row, row, half);
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&s.bar_a[half]);
-      if (tid == 0) TL(34 + layer * 3);
-      mbar_wait(&s.bar_s, ph_s);
-      ph_s ^= 1;
-      if (tid == 0) TL(35 + layer * 3);
-      if (layer == 0) {
-        // ---- new latent: normalize_h_state (networks.py:191-196) and its three copies; thread
-        // (row, half) owns latent columns [32*half, 32*half + 32), the row's two threads exchange
-        // their partial (min, max) through shared memory and a 64-thread named barrier per lane quarter.
-        tc_fence_after();
-        float raw[32];
-        tmem_ld32(tmem_row + 256 + half * 32, raw);
-        if (tid == 0) TL(56);
-        float mn4[4], mx4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mn4[i] = mx4[i] = raw[i];
-#pragma unroll
-        for (int i = 4; i < 32; ++i) {
-          mn4[i & 3] = fminf(mn4[i & 3], raw[i]);
-          mx4[i & 3] = fmaxf(mx4[i & 3], raw[i]);
-        }
-        s.row_minmax[half][row] = make_float2(fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3])),
-                                              fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
-        if (tid == 0) TL(57);
-        const float2 m0 = s.row_minmax[0][row], m1 = s.row_minmax[1][row];
-        const float mn = fminf(m0.x, m1.x), mx = fmaxf(m0.y, m1.y);
-        const float inv = 1.0f / ((mx - mn) + 1e-8f);
-        const int64_t orow = item * out_rows_per_item + out_row;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float hn[8];
-          uint32_t pr[4], ph[4];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) hn[j] = (raw[c * 8 + j] - mn) * inv;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            pr[j] = pack_bf16(raw[c * 8 + 2 * j], raw[c * 8 + 2 * j + 1]);
-            ph[j] = pack_bf16(hn[2 * j], hn[2 * j + 1]);
-          }
-          *reinterpret_cast<uint4*>(s.a0 + sw128(row, half * 4 + c)) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-          *reinterpret_cast<uint4*>(s.ahn + sw128(row, half * 4 + c)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          if (latent_dtype == HMZ_LATENT_F32 && item < n) {  // float32 store keeps the per-row form (parity-mode stores)
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(lat_out) + orow * kLatent + half * 32 + c * 8);
-            __stcs(dst, make_float4(hn[0], hn[1], hn[2], hn[3]));
-            __stcs(dst + 1, make_float4(hn[4], hn[5], hn[6], hn[7]));
-          }
-        }
-        if (latent_dtype != HMZ_LATENT_F32) {
-          // bf16 rows leave through the normalised tile in shared memory so that 8 consecutive lanes
-          // write one 128-byte row: the two warps of a lane quarter copy out 16 rows each.
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
-          const int lane = tid & 31, chunk = lane & 7;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r2 = (warp & 3) * 32 + half * 16 + i * 4 + (lane >> 3);
-            const int64_t it2 = row0 + r2;
-            const uint4 val = *reinterpret_cast<const uint4*>(s.ahn + sw128(r2, chunk));
-            if (it2 < n)
-              __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(lat_out) + (it2 * out_rows_per_item + out_row) * kLatent + chunk * 8), val);
-          }
-        }
-        if (tid == 0) TL(58);
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&s.bar_lat);
-        if (tid == 0) TL(49);
-      }
-    }
-  } else {
-    // ============================== small-epilogue warps ==============================
-    const int row = tid - kHiddenThreads;
-    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int64_t item = row0 + row;
-    uint32_t ph_s = 0;
-    {  // the extra A slice of this row: one-hot(action) at k = 0..5, the constant 1 at k = 6
-      const int act = act_early < kActions ? act_early : kActions - 1;
-      uint32_t w[4] = {0u, 0u, 0u, 0x3F80u};  // k = 6 -> 1.0 (bf16 0x3F80), k = 7 -> 0
-      w[act >> 1] |= 0x3F80u << ((act & 1) * 16);
-      *reinterpret_cast<uint4*>(s.ax + plain_off(row, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<uint4*>(s.ax + plain_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
-      fence_proxy_async();
-      mbar_arrive(&s.bar_g);
-    }
-    mbar_wait(&s.bar_s, ph_s);  // dynamics layer 2: consumed by the hidden warps (latent epilogue)
-    ph_s ^= 1;
-    // ---- head outputs
-#pragma unroll 1
-    for (int head = 0; head < 3; ++head) {
-      mbar_wait(&s.bar_s, ph_s);
-      ph_s ^= 1;
-      tc_fence_after();
-      if (row == 0) TL(50 + head * 2);
-      if (head == 1) {  // F.softmax(pi_logits) (networks.py:109)
-        float lg[16];
-        tmem_ld16(tmem_row + 256, lg);
-        float mx = lg[0], den = 0.f;
-#pragma unroll
-        for (int a = 1; a < kActions; ++a) mx = fmaxf(mx, lg[a]);
-#pragma unroll
-        for (int a = 0; a < kActions; ++a) {
-          lg[a] = exp2f((lg[a] - mx) * 1.4426950408889634f);
-          den += lg[a];
-        }
-        const float inv = 1.0f / den;
-        if (item < n) {
-#pragma unroll
-          for (int a = 0; a < kActions; ++a) p_out[item * kActions + a] = lg[a] * inv;
-        }
-      } else {
-        const float x = support_epilogue(tmem_row);
-        if (item < n) (head == 0 ? r_out : v_out)[item] = x;
-      }
-      tc_fence_before();
-      if (head < 2) mbar_arrive(&s.bar_fin);
-      if (row == 0) TL(51 + head * 2);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (tid == 0) TL(63);
-  if (warp == 0) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-  }
-}
 
 // =====================================================================================
 // net_recurrent_tc (v4): two 128-search tiles per CTA pass, ping-ponged.
@@ -755,11 +316,16 @@ __device__ __forceinline__ void hidden_epilogue_tmem(uint32_t h) {
 
 #define TL4(slot) do { if (timeline && blockIdx.x == 0 && pass == 0) g_timeline[slot] = clock64(); } while (0)
 
+// kInitial = false: recurrent_inference — networks dynamics (g), reward, policy, value; input = gathered latents.
+// kInitial = true : initial_inference  — networks representation (h), policy, value; input = one-hot of env words.
+// The network index `net` keeps the recurrent numbering (0 = g / h, 1 = reward, 2 = policy, 3 = value);
+// the root inference simply skips net 1.
+template <bool kInitial>
 __global__ void __launch_bounds__(kThreads, 1)
-net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_t in_rows_per_item,
-                 const uint16_t* __restrict__ in_row, const uint8_t* __restrict__ actions, void* lat_out,
-                 int64_t out_rows_per_item, int64_t out_row, int latent_dtype, float* __restrict__ r_out,
-                 float* __restrict__ p_out, float* __restrict__ v_out, int64_t n, int n_pairs, int timeline) {
+net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_t in_rows_per_item,
+       const uint16_t* __restrict__ in_row, const uint8_t* __restrict__ actions, const uint32_t* __restrict__ words, int n_disks,
+       void* lat_out, int64_t out_rows_per_item, int64_t out_row, int latent_dtype, float* __restrict__ r_out,
+       float* __restrict__ p_out, float* __restrict__ v_out, int64_t n, int n_pairs, int timeline) {
   extern __shared__ uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -803,10 +369,12 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {
+        if (kInitial && (i >> 1) == 1) continue;  // no reward head at the root
         const int kind = i & 1;
         const uint32_t u = use[kind], slot = u & 1u;
         if (u >= 2u) mbar_wait(&s.bar_wfree[kind][slot], ((u >> 1) - 1u) & 1u);
-        if (elect_one()) tma_load(kind ? s.ws[slot] : s.wf[slot], wsec + c_block_off[i], c_block_bytes[i], &s.bar_wfull[kind][slot]);
+        const uint32_t off = (kInitial && i < 2) ? (i == 0 ? kWh1 : kWh2) : c_block_off[i];  // representation_net at the root
+        if (elect_one()) tma_load(kind ? s.ws[slot] : s.wf[slot], wsec + off, c_block_bytes[i], &s.bar_wfull[kind][slot]);
         __syncwarp();
         use[kind] = u + 1u;
       }
@@ -823,7 +391,8 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
     int ev = 0;
     for (int pass = 0, pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pass) {
 #pragma unroll 1
-      for (int net = 0; net < 4; ++net) {  // dynamics, reward, policy, value
+      for (int net = 0; net < 4; ++net) {  // dynamics / representation, reward, policy, value
+        if (kInitial && net == 1) continue;
         // ---- first layer: H[0:256) = [A | AX] x W1'^T
         {
           const uint32_t slot = use_f & 1u;
@@ -837,7 +406,9 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
             if (net == 0) mbar_wait(&s.bar_g[t], ph_g);
             if (net == 1) mbar_wait(&s.bar_raw[t], ph_raw);  // raw latent tile written, O copied out
             if (net == 2) mbar_wait(&s.bar_hn[t], ph_hn);    // normalised latent tile written
-            if (net != 1 && !(first && net == 0)) {  // O (inside H) must have been copied out by the output warps
+            // O (inside H) must have been copied out: by the output warps after a head, by the latent epilogue
+            // (bar_raw / bar_hn above) after the first network
+            if (net == 3 || (net == 2 && !kInitial) || (net == 0 && !first)) {
               mbar_wait(&s.bar_fin[t], ph_fin[t]);
               ph_fin[t] ^= 1;
             }
@@ -915,6 +486,17 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
         for (int i = 0; i < 4; ++i) {
           const int grow = (ltid >> 3) + 32 * i;
           const int64_t it = (row0 + grow) < n ? (row0 + grow) : n - 1;
+          if (kInitial) {  // utils.oneHot_encoding (utils.py:9-25) of the env word: columns 8 chunk .. 8 chunk + 7
+            const uint32_t w = words[it];
+            uint32_t v[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int col = chunk * 8 + j, d = col / 3;
+              if (col < 3 * n_disks && ((w >> (2 * d)) & 3u) == (uint32_t)(col - 3 * d)) v[j >> 1] |= 0x3F80u << ((j & 1) * 16);
+            }
+            gathered[i] = make_uint4(v[0], v[1], v[2], v[3]);
+            continue;
+          }
           const int64_t irow = it * in_rows_per_item + (in_row ? (int64_t)in_row[it] : 0);
           if (latent_dtype == HMZ_LATENT_F32) {
             const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(lat_in) + irow * kLatent + chunk * 8);
@@ -932,6 +514,7 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
       }
 #pragma unroll 1
       for (int layer = 0; layer < 4; ++layer) {
+        if (kInitial && layer == 1) continue;
         mbar_wait(&s.bar_d[t], ph_d);
         ph_d ^= 1;
         tc_fence_after();
@@ -1024,17 +607,20 @@ net_recurrent_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_
 #pragma unroll
       for (int t = 0; t < 2; ++t) {  // the extra A slice of this row: one-hot(action) at k = 0..5, the constant 1 at k = 6
         const int64_t item = ((int64_t)pair * 2 + t) * kM + row;
-        int act = actions[item < n ? item : n - 1];
-        act = act < kActions ? act : kActions - 1;
         uint32_t w[4] = {0u, 0u, 0u, 0x3F80u};  // k = 6 -> 1.0 (bf16 0x3F80), k = 7 -> 0
-        w[act >> 1] |= 0x3F80u << ((act & 1) * 16);
+        if (!kInitial) {
+          int act = actions[item < n ? item : n - 1];
+          act = act < kActions ? act : kActions - 1;
+          w[act >> 1] |= 0x3F80u << ((act & 1) * 16);
+        }
         *reinterpret_cast<uint4*>(s.t[t].ax + plain_off(row, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(s.t[t].ax + plain_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async();
         mbar_arrive(&s.bar_g[t]);
       }
 #pragma unroll 1
-      for (int head = 0; head < 3; ++head) {
+      for (int head = 0; head < 3; ++head) {  // reward, policy, value
+        if (kInitial && head == 0) continue;
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
           const int64_t item = ((int64_t)pair * 2 + t) * kM + row;
@@ -1159,6 +745,11 @@ void tc_pack(const float* const* t, int n_disks, void* out) {
   pack_extra(sec + kWg1 + 256 * 128, t[4], t[5], kHidden, in_g1, 256, kLatent, kActions);
   pack_kmajor_sw128(sec + kWg2, t[6], kLatent, kHidden, 64, 0, 4);
   pack_extra(sec + kWg2 + 64 * 128 * 4, t[6], t[7], kLatent, kHidden, 64, 0, 0);
+  // representation_net (root inference): Linear(3N, 256) on the one-hot observation padded to K = 64, Linear(256, 64)
+  pack_kmajor_sw128(sec + kWh1, t[0], kHidden, 3 * n_disks, 256, 0, 1);
+  pack_extra(sec + kWh1 + 256 * 128, t[0], t[1], kHidden, 3 * n_disks, 256, 0, 0);
+  pack_kmajor_sw128(sec + kWh2, t[2], kLatent, kHidden, 64, 0, 4);
+  pack_extra(sec + kWh2 + 64 * 128 * 4, t[2], t[3], kLatent, kHidden, 64, 0, 0);
   const struct { uint32_t w1, w2; int i; int out2, pad2; } heads[3] = {
       {kWr1, kWr2, 8, kSupport, 48}, {kWp1, kWp2, 12, kActions, 16}, {kWv1, kWv2, 16, kSupport, 48}};
   for (const auto& h : heads) {
@@ -1178,39 +769,51 @@ int tc_debug_read_timeline(unsigned long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, tc::g_timeline, sizeof(unsigned long long) * 96) == cudaSuccess ? HMZ_OK : HMZ_ERR_CUDA;
 }
 
-static int tc_use_v3() {
-  static const int on = getenv("HMZ_TC_V3") ? atoi(getenv("HMZ_TC_V3")) : 0;
-  return on;
+static int tc_prepare(int* smem_bytes) {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)");
+  *smem_bytes = (int)sizeof(tc::v4::Smem) + 1024;
+  if (done_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(tc::v4::net_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::v4::net_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem_bytes);
+    if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaFuncSetAttribute(net_tc): %s", cudaGetErrorString(e));
+    done_dev = dev;
+  }
+  return HMZ_OK;
+}
+
+static unsigned tc_grid(int64_t n, int* n_pairs) {
+  const int64_t pairs = (n + 2 * tc::kM - 1) / (2 * tc::kM);
+  const int sms = sm_count();
+  *n_pairs = (int)pairs;
+  return (unsigned)(pairs < sms ? pairs : sms);
 }
 
 int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
                      const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row,
                      int latent_dtype, float* r, float* p, float* v, int64_t n, cudaStream_t stream) {
-  static thread_local int done_dev = -1;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)");
-  const int smem_v3 = (int)sizeof(tc::Smem) + 1024, smem_v4 = (int)sizeof(tc::v4::Smem) + 1024;
-  if (done_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(tc::net_recurrent_tc_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v3);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::v4::net_recurrent_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v4);
-    if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaFuncSetAttribute(net_recurrent_tc): %s", cudaGetErrorString(e));
-    done_dev = dev;
-  }
-  if (tc_use_v3()) {
-    const unsigned grid = (unsigned)((n + tc::kM - 1) / tc::kM);
-    tc::net_recurrent_tc_v3<<<grid, tc::kThreads, smem_v3, stream>>>((const uint8_t*)weights, lat_in, in_rows_per_item, in_row,
-                                                                     actions, lat_out, out_rows_per_item, out_row,
-                                                                     latent_dtype, r, p, v, n, tc_timeline_enabled());
-    return check_launch("net_recurrent_tc_v3");
-  }
-  const int64_t n_pairs = (n + 2 * tc::kM - 1) / (2 * tc::kM);
-  const int sms = sm_count();
-  const unsigned grid = (unsigned)(n_pairs < sms ? n_pairs : sms);
-  cudaError_t e = launch_pdl(tc::v4::net_recurrent_tc, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem_v4, stream,
-                             (const uint8_t*)weights, lat_in, in_rows_per_item, in_row, actions, lat_out, out_rows_per_item, out_row,
-                             latent_dtype, r, p, v, n, (int)n_pairs, tc_timeline_enabled());
-  if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_recurrent_tc launch: %s", cudaGetErrorString(e));
-  return check_launch("net_recurrent_tc");
+  int smem = 0, n_pairs = 0;
+  if (int rc = tc_prepare(&smem)) return rc;
+  const unsigned grid = tc_grid(n, &n_pairs);
+  cudaError_t e = launch_pdl(tc::v4::net_tc<false>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream,
+                             (const uint8_t*)weights, lat_in, in_rows_per_item, in_row, actions, (const uint32_t*)nullptr, 0,
+                             lat_out, out_rows_per_item, out_row, latent_dtype, r, p, v, n, n_pairs, tc_timeline_enabled());
+  if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_tc<recurrent> launch: %s", cudaGetErrorString(e));
+  return check_launch("net_tc<recurrent>");
+}
+
+int tc_net_initial(const void* weights, int n_disks, const uint32_t* words, void* lat_out, int64_t out_rows_per_item,
+                   int latent_dtype, float* p0, float* v0, int64_t n, cudaStream_t stream) {
+  int smem = 0, n_pairs = 0;
+  if (int rc = tc_prepare(&smem)) return rc;
+  const unsigned grid = tc_grid(n, &n_pairs);
+  cudaError_t e = launch_pdl(tc::v4::net_tc<true>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream,
+                             (const uint8_t*)weights, (const void*)nullptr, (int64_t)1, (const uint16_t*)nullptr,
+                             (const uint8_t*)nullptr, words, n_disks, lat_out, out_rows_per_item, (int64_t)0, latent_dtype,
+                             (float*)nullptr, p0, v0, n, n_pairs, 0);
+  if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_tc<initial> launch: %s", cudaGetErrorString(e));
+  return check_launch("net_tc<initial>");
 }
 
 }  // namespace hmz

@@ -158,6 +158,29 @@ def test_recurrent_tcgen05_bf16_matches_reference(golden, n, count, latent_dtype
     assert np.all(np.abs(vv - g[f"n{n}_v"][idx]) <= BF16_TOL * np.maximum(1.0, np.abs(g[f"n{n}_v"][idx])))
 
 
+@pytest.mark.parametrize("n", [3, 5, 10])
+@pytest.mark.parametrize("latent_dtype", [0, 1])
+def test_initial_tcgen05_bf16_matches_reference(golden, n, latent_dtype):
+    """HMZ_MODE_BF16 root inference from packed env words (tcgen05 kernel, one-hot tile built on device):
+    h0, p0 within 2e-2 absolute, v0 within 2e-2 of max(1, |ref|)."""
+    from muzero_hanoi_b200.engine import VecHanoi
+
+    g = golden("net_io.npz")
+    count, E = 96, 3
+    w = _weights(n, int(g[f"n{n}_weight_seed"]), mode=1)
+    env = VecHanoi(n, 200, count)
+    env.set_state_indices(g[f"n{n}_state_idx"].astype(np.int32))
+    h = torch.zeros(count, E, 64, device="cuda", dtype=torch.bfloat16 if latent_dtype else torch.float32)
+    p0, v0 = torch.empty(count, 6, device="cuda"), torch.empty(count, device="cuda")
+    w.initial(count, words=env.words, latents_out=h, out_rows_per_item=E, latent_dtype=latent_dtype, p0=p0, v0=v0)
+    torch.cuda.synchronize()
+    hh = h.float().cpu().numpy()
+    assert _bf16_close(hh[:, 0], g[f"n{n}_h0"], 1.0) and not hh[:, 1:].any()  # only record 0 of each item is written
+    assert _bf16_close(p0.cpu().numpy(), g[f"n{n}_p0"], 1.0)
+    vv = v0.cpu().numpy()
+    assert np.all(np.abs(vv - g[f"n{n}_v0"]) <= BF16_TOL * np.maximum(1.0, np.abs(g[f"n{n}_v0"])))
+
+
 def test_bf16_mode_search_runs_and_agrees_with_fp32_mode():
     """Throughput mode end to end: same searches in bf16 and fp32 modes give visit counts that sum to
     S and root policies that are close (bf16 rounding moves a few visits, not the search)."""
