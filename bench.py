@@ -336,8 +336,21 @@ def run_ours(args):
                 "peak_source": peaks["source"],
                 "algorithmic": f"{bytes_per_sim:.0f} B/sim x {B} sims per launch (mean leaf depth {depth})"}
 
-    roofline = roofline_of(dominant)
-    roofline_other = roofline_of("backup_select" if dominant == "net_recurrent" else "net_recurrent")
+    try:  # DRAM traffic per launch from the committed ncu --set full capture of this workload (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f)
+    except (OSError, ValueError):
+        traffic = {}
+
+    def with_traffic(r, name):
+        t = traffic.get(name, {}).get("dram_bytes_per_launch") if B == GAMES_PER_GPU and S == N_SIMS else None
+        r["traffic"] = t
+        r["traffic_source"] = traffic.get("source") if t else None
+        return r
+
+    roofline = with_traffic(roofline_of(dominant), dominant)
+    other = "backup_select" if dominant == "net_recurrent" else "net_recurrent"
+    roofline_other = with_traffic(roofline_of(other), other)
     # ---- end to end: env words from pinned host memory in, move records back to the host, every step
     h_words = torch.empty(B, dtype=torch.int32).pin_memory()
     h_words.copy_(sp.env.words.cpu())
