@@ -796,7 +796,7 @@ int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_pe
   int smem = 0, n_pairs = 0;
   if (int rc = tc_prepare(&smem)) return rc;
   const unsigned grid = tc_grid(n, &n_pairs);
-  cudaError_t e = launch_pdl(tc::v4::net_tc<false>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream,
+  cudaError_t e = launch_pdl(1, tc::v4::net_tc<false>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream,
                              (const uint8_t*)weights, lat_in, in_rows_per_item, in_row, actions, (const uint32_t*)nullptr, 0,
                              lat_out, out_rows_per_item, out_row, latent_dtype, r, p, v, n, n_pairs, tc_timeline_enabled());
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_tc<recurrent> launch: %s", cudaGetErrorString(e));
@@ -808,7 +808,7 @@ int tc_net_initial(const void* weights, int n_disks, const uint32_t* words, void
   int smem = 0, n_pairs = 0;
   if (int rc = tc_prepare(&smem)) return rc;
   const unsigned grid = tc_grid(n, &n_pairs);
-  cudaError_t e = launch_pdl(tc::v4::net_tc<true>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream,
+  cudaError_t e = launch_pdl(1, tc::v4::net_tc<true>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream,
                              (const uint8_t*)weights, (const void*)nullptr, (int64_t)1, (const uint16_t*)nullptr,
                              (const uint8_t*)nullptr, words, n_disks, lat_out, out_rows_per_item, (int64_t)0, latent_dtype,
                              (float*)nullptr, p0, v0, n, n_pairs, 0);

@@ -57,13 +57,14 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
                                                               uint16_t* __restrict__ leaf_depth, uint8_t* __restrict__ path_out,
                                                               int path_cap, uint32_t* __restrict__ path_ent) {
   const int half = threadIdx.x & 1;
-  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
-  if (b >= s.n_searches) return;  // whole pairs leave together: shuffles are pair-masked
+  const int64_t b_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
+  const bool valid = b_raw < s.n_searches;  // out-of-range pairs stay in the warp-uniform walk, masked
+  const int64_t b = valid ? b_raw : s.n_searches - 1;
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
   const Leaf leaf = select_leaf(s.nodes + b * s.n_records, rp, s.minmax[2 * b], s.minmax[2 * b + 1], sim, ucb_table,
                                 discount, half, path_out ? path_out + b * path_cap : nullptr, path_cap,
-                                path_ent ? path_ent + b * kPathCap : nullptr);
-  if (half == 0) {
+                                path_ent ? path_ent + b * kPathCap : nullptr, false, valid);
+  if (half == 0 && valid) {
     leaf_parent[b] = (uint16_t)leaf.parent;
     leaf_action[b] = (uint8_t)leaf.action;
     if (leaf_depth) leaf_depth[b] = (uint16_t)leaf.depth;
@@ -84,53 +85,60 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
                                                                      const float* __restrict__ r, const float* __restrict__ p,
                                                                      const float* __restrict__ v, int do_select) {
   const int half = threadIdx.x & 1;
-  const unsigned pair = 3u << ((threadIdx.x & 31) & ~1);
-  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
+  const int64_t b_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
   pdl_launch_dependents();
   pdl_wait();  // everything below reads what the network kernel wrote
-  if (b >= s.n_searches) return;
-  const bool tl = kTL && b == (g_tree_timeline_search & 0xFFFFFFFFll) && sim == (int)(g_tree_timeline_search >> 32) && half == 0;
+  const bool valid = b_raw < s.n_searches;  // out-of-range pairs stay for the warp-uniform walk, masked
+  const int64_t b = valid ? b_raw : s.n_searches - 1;
+  const bool tl = kTL && valid && b == (g_tree_timeline_search & 0xFFFFFFFFll) && sim == (int)(g_tree_timeline_search >> 32) && half == 0;
   tree_mark<kTL>(0, tl);
   hmz_node_t* nodes = s.nodes + b * s.n_records;
   uint32_t* path = path_ent ? path_ent + b * kPathCap : nullptr;
-  const int pe = leaf_parent[b], pa = leaf_action[b];
-  tree_mark<kTL>(1, tl, (uint32_t)(pe + pa));
-  const int depth = (path != nullptr && leaf_depth != nullptr) ? (int)leaf_depth[b] : kPathCap + 1;
-  // everything the backup needs that depends only on the search index is requested up front, in one
-  // memory round trip: leaf scalars, network outputs, min/max (the leaf-side path entries follow the depth)
-  uint4 ent4 = make_uint4(0u, 0u, 0u, 0u);
-  if (half == 0 && path != nullptr && depth <= kPathCap) ent4 = *reinterpret_cast<const uint4*>(path + ((depth - 1) & ~3));
-  double mn = s.minmax[2 * b], mx = s.minmax[2 * b + 1];
-  const float r_leaf = r[b];
-  const double v_leaf = (double)v[b];
-  write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
-  if (half == 0) {
-    double root_w = s.root_W[b];
+  double mn = 0.0, mx = 0.0;
+  if (valid) {
+    const int pe = leaf_parent[b], pa = leaf_action[b];
+    tree_mark<kTL>(1, tl, (uint32_t)(pe + pa));
+    const int depth = (path != nullptr && leaf_depth != nullptr) ? (int)leaf_depth[b] : kPathCap + 1;
+    // everything the backup needs that depends only on the search index is requested up front, in one
+    // memory round trip: leaf scalars, network outputs, min/max (the leaf-side path entries follow the depth)
+    uint4 ent4 = make_uint4(0u, 0u, 0u, 0u);
+    if (half == 0 && path != nullptr && depth <= kPathCap) ent4 = *reinterpret_cast<const uint4*>(path + ((depth - 1) & ~3));
+    mn = s.minmax[2 * b];
+    mx = s.minmax[2 * b + 1];
+    const float r_leaf = r[b];
+    const double v_leaf = (double)v[b];
+    write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
+    tree_mark<kTL>(6, tl, __float_as_uint(r_leaf));
+    if (half == 0) {
+      double root_w = s.root_W[b];
+      tree_mark<kTL>(7, tl, (uint32_t)__double2loint(root_w) ^ (uint32_t)__double2loint(mn));
 #if defined(HMZ_ABLATE) && (HMZ_ABLATE & 2)  // timing experiment only: no backup
-    if (depth < 0)
+      if (depth < 0)
 #else
-    if (depth <= kPathCap)
+      if (depth <= kPathCap)
 #endif
-      backup_path(nodes, path, ent4, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
-    else
-      backup_walk(nodes, pe, pa, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
-    s.root_W[b] = root_w;
-    s.minmax[2 * b] = mn;
-    s.minmax[2 * b + 1] = mx;
-    if (tl) {
-      g_tree_timeline[2] = (unsigned long long)depth;
-      tree_mark<kTL>(3, tl, (uint32_t)__double2loint(mn));
+        backup_path(nodes, path, ent4, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx, tl);
+      else
+        backup_walk(nodes, pe, pa, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
+      s.root_W[b] = root_w;
+      s.minmax[2 * b] = mn;
+      s.minmax[2 * b + 1] = mx;
+      if (tl) {
+        g_tree_timeline[2] = (unsigned long long)depth;
+        tree_mark<kTL>(3, tl, (uint32_t)__double2loint(mn));
+      }
     }
   }
 #if defined(HMZ_ABLATE) && (HMZ_ABLATE & 4)  // timing experiment only: no selection
   if (sim >= 0) return;
 #endif
   if (!do_select) return;
-  mn = __shfl_sync(pair, mn, (threadIdx.x & 31) & ~1);  // also orders lane 0's record updates before the pair's next walk
-  mx = __shfl_sync(pair, mx, (threadIdx.x & 31) & ~1);
+  // lane 0's (min, max) to its partner; the shuffle also orders lane 0's record updates before the pair's next walk
+  mn = __shfl_sync(0xffffffffu, mn, (threadIdx.x & 31) & ~1);
+  mx = __shfl_sync(0xffffffffu, mx, (threadIdx.x & 31) & ~1);
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
-  const Leaf leaf = select_leaf<kTL>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path, tl);
-  if (half == 0) {
+  const Leaf leaf = select_leaf<kTL>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path, tl, valid);
+  if (half == 0 && valid) {
     leaf_parent[b] = (uint16_t)leaf.parent;
     leaf_action[b] = (uint8_t)leaf.action;
     leaf_depth[b] = (uint16_t)leaf.depth;
@@ -491,7 +499,7 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
   ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
   const int do_select = sim + 1 < n_simulations ? 1 : 0;
   const float *cr = sc.r, *cp = sc.p, *cv = sc.v;
-  cudaError_t e = launch_pdl(g_tree_tl_search >= 0 ? search_backup_select<true> : search_backup_select<false>, dim3(search_grid(B)),
+  cudaError_t e = launch_pdl(2, g_tree_tl_search >= 0 ? search_backup_select<true> : search_backup_select<false>, dim3(search_grid(B)),
                              dim3(kTreeThreads), 0, st, *s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path, cr, cp, cv,
                              do_select);
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "search_backup_select launch: %s", cudaGetErrorString(e));

@@ -104,9 +104,10 @@ __device__ __forceinline__ void write_fresh_half(hmz_node_t* rec, int half, cons
 constexpr int kRcpTable = 4096;
 static __device__ double g_rcp[kRcpTable + 1];  // g_rcp[k] = RN(1 / k) for k >= 1 (filled by the host, IEEE division)
 
+// |a| comfortably normal (2^-830 <= |a| < 2^830), tested on the exponent bits with integer instructions
 __device__ __forceinline__ bool div_fast_ok(double a) {
-  const double m = fabs(a);
-  return m > 1e-250 && m < 1e250;
+  const unsigned hi = (unsigned)__double2hiint(a) & 0x7FFFFFFFu;
+  return (hi - 0x0C100000u) < (0x73D00000u - 0x0C100000u);
 }
 __device__ __forceinline__ double div_refine(double a, double b, double y) {
   double q = __dmul_rn(a, y);
@@ -115,11 +116,16 @@ __device__ __forceinline__ double div_refine(double a, double b, double y) {
   r = __fma_rn(-b, q, a);
   return __fma_rn(r, y, q);
 }
-// a / n for a visit count n >= 1
+// An operand the two-correction division handles exactly: +0 or comfortably normal.
+__device__ __forceinline__ bool div_operand_ok(double a) {
+  return (__double_as_longlong(a) == 0ll) | div_fast_ok(a);
+}
+// a / n for a visit count n >= 1: the shortcut is evaluated unconditionally (straight-line code), the rare
+// operand outside its proven range takes the generic division afterwards
 __device__ __forceinline__ double div_by_count(double a, int n) {
-  if (a == 0.0) return a;  // +-0 / n
-  if (n <= kRcpTable && div_fast_ok(a)) return div_refine(a, (double)n, __ldg(&g_rcp[n]));
-  return __ddiv_rn(a, (double)n);
+  const double q = div_refine(a, (double)n, __ldg(&g_rcp[min(n, kRcpTable)]));
+  if ((n > kRcpTable) | !div_operand_ok(a)) return __ddiv_rn(a, (double)n);
+  return q;
 }
 // a / b with y = __drcp_rn(b) precomputed; y_ok = b is positive, comfortably normal and its significand is not all ones
 __device__ __forceinline__ double div_by_known(double a, double b, double y, bool y_ok) {
@@ -128,7 +134,7 @@ __device__ __forceinline__ double div_by_known(double a, double b, double y, boo
 }
 __device__ __forceinline__ bool rcp_usable(double b) {
   const unsigned long long bits = (unsigned long long)__double_as_longlong(b);
-  return b > 1e-250 && b < 1e250 && (bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull;
+  return (b > 0.0) & div_fast_ok(b) & ((bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull);
 }
 
 __device__ __forceinline__ void minmax_update(double x, double& mn, double& mx) {
@@ -144,11 +150,6 @@ __device__ __forceinline__ void prefetch_record(const void* rec) {
 #pragma unroll
   for (int k = 0; k < HMZ_PREFETCH_SECTORS; ++k)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec) + 32 * k * (4 / HMZ_PREFETCH_SECTORS)));
-}
-
-// An operand the two-correction division handles exactly: +0 or comfortably normal.
-__device__ __forceinline__ bool div_operand_ok(double a) {
-  return __double_as_longlong(a) == 0ll || div_fast_ok(a);
 }
 
 // Reference-order evaluation of one child (the slow, always-exact form): used when an operand falls
@@ -176,40 +177,42 @@ __device__ __noinline__ float child_score_exact(double W, float rwd, int n, floa
 // between them), so their float64 chains interleave: every division is the two-correction form of
 // div_refine on reciprocals fetched up front, unvisited children are computed and discarded, and the
 // rare operand outside the proven range re-evaluates the lane's children with child_score_exact.
+// The loop is WARP-UNIFORM: every lane stays in it until the deepest of the warp's 16 walks has ended
+// (`active` masks the memory accesses of finished or out-of-range pairs), so the pair exchange is a plain
+// full-mask shuffle — a pair-masked shuffle inside a divergent loop costs a MATCH/REDUX/VOTE sequence per
+// call — and the walk needs no reconvergence bookkeeping.  ALL 32 lanes of the warp must call it.
 template <bool kTL = false>
 __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const double* __restrict__ root_prior64, double mn,
                                             double mx, int root_n, const double* __restrict__ ucb_table,
                                             double discount, int half, uint8_t* __restrict__ path_out, int path_cap,
-                                            uint32_t* __restrict__ path_ent, bool tl_on = false) {
-  const int lane = threadIdx.x & 31;
-  const unsigned pair = 3u << (lane & ~1);
+                                            uint32_t* __restrict__ path_ent, bool tl_on = false, bool active = true) {
   const bool normalise = mx > mn;  // MinMaxStats.normalize (MCTS/utils_mcts.py:12-16)
   const double range = __dsub_rn(mx, mn);
-  const bool range_ok = normalise && rcp_usable(range);
+  const bool range_ok = normalise & rcp_usable(range);
   const double range_rcp = range_ok ? __drcp_rn(range) : 0.0;
   int e = 0, n_parent = root_n, depth = 0;
   Leaf leaf{0, 0, 0};
-  while (true) {
-    const uint4* hp = reinterpret_cast<const uint4*>(&nodes[e].h[half]);
-    uint4 q0, q1, q2, q3;
-    ld256(hp, q0, q1);
-    ld256(hp + 2, q2, q3);
-    const double tn = ucb_table[n_parent];
-    if (depth < 8) tree_mark<kTL>(8 + 2 * depth, tl_on, q0.w ^ q1.w ^ q2.w ^ q3.w);
-    const bool use64 = e == 0 && root_prior64 != nullptr;
+  uint4 q0 = make_uint4(0u, 0u, 0u, 0xFFFF0000u), q1 = q0, q2 = q0, q3 = make_uint4(0u, 0u, 0u, 0u);
+  while (__any_sync(0xffffffffu, active)) {
+    const bool use64 = (e == 0) & (root_prior64 != nullptr);
     double rp64[3] = {0.0, 0.0, 0.0};
-    if (use64) {  // only the (noised) root has float64 priors; requested together with the record
+    double tn = 0.0;
+    if (active) {
+      const uint4* hp = reinterpret_cast<const uint4*>(&nodes[e].h[half]);
+      ld256(hp, q0, q1);
+      ld256(hp + 2, q2, q3);
+      tn = ucb_table[n_parent];
+      if (use64) {  // only the (noised) root has float64 priors; requested together with the record
 #pragma unroll
-      for (int j = 0; j < 3; ++j) rp64[j] = root_prior64[3 * half + j];
+        for (int j = 0; j < 3; ++j) rp64[j] = root_prior64[3 * half + j];
+      }
     }
+    if (depth < 8) tree_mark<kTL>(8 + 2 * depth, tl_on, q0.w ^ q1.w ^ q2.w ^ q3.w);
     Slot c[3] = {Slot::unpack(q0), Slot::unpack(q1), Slot::unpack(q2)};
 #if HMZ_PREFETCH_SECTORS > 0
-    // The walk continues in one of the expanded children: request their records now, so that the fetch
-    // overlaps the float64 evaluation below instead of following it (one dependent memory round trip per
-    // level otherwise).  Costs extra record reads; the kernel is latency-bound, not bandwidth-bound.
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      if (c[j].child != (int)HMZ_NO_CHILD) prefetch_record(&nodes[c[j].child]);
+      if (active && c[j].child != (int)HMZ_NO_CHILD) prefetch_record(&nodes[c[j].child]);
 #endif
     const float prior[3] = {__uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z)};
     double y[3], yw[3];
@@ -238,11 +241,12 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
       // float64 prior (noised root): product in float64; float32 prior: weak scalar -> float32 product (node.py:122)
       const float u = use64 ? __double2float_rn(__dmul_rn(rp64[j], w)) : __fmul_rn(prior[j], __double2float_rn(w));
       score[j] = __fadd_rn(qf, u);  // node.py:83 on float32 arrays
-      exact_needed |= n + 1 > kRcpTable;
-      exact_needed |= n > 0 && (!div_operand_ok(c[j].W) || (normalise && (!range_ok || !div_operand_ok(num))));
+      // bitwise, not short-circuit: a data-dependent branch here would fence the three children's chains apart
+      exact_needed |= (n + 1 > kRcpTable) |
+                      ((n > 0) & (!div_operand_ok(c[j].W) | (normalise & (!range_ok | !div_operand_ok(num)))));
     }
 #endif
-    if (exact_needed) {
+    if (exact_needed & active) {
 #pragma unroll
       for (int j = 0; j < 3; ++j)
         score[j] = child_score_exact(c[j].W, c[j].rwd, c[j].n, prior[j], rp64[j], use64, tn, discount, mn, range, normalise);
@@ -258,30 +262,34 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
         best_n = c[j].n;
       }
     // merge the two halves: actions 0..2 (lane 0) beat 3..5 (lane 1) on equal scores
-    const float other_score = __shfl_xor_sync(pair, best_score, 1);
-    const int other_pack = __shfl_xor_sync(pair, best | (best_child << 16), 1);
-    const int other_n = __shfl_xor_sync(pair, best_n, 1);
+    const float other_score = __shfl_xor_sync(0xffffffffu, best_score, 1);
+    const int other_pack = __shfl_xor_sync(0xffffffffu, best | (best_child << 16), 1);
+    const int other_n = __shfl_xor_sync(0xffffffffu, best_n, 1);
     const bool take_other = half == 0 ? (other_score > best_score) : !(best_score > other_score);
     if (take_other) {
       best = other_pack & 7;
       best_child = (int)((unsigned)other_pack >> 16);
       best_n = other_n;
     }
-    if (half == 0) {
-      if (path_out != nullptr && depth < path_cap) path_out[depth] = (uint8_t)best;
-      if (path_ent != nullptr && depth < kPathCap) path_ent[depth] = (uint32_t)e | ((uint32_t)best << 16);
+    if (active) {
+      if (half == 0) {
+        if (path_out != nullptr && depth < path_cap) path_out[depth] = (uint8_t)best;
+        if (path_ent != nullptr && depth < kPathCap) path_ent[depth] = (uint32_t)e | ((uint32_t)best << 16);
+      }
+      if (depth < 8) tree_mark<kTL>(9 + 2 * depth, tl_on, (uint32_t)best_child);
+      ++depth;
+      if (best_child == (int)HMZ_NO_CHILD) {
+        leaf.parent = e;
+        leaf.action = best;
+        leaf.depth = depth;
+        active = false;
+      } else {
+        e = best_child;
+        n_parent = best_n;
+      }
     }
-    if (depth < 8) tree_mark<kTL>(9 + 2 * depth, tl_on, (uint32_t)best_child);
-    ++depth;
-    if (best_child == (int)HMZ_NO_CHILD) {
-      leaf.parent = e;
-      leaf.action = best;
-      leaf.depth = depth;
-      return leaf;
-    }
-    e = best_child;
-    n_parent = best_n;
   }
+  return leaf;
 }
 
 // node.expand bookkeeping on the parent slot + Node.backup (MCTS/node.py:53-70) from the leaf to
@@ -319,12 +327,15 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
 // are bit-identical.  The batch loop is deliberately not unrolled: registers (occupancy) matter more
 // to this latency-bound kernel than the second batch's instruction-level parallelism.
 __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& ent4, int k0, int depth, int sim, float r,
-                                              double& value, double discount, double& mn, double& mx) {
+                                              double& value, double discount, double& mn, double& mx, bool tl = false,
+                                              int tl_slot = 0) {
   const uint32_t ent[4] = {ent4.x, ent4.y, ent4.z, ent4.w};
+  if (tl) tree_mark<true>(tl_slot, true, ent4.x);
   uint4 raw[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     if (k0 + j < depth) raw[j] = *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16));
+  if (tl) tree_mark<true>(tl_slot + 1, true, raw[0].w ^ ((k0 + 1 < depth) ? raw[1].w : 0u) ^ ((k0 + 2 < depth) ? raw[2].w : 0u) ^ ((k0 + 3 < depth) ? raw[3].w : 0u));
 #pragma unroll
   for (int j = 3; j >= 0; --j) {
     if (k0 + j < depth) {
@@ -341,15 +352,18 @@ __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& en
       value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
     }
   }
+  if (tl) tree_mark<true>(tl_slot + 2, true, (uint32_t)__double2loint(value));
 }
 
 // ent_first: path entries of the leaf-side batch, loaded by the caller together with the leaf scalars.
 __device__ __forceinline__ void backup_path(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, uint4 ent4, int depth,
                                             int sim, float r, double value, double discount, double& root_w, double& mn,
-                                            double& mx) {
+                                            double& mx, bool tl = false) {
+  int tl_slot = 24;
 #pragma unroll 1
   for (int k0 = (depth - 1) & ~3; k0 >= 0; k0 -= 4) {
-    backup_batch4(nodes, ent4, k0, depth, sim, r, value, discount, mn, mx);
+    backup_batch4(nodes, ent4, k0, depth, sim, r, value, discount, mn, mx, tl, tl_slot);
+    tl_slot += 3;
     if (k0 >= 4) ent4 = *reinterpret_cast<const uint4*>(path_ent + k0 - 4);
   }
   root_w = __dadd_rn(root_w, value);

@@ -29,7 +29,11 @@ for search in [int(x) for x in os.environ.get("SEARCHES", "0,1,17,5000,30000,300
     t = np.array(list(buf), dtype=np.int64)
     print(f"search {search}: backed-up depth {t[2]}, next path depth {t[4]}")
     t0 = t[0]
-    marks = [(0, "entry"), (1, "leaf scalars loaded"), (3, "backup done (stores issued)")]
+    marks = [(0, "entry"), (1, "leaf scalars loaded"), (6, "fresh record written, r loaded"), (7, "root W / min-max loaded"),
+             (3, "backup done (stores issued)")]
+    for bt in range(4):
+        marks += [(24 + 3 * bt, f"backup batch {bt}: path entries loaded"), (25 + 3 * bt, f"backup batch {bt}: slots loaded"),
+                  (26 + 3 * bt, f"backup batch {bt}: recurrence done")]
     for d in range(8):
         marks += [(8 + 2 * d, f"select level {d}: record loaded"), (9 + 2 * d, f"select level {d}: arg-max done")]
     marks += [(5, "end")]
