@@ -298,7 +298,9 @@ __device__ __forceinline__ void hidden_chunk_tmem(uint32_t dst, const uint32_t (
 }
 // Hidden-layer epilogue of one column half: H[0:128) float32 -> relu -> bf16 -> A1 in H[0:64), in place.
 // Chunk c (columns 16c..16c+15) lands in columns 8c..8c+7, always behind the read pointer; the TMEM
-// load of chunk c+1 is in flight while chunk c is converted.
+// load of chunk c+1 is in flight while chunk c is converted.  (tcgen05.wait::ld waits for EVERY outstanding
+// load, so each chunk still exposes most of one TMEM load latency, ~170 clk; requesting 64 columns per wait
+// was measured SLOWER: the 64 live registers spill under the 80-register cap of a 704-thread CTA.)
 __device__ __forceinline__ void hidden_epilogue_tmem(uint32_t h) {
   uint32_t va[16], vb[16];
   tmem_ld16_issue(h, va);
@@ -320,8 +322,16 @@ __device__ __forceinline__ void hidden_epilogue_tmem(uint32_t h) {
 // kInitial = true : initial_inference  — networks representation (h), policy, value; input = one-hot of env words.
 // The network index `net` keeps the recurrent numbering (0 = g / h, 1 = reward, 2 = policy, 3 = value);
 // the root inference simply skips net 1.
+// HMZ_TC_MAXNREG (tuning switch): cap the kernel at fewer registers so that tree-kernel blocks of other search
+// groups can share the SM (704 threads x 64 registers leave 20 K registers = two 128-thread blocks at 80);
+// measured: no gain, the default keeps 80 registers
+#ifdef HMZ_TC_MAXNREG
+#define HMZ_TC_BOUNDS __maxnreg__(HMZ_TC_MAXNREG)
+#else
+#define HMZ_TC_BOUNDS __launch_bounds__(kThreads, 1)
+#endif
 template <bool kInitial>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void HMZ_TC_BOUNDS
 net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_t in_rows_per_item,
        const uint16_t* __restrict__ in_row, const uint8_t* __restrict__ actions, const uint32_t* __restrict__ words, int n_disks,
        void* lat_out, int64_t out_rows_per_item, int64_t out_row, int latent_dtype, float* __restrict__ r_out,
@@ -396,7 +406,9 @@ net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_
         // ---- first layer: H[0:256) = [A | AX] x W1'^T
         {
           const uint32_t slot = use_f & 1u;
+          if (elect_one()) TL4(16 + net);
           mbar_wait(&s.bar_wfull[0][slot], (use_f >> 1) & 1u);
+          if (elect_one()) TL4(24 + net);
           const uint32_t wf = smem_u32(s.wf[slot]);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
@@ -437,7 +449,9 @@ net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_
           const uint32_t n2 = net == 0 ? 64u : (net == 2 ? 16u : 48u);
           const uint32_t id2 = umma_idesc(n2);
           const uint32_t slot = use_s & 1u;
+          if (elect_one()) TL4(20 + net);
           mbar_wait(&s.bar_wfull[1][slot], (use_s >> 1) & 1u);
+          if (elect_one()) TL4(28 + net);
           const uint32_t ws = smem_u32(s.ws[slot]);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {

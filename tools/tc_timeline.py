@@ -42,6 +42,11 @@ else:  # v4: two tiles per CTA
             for t in range(2):
                 names[ev] = f"T{t} mma {net}: {what}"
                 ev += 1
+    for i, net in enumerate("grpv"):
+        names[16 + i] = f"mma {net}: L1 issue point reached (waiting W1)"
+        names[24 + i] = f"mma {net}: W1 landed"
+        names[20 + i] = f"mma {net}: L2 issue point reached (waiting W2)"
+        names[28 + i] = f"mma {net}: W2 landed"
     for t in range(2):
         names[86 + t * 8] = f"T{t} hid: raw latent published"
         names[44 + t * 8] = f"T{t} hid: saw dynamics L2 complete"
