@@ -213,3 +213,43 @@ def test_node_view_matches_tree_store(golden):
     with pytest.raises(ValueError, match="Expand leaf node first"):
         leaf.best_child(mcts, mm)
     assert leaf.N == 0 and leaf.Q == 0.0 and leaf.h_state is None and leaf.children == []
+
+
+def test_full_size_config3_grouping_invariance_and_properties():
+    """BASELINE.json configs[2] size (N = 5, 65,536 searches x 100 simulations, throughput mode): results must
+    not depend on how hmz_search_run cuts the batch into concurrent stream groups (the groups only change
+    scheduling: separate streams, programmatic dependent launches), and the size-independent invariants of a
+    search must hold: visits sum to S, the play policy sums to 1, the root value is a discounted mixture of
+    rewards / values and therefore bounded, the sampled action has a visited child."""
+    from muzero_hanoi_b200 import _lib
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    n, B, S = 5, 65536, 100
+    lib = _lib.load()
+    w = PackedWeights(port.make_weights(n, 21), n, _lib.MODE_BF16)
+    env = VecHanoi(n, 200, B)
+    env.random_reset(seed=2)
+    rng = np.random.default_rng(4)
+    noise = torch.from_numpy(rng.dirichlet(np.full(6, 0.25), B)).cuda()
+    uni = torch.from_numpy(rng.random(B)).cuda()
+    outs = []
+    try:
+        for groups in (1, 4, 7):
+            _lib.check(lib.hmz_search_set_groups(groups))
+            m = BatchedMCTS(0.8, 0.25, S, B, latent_dtype=_lib.LATENT_BF16)
+            action, pi, q, visits = m.run_mcts(w, words=env.words, temperature=1.0, deterministic=False, noise=noise,
+                                               uniforms=uni)
+            torch.cuda.synchronize()
+            outs.append((action.cpu().numpy(), pi.cpu().numpy(), q.cpu().numpy(), visits.cpu().numpy(),
+                         m.store.minmax.cpu().numpy()))
+    finally:
+        _lib.check(lib.hmz_search_set_groups(0))
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)  # bit for bit, float64 root values and min/max included
+    action, pi, q, visits, mm = outs[0]
+    assert (visits.sum(1) == S).all() and (visits >= 0).all()
+    assert np.allclose(pi.sum(1), 1.0, atol=1e-12) and np.array_equal(pi, visits / visits.sum(1, keepdims=True))
+    assert np.isfinite(q).all() and (np.abs(q) <= 278.61 / (1 - 0.8)).all()  # |r|, |v| <= 278.604 (support +-16)
+    assert (visits[np.arange(B), action] > 0).all()
+    assert (mm[:, 0] <= mm[:, 1]).all()
