@@ -300,7 +300,8 @@ __device__ __forceinline__ void hidden_chunk_tmem(uint32_t dst, const uint32_t (
 // Chunk c (columns 16c..16c+15) lands in columns 8c..8c+7, always behind the read pointer; the TMEM
 // load of chunk c+1 is in flight while chunk c is converted.  (tcgen05.wait::ld waits for EVERY outstanding
 // load, so each chunk still exposes most of one TMEM load latency, ~170 clk; requesting 64 columns per wait
-// was measured SLOWER: the 64 live registers spill under the 80-register cap of a 704-thread CTA.)
+// was measured SLOWER: the 64 live registers spill under the 80-register cap of a 704-thread CTA; 32 columns
+// per wait without double buffering was slower too, 30.8 vs 27.3 us per launch.)
 __device__ __forceinline__ void hidden_epilogue_tmem(uint32_t h) {
   uint32_t va[16], vb[16];
   tmem_ld16_issue(h, va);
