@@ -69,6 +69,22 @@ __device__ __forceinline__ void ld256(const void* p, uint4& lo, uint4& hi) {
                : "l"(p)
                : "memory");
 }
+#ifndef HMZ_L2_HINTS
+#define HMZ_L2_HINTS 0
+#endif
+// the same with L2 eviction priorities (the .L2:: qualifiers exist for the 256-bit forms only): root records are
+// re-read by every simulation (evict_last), freshly expanded records are not needed soon (evict_first)
+__device__ __forceinline__ void ld256_keep(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.L2::evict_last.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st256_stream(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.L2::evict_first.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
 __device__ __forceinline__ void st256(void* p, const uint4& lo, const uint4& hi) {
   asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
                "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
@@ -85,8 +101,13 @@ __device__ __forceinline__ void write_fresh_half(hmz_node_t* rec, int half, cons
                                                  int parent_action) {
   uint4* dst = reinterpret_cast<uint4*>(&rec->h[half]);
   const uint4 empty = make_uint4(0u, 0u, 0u, 0xFFFF0000u);  // W = 0, rwd = 0, N = 0, child = HMZ_NO_CHILD
-  st256(dst, empty, empty);
-  st256(dst + 2, empty,
+#if HMZ_L2_HINTS & 2
+#define HMZ_ST_FRESH st256_stream
+#else
+#define HMZ_ST_FRESH st256
+#endif
+  HMZ_ST_FRESH(dst, empty, empty);
+  HMZ_ST_FRESH(dst + 2, empty,
         make_uint4(__float_as_uint(pr[3 * half]), __float_as_uint(pr[3 * half + 1]), __float_as_uint(pr[3 * half + 2]),
                    half == 0 ? ((uint32_t)parent | ((uint32_t)parent_action << 16)) : 0u));
 }
@@ -199,8 +220,16 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
     double tn = 0.0;
     if (active) {
       const uint4* hp = reinterpret_cast<const uint4*>(&nodes[e].h[half]);
-      ld256(hp, q0, q1);
-      ld256(hp + 2, q2, q3);
+#if HMZ_L2_HINTS & 1
+      if (e == 0) {
+        ld256_keep(hp, q0, q1);
+        ld256_keep(hp + 2, q2, q3);
+      } else
+#endif
+      {
+        ld256(hp, q0, q1);
+        ld256(hp + 2, q2, q3);
+      }
       tn = ucb_table[n_parent];
       if (use64) {  // only the (noised) root has float64 priors; requested together with the record
 #pragma unroll
