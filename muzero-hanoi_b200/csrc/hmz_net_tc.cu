@@ -301,7 +301,10 @@ __device__ __forceinline__ void hidden_chunk_tmem(uint32_t dst, const uint32_t (
 // load of chunk c+1 is in flight while chunk c is converted.  (tcgen05.wait::ld waits for EVERY outstanding
 // load, so each chunk still exposes most of one TMEM load latency, ~170 clk; requesting 64 columns per wait
 // was measured SLOWER: the 64 live registers spill under the 80-register cap of a 704-thread CTA; 32 columns
-// per wait without double buffering was slower too, 30.8 vs 27.3 us per launch.)
+// per wait without double buffering was slower too, 30.8 vs 27.3 us per launch.  Pooling all 16 epilogue
+// warps on one tile's layer at a time (4 chunks per warp, 750 clk per layer instead of ~1,400) was also tried:
+// the packed activations then leave only 32-column holes, every second layer needs two accumulators and twice
+// the tcgen05.mma instructions from the single issuing lane, and the latent epilogues serialise: 29.1 us.)
 __device__ __forceinline__ void hidden_epilogue_tmem(uint32_t h) {
   uint32_t va[16], vb[16];
   tmem_ld16_issue(h, va);
