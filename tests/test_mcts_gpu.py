@@ -253,3 +253,32 @@ def test_full_size_config3_grouping_invariance_and_properties():
     assert np.isfinite(q).all() and (np.abs(q) <= 278.61 / (1 - 0.8)).all()  # |r|, |v| <= 278.604 (support +-16)
     assert (visits[np.arange(B), action] > 0).all()
     assert (mm[:, 0] <= mm[:, 1]).all()
+
+
+def test_long_search_beyond_reciprocal_table_bit_exact():
+    """S = 14,000 >> the 4,096-entry reciprocal table of the exact-division shortcut: visit counts beyond the table
+    take the generic-division fallback (child_score_exact / __ddiv_rn) in both the split-phase kernels (checked
+    against the C oracle) and the fused hot-loop kernel (must equal the split phases bit for bit)."""
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    n, B, S = 3, 4, 14000
+    weights = PackedWeights(port.make_weights(n, 8), n)
+    env = VecHanoi(n, 200, B)
+    env.set_state_indices(np.array([0, 9, 13, 25], dtype=np.int32))
+    mcts = BatchedMCTS(0.8, 0.0, S, B)
+    mm0 = mcts.store.minmax.cpu().numpy().copy()
+    p0, r, p, v, depth = _split_search(mcts, weights, env.words, None)
+    _, _, q, visits = mcts.root_policy(0.0, True)
+    torch.cuda.synchronize()
+    assert visits.max().item() > 4096  # some child's count really leaves the table
+    mm = mm0.copy()
+    o_visits, o_q, o_depth = cport.search_injected(p0.cpu().numpy().astype(np.float64), False, mm, r.cpu().numpy(), p.cpu().numpy(),
+                                                   v.cpu().numpy(), 0.8, port.ucb_table(S + 1), want_depth=True)
+    assert np.array_equal(visits.cpu().numpy(), o_visits) and np.array_equal(q.cpu().numpy(), o_q)
+    assert np.array_equal(depth.cpu().numpy().astype(np.uint16), o_depth)
+    assert np.array_equal(mcts.store.minmax.cpu().numpy(), mm)
+    fused = BatchedMCTS(0.8, 0.0, S, B)
+    _, _, q2, visits2 = fused.run_mcts(weights, words=env.words, temperature=0.0, deterministic=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(visits2.cpu().numpy(), o_visits) and np.array_equal(q2.cpu().numpy(), o_q)
+    assert np.array_equal(fused.store.minmax.cpu().numpy(), mm)
