@@ -311,6 +311,11 @@ int hmz_episode_close(const uint8_t* flags, const int32_t* cur_slot, int64_t n_g
  * as the reference does; the discounted reward sum reproduces CPython's compensated float sum(). */
 int hmz_episode_returns(const uint8_t* ep_flags, const double* ep_root_q, const int32_t* ep_len, int64_t n_games, int t_max,
                         const double* discount_pow, int n_step, double* returns, float* priority, void* stream);
+/* compute_MCreturns (utils.py:75-86), the TD_return = False branch of Muzero._play_game (:193-194), with the same
+ * outputs as hmz_episode_returns.  discount_pow[i] = discount ** i for i in [0, t_max) as NumPy's power ufunc
+ * evaluates it on the host (the reference computes `discount ** np.array(range(T))`). */
+int hmz_episode_mc_returns(const uint8_t* ep_flags, const double* ep_root_q, const int32_t* ep_len, int64_t n_games, int t_max,
+                           const double* discount_pow, double* returns, float* priority, void* stream);
 /* Replay rows of the finished episodes: row_base[g] = ptr + exclusive prefix sum of the stored lengths
  * (or -1), *total_out = rows to add.  only_solved != 0 keeps an episode only if returns[-1] > 0
  * (training_loop, Muzero.py:98). */

@@ -92,6 +92,29 @@ __global__ void __launch_bounds__(256) episode_returns(const uint8_t* __restrict
   }
 }
 
+// compute_MCreturns (utils.py:75-86, the TD_return = False branch of Muzero._play_game) + priorities: one thread
+// per game walks its episode from the end — np.cumsum over the flipped discounted rewards is a sequential
+// float64 sum — and divides by the discount of each step.  discount_pow[i] = discount ** i as NumPy's power
+// ufunc evaluates it (its vectorised pow differs from libm's in the last bit for some exponents).
+__global__ void __launch_bounds__(256) episode_mc_returns(const uint8_t* __restrict__ ep_flags, const double* __restrict__ ep_root_q,
+                                                         const int32_t* __restrict__ ep_len, int64_t n, int t_max,
+                                                         const double* __restrict__ discount_pow, double* __restrict__ returns,
+                                                         float* __restrict__ priority) {
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
+    const int len = ep_len[g] < t_max ? ep_len[g] : t_max;
+    double acc = 0.0;
+    for (int t = len - 1; t >= 0; --t) {
+      const int64_t at = (int64_t)t * n + g;
+      const double d = discount_pow[t];
+      const double x = __dmul_rn(d, reward_of(ep_flags[at]));
+      acc = (t == len - 1) ? x : __dadd_rn(acc, x);
+      const double value = __ddiv_rn(acc, d);
+      returns[at] = value;
+      if (priority) priority[at] = fabsf(__fsub_rn((float)value, (float)ep_root_q[at]));
+    }
+  }
+}
+
 // Which finished episodes enter the replay ring (training_loop stores an episode only if
 // returns[-1, 0] > 0, Muzero.py:98) and where: row_base[g] = ptr + exclusive prefix sum of the stored
 // lengths (mod capacity applied by the writer), -1 for games that store nothing.  One block; the batch
@@ -235,6 +258,17 @@ int hmz_episode_returns(const uint8_t* ep_flags, const double* ep_root_q, const 
   episode_returns<<<grid_for(n_games * t_max, 256, 8), 256, 0, (cudaStream_t)stream>>>(ep_flags, ep_root_q, ep_len, n_games, t_max,
                                                                                        discount_pow, n_step, returns, priority);
   return check_launch("episode_returns");
+}
+
+int hmz_episode_mc_returns(const uint8_t* ep_flags, const double* ep_root_q, const int32_t* ep_len, int64_t n_games, int t_max,
+                           const double* discount_pow, double* returns, float* priority, void* stream) {
+  ProfScope prof_scope(HMZ_PROF_OTHER, stream);
+  if (n_games == 0) return HMZ_OK;
+  if (!ep_flags || !ep_len || !discount_pow || !returns || (priority && !ep_root_q) || n_games < 0 || t_max < 1)
+    return fail(HMZ_ERR_INVALID, "hmz_episode_mc_returns: bad arguments");
+  episode_mc_returns<<<grid_for(n_games, 256, 8), 256, 0, (cudaStream_t)stream>>>(ep_flags, ep_root_q, ep_len, n_games, t_max,
+                                                                                  discount_pow, returns, priority);
+  return check_launch("episode_mc_returns");
 }
 
 int hmz_episode_rows(const int32_t* ep_len, const double* returns, int64_t n_games, int64_t ptr, int only_solved,

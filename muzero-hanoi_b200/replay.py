@@ -42,6 +42,7 @@ class EpisodeStore:
         self.row_base = torch.full((B,), -1, dtype=torch.int64, device=dev)
         self.total = torch.zeros(1, dtype=torch.int64, device=dev)
         self._pow = None
+        self._mc_pow = None
 
     def record(self, words, action, visits, root_q, action_u8_out=None):
         """Muzero.py:179-183 for every game (before the env step)."""
@@ -62,6 +63,15 @@ class EpisodeStore:
         check(self.lib.hmz_episode_returns(ptr(self.flags), ptr(self.root_q), ptr(self.ep_len), self.B, self.t_max,
                                            ptr(self._pow[1]), int(n_step), ptr(self.returns), ptr(self.priority),
                                            current_stream()))
+        return self.returns, self.priority
+
+    def post_process_mc(self, discount):
+        """compute_MCreturns (utils.py:75-86, TD_return=False) + priorities of every finished episode."""
+        if self._mc_pow is None or self._mc_pow[0] != float(discount):
+            # the reference evaluates `discount ** np.array(range(T))` with NumPy's power ufunc (not libm's pow)
+            self._mc_pow = (float(discount), torch.from_numpy(float(discount) ** np.arange(self.t_max)).to(self.device))
+        check(self.lib.hmz_episode_mc_returns(ptr(self.flags), ptr(self.root_q), ptr(self.ep_len), self.B, self.t_max,
+                                              ptr(self._mc_pow[1]), ptr(self.returns), ptr(self.priority), current_stream()))
         return self.returns, self.priority
 
 

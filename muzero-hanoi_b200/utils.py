@@ -1,5 +1,5 @@
 """Drop-in for the acting-path half of the reference's utils.py (oneHot_encoding :9-25,
-compute_n_step_returns :28-72, adjust_temperature :89-96).  Plotting / logging helpers of the reference
+compute_n_step_returns :28-72, compute_MCreturns :75-86, adjust_temperature :89-96).  Plotting / logging helpers of the reference
 are out of scope."""
 import numpy as np
 
@@ -46,4 +46,25 @@ def compute_n_step_returns(rwds, root_values, n_step, discount):
     st.root_q[:, 0] = torch.tensor([float(q) for q in root_values], dtype=torch.float64)
     st.ep_len.fill_(T)
     ret, _ = st.post_process(n_step, discount)
+    return ret[:, 0].cpu().tolist()
+
+
+def compute_MCreturns(rwds, discount):
+    """Discounted reward-to-go of one episode (reference utils.py:75-86), on the device kernel."""
+    import torch
+
+    from .replay import EpisodeStore
+
+    T = len(rwds)
+    if T == 0:
+        return []
+    codes = {0: 0, 100: 4 | 1, -100 / 1000: 2}
+    try:
+        flags = [codes[r] for r in rwds]
+    except KeyError as e:
+        raise ValueError(f"reward {e.args[0]!r} is not one the Hanoi env produces") from None
+    st = EpisodeStore(1, T, 1)
+    st.flags[:, 0] = torch.tensor(flags, dtype=torch.uint8)
+    st.ep_len.fill_(T)
+    ret, _ = st.post_process_mc(discount)
     return ret[:, 0].cpu().tolist()

@@ -244,6 +244,9 @@ def gen_episode_post(ref):
         assert returns == port.n_step_returns(rw, root_q, n_step, discount), "port n-step returns != reference"
         prio = np.abs(np.array(returns, dtype=np.float32) - np.array(root_q, dtype=np.float32))
         assert np.array_equal(prio, port.priorities(returns, root_q))
+        mc = ref.compute_MCreturns(rw, discount)  # the TD_return=False branch of Muzero._play_game (Muzero.py:193-194)
+        assert [float(x) for x in mc] == port.mc_returns(rw, discount), "port MC returns != reference"
+        mc_prio = np.abs(np.array(mc, dtype=np.float32) - np.array(root_q, dtype=np.float32))
         dummy = types.SimpleNamespace(unroll_n_steps=unroll, n_action=6)
         np.random.seed(100 + k)
         st, o_r, o_a, o_p, o_g = ref_muzero.Muzero.organise_transitions(dummy, list(states), list(rw), list(actions), list(pis),
@@ -255,7 +258,7 @@ def gen_episode_post(ref):
             assert a.dtype == b.dtype and np.array_equal(a, b), "port organise_transitions != reference"
         out.update({f"e{k}_reward_code": codes.astype(np.uint8), f"e{k}_visits": visits.astype(np.int32), f"e{k}_root_q": np.array(root_q),
                     f"e{k}_action": np.array(actions, np.int32), f"e{k}_returns": np.array(returns, np.float64), f"e{k}_priority": prio,
-                    f"e{k}_absorbing": np.int64(absorbing), f"e{k}_o_r": o_r, f"e{k}_o_a": o_a, f"e{k}_o_p": o_p, f"e{k}_o_g": o_g})
+                    f"e{k}_absorbing": np.int64(absorbing), f"e{k}_mc_returns": np.array(mc, np.float64), f"e{k}_mc_priority": mc_prio, f"e{k}_o_r": o_r, f"e{k}_o_a": o_a, f"e{k}_o_p": o_p, f"e{k}_o_g": o_g})
     out.update(n_episodes=len(lengths), n_step=n_step, discount=discount, unroll=unroll)
     np.savez_compressed(os.path.join(GOLDEN, "episode_post.npz"), **out)
     print(f"episode post-processing: {len(lengths)} episodes ok (returns, priorities, transitions)")

@@ -483,6 +483,20 @@ def n_step_returns(rwds, root_values, n_step, discount):
     return out
 
 
+def mc_returns(rwds, discount):
+    """utils.py:75-86 (compute_MCreturns): discounted reward-to-go through NumPy's flip / cumsum / divide."""
+    T = len(rwds)
+    # np.power(float, int array): NumPy's own (SIMD) pow, which differs from libm pow() in the last bit for some
+    # exponents — the table has to come from NumPy itself; element i does not depend on the array length
+    disc = [float(x) for x in discount ** np.arange(T)]
+    acc, out = 0.0, [0.0] * T
+    for t in range(T - 1, -1, -1):  # np.cumsum over the flipped array: sequential float64 adds from the end
+        x = disc[t] * float(rwds[t])
+        acc = x if t == T - 1 else acc + x
+        out[t] = acc / disc[t]
+    return out
+
+
 def priorities(returns, root_values):
     """Muzero.py:197-200: |float32(return) - float32(root value)|."""
     return np.abs(np.array(returns, dtype=np.float32) - np.array(root_values, dtype=np.float32))

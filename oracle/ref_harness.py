@@ -49,6 +49,7 @@ def import_reference():
         MuZeroNet=ref_net.MuZeroNet,
         oneHot_encoding=ref_utils.oneHot_encoding,
         compute_n_step_returns=ref_utils.compute_n_step_returns,
+        compute_MCreturns=ref_utils.compute_MCreturns,
         adjust_temperature=ref_utils.adjust_temperature,
     )
 

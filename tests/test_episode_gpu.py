@@ -46,6 +46,19 @@ def test_returns_and_priorities_bit_exact(golden):
         assert np.array_equal(prio[:T, k], g[f"e{k}_priority"]), k     # float32, bit for bit
 
 
+def test_mc_returns_and_priorities_bit_exact(golden):
+    """TD_return=False branch: compute_MCreturns (utils.py:75-86) incl. NumPy's own pow for the discounts."""
+    g = golden("episode_post.npz")
+    st, _, ep_len = _fill_store(g)
+    ret, prio = st.post_process_mc(float(g["discount"]))
+    torch.cuda.synchronize()
+    ret, prio = ret.cpu().numpy(), prio.cpu().numpy()
+    for k in range(int(g["n_episodes"])):
+        T = ep_len[k]
+        assert np.array_equal(ret[:T, k], g[f"e{k}_mc_returns"]), k
+        assert np.array_equal(prio[:T, k], g[f"e{k}_mc_priority"]), k
+
+
 @pytest.mark.parametrize("capacity", [1000, 300])
 def test_unroll_into_replay_ring_matches_organise_transitions(golden, capacity):
     """Rows land in episode order from ptr with buffer.py's wrap-around; content equals the reference's arrays."""

@@ -205,6 +205,8 @@ def test_episode_post_matches_reference(golden):
         returns = port.n_step_returns(rw, root_q, n_step, discount)
         assert np.array_equal(np.array(returns, np.float64), g[f"e{k}_returns"])
         assert np.array_equal(port.priorities(returns, root_q), g[f"e{k}_priority"])
+        assert np.array_equal(np.array(port.mc_returns(rw, discount)), g[f"e{k}_mc_returns"])
+        assert np.array_equal(port.priorities(port.mc_returns(rw, discount), root_q), g[f"e{k}_mc_priority"])
         states = [np.zeros(15)] * len(rw)
         _, o_r, o_a, o_p, o_g = port.organise_transitions(states, rw, actions, pis, returns, unroll, 6, int(g[f"e{k}_absorbing"]))
         for name, arr in (("o_r", o_r), ("o_a", o_a), ("o_p", o_p), ("o_g", o_g)):
