@@ -795,6 +795,9 @@ static int tc_prepare(int* smem_bytes) {
   if (done_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(tc::v4::net_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::v4::net_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem_bytes);
+    const int carve = getenv("HMZ_TC_CARVEOUT") ? atoi(getenv("HMZ_TC_CARVEOUT")) : -1;  // tuning switch, default: unset
+    if (e == cudaSuccess && carve >= 0) e = cudaFuncSetAttribute(tc::v4::net_tc<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (e == cudaSuccess && carve >= 0) e = cudaFuncSetAttribute(tc::v4::net_tc<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaFuncSetAttribute(net_tc): %s", cudaGetErrorString(e));
     done_dev = dev;
   }
