@@ -5,6 +5,8 @@
 // hmz_tree.cuh.  These kernels are latency-bound gathers (one 128-byte record per tree level, one
 // 16-byte slot per backup step); there is no contraction here and nothing for tensor cores to do.
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "hmz_common.cuh"
 #include "hmz_tree.cuh"
@@ -531,8 +533,8 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
   return check_launch("search_backup_select");
 }
 
-int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_simulations, const double* ucb_table,
-                   double discount, void* stream) {
+static int search_run_direct(const hmz_search_t* s, const void* weights, int mode, int n_simulations, const double* ucb_table,
+                             double discount, void* stream) {
   if (int rc = check_search(s, "hmz_search_run")) return rc;
   if (s->n_searches == 0 || n_simulations == 0) return HMZ_OK;
   if (!weights || !ucb_table || !s->workspace || !s->latents || n_simulations < 0 ||
@@ -582,6 +584,96 @@ int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_s
     cudaStreamWaitEvent(main_stream, gs->done[g], 0);
   }
   return rc;
+}
+
+// ---- optional CUDA-graph replay of the whole search (HMZ_GRAPH=1) -------------------------------------------
+// The launch sequence of one hmz_search_run call (groups x simulations x 2 kernels, programmatic edges
+// included) is captured once per distinct argument set on an internal stream and replayed; the caller's stream
+// is joined around the replay with events.  Tooling / tuning switch: off by default.
+namespace {
+struct GraphEntry {
+  unsigned long long key[8];
+  cudaGraphExec_t exec;
+  long long kernels;
+};
+struct GraphCache {
+  int dev = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  std::vector<GraphEntry> entries;
+};
+int graph_mode() {
+  static const int on = getenv("HMZ_GRAPH") ? atoi(getenv("HMZ_GRAPH")) : 0;
+  return on;
+}
+}  // namespace
+
+static int search_run_graph(const hmz_search_t* s, const void* weights, int mode, int n_simulations, const double* ucb_table,
+                            double discount, void* stream) {
+  static thread_local GraphCache gc;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed");
+  if (gc.dev != dev) {
+    gc = GraphCache();
+    gc.dev = dev;
+    if (cudaStreamCreateWithFlags(&gc.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&gc.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&gc.join, cudaEventDisableTiming) != cudaSuccess)
+      return fail(HMZ_ERR_CUDA, "graph stream / event creation failed");
+  }
+  unsigned long long dbits;
+  memcpy(&dbits, &discount, 8);
+  const unsigned long long key[8] = {(unsigned long long)(uintptr_t)s->nodes, (unsigned long long)(uintptr_t)s->latents,
+                                     (unsigned long long)(uintptr_t)s->workspace, (unsigned long long)(uintptr_t)weights,
+                                     (unsigned long long)s->n_searches | ((unsigned long long)n_simulations << 40),
+                                     (unsigned long long)(uintptr_t)ucb_table, dbits,
+                                     (unsigned long long)s->n_records | ((unsigned long long)mode << 32) |
+                                         ((unsigned long long)s->root_prior_is_f64 << 40) | ((unsigned long long)s->latent_dtype << 44) |
+                                         ((unsigned long long)g_search_groups.load() << 48)};
+  GraphEntry* hit = nullptr;
+  for (auto& e : gc.entries)
+    if (memcmp(e.key, key, sizeof(key)) == 0) hit = &e;
+  if (!hit) {
+    if (int rc = check_search(s, "hmz_search_run")) return rc;  // one-time uploads happen outside the capture
+    const long long before = g_launches.load();
+    if (cudaStreamBeginCapture(gc.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+      return fail(HMZ_ERR_CUDA, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const int rc = search_run_direct(s, weights, mode, n_simulations, ucb_table, discount, (void*)gc.stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(gc.stream, &graph);
+    if (rc != HMZ_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess || !graph) return fail(HMZ_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    GraphEntry ne;
+    memcpy(ne.key, key, sizeof(key));
+    ne.kernels = g_launches.load() - before;
+    g_launches.store(before);  // capturing launched nothing
+    const cudaError_t ei = cudaGraphInstantiate(&ne.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+    if (gc.entries.size() >= 8) {  // tiny cache: drop the oldest
+      cudaGraphExecDestroy(gc.entries.front().exec);
+      gc.entries.erase(gc.entries.begin());
+    }
+    gc.entries.push_back(ne);
+    hit = &gc.entries.back();
+  }
+  cudaStream_t caller = (cudaStream_t)stream;
+  if (cudaEventRecord(gc.fork, caller) != cudaSuccess || cudaStreamWaitEvent(gc.stream, gc.fork, 0) != cudaSuccess ||
+      cudaGraphLaunch(hit->exec, gc.stream) != cudaSuccess || cudaEventRecord(gc.join, gc.stream) != cudaSuccess ||
+      cudaStreamWaitEvent(caller, gc.join, 0) != cudaSuccess)
+    return fail(HMZ_ERR_CUDA, "graph replay failed: %s", cudaGetErrorString(cudaGetLastError()));
+  g_launches.fetch_add(hit->kernels);
+  return HMZ_OK;
+}
+
+int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_simulations, const double* ucb_table,
+                   double discount, void* stream) {
+  if (graph_mode() && s && s->n_searches > 0 && n_simulations > 0 && g_prof_on.load() == 0 && g_tree_tl_search < 0)
+    return search_run_graph(s, weights, mode, n_simulations, ucb_table, discount, stream);
+  return search_run_direct(s, weights, mode, n_simulations, ucb_table, discount, stream);
 }
 
 }  // extern "C"
