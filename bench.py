@@ -153,6 +153,61 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ ours
+def measure_extras(dev, weights, peaks, timed):
+    """SURVEY §8f rows 1-3 at BASELINE sizes: episode post-processing kernels, replay-ring insertion and the
+    batched acting-evaluation harness.  Synthetic finished episodes (random lengths, flags, visit counts)."""
+    import numpy as np
+    import torch
+
+    from muzero_hanoi_b200 import _lib, acting
+    from muzero_hanoi_b200.engine import PackedWeights
+    from muzero_hanoi_b200.replay import EpisodeStore, ReplayRing
+    from oracle import port
+
+    B, T, n = GAMES_PER_GPU, MAX_STEPS, N_DISKS
+    st = EpisodeStore(B, T, n, dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    st.ep_len.copy_(torch.randint(1, T + 1, (B,), generator=g, device=dev, dtype=torch.int32))
+    st.flags.copy_((torch.rand(T, B, generator=g, device=dev) < 0.25).to(torch.uint8) * 2)
+    last = (st.ep_len.long() - 1).clamp(min=0)
+    st.flags[last, torch.arange(B, device=dev)] = 5  # every episode ends solved: all of them enter the ring
+    st.root_q.copy_(torch.randn(T, B, generator=g, device=dev, dtype=torch.float64) * 20)
+    st.visits.copy_(torch.randint(1, 40, (T, B, 6), generator=g, device=dev, dtype=torch.int16))
+    st.state.copy_(torch.randint(0, 1 << (2 * n), (T, B), generator=g, device=dev, dtype=torch.int32))
+    steps = int(st.ep_len.sum().item())
+    ms_ret = timed(lambda: st.post_process(10, DISCOUNT), 10) / 10
+    ms_mc = timed(lambda: st.post_process_mc(DISCOUNT), 10) / 10
+    ring = ReplayRing(steps + 1024, 5, 3 * n, 6, dev)
+
+    def add():
+        ring.ptr, ring.is_full = 0, False
+        ring.add_episodes(st, temperature=TEMPERATURE, only_solved=True)
+    add()
+    ms_add = timed(add, 5) / 5
+    row_bytes = 4 * 3 * n + 5 * 4 + 5 * 8 + 5 * 6 * 4 + 5 * 4 + 4
+    out = {"episodes": B, "transitions": steps, "t_max": T,
+           "n_step_returns": {"ms": ms_ret, "transitions_per_s": steps / (ms_ret * 1e-3),
+                              "gbs": steps * 21 / (ms_ret * 1e-3) / 1e9, "algorithmic": "21 B / transition (flags 1, root_q 8, return 8, priority 4)"},
+           "mc_returns": {"ms": ms_mc, "transitions_per_s": steps / (ms_mc * 1e-3)},
+           "replay_add": {"ms": ms_add, "rows_per_s": steps / (ms_add * 1e-3), "gbs": steps * (row_bytes + 30) / (ms_add * 1e-3) / 1e9,
+                          "frac_of_hbm": steps * (row_bytes + 30) / (ms_add * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "algorithmic": f"{row_bytes} B row written + 30 B episode record read per transition; includes the "
+                                         "row-assignment scan and one scalar read-back"}}
+    # acting harness at BASELINE.json configs[4] semantics (N=4, random starts, S=200, T=0), reduced episode count
+    n4, eps, sims = 4, 4096, 200
+    w4 = PackedWeights(port.make_weights(n4, 7), n4, _lib.MODE_BF16, dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, det = acting.get_results(w4, n4, MAX_STEPS, eps, [sims], 0.0, seed=1, return_details=True)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    moves = int(det[0]["steps"].max())
+    out["acting_harness"] = {"workload": f"hanoi{n4}_{eps}episodes_x{sims}sims_T0 (BASELINE.json configs[4] semantics)",
+                             "wall_s": wall, "moves_played": moves, "sims_per_s": eps * sims * moves / wall,
+                             "mean_error": float(det[0]["errors"].mean()), "episodes_per_s": eps / wall}
+    return out
+
+
 def workload_config(args, world):
     return {
         "workload": f"hanoi{N_DISKS}_selfplay_{GAMES_PER_GPU}games_per_gpu_x{N_SIMS}sims (BASELINE.json configs[2])",
@@ -406,6 +461,11 @@ def run_ours(args):
                                  "algorithmic": f"{ENV_BYTES_PER_STEP} B/step x {nenv} steps per launch"}}
         del env, acts
 
+    # ---- §8f rows (episode post-processing, replay ring, acting harness): measured only on request
+    extras = None
+    if args.extras and rank == 0:
+        extras = measure_extras(dev, weights, peaks, timed)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": sims_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -420,6 +480,8 @@ def run_ours(args):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if extras is not None:
+            line["extras"] = extras
         emit(line)
     if world > 1:
         dist.barrier()
@@ -438,6 +500,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-env", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time the SURVEY §8f rows (episode kernels, replay ring, acting harness)")
     ap.add_argument("--groups", type=int, default=0, help="concurrent search groups in hmz_search_run (0 = auto)")
     args = ap.parse_args()
     claim_stdout()
