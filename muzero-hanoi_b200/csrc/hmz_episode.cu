@@ -14,6 +14,8 @@
 //   sum([...])       CPython's float sum: first add exact, then Neumaier-compensated (bltinmodule.c)
 //   everything float64 with explicit round-to-nearest ops (no FMA contraction), cast to float32 where
 //   NumPy does (priority operands, replay rows).
+#include <cstdlib>
+
 #include "hmz_common.cuh"
 
 namespace hmz {
@@ -220,6 +222,81 @@ __global__ void __launch_bounds__(256) episode_unroll(
   }
 }
 
+
+// Same rows, one WARP per game: the episode's per-step inputs are gathered once into shared memory (the
+// [t][game] store makes those reads one sector each), the play policy is evaluated once per step instead of once
+// per (row, unroll slot), and every output array is then written with consecutive lanes on consecutive words —
+// rows of one episode are consecutive in the ring, so the stores are full 128-byte lines.
+struct StepStage {  // 44 bytes per episode step
+  float reward, ret, priority;
+  uint32_t state;
+  float pi[6];
+  uint32_t action;
+};
+__global__ void __launch_bounds__(128) episode_unroll_warp(
+    const uint32_t* __restrict__ ep_state, const uint8_t* __restrict__ ep_action, const uint8_t* __restrict__ ep_flags,
+    const uint16_t* __restrict__ ep_visits, const double* __restrict__ returns, const float* __restrict__ priority,
+    const int32_t* __restrict__ ep_len, const int64_t* __restrict__ row_base, const uint8_t* __restrict__ absorbing_action,
+    int64_t n, int t_max, int n_disks, int unroll, int exponent, int64_t capacity, float* __restrict__ buf_states,
+    float* __restrict__ buf_rwds, int64_t* __restrict__ buf_actions, float* __restrict__ buf_pi, float* __restrict__ buf_returns,
+    float* __restrict__ buf_priority) {
+  extern __shared__ StepStage stage_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  StepStage* stage = stage_all + (size_t)warp * t_max;
+  const int d_state = 3 * n_disks;
+  for (int64_t g = (int64_t)blockIdx.x * warps + warp; g < n; g += (int64_t)gridDim.x * warps) {
+    const int len = ep_len[g] < t_max ? ep_len[g] : t_max;
+    const int64_t rb = row_base[g];
+    if (len <= 0 || rb < 0) continue;  // warp-uniform
+    __syncwarp();
+    for (int t = lane; t < len; t += 32) {
+      const int64_t at = (int64_t)t * n + g;
+      StepStage st;
+      st.reward = (float)reward_of(ep_flags[at]);
+      st.ret = (float)returns[at];
+      st.priority = priority[at];
+      st.state = ep_state[at];
+      st.action = ep_action[at];
+      double wv[6];  // generate_play_policy (MCTS/mcts.py:154-176): visits ** exponent / sum, float64, then float32 rows
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double x = (double)ep_visits[at * 6 + a];
+        double y = x;
+        for (int e = 1; e < exponent; ++e) y = __dmul_rn(y, x);
+        wv[a] = y;
+      }
+      double rest = 0.0;  // np.sum of 6 doubles: first element + (0 + the rest, left to right)
+#pragma unroll
+      for (int a = 1; a < 6; ++a) rest = __dadd_rn(rest, wv[a]);
+      const double tot = __dadd_rn(wv[0], rest);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) st.pi[a] = (float)__ddiv_rn(wv[a], tot);
+      stage[t] = st;
+    }
+    __syncwarp();
+    const int64_t absorbing = (int64_t)absorbing_action[g];
+    const float uniform = (float)(1.0 / 6.0);
+    // states [len][3N]: utils.oneHot_encoding of the env word
+    for (int w = lane; w < len * d_state; w += 32) {
+      const int t = w / d_state, c = w - t * d_state, d = c / 3;
+      buf_states[((rb + t) % capacity) * d_state + c] = (((stage[t].state >> (2 * d)) & 3u) == (uint32_t)(c - 3 * d)) ? 1.0f : 0.0f;
+    }
+    for (int t = lane; t < len; t += 32) buf_priority[(rb + t) % capacity] = stage[t].priority;
+    // [len][unroll] arrays: rewards, returns, actions; beyond the episode end the absorbing padding (Muzero.py:296-307)
+    for (int w = lane; w < len * unroll; w += 32) {
+      const int t = w / unroll, k = w - t * unroll, j = t + k;
+      const int64_t o = ((rb + t) % capacity) * unroll + k;
+      buf_rwds[o] = j < len ? stage[j].reward : 0.0f;
+      buf_returns[o] = j < len ? stage[j].ret : 0.0f;
+      buf_actions[o] = j < len ? (int64_t)stage[j].action : absorbing;
+    }
+    for (int w = lane; w < len * unroll * 6; w += 32) {
+      const int t = w / (unroll * 6), r = w - t * unroll * 6, k = r / 6, a = r - k * 6, j = t + k;
+      buf_pi[((rb + t) % capacity) * unroll * 6 + r] = j < len ? stage[j].pi[a] : uniform;
+    }
+  }
+}
+
 }  // namespace hmz
 
 using namespace hmz;
@@ -301,6 +378,13 @@ int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const
   const int iex = (int)ex;
   if ((double)iex != ex)
     return fail(HMZ_ERR_UNSUPPORTED, "hmz_episode_unroll: temperature %g gives the non-integer exponent %g", temperature, ex);
+  const size_t stage_bytes = (size_t)t_max * sizeof(StepStage);
+  if (stage_bytes * 4 <= 48 * 1024 && !getenv("HMZ_UNROLL_SCALAR")) {  // warp-per-game form: staging fits the default shared memory
+    episode_unroll_warp<<<grid_for(n_games, 4, 8), 128, stage_bytes * 4, (cudaStream_t)stream>>>(
+        ep_state, ep_action, ep_flags, ep_visits, returns, priority, ep_len, row_base, absorbing_action, n_games, t_max, n_disks,
+        unroll, iex, capacity, buf_states, buf_rwds, buf_actions, buf_pi, buf_returns, buf_priority);
+    return check_launch("episode_unroll_warp");
+  }
   episode_unroll<<<grid_for(n_games * t_max, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       ep_state, ep_action, ep_flags, ep_visits, returns, priority, ep_len, row_base, absorbing_action, n_games, t_max, n_disks, unroll,
       iex, capacity, buf_states, buf_rwds, buf_actions, buf_pi, buf_returns, buf_priority);
