@@ -341,6 +341,26 @@ int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const
 int hmz_eval_track(const uint8_t* flags, int move_index, int64_t n_games, int32_t* steps, int32_t* illegal_moves, void* stream);
 int hmz_eval_errors(const int32_t* steps, const uint32_t* min_moves, int64_t n_games, int32_t* errors, void* stream);
 
+/* ------------------------------------------------------------------ learner ----------------
+ * Muzero._update (Muzero.py:209-274) + MuZeroNet.update (networks.py:118-122; Adam, networks.py:69) for one batch:
+ * the unrolled forward pass, the losses (squared error on the transformed value / reward, cross entropy on the
+ * policy, per-sample importance weights, mean, gradient x 1/unroll), the 0.5 gradient hook on the dynamics
+ * latents (:235), the backward pass and the Adam step, all float32.
+ *   params / grads / adam_m / adam_v: hmz_learner_param_count(n_disks) floats each — the 20 tensors of
+ *       MuZeroNet.state_dict() concatenated in state_dict order, each in torch's [out][in] layout
+ *   states f32 [batch][3N], rwds / returns f32 [batch][unroll], actions i64 [batch][unroll],
+ *   pi_probs f32 [batch][unroll][6], priority_w f32 [batch] or NULL (uniform replay)
+ *   step_index: 1 for the first update (Adam bias correction)
+ *   new_priorities (nullable) f32 [batch] = |value prediction - return| of unroll step 0 (:253-258)
+ *   losses_out f32 [3] (device) = means of the value, reward and policy losses (:269-273)
+ *   apply_update == 0: gradients only (grads is an output either way). */
+int64_t hmz_learner_param_count(int n_disks);
+int64_t hmz_learner_workspace_bytes(int n_disks, int batch, int unroll);
+int hmz_learner_step(float* params, float* grads, float* adam_m, float* adam_v, void* workspace, int n_disks, int batch, int unroll,
+                     const float* states, const float* rwds, const int64_t* actions, const float* pi_probs, const float* returns,
+                     const float* priority_w, float lr, float beta1, float beta2, float eps, int64_t step_index,
+                     float* new_priorities, float* losses_out, int apply_update, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,10 @@ SIGNATURES = {
     "hmz_rng_dirichlet": (_I, [_P, _L, _D, _U64, _U64, _P]),
     "hmz_rng_uniform": (_I, [_P, _L, _U64, _U64, _P]),
     "hmz_traj_record": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "hmz_learner_param_count": (_L, [_I]),
+    "hmz_learner_workspace_bytes": (_L, [_I, _I, _I]),
+    "hmz_learner_step": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _L,
+                         _P, _P, _I, _P]),
     "hmz_eval_track": (_I, [_P, _I, _L, _P, _P, _P]),
     "hmz_eval_errors": (_I, [_P, _P, _L, _P, _P]),
     "hmz_episode_record": (_I, [_P, _P, _P, _P, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P]),

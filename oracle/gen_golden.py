@@ -264,6 +264,47 @@ def gen_episode_post(ref):
     print(f"episode post-processing: {len(lengths)} episodes ok (returns, priorities, transitions)")
 
 
+def gen_learner(ref):
+    """Two consecutive Muzero._update calls (Muzero.py:209-274, Adam of networks.py:69) of the unmodified reference on a
+    synthetic batch: gradients after the first update and parameters after the second."""
+    import torch
+
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    import Muzero as ref_muzero  # noqa: E402
+
+    n, B, K = 3, 48, 5
+    rng = np.random.default_rng(31)
+    torch.manual_seed(0)
+    m = ref_muzero.Muzero(env=None, s_space_size=3 * n, n_action=6, discount=0.8, dirichlet_alpha=0.25, n_mcts_simulations=5,
+                          unroll_n_steps=K, batch_s=B, TD_return=True, n_TD_step=10, lr=0.002, buffer_size=64,
+                          priority_replay=True, device="cpu")
+    sd = port.make_weights(n, 17)
+    m.networks.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    batches = []
+    for _ in range(2):
+        states = np.stack([port.one_hot(port.index_to_state(int(i), n)) for i in rng.integers(0, 27, B)]).astype(np.float32)
+        rwds = rng.choice(np.array([0.0, 100.0, -0.1], np.float32), size=(B, K), p=[0.7, 0.1, 0.2]).astype(np.float32)
+        actions = rng.integers(0, 6, (B, K)).astype(np.int64)
+        pi = rng.dirichlet(np.ones(6), size=(B, K)).astype(np.float32)
+        returns = (rng.normal(0, 20, (B, K))).astype(np.float32)
+        w = rng.uniform(0.2, 1.0, B).astype(np.float32)
+        batches.append((states, rwds, actions, pi, returns, w))
+    out = dict(n=n, B=B, K=K, weight_seed=17, lr=0.002)
+    for i, (states, rwds, actions, pi, returns, w) in enumerate(batches):
+        new_p, v_loss, r_loss, p_loss = m._update(torch.from_numpy(states), torch.from_numpy(rwds), torch.from_numpy(actions),
+                                                  torch.from_numpy(pi), torch.from_numpy(returns), torch.from_numpy(w))
+        out.update({f"b{i}_states": states, f"b{i}_rwds": rwds, f"b{i}_actions": actions, f"b{i}_pi": pi, f"b{i}_returns": returns,
+                    f"b{i}_w": w, f"b{i}_new_priorities": np.asarray(new_p, np.float32),
+                    f"b{i}_losses": np.array([float(v_loss), float(r_loss), float(p_loss)], np.float32)})
+        if i == 0:
+            for k, prm in m.networks.named_parameters():
+                out[f"grad0_{k}"] = prm.grad.detach().numpy().copy()
+    for k, prm in m.networks.named_parameters():
+        out[f"param2_{k}"] = prm.detach().numpy().copy()
+    np.savez_compressed(os.path.join(GOLDEN, "learner.npz"), **out)
+    print("learner: two reference updates recorded (losses %s)" % out["b1_losses"])
+
+
 def check_choice_hook():
     """The uniform-as-input restatement of np.random.choice(p=...) equals numpy's legacy path."""
     rs = np.random.RandomState(7)
@@ -286,6 +327,7 @@ def main():
         gen_search(ref, name, cfg)
     gen_net_io(ref)
     gen_episode_post(ref)
+    gen_learner(ref)
     manifest = dict(
         generated_by="python -m oracle.gen_golden",
         reference="A-Andrews/Muzero-Hanoi (unmodified, /root/reference)",
