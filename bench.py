@@ -202,6 +202,47 @@ def measure_extras(dev, weights, peaks, timed):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     moves = int(det[0]["steps"].max())
+    # learner step (Muzero._update + Adam) at the reference's default batch (TrainingConfig: batch 256, unroll 5)
+    from muzero_hanoi_b200.learner import Learner
+    from muzero_hanoi_b200.networks import MuZeroNet
+
+    Bl, Kl = 256, 5
+    rng = np.random.default_rng(3)
+    sd = port.make_weights(n, 9)
+    batch = (np.stack([port.one_hot(port.index_to_state(int(i), n)) for i in rng.integers(0, 3 ** n, Bl)]).astype(np.float32),
+             rng.choice(np.array([0.0, 100.0, -0.1], np.float32), size=(Bl, Kl)).astype(np.float32),
+             rng.integers(0, 6, (Bl, Kl)).astype(np.int64), rng.dirichlet(np.ones(6), size=(Bl, Kl)).astype(np.float32),
+             rng.normal(0, 20, (Bl, Kl)).astype(np.float32), rng.uniform(0.2, 1.0, Bl).astype(np.float32))
+    ln = Learner(sd, n, Kl, device=dev)
+    dbatch = [torch.as_tensor(x, device=dev) for x in batch]
+    ln.update(*dbatch)
+    ms_upd = timed(lambda: ln.update(*dbatch), 20) / 20
+    # the reference's own step: torch CPU autograd + Adam through the same modules (all host threads torch wants)
+    import torch.nn.functional as F
+    net = MuZeroNet(3 * n, 6, 0.002, "cpu", TD_return=True)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    tb = [torch.from_numpy(x) for x in batch]
+
+    def ref_update():
+        h = net.represent(tb[0])
+        loss = 0
+        for t in range(Kl):
+            pl, pv = net.prediction(h)
+            h, pr = net.dynamics(h, F.one_hot(tb[2][:, t], 6).to(torch.long))
+            h.register_hook(lambda grad: grad * 0.5)
+            loss = loss + F.mse_loss(pv.squeeze(), tb[4][:, t], reduction="none") + F.mse_loss(pr.squeeze(), tb[1][:, t], reduction="none") \
+                + F.cross_entropy(pl, tb[3][:, t], reduction="none")
+        loss = (loss * tb[5]).mean()
+        loss.register_hook(lambda grad: grad * (1 / Kl))
+        net.update(loss)
+    ref_update()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ref_update()
+    ms_ref = (time.perf_counter() - t0) / 10 * 1e3
+    out["learner_step"] = {"workload": f"Muzero._update batch {Bl} x unroll {Kl}, N={n} (TrainingConfig defaults)", "ms": ms_upd,
+                           "updates_per_s": 1e3 / ms_upd, "cpu_torch_ms": ms_ref, "cpu_torch_threads": torch.get_num_threads(),
+                           "note": "includes the host-side loss read-back of every update"}
     out["acting_harness"] = {"workload": f"hanoi{n4}_{eps}episodes_x{sims}sims_T0 (BASELINE.json configs[4] semantics)",
                              "wall_s": wall, "moves_played": moves, "sims_per_s": eps * sims * moves / wall,
                              "mean_error": float(det[0]["errors"].mean()), "episodes_per_s": eps / wall}

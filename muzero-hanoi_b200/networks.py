@@ -3,8 +3,8 @@ names, state_dict keys and method signatures (cites are reference networks.py:li
 
 The ACTING methods — initial_inference and recurrent_inference, the only ones on the self-play
 hot path (MCTS/mcts.py:50,102 of the reference) — run on the libhmz kernels.  represent /
-dynamics / prediction / update keep their torch-module form because the learner and the
-gradient analyses differentiate through them (out of the hot-path scope)."""
+dynamics / prediction / update keep their torch-module form for the reference's gradient analyses; the
+training step itself also exists on the device (learner.Learner)."""
 import numpy as np
 import torch
 import torch.nn as nn
