@@ -144,6 +144,16 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
     leaf_parent[b] = (uint16_t)leaf.parent;
     leaf_action[b] = (uint8_t)leaf.action;
     leaf_depth[b] = (uint16_t)leaf.depth;
+#ifndef HMZ_NO_LATENT_PREFETCH
+    // The network kernel that follows gathers the parent's latent row (written many simulations ago, long gone
+    // from L2): ask for it now, a whole kernel launch ahead of its use.
+    if (s.latents != nullptr) {
+      const size_t row_bytes = s.latent_dtype == HMZ_LATENT_F32 ? 256 : 128;
+      const char* row = reinterpret_cast<const char*>(s.latents) + ((size_t)b * s.n_records + leaf.parent) * row_bytes;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+      if (row_bytes == 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+    }
+#endif
     if (tl) {
       g_tree_timeline[4] = (unsigned long long)leaf.depth;
       tree_mark<kTL>(5, tl);
