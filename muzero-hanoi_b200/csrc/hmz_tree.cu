@@ -114,11 +114,7 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
     if (half == 0) {
       double root_w = s.root_W[b];
       tree_mark<kTL>(7, tl, (uint32_t)__double2loint(root_w) ^ (uint32_t)__double2loint(mn));
-#if defined(HMZ_ABLATE) && (HMZ_ABLATE & 2)  // timing experiment only: no backup
-      if (depth < 0)
-#else
       if (depth <= kPathCap)
-#endif
         backup_path(nodes, path, ent4, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx, tl);
       else
         backup_walk(nodes, pe, pa, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
@@ -131,9 +127,6 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
       }
     }
   }
-#if defined(HMZ_ABLATE) && (HMZ_ABLATE & 4)  // timing experiment only: no selection
-  if (sim >= 0) return;
-#endif
   if (!do_select) return;
   // lane 0's (min, max) to its partner; the shuffle also orders lane 0's record updates before the pair's next walk
   mn = __shfl_sync(0xffffffffu, mn, (threadIdx.x & 31) & ~1);

@@ -252,11 +252,6 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
     }
     float score[3];
     bool exact_needed = !div_operand_ok(tn);
-#if defined(HMZ_ABLATE) && (HMZ_ABLATE & 1)  // timing experiment only: no float64 evaluation
-#pragma unroll
-    for (int j = 0; j < 3; ++j) score[j] = prior[j] + (float)c[j].n * 1e-3f + __double2float_rn(y[j] + yw[j]) * 1e-9f;
-    exact_needed = false;
-#else
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int n = c[j].n;
@@ -274,7 +269,6 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
       exact_needed |= (n + 1 > kRcpTable) |
                       ((n > 0) & (!div_operand_ok(c[j].W) | (normalise & (!range_ok | !div_operand_ok(num)))));
     }
-#endif
     if (exact_needed & active) {
 #pragma unroll
       for (int j = 0; j < 3; ++j)
