@@ -195,17 +195,11 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-// relu on two packed bf16 (rounding to bf16 preserves sign and zero, so relu commutes with it)
-__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
-  uint32_t r;
-  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
-  return r;
-}
 // 16-byte chunk `chunk` (8 bf16) of row `row` inside a [rows][128 B] SWIZZLE_128B K-atom
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 // =====================================================================================
-// net_recurrent_tc (v4): two 128-search tiles per CTA pass, ping-ponged.
+// net_tc (v4): two 128-search tiles per CTA pass, ping-ponged.
 //
 //   * Both tiles consume every weight block from the same shared-memory copy (double-buffered
 //     per layer kind, streamed by a dedicated loader warp), which halves the L2 -> SM weight
