@@ -290,6 +290,45 @@ int hmz_traj_record(const uint32_t* words, const int32_t* action, const int32_t*
                     uint32_t* traj_state, uint8_t* traj_action, uint16_t* traj_visits, float* traj_root_q,
                     uint8_t* action_u8_out, int64_t n_games, void* stream);
 
+/* One move of every game, fused on the host side of the ABI (the `hmz_selfplay_round` of SURVEY.md §8b): the loop body
+ * of Muzero._play_game (Muzero.py:165-186) for all games — hmz_net_initial, hmz_rng_dirichlet / hmz_rng_uniform keyed by
+ * (seed, game, move_index), hmz_search_begin_p0, hmz_search_run, hmz_search_root_policy (sampled action),
+ * hmz_traj_record (+ hmz_episode_record / hmz_episode_close when the ep_* buffers are given), hmz_env_step with
+ * auto-reset — enqueued on `stream` without any host synchronisation.  All pointers are caller-owned device buffers. */
+typedef struct hmz_selfplay {
+  hmz_search_t search;      /* root_prior_is_f64 must equal (dirichlet_alpha > 0 && exploration_eps > 0) */
+  const void* weights;      /* hmz_weights_pack blob */
+  const double* ucb_table;  /* as hmz_search_select */
+  uint32_t* words;          /* [B] env words (stepped in place) */
+  float* p0;                /* [B][6] root policy */
+  float* v0;                /* [B] root value */
+  double* noise;            /* [B][6] Dirichlet draws (nullable when dirichlet_alpha == 0) */
+  double* uniform;          /* [B] sampling uniforms */
+  int32_t* visits;          /* [B][6] root child visit counts of the move */
+  double* root_q;           /* [B] root_node.Q */
+  int32_t* action;          /* [B] sampled action */
+  uint8_t* action_u8;       /* [B] the same, as the env kernel reads it */
+  float* step_reward;       /* [B] reward of the move (a trajectory-ring row) */
+  uint8_t* step_flags;      /* [B] HMZ_FLAG_* of the move (a trajectory-ring row) */
+  uint32_t* traj_state;     /* trajectory-ring rows, nullable individually (hmz_traj_record) */
+  uint8_t* traj_action;
+  uint16_t* traj_visits;
+  float* traj_root_q;
+  uint32_t* ep_state;       /* episode store (hmz_episode_record / _close), all NULL to skip */
+  uint8_t* ep_action;
+  uint8_t* ep_flags;
+  uint16_t* ep_visits;
+  double* ep_root_q;
+  int32_t* ep_cur_slot;
+  int32_t* ep_len;
+  double discount, dirichlet_alpha, exploration_eps, temperature;
+  uint64_t seed;
+  int32_t mode, n_disks, max_steps, goal_peg, n_simulations, ep_t_max;
+  uint32_t reset_word;
+  int32_t reserved;
+} hmz_selfplay_t;
+int hmz_selfplay_move(const hmz_selfplay_t* sp, uint64_t move_index, void* stream);
+
 /* ------------------------------------------------------------------ episode post-processing ---
  * The tail of Muzero._play_game (Muzero.py:189-205) and Buffer.add (buffer.py:47-83) on the device.
  * Episode store: struct-of-arrays [t_max][n_games], slot = the game's own step counter (the counter

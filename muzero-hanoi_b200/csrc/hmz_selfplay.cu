@@ -131,4 +131,46 @@ int hmz_traj_record(const uint32_t* words, const int32_t* action, const int32_t*
   return check_launch("traj_record");
 }
 
+// One move of every game (Muzero._play_game loop body, Muzero.py:165-186): root inference -> Dirichlet mix ->
+// n_simulations fused simulations -> root policy + sampled action -> trajectory / episode record -> env step.
+// A composition of the entry points above: no host synchronisation, everything on `stream`.
+int hmz_selfplay_move(const hmz_selfplay_t* sp, uint64_t move_index, void* stream) {
+  if (!sp) return fail(HMZ_ERR_INVALID, "hmz_selfplay_move: null descriptor");
+  const hmz_search_t* s = &sp->search;
+  const int64_t B = s->n_searches;
+  if (B == 0) return HMZ_OK;
+  if (!sp->weights || !sp->words || !sp->p0 || !sp->v0 || !sp->uniform || !sp->visits || !sp->root_q || !sp->action ||
+      !sp->action_u8 || !sp->step_reward || !sp->step_flags || !sp->ucb_table || s->n_searches < 0)
+    return fail(HMZ_ERR_INVALID, "hmz_selfplay_move: null buffer in descriptor");
+  const bool use_noise = sp->dirichlet_alpha > 0.0 && sp->exploration_eps > 0.0;
+  if (use_noise && !sp->noise) return fail(HMZ_ERR_INVALID, "hmz_selfplay_move: noise buffer required when dirichlet_alpha > 0");
+  if (s->root_prior_is_f64 != (use_noise ? 1 : 0))
+    return fail(HMZ_ERR_INVALID, "hmz_selfplay_move: search.root_prior_is_f64 must be %d", use_noise ? 1 : 0);
+  if (int rc = hmz_net_initial(sp->weights, sp->mode, sp->n_disks, sp->words, nullptr, s->latents, s->n_records, s->latent_dtype,
+                               sp->p0, sp->v0, B, stream))
+    return rc;
+  if (use_noise)
+    if (int rc = hmz_rng_dirichlet(sp->noise, B, sp->dirichlet_alpha, sp->seed, move_index, stream)) return rc;
+  if (int rc = hmz_rng_uniform(sp->uniform, B, sp->seed, move_index, stream)) return rc;
+  if (int rc = hmz_search_begin_p0(s, sp->p0, use_noise ? sp->noise : nullptr, sp->exploration_eps, stream)) return rc;
+  if (int rc = hmz_search_run(s, sp->weights, sp->mode, sp->n_simulations, sp->ucb_table, sp->discount, stream)) return rc;
+  if (int rc = hmz_search_root_policy(s, sp->n_simulations, sp->temperature, 0, sp->uniform, sp->visits, nullptr, sp->root_q,
+                                      sp->action, stream))
+    return rc;
+  if (int rc = hmz_traj_record(sp->words, sp->action, sp->visits, sp->root_q, sp->traj_state, sp->traj_action, sp->traj_visits,
+                               sp->traj_root_q, sp->action_u8, B, stream))
+    return rc;
+  if (sp->ep_state) {
+    if (int rc = hmz_episode_record(sp->words, sp->action, sp->visits, sp->root_q, sp->n_disks, sp->ep_t_max, B, sp->ep_state,
+                                    sp->ep_action, sp->ep_visits, sp->ep_root_q, sp->ep_cur_slot, nullptr, stream))
+      return rc;
+  }
+  if (int rc = hmz_env_step(sp->words, sp->action_u8, sp->step_reward, sp->step_flags, nullptr, B, sp->n_disks, sp->max_steps,
+                            sp->goal_peg, 1, sp->reset_word, stream))
+    return rc;
+  if (sp->ep_state)
+    if (int rc = hmz_episode_close(sp->step_flags, sp->ep_cur_slot, B, sp->ep_flags, sp->ep_len, stream)) return rc;
+  return HMZ_OK;
+}
+
 }  // extern "C"

@@ -401,38 +401,29 @@ class SelfPlay:
         self.env.reset()
 
     def move(self):
-        """One move of every game; returns the ring slot that was written.  No host sync."""
-        env, m, st, lib = self.env, self.mcts, self.mcts.store, self.lib
-        stream = current_stream()
+        """One move of every game (hmz_selfplay_move: one C call, no host sync); returns the ring slot that was written."""
+        env, m, st = self.env, self.mcts, self.mcts.store
         t, ctr = self.moves_done % self.T, self.moves_done
-        self.weights.initial(self.B, words=env.words, latents_out=st.latents, out_rows_per_item=st.n_records,
-                             latent_dtype=st.latent_dtype, p0=self.p0, v0=self.v0)
         use_noise = m.root_dirichlet_alpha > 0.0 and m.root_exploration_eps > 0.0
-        if use_noise:
-            check(lib.hmz_rng_dirichlet(ptr(self.noise), self.B, float(m.root_dirichlet_alpha), self.seed, ctr, stream))
-        check(lib.hmz_rng_uniform(ptr(self.uniform), self.B, self.seed, ctr, stream))
         st.desc.root_prior_is_f64 = int(use_noise)
-        check(lib.hmz_search_begin_p0(C.byref(st.desc), ptr(self.p0), ptr(self.noise) if use_noise else None,
-                                      float(m.root_exploration_eps), stream))
-        check(lib.hmz_search_run(C.byref(st.desc), self.weights.ptr, self.weights.mode, self.S, ptr(m._table),
-                                 m.discount, stream))
-        check(lib.hmz_search_root_policy(C.byref(st.desc), self.S, self.temperature, 0, ptr(self.uniform),
-                                         ptr(m.visits), None, ptr(m.root_q), ptr(m.action), stream))
-        check(lib.hmz_traj_record(ptr(env.words), ptr(m.action), ptr(m.visits), ptr(m.root_q), ptr(self.traj_state[t]),
-                                  ptr(self.traj_action[t]), ptr(self.traj_visits[t]), ptr(self.traj_root_q[t]),
-                                  ptr(self.action_u8), self.B, stream))
-        if self.episodes is not None:
-            self.episodes.record(env.words, m.action, m.visits, m.root_q)
-        check(lib.hmz_env_step(ptr(env.words), ptr(self.action_u8), ptr(self.traj_reward[t]), ptr(self.traj_flags[t]),
-                               None, self.B, env.discs, env.max_steps, env.goal_peg, 1, env.reset_word, stream))
-        if self.episodes is not None:
-            self.episodes.close(self.traj_flags[t])
+        ep = self.episodes
+        d = _lib.SelfPlayDesc(
+            search=st.desc, weights=self.weights.ptr.value, ucb_table=m._table.data_ptr(), words=env.words.data_ptr(),
+            p0=self.p0.data_ptr(), v0=self.v0.data_ptr(), noise=self.noise.data_ptr() if use_noise else None,
+            uniform=self.uniform.data_ptr(), visits=m.visits.data_ptr(), root_q=m.root_q.data_ptr(), action=m.action.data_ptr(),
+            action_u8=self.action_u8.data_ptr(), step_reward=self.traj_reward[t].data_ptr(), step_flags=self.traj_flags[t].data_ptr(),
+            traj_state=self.traj_state[t].data_ptr(), traj_action=self.traj_action[t].data_ptr(),
+            traj_visits=self.traj_visits[t].data_ptr(), traj_root_q=self.traj_root_q[t].data_ptr(),
+            ep_state=ep.state.data_ptr() if ep else None, ep_action=ep.action.data_ptr() if ep else None,
+            ep_flags=ep.flags.data_ptr() if ep else None, ep_visits=ep.visits.data_ptr() if ep else None,
+            ep_root_q=ep.root_q.data_ptr() if ep else None, ep_cur_slot=ep.cur_slot.data_ptr() if ep else None,
+            ep_len=ep.ep_len.data_ptr() if ep else None, discount=m.discount, dirichlet_alpha=float(m.root_dirichlet_alpha),
+            exploration_eps=float(m.root_exploration_eps), temperature=self.temperature, seed=self.seed, mode=self.weights.mode,
+            n_disks=env.discs, max_steps=env.max_steps, goal_peg=env.goal_peg, n_simulations=self.S,
+            ep_t_max=ep.t_max if ep else 0, reset_word=env.reset_word, reserved=0)
+        check(self.lib.hmz_selfplay_move(C.byref(d), ctr, current_stream()))
         self.moves_done += 1
         return t
-
-    def launches_per_move(self):
-        use_noise = self.mcts.root_dirichlet_alpha > 0.0 and self.mcts.root_exploration_eps > 0.0
-        return 3 * self.S + 6 + int(use_noise) + (2 if self.episodes is not None else 0)
 
     def record_bytes_per_game(self):
         return 4 + 1 + 4 + 1 + 12 + 4  # state, action, reward, flags, visits, root_q
