@@ -314,7 +314,7 @@ __device__ __forceinline__ void hidden_epilogue_tmem(uint32_t h) {
   tmem_st_wait();
 }
 
-#define TL4(slot) do { if (timeline && blockIdx.x == 0 && pass == 0) g_timeline[slot] = clock64(); } while (0)
+#define TL4(slot) do { if ((timeline & 1) && blockIdx.x == 0 && pass == 0) g_timeline[slot] = clock64(); } while (0)
 
 // kInitial = false: recurrent_inference — networks dynamics (g), reward, policy, value; input = gathered latents.
 // kInitial = true : initial_inference  — networks representation (h), policy, value; input = one-hot of env words.
@@ -337,6 +337,16 @@ net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_
   extern __shared__ uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5;
+// (the clock is read through an asm with a memory clobber so that it cannot be scheduled above a barrier)
+#define TL4_CTA(slot)                                                        \
+  do {                                                                       \
+    if ((timeline & 1) && blockIdx.x == 0 && tid == 0) {                     \
+      unsigned long long now_;                                               \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_)::"memory");         \
+      g_timeline[slot] = now_;                                               \
+    }                                                                        \
+  } while (0)
+  TL4_CTA(60);
 
   if (tid == 0) {
     for (int k = 0; k < 2; ++k)
@@ -366,10 +376,20 @@ net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
+  TL4_CTA(61);
   // Programmatic dependent launch: barrier init, TMEM allocation and (loader warp) the first weight
   // blocks do not depend on the preceding tree kernel; everything that reads its outputs does.
-  pdl_launch_dependents();
-  if (warp != kLoaderWarp && warp != kMmaWarp) pdl_wait();
+  // The dependents (the next tree kernel) are signalled only AFTER this kernel's own wait: that kernel reads
+  // what the previous tree kernel wrote before it waits for this one, so it must not start before the
+  // previous tree kernel has completed.  (The loader warp waits after its first four weight blocks.)
+  const bool late_signal = (timeline & 2) != 0;  // HMZ_PDL bit 2
+  const int signal_net = ((timeline >> 2) & 7) - 1;  // HMZ_PDL_NET_AT: -1 = here
+  if (!late_signal && signal_net < 0) pdl_launch_dependents();
+  if (warp != kLoaderWarp && (late_signal || warp != kMmaWarp)) {
+    pdl_wait();
+    if (late_signal && signal_net < 0) pdl_launch_dependents();
+  }
+  TL4_CTA(62);
 
   if (warp == kLoaderWarp) {
     // ================================= loader warp =================================
@@ -378,6 +398,10 @@ net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {
         if (kInitial && (i >> 1) == 1) continue;  // no reward head at the root
+        if (late_signal && i == 4 && pair == (int)blockIdx.x) {  // the first four blocks are in flight: now order after the preceding kernel
+          pdl_wait();
+          if (signal_net < 0) pdl_launch_dependents();
+        }
         const int kind = i & 1;
         const uint32_t u = use[kind], slot = u & 1u;
         if (u >= 2u) mbar_wait(&s.bar_wfree[kind][slot], ((u >> 1) - 1u) & 1u);
@@ -401,6 +425,7 @@ net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_
 #pragma unroll 1
       for (int net = 0; net < 4; ++net) {  // dynamics / representation, reward, policy, value
         if (kInitial && net == 1) continue;
+        if (net == signal_net && pair + (int)gridDim.x >= n_pairs) pdl_launch_dependents();
         // ---- first layer: H[0:256) = [A | AX] x W1'^T
         {
           const uint32_t slot = use_f & 1u;
@@ -690,6 +715,7 @@ net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_
 
   tc_fence_before();
   __syncthreads();
+  TL4_CTA(63);
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -813,7 +839,7 @@ int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_pe
   const unsigned grid = tc_grid(n, &n_pairs);
   cudaError_t e = launch_pdl(1, tc::v4::net_tc<false>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream,
                              (const uint8_t*)weights, lat_in, in_rows_per_item, in_row, actions, (const uint32_t*)nullptr, 0,
-                             lat_out, out_rows_per_item, out_row, latent_dtype, r, p, v, n, n_pairs, tc_timeline_enabled());
+                             lat_out, out_rows_per_item, out_row, latent_dtype, r, p, v, n, n_pairs, tc_timeline_enabled() | (pdl_prewait() << 1) | ((pdl_net_at() + 1) << 2));
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_tc<recurrent> launch: %s", cudaGetErrorString(e));
   return check_launch("net_tc<recurrent>");
 }
@@ -826,7 +852,7 @@ int tc_net_initial(const void* weights, int n_disks, const uint32_t* words, void
   cudaError_t e = launch_pdl(1, tc::v4::net_tc<true>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream,
                              (const uint8_t*)weights, (const void*)nullptr, (int64_t)1, (const uint16_t*)nullptr,
                              (const uint8_t*)nullptr, words, n_disks, lat_out, out_rows_per_item, (int64_t)0, latent_dtype,
-                             (float*)nullptr, p0, v0, n, n_pairs, 0);
+                             (float*)nullptr, p0, v0, n, n_pairs, (pdl_prewait() << 1) | ((pdl_net_at() + 1) << 2));
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_tc<initial> launch: %s", cudaGetErrorString(e));
   return check_launch("net_tc<initial>");
 }

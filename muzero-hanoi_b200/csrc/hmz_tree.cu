@@ -88,34 +88,48 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
                                                                      const float* __restrict__ v, int do_select) {
   const int half = threadIdx.x & 1;
   const int64_t b_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
-  pdl_launch_dependents();
-  pdl_wait();  // everything below reads what the network kernel wrote
+  const int signal_at = (do_select >> 2) & 3;  // HMZ_PDL_TREE_AT
+  if (signal_at == 0) pdl_launch_dependents();
+  if (!(do_select & 2)) pdl_wait();  // HMZ_PDL bit 2 off: nothing is read before the wait
   const bool valid = b_raw < s.n_searches;  // out-of-range pairs stay for the warp-uniform walk, masked
   const int64_t b = valid ? b_raw : s.n_searches - 1;
   const bool tl = kTL && valid && b == (g_tree_timeline_search & 0xFFFFFFFFll) && sim == (int)(g_tree_timeline_search >> 32) && half == 0;
   tree_mark<kTL>(0, tl);
   hmz_node_t* nodes = s.nodes + b * s.n_records;
   uint32_t* path = path_ent ? path_ent + b * kPathCap : nullptr;
-  double mn = 0.0, mx = 0.0;
+  // Before waiting for the network kernel: everything the backup needs that the PREVIOUS tree kernel wrote
+  // (leaf scalars, the leaf-side path entries and their slots, min/max, the root's W).  The network kernel
+  // only signals its dependents after its own wait, so that kernel has completed by the time this one runs.
+  double mn = 0.0, mx = 0.0, root_w = 0.0;
+  int pe = 0, pa = 0, depth = kPathCap + 1;
+  uint4 ent4 = make_uint4(0u, 0u, 0u, 0u);
+  uint4 raw[4];
+  raw[0] = make_uint4(0u, 0u, 0u, 0u);
   if (valid) {
-    const int pe = leaf_parent[b], pa = leaf_action[b];
-    tree_mark<kTL>(1, tl, (uint32_t)(pe + pa));
-    const int depth = (path != nullptr && leaf_depth != nullptr) ? (int)leaf_depth[b] : kPathCap + 1;
-    // everything the backup needs that depends only on the search index is requested up front, in one
-    // memory round trip: leaf scalars, network outputs, min/max (the leaf-side path entries follow the depth)
-    uint4 ent4 = make_uint4(0u, 0u, 0u, 0u);
-    if (half == 0 && path != nullptr && depth <= kPathCap) ent4 = *reinterpret_cast<const uint4*>(path + ((depth - 1) & ~3));
-    mn = s.minmax[2 * b];
-    mx = s.minmax[2 * b + 1];
+    pe = leaf_parent[b];
+    pa = leaf_action[b];
+    if (path != nullptr && leaf_depth != nullptr) depth = (int)leaf_depth[b];
+    if (half == 0) {
+      mn = s.minmax[2 * b];
+      mx = s.minmax[2 * b + 1];
+      root_w = s.root_W[b];
+      if (depth <= kPathCap) {
+        ent4 = *reinterpret_cast<const uint4*>(path + ((depth - 1) & ~3));
+        load_batch4(nodes, ent4, (depth - 1) & ~3, depth, raw);
+      }
+    }
+  }
+  tree_mark<kTL>(1, tl, (uint32_t)(pe + pa) ^ raw[0].w);
+  pdl_wait();  // everything below reads what the network kernel wrote
+  if (valid) {
     const float r_leaf = r[b];
     const double v_leaf = (double)v[b];
     write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
     tree_mark<kTL>(6, tl, __float_as_uint(r_leaf));
     if (half == 0) {
-      double root_w = s.root_W[b];
       tree_mark<kTL>(7, tl, (uint32_t)__double2loint(root_w) ^ (uint32_t)__double2loint(mn));
       if (depth <= kPathCap)
-        backup_path(nodes, path, ent4, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx, tl);
+        backup_path(nodes, path, ent4, raw, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx, tl);
       else
         backup_walk(nodes, pe, pa, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
       s.root_W[b] = root_w;
@@ -127,12 +141,14 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
       }
     }
   }
-  if (!do_select) return;
+  if (signal_at == 1) pdl_launch_dependents();
+  if (!(do_select & 1)) return;
   // lane 0's (min, max) to its partner; the shuffle also orders lane 0's record updates before the pair's next walk
   mn = __shfl_sync(0xffffffffu, mn, (threadIdx.x & 31) & ~1);
   mx = __shfl_sync(0xffffffffu, mx, (threadIdx.x & 31) & ~1);
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
   const Leaf leaf = select_leaf<kTL>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path, tl, valid);
+  if (signal_at == 2) pdl_launch_dependents();
   if (half == 0 && valid) {
     leaf_parent[b] = (uint16_t)leaf.parent;
     leaf_action[b] = (uint8_t)leaf.action;
@@ -527,7 +543,7 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
                                  s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
     return rc;
   ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
-  const int do_select = sim + 1 < n_simulations ? 1 : 0;
+  const int do_select = (sim + 1 < n_simulations ? 1 : 0) | (pdl_prewait() << 1) | ((pdl_tree_at() & 3) << 2);
   const float *cr = sc.r, *cp = sc.p, *cv = sc.v;
   cudaError_t e = launch_pdl(2, g_tree_tl_search >= 0 ? search_backup_select<true> : search_backup_select<false>, dim3(search_grid(B)),
                              dim3(kTreeThreads), 0, st, *s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path, cr, cp, cv,

@@ -349,15 +349,17 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
 // float64 recurrence runs in registers.  Operation for operation identical to backup_walk, so results
 // are bit-identical.  The batch loop is deliberately not unrolled: registers (occupancy) matter more
 // to this latency-bound kernel than the second batch's instruction-level parallelism.
-__device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& ent4, int k0, int depth, int sim, float r,
-                                              double& value, double discount, double& mn, double& mx, bool tl = false,
-                                              int tl_slot = 0) {
+__device__ __forceinline__ void load_batch4(hmz_node_t* nodes, const uint4& ent4, int k0, int depth, uint4 (&raw)[4]) {
   const uint32_t ent[4] = {ent4.x, ent4.y, ent4.z, ent4.w};
-  if (tl) tree_mark<true>(tl_slot, true, ent4.x);
-  uint4 raw[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     if (k0 + j < depth) raw[j] = *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16));
+}
+
+__device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& ent4, const uint4 (&raw)[4], int k0, int depth,
+                                              int sim, float r, double& value, double discount, double& mn, double& mx,
+                                              bool tl = false, int tl_slot = 0) {
+  const uint32_t ent[4] = {ent4.x, ent4.y, ent4.z, ent4.w};
   if (tl) tree_mark<true>(tl_slot + 1, true, raw[0].w ^ ((k0 + 1 < depth) ? raw[1].w : 0u) ^ ((k0 + 2 < depth) ? raw[2].w : 0u) ^ ((k0 + 3 < depth) ? raw[3].w : 0u));
 #pragma unroll
   for (int j = 3; j >= 0; --j) {
@@ -378,16 +380,20 @@ __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& en
   if (tl) tree_mark<true>(tl_slot + 2, true, (uint32_t)__double2loint(value));
 }
 
-// ent_first: path entries of the leaf-side batch, loaded by the caller together with the leaf scalars.
-__device__ __forceinline__ void backup_path(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, uint4 ent4, int depth,
-                                            int sim, float r, double value, double discount, double& root_w, double& mn,
-                                            double& mx, bool tl = false) {
+// ent4 / raw: path entries and slots of the leaf-side batch, loaded by the caller (before it waits for the
+// network kernel: they were written by the previous tree kernel).
+__device__ __forceinline__ void backup_path(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, uint4 ent4, uint4 (&raw)[4],
+                                            int depth, int sim, float r, double value, double discount, double& root_w,
+                                            double& mn, double& mx, bool tl = false) {
   int tl_slot = 24;
 #pragma unroll 1
   for (int k0 = (depth - 1) & ~3; k0 >= 0; k0 -= 4) {
-    backup_batch4(nodes, ent4, k0, depth, sim, r, value, discount, mn, mx, tl, tl_slot);
+    backup_batch4(nodes, ent4, raw, k0, depth, sim, r, value, discount, mn, mx, tl, tl_slot);
     tl_slot += 3;
-    if (k0 >= 4) ent4 = *reinterpret_cast<const uint4*>(path_ent + k0 - 4);
+    if (k0 >= 4) {
+      ent4 = *reinterpret_cast<const uint4*>(path_ent + k0 - 4);
+      load_batch4(nodes, ent4, k0 - 4, depth, raw);
+    }
   }
   root_w = __dadd_rn(root_w, value);
   minmax_update(__dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1))), mn, mx);

@@ -7,7 +7,7 @@ from muzero_hanoi_b200 import _lib
 from muzero_hanoi_b200.engine import PackedWeights
 from muzero_hanoi_b200.networks import MuZeroNet
 torch.manual_seed(0)
-n = 65536
+n = int(os.environ.get("N", 65536))
 net = MuZeroNet(15, 6, 0.002, "cpu", TD_return=True)
 w = PackedWeights(net.state_dict(), 5, 1)
 h_in = torch.rand(n, 64, device="cuda").to(torch.bfloat16)
@@ -35,7 +35,7 @@ if os.environ.get("HMZ_TC_V3"):
         names[34 + ly * 3] = f"hid {nm}: epilogue done"
         names[35 + ly * 3] = f"hid {nm}: saw second layer"
 else:  # v4: two tiles per CTA
-    names = {}
+    names = {60: "CTA: kernel entry", 61: "CTA: barriers + TMEM ready", 62: "CTA: past the PDL wait", 63: "CTA: all warps done"}
     ev = 0
     for net in "grpv":
         for what in ["L1 inputs ready", "L2 inputs ready (A1 written)"]:
