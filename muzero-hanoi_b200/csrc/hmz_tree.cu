@@ -13,7 +13,12 @@
 
 namespace hmz {
 
-constexpr int kTreeThreads = 128;                    // 4 warps x 16 searches
+// Warps never synchronise with each other, so the block size only sets the granularity at which finished
+// work frees its registers for the next block: a block lives as long as the DEEPEST of its walks.
+#ifndef HMZ_TREE_THREADS
+#define HMZ_TREE_THREADS 128
+#endif
+constexpr int kTreeThreads = HMZ_TREE_THREADS;       // 16 searches per warp
 constexpr int kSearchesPerBlock = kTreeThreads / 2;  // one lane pair per search
 constexpr int kLatentWidth = HMZ_LATENT;
 
@@ -57,7 +62,7 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
                                                               double discount, uint16_t* __restrict__ leaf_parent,
                                                               uint8_t* __restrict__ leaf_action,
                                                               uint16_t* __restrict__ leaf_depth, uint8_t* __restrict__ path_out,
-                                                              int path_cap, uint32_t* __restrict__ path_ent) {
+                                                              int path_cap, uint4* __restrict__ path_elem) {
   const int half = threadIdx.x & 1;
   const int64_t b_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
   const bool valid = b_raw < s.n_searches;  // out-of-range pairs stay in the warp-uniform walk, masked
@@ -65,7 +70,7 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
   const Leaf leaf = select_leaf(s.nodes + b * s.n_records, rp, s.minmax[2 * b], s.minmax[2 * b + 1], sim, ucb_table,
                                 discount, half, path_out ? path_out + b * path_cap : nullptr, path_cap,
-                                path_ent ? path_ent + b * kPathCap : nullptr, false, valid);
+                                path_elem ? path_elem + b * (2 * kPathCap) : nullptr, false, valid);
   if (half == 0 && valid) {
     leaf_parent[b] = (uint16_t)leaf.parent;
     leaf_action[b] = (uint8_t)leaf.action;
@@ -75,15 +80,16 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
 
 // Phases 2b + 3 of simulation `sim` (expansion with the network outputs, backup), optionally followed
 // at once by the selection of simulation `sim + 1` — the fused hot-loop form: the path just updated
-// is still in this SM's L1 and the next walk usually shares its prefix.  With path_ent the backup
-// loads all path slots up front; without it (split-phase API) it walks the parent links.
+// is still in this SM's L1 and the next walk usually shares its prefix.  With path elements (slot + entry
+// per level, recorded by the previous walk) the backup needs one round trip for its inputs; without them
+// (split-phase API) it walks the parent links.
 #ifndef HMZ_TREE_MIN_BLOCKS
-#define HMZ_TREE_MIN_BLOCKS 5
+#define HMZ_TREE_MIN_BLOCKS (640 / HMZ_TREE_THREADS)  // 20 warps per SM (96 registers)
 #endif
 template <bool kTL>
 __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
                                                                      double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
-                                                                     uint16_t* leaf_depth, uint32_t* path_ent,
+                                                                     uint16_t* leaf_depth, uint4* path_elem,
                                                                      const float* __restrict__ r, const float* __restrict__ p,
                                                                      const float* __restrict__ v, int do_select) {
   const int half = threadIdx.x & 1;
@@ -96,49 +102,61 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
   const bool tl = kTL && valid && b == (g_tree_timeline_search & 0xFFFFFFFFll) && sim == (int)(g_tree_timeline_search >> 32) && half == 0;
   tree_mark<kTL>(0, tl);
   hmz_node_t* nodes = s.nodes + b * s.n_records;
-  uint32_t* path = path_ent ? path_ent + b * kPathCap : nullptr;
+  uint4* path = path_elem ? path_elem + b * (2 * kPathCap) : nullptr;
   // Before waiting for the network kernel: everything the backup needs that the PREVIOUS tree kernel wrote
-  // (leaf scalars, the leaf-side path entries and their slots, min/max, the root's W).  The network kernel
-  // only signals its dependents after its own wait, so that kernel has completed by the time this one runs.
+  // (leaf scalars, min/max, the root's W, and the path elements = slot + entry per level, at addresses that
+  // depend only on the search index: ONE round trip for paths of up to four levels).  The network kernel only
+  // signals its dependents after its own wait, so that kernel has completed by the time this one runs.
+  // Lane 0 of the pair owns levels 0..3 and the root, lane 1 the levels from 4 on (leaf side first).
   double mn = 0.0, mx = 0.0, root_w = 0.0;
   int pe = 0, pa = 0, depth = kPathCap + 1;
-  uint4 ent4 = make_uint4(0u, 0u, 0u, 0u);
-  uint4 raw[4];
-  raw[0] = make_uint4(0u, 0u, 0u, 0u);
+  PathBatch pb;
+  pb.slot[0] = make_uint4(0u, 0u, 0u, 0u);
   if (valid) {
+    if (half == 0 && path != nullptr) load_batch4(path, 0, 4, pb);  // unconditionally: the depth is not known yet
     pe = leaf_parent[b];
     pa = leaf_action[b];
     if (path != nullptr && leaf_depth != nullptr) depth = (int)leaf_depth[b];
-    if (half == 0) {
-      mn = s.minmax[2 * b];
-      mx = s.minmax[2 * b + 1];
-      root_w = s.root_W[b];
-      if (depth <= kPathCap) {
-        ent4 = *reinterpret_cast<const uint4*>(path + ((depth - 1) & ~3));
-        load_batch4(nodes, ent4, (depth - 1) & ~3, depth, raw);
-      }
-    }
+    mn = s.minmax[2 * b];
+    mx = s.minmax[2 * b + 1];
+    if (half == 0) root_w = s.root_W[b];
+    if (half == 1 && depth > 4 && depth <= kPathCap) load_batch4(path, (depth - 1) & ~3, depth, pb);
   }
-  tree_mark<kTL>(1, tl, (uint32_t)(pe + pa) ^ raw[0].w);
+  tree_mark<kTL>(1, tl, (uint32_t)(pe + pa) ^ pb.slot[0].w);
   pdl_wait();  // everything below reads what the network kernel wrote
+  float r_leaf = 0.f;
+  double value = 0.0;
+  const bool by_path = depth <= kPathCap;
   if (valid) {
-    const float r_leaf = r[b];
-    const double v_leaf = (double)v[b];
+    r_leaf = r[b];
+    value = (double)v[b];
     write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
     tree_mark<kTL>(6, tl, __float_as_uint(r_leaf));
-    if (half == 0) {
-      tree_mark<kTL>(7, tl, (uint32_t)__double2loint(root_w) ^ (uint32_t)__double2loint(mn));
-      if (depth <= kPathCap)
-        backup_path(nodes, path, ent4, raw, depth, sim, r_leaf, v_leaf, discount, root_w, mn, mx, tl);
-      else
-        backup_walk(nodes, pe, pa, sim, r_leaf, v_leaf, discount, root_w, mn, mx);
-      s.root_W[b] = root_w;
-      s.minmax[2 * b] = mn;
-      s.minmax[2 * b + 1] = mx;
-      if (tl) {
-        g_tree_timeline[2] = (unsigned long long)depth;
-        tree_mark<kTL>(3, tl, (uint32_t)__double2loint(mn));
-      }
+    if (half == 1 && by_path && depth > 4) backup_deep(nodes, path, pb, depth, sim, r_leaf, value, discount, mn, mx);
+  }
+  {  // lane 1's running (value, min, max) to lane 0
+    const int src = (threadIdx.x & 31) | 1;
+    const double v1 = __shfl_sync(0xffffffffu, value, src);
+    const double mn1 = __shfl_sync(0xffffffffu, mn, src);
+    const double mx1 = __shfl_sync(0xffffffffu, mx, src);
+    if (half == 0 && by_path && depth > 4) {
+      value = v1;
+      mn = mn1;
+      mx = mx1;
+    }
+  }
+  if (valid && half == 0) {
+    tree_mark<kTL>(7, tl, (uint32_t)__double2loint(root_w) ^ (uint32_t)__double2loint(mn));
+    if (by_path)
+      backup_top(nodes, pb, depth, sim, r_leaf, value, discount, root_w, mn, mx);
+    else
+      backup_walk(nodes, pe, pa, sim, r_leaf, value, discount, root_w, mn, mx);
+    s.root_W[b] = root_w;
+    s.minmax[2 * b] = mn;
+    s.minmax[2 * b + 1] = mx;
+    if (tl) {
+      g_tree_timeline[2] = (unsigned long long)depth;
+      tree_mark<kTL>(3, tl, (uint32_t)__double2loint(mn));
     }
   }
   if (signal_at == 1) pdl_launch_dependents();
@@ -383,7 +401,7 @@ int hmz_debug_tree_timeline(long long search, unsigned long long* host_out) {
 
 int64_t hmz_search_workspace_bytes(int64_t n_searches) {
   if (n_searches < 0) return -1;
-  return ((n_searches + 63) / 64) * 64 * 168 + 512;  // p[6] r v, leaf_parent/action/depth, 32 path words per search
+  return ((n_searches + 63) / 64) * 64 * (40 + 32 * kPathCap) + 512;  // p[6] r v, leaf_parent/action/depth, kPathCap path elements of 32 B per search
 }
 
 int hmz_search_minmax_reset(double* minmax, int64_t n, void* stream) {
@@ -511,7 +529,7 @@ struct SimScratch {
   float *p, *r, *v;
   uint16_t *lp, *depth;
   uint8_t* la;
-  uint32_t* path;
+  uint4* path;
 };
 SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -522,7 +540,7 @@ SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
   sc.lp = (uint16_t*)(ws + padded_total * 32) + lo;
   sc.la = (uint8_t*)(ws + padded_total * 34) + lo;
   sc.depth = (uint16_t*)(ws + padded_total * 36) + lo;
-  sc.path = (uint32_t*)(ws + padded_total * 40) + lo * kPathCap;
+  sc.path = (uint4*)(ws + padded_total * 40) + lo * (2 * kPathCap);
   return sc;
 }
 }  // namespace

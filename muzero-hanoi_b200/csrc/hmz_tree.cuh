@@ -193,7 +193,9 @@ __device__ __noinline__ float child_score_exact(double W, float rwd, int n, floa
 //   root_n        root.N  (= number of completed simulations)
 //   root_prior64  float64 root priors when the root was Dirichlet-noised, else nullptr
 //   path_out      nullable [path_cap] bytes: chosen action per level (diagnostics)
-//   path_ent      nullable [kPathCap] words: (record | action << 16) per level, for the backup
+//   path_elem     nullable [kPathCap] 32-byte elements, one per level, for the next backup: the chosen child's
+//                 16-byte slot AS READ HERE (nothing touches the tree until that backup) and the word
+//                 (record | action << 16) — so the backup needs no second, dependent round trip for the slots
 // The three children of a lane are evaluated as ONE straight-line block (no data-dependent branch
 // between them), so their float64 chains interleave: every division is the two-correction form of
 // div_refine on reciprocals fetched up front, unvisited children are computed and discarded, and the
@@ -206,7 +208,7 @@ template <bool kTL = false>
 __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const double* __restrict__ root_prior64, double mn,
                                             double mx, int root_n, const double* __restrict__ ucb_table,
                                             double discount, int half, uint8_t* __restrict__ path_out, int path_cap,
-                                            uint32_t* __restrict__ path_ent, bool tl_on = false, bool active = true) {
+                                            uint4* __restrict__ path_elem, bool tl_on = false, bool active = true) {
   const bool normalise = mx > mn;  // MinMaxStats.normalize (MCTS/utils_mcts.py:12-16)
   const double range = __dsub_rn(mx, mn);
   const bool range_ok = normalise & rcp_usable(range);
@@ -297,7 +299,11 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
     if (active) {
       if (half == 0) {
         if (path_out != nullptr && depth < path_cap) path_out[depth] = (uint8_t)best;
-        if (path_ent != nullptr && depth < kPathCap) path_ent[depth] = (uint32_t)e | ((uint32_t)best << 16);
+      }
+      if (path_elem != nullptr && depth < kPathCap && (best >= 3) == (half == 1)) {  // the lane that holds the chosen slot
+        const int j = best - 3 * half;
+        const uint4 qs = j == 0 ? q0 : (j == 1 ? q1 : q2);
+        st256(path_elem + 2 * depth, qs, make_uint4((uint32_t)e | ((uint32_t)best << 16), 0u, 0u, 0u));
       }
       if (depth < 8) tree_mark<kTL>(9 + 2 * depth, tl_on, (uint32_t)best_child);
       ++depth;
@@ -344,57 +350,58 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
   minmax_update(__dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1))), mn, mx);
 }
 
-// Same backup for a path of depth <= kPathCap recorded by select_leaf, four levels per batch (leaf-side
-// batch first): the batch's slots are loaded together (one memory round trip), then the leaf-to-root
-// float64 recurrence runs in registers.  Operation for operation identical to backup_walk, so results
-// are bit-identical.  The batch loop is deliberately not unrolled: registers (occupancy) matter more
-// to this latency-bound kernel than the second batch's instruction-level parallelism.
-__device__ __forceinline__ void load_batch4(hmz_node_t* nodes, const uint4& ent4, int k0, int depth, uint4 (&raw)[4]) {
-  const uint32_t ent[4] = {ent4.x, ent4.y, ent4.z, ent4.w};
+// Same backup for a path of depth <= kPathCap recorded by select_leaf as 32-byte path elements (slot + entry), four
+// levels per batch.  A batch is loaded with four independent 256-bit loads from consecutive addresses that depend
+// only on the search index, then the leaf-to-root float64 recurrence runs in registers and the updated slots are
+// stored to their home records.  Operation for operation identical to backup_walk, so results are bit-identical.
+struct PathBatch {
+  uint4 slot[4];
+  uint32_t ent[4];
+};
+
+__device__ __forceinline__ void load_batch4(const uint4* __restrict__ path_elem, int k0, int depth, PathBatch& pb) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (k0 + j < depth) raw[j] = *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16));
+  for (int j = 0; j < 4; ++j) {
+    uint4 meta = make_uint4(0u, 0u, 0u, 0u);
+    if (k0 + j < depth) ld256(path_elem + 2 * (k0 + j), pb.slot[j], meta);
+    pb.ent[j] = meta.x;
+  }
 }
 
-__device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const uint4& ent4, const uint4 (&raw)[4], int k0, int depth,
-                                              int sim, float r, double& value, double discount, double& mn, double& mx,
-                                              bool tl = false, int tl_slot = 0) {
-  const uint32_t ent[4] = {ent4.x, ent4.y, ent4.z, ent4.w};
-  if (tl) tree_mark<true>(tl_slot + 1, true, raw[0].w ^ ((k0 + 1 < depth) ? raw[1].w : 0u) ^ ((k0 + 2 < depth) ? raw[2].w : 0u) ^ ((k0 + 3 < depth) ? raw[3].w : 0u));
+__device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const PathBatch& pb, int k0, int depth, int sim, float r,
+                                              double& value, double discount, double& mn, double& mx) {
 #pragma unroll
   for (int j = 3; j >= 0; --j) {
     if (k0 + j < depth) {
-      Slot c = Slot::unpack(raw[j]);
+      Slot c = Slot::unpack(pb.slot[j]);
       if (k0 + j == depth - 1) {  // the leaf slot: Node.expand bookkeeping on the parent (node.py:44-49)
         c.rwd = r;
         c.child = sim + 1;
       }
       c.W = __dadd_rn(c.W, value);  // current.W += value
       c.n += 1;                     // current.N += 1
-      *slot_ptr(nodes, (int)(ent[j] & 0xFFFFu), (int)(ent[j] >> 16)) = c.pack();
+      *slot_ptr(nodes, (int)(pb.ent[j] & 0xFFFFu), (int)(pb.ent[j] >> 16)) = c.pack();
       const double rwd = (double)c.rwd;
       minmax_update(__dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n))), mn, mx);
       value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
     }
   }
-  if (tl) tree_mark<true>(tl_slot + 2, true, (uint32_t)__double2loint(value));
 }
 
-// ent4 / raw: path entries and slots of the leaf-side batch, loaded by the caller (before it waits for the
-// network kernel: they were written by the previous tree kernel).
-__device__ __forceinline__ void backup_path(hmz_node_t* nodes, const uint32_t* __restrict__ path_ent, uint4 ent4, uint4 (&raw)[4],
-                                            int depth, int sim, float r, double value, double discount, double& root_w,
-                                            double& mn, double& mx, bool tl = false) {
-  int tl_slot = 24;
+// Levels >= 4, leaf side first (lane 1 of the pair): `pb` holds the leaf-side batch k_top = (depth - 1) & ~3 >= 4.
+__device__ __forceinline__ void backup_deep(hmz_node_t* nodes, const uint4* __restrict__ path_elem, PathBatch& pb, int depth, int sim,
+                                            float r, double& value, double discount, double& mn, double& mx) {
 #pragma unroll 1
-  for (int k0 = (depth - 1) & ~3; k0 >= 0; k0 -= 4) {
-    backup_batch4(nodes, ent4, raw, k0, depth, sim, r, value, discount, mn, mx, tl, tl_slot);
-    tl_slot += 3;
-    if (k0 >= 4) {
-      ent4 = *reinterpret_cast<const uint4*>(path_ent + k0 - 4);
-      load_batch4(nodes, ent4, k0 - 4, depth, raw);
-    }
+  for (int k0 = (depth - 1) & ~3; k0 >= 4; k0 -= 4) {
+    backup_batch4(nodes, pb, k0, depth, sim, r, value, discount, mn, mx);
+    if (k0 >= 8) load_batch4(path_elem, k0 - 4, depth, pb);
   }
+}
+
+// Levels 0..3 and the root itself (lane 0 of the pair): rwd = 0.0 at the root (MCTS/mcts.py:69), N = sim + 1 after this backup.
+__device__ __forceinline__ void backup_top(hmz_node_t* nodes, const PathBatch& pb, int depth, int sim, float r, double value,
+                                           double discount, double& root_w, double& mn, double& mx) {
+  backup_batch4(nodes, pb, 0, depth, sim, r, value, discount, mn, mx);
   root_w = __dadd_rn(root_w, value);
   minmax_update(__dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1))), mn, mx);
 }
