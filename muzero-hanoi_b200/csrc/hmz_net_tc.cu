@@ -348,23 +348,26 @@ net_tc(const uint8_t* __restrict__ wsec, const void* __restrict__ lat_in, int64_
   } while (0)
   TL4_CTA(60);
 
-  if (tid == 0) {
+  // barrier initialisation is spread over one lane of each of warps 1-3 while warp 0 allocates TMEM
+  if (tid == 32) {
     for (int k = 0; k < 2; ++k)
       for (int j = 0; j < 2; ++j) {
         mbar_init(&s.bar_wfull[k][j], 1);
         mbar_init(&s.bar_wfree[k][j], 1);
       }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s.bar_g[t], kHidThreadsPerTile + 128);
-      mbar_init(&s.bar_d[t], 1);
-      mbar_init(&s.bar_a[t], kHidThreadsPerTile);
-      mbar_init(&s.bar_o[t], 1);
-      mbar_init(&s.bar_s[t], 1);
-      mbar_init(&s.bar_raw[t], kHidThreadsPerTile);
-      mbar_init(&s.bar_hn[t], kHidThreadsPerTile);
-      mbar_init(&s.bar_fin[t], 128);
-    }
     mbar_init(&s.bar_end, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid == 64 || tid == 96) {
+    const int t = (tid >> 5) - 2;
+    mbar_init(&s.bar_g[t], kHidThreadsPerTile + 128);
+    mbar_init(&s.bar_d[t], 1);
+    mbar_init(&s.bar_a[t], kHidThreadsPerTile);
+    mbar_init(&s.bar_o[t], 1);
+    mbar_init(&s.bar_s[t], 1);
+    mbar_init(&s.bar_raw[t], kHidThreadsPerTile);
+    mbar_init(&s.bar_hn[t], kHidThreadsPerTile);
+    mbar_init(&s.bar_fin[t], 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {  // TMEM: all 512 columns (one CTA per SM)
