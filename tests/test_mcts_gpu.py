@@ -282,3 +282,37 @@ def test_long_search_beyond_reciprocal_table_bit_exact():
     torch.cuda.synchronize()
     assert np.array_equal(visits2.cpu().numpy(), o_visits) and np.array_equal(q2.cpu().numpy(), o_q)
     assert np.array_equal(fused.store.minmax.cpu().numpy(), mm)
+
+
+def test_fused_backup_deep_chains_bit_exact():
+    """A policy head with one dominant action makes every search a chain that deepens with each simulation: walk
+    depths run from 1 past 4 (lane 1's share of the path elements), past 8 (further batches loaded inside the
+    backup) and past the 32 recorded levels (parent-link fallback).  The fused hot-loop kernel must equal the C
+    oracle bit for bit on visit counts, root values, min/max and — through the split-phase run that records them —
+    leaf depths."""
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    n, B, S = 4, 2048, 60
+    sd = {k: np.array(v, copy=True) for k, v in port.make_weights(n, 31).items()}
+    bias = sd["policy_net.2.bias"]
+    bias[:] += np.array([12.0, 0.0, 6.0, 0.0, 0.0, 0.0], dtype=bias.dtype)  # action 0 dominates, action 2 a distant second
+    weights = PackedWeights(sd, n)
+    env = VecHanoi(n, 200, B)
+    env.random_reset(seed=9)
+    mcts = BatchedMCTS(0.8, 0.0, S, B)
+    mm = mcts.store.minmax.cpu().numpy().copy()
+    p0, r, p, v, depth = _split_search(mcts, weights, env.words, None)
+    torch.cuda.synchronize()
+    o_visits, o_q, o_depth = cport.search_injected(p0.cpu().numpy().astype(np.float64), False, mm, r.cpu().numpy(), p.cpu().numpy(),
+                                                   v.cpu().numpy(), 0.8, port.ucb_table(S + 1), want_depth=True)
+    d = depth.cpu().numpy().astype(np.uint16)
+    assert np.array_equal(d, o_depth)
+    assert d.max() > 32 and ((d > 4) & (d <= 8)).any() and ((d > 8) & (d <= 32)).any() and (d <= 4).any()
+    for groups_B in (B, 100):  # a ragged last block as well
+        fused = BatchedMCTS(0.8, 0.0, S, groups_B)
+        sub = VecHanoi(n, 200, groups_B)
+        sub.words.copy_(env.words[:groups_B])
+        _, _, q2, visits2 = fused.run_mcts(weights, words=sub.words, temperature=0.0, deterministic=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(visits2.cpu().numpy(), o_visits[:groups_B]) and np.array_equal(q2.cpu().numpy(), o_q[:groups_B])
+        assert np.array_equal(fused.store.minmax.cpu().numpy(), mm[:groups_B])
