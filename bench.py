@@ -417,7 +417,7 @@ def run_ours(args):
         if name == "net_recurrent":
             achieved = FLOP_PER_SIM * B / per_launch_s / 1e12
             peak = peaks["bf16_tflops_sustained"]
-            return {"kernel": "net_recurrent_tc (fused g + reward/policy/value heads, tcgen05)", "bound": "tensor",
+            return {"kernel": "net_tc<recurrent> (fused g + reward/policy/value heads, tcgen05)", "bound": "tensor",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peaks["source"] + ", sustained bf16",
                     "algorithmic": f"{FLOP_PER_SIM} FLOP/sim x {B} sims per launch"}
