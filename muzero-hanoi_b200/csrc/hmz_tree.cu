@@ -86,10 +86,12 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
 #ifndef HMZ_TREE_MIN_BLOCKS
 #define HMZ_TREE_MIN_BLOCKS (640 / HMZ_TREE_THREADS)  // 20 warps per SM (96 registers)
 #endif
-template <bool kTL>
+// kTrusted (hmz_search_run only): `wild_flags[search]` is the sticky "a backup wrote an untame W or Q" flag of
+// is_tame(); the walk then skips its per-operand range tests.  The split-phase API keeps the tests.
+template <bool kTL, bool kTrusted>
 __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
                                                                      double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
-                                                                     uint16_t* leaf_depth, uint4* path_elem,
+                                                                     uint16_t* leaf_depth, uint4* path_elem, uint8_t* wild_flags,
                                                                      const float* __restrict__ r, const float* __restrict__ p,
                                                                      const float* __restrict__ v, int do_select) {
   const int half = threadIdx.x & 1;
@@ -112,7 +114,9 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
   int pe = 0, pa = 0, depth = kPathCap + 1;
   PathBatch pb;
   pb.slot[0] = make_uint4(0u, 0u, 0u, 0u);
+  bool wild = false, was_wild = false;
   if (valid) {
+    if (kTrusted && half == 0) was_wild = wild = wild_flags[b] != 0;
     if (half == 0 && path != nullptr) load_batch4(path, 0, 4, pb);  // unconditionally: the depth is not known yet
     pe = leaf_parent[b];
     pa = leaf_action[b];
@@ -132,25 +136,28 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
     value = (double)v[b];
     write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
     tree_mark<kTL>(6, tl, __float_as_uint(r_leaf));
-    if (half == 1 && by_path && depth > 4) backup_deep(nodes, path, pb, depth, sim, r_leaf, value, discount, mn, mx);
+    if (half == 1 && by_path && depth > 4) backup_deep(nodes, path, pb, depth, sim, r_leaf, value, discount, mn, mx, wild);
   }
   {  // lane 1's running (value, min, max) to lane 0
     const int src = (threadIdx.x & 31) | 1;
     const double v1 = __shfl_sync(0xffffffffu, value, src);
     const double mn1 = __shfl_sync(0xffffffffu, mn, src);
     const double mx1 = __shfl_sync(0xffffffffu, mx, src);
+    const bool wild1 = __shfl_sync(0xffffffffu, (int)wild, src) != 0;
     if (half == 0 && by_path && depth > 4) {
       value = v1;
       mn = mn1;
       mx = mx1;
+      wild |= wild1;
     }
   }
   if (valid && half == 0) {
     tree_mark<kTL>(7, tl, (uint32_t)__double2loint(root_w) ^ (uint32_t)__double2loint(mn));
     if (by_path)
-      backup_top(nodes, pb, depth, sim, r_leaf, value, discount, root_w, mn, mx);
+      backup_top(nodes, pb, depth, sim, r_leaf, value, discount, root_w, mn, mx, wild);
     else
-      backup_walk(nodes, pe, pa, sim, r_leaf, value, discount, root_w, mn, mx);
+      backup_walk(nodes, pe, pa, sim, r_leaf, value, discount, root_w, mn, mx, wild);
+    if (kTrusted && wild && !was_wild) wild_flags[b] = 1;
     s.root_W[b] = root_w;
     s.minmax[2 * b] = mn;
     s.minmax[2 * b + 1] = mx;
@@ -164,8 +171,9 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
   // lane 0's (min, max) to its partner; the shuffle also orders lane 0's record updates before the pair's next walk
   mn = __shfl_sync(0xffffffffu, mn, (threadIdx.x & 31) & ~1);
   mx = __shfl_sync(0xffffffffu, mx, (threadIdx.x & 31) & ~1);
+  if (kTrusted) wild = __shfl_sync(0xffffffffu, (int)wild, (threadIdx.x & 31) & ~1) != 0;
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
-  const Leaf leaf = select_leaf<kTL>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path, tl, valid);
+  const Leaf leaf = select_leaf<kTL, kTrusted>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path, tl, valid, wild);
   if (signal_at == 2) pdl_launch_dependents();
   if (half == 0 && valid) {
     leaf_parent[b] = (uint16_t)leaf.parent;
@@ -360,8 +368,9 @@ static int ensure_tree_attrs() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)");
   if (done_dev == dev || tree_carveout() < 0) return HMZ_OK;
-  cudaError_t e = cudaFuncSetAttribute(search_backup_select<false>, cudaFuncAttributePreferredSharedMemoryCarveout, tree_carveout());
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(search_backup_select<true>, cudaFuncAttributePreferredSharedMemoryCarveout, tree_carveout());
+  cudaError_t e = cudaFuncSetAttribute(search_backup_select<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, tree_carveout());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(search_backup_select<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, tree_carveout());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(search_backup_select<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, tree_carveout());
   if (e == cudaSuccess) e = cudaFuncSetAttribute(search_select, cudaFuncAttributePreferredSharedMemoryCarveout, tree_carveout());
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
   done_dev = dev;
@@ -401,7 +410,8 @@ int hmz_debug_tree_timeline(long long search, unsigned long long* host_out) {
 
 int64_t hmz_search_workspace_bytes(int64_t n_searches) {
   if (n_searches < 0) return -1;
-  return ((n_searches + 63) / 64) * 64 * (40 + 32 * kPathCap) + 512;  // p[6] r v, leaf_parent/action/depth, kPathCap path elements of 32 B per search
+  // p[6] r v, leaf_parent/action/depth, the sticky "wild" flag, kPathCap path elements of 32 B per search
+  return ((n_searches + 63) / 64) * 64 * (40 + 32 * kPathCap) + 512;
 }
 
 int hmz_search_minmax_reset(double* minmax, int64_t n, void* stream) {
@@ -466,9 +476,9 @@ int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, co
   if (!leaf_parent || !leaf_action || !r || !p || !v || sim < 0 || sim + 1 >= s->n_records)
     return fail(HMZ_ERR_INVALID, "hmz_search_expand_backup: bad arguments (sim=%d, n_records=%d)", sim, s->n_records);
   // split-phase form: no recorded path, the backup walks the parent links
-  search_backup_select<false><<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(
+  search_backup_select<false, false><<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(
       *s, sim, nullptr, discount, const_cast<uint16_t*>(leaf_parent), const_cast<uint8_t*>(leaf_action), nullptr, nullptr,
-      r, p, v, 0);
+      nullptr, r, p, v, 0);
   return check_launch("search_expand_backup");
 }
 
@@ -528,7 +538,7 @@ int get_group_streams(int want, GroupStreams** out) {
 struct SimScratch {
   float *p, *r, *v;
   uint16_t *lp, *depth;
-  uint8_t* la;
+  uint8_t *la, *wild;
   uint4* path;
 };
 SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
@@ -540,6 +550,7 @@ SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
   sc.lp = (uint16_t*)(ws + padded_total * 32) + lo;
   sc.la = (uint8_t*)(ws + padded_total * 34) + lo;
   sc.depth = (uint16_t*)(ws + padded_total * 36) + lo;
+  sc.wild = (uint8_t*)(ws + padded_total * 38) + lo;
   sc.path = (uint4*)(ws + padded_total * 40) + lo * (2 * kPathCap);
   return sc;
 }
@@ -553,6 +564,7 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   if (sim == 0) {
     ProfScope prof_scope(HMZ_PROF_SELECT, stream);
+    if (cudaMemsetAsync(sc.wild, 0, (size_t)B, st) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaMemsetAsync(wild flags) failed");
     search_select<<<search_grid(B), kTreeThreads, 0, st>>>(*s, 0, ucb_table, discount, sc.lp, sc.la, sc.depth, nullptr, 0,
                                                           sc.path);
     if (int rc = check_launch("search_select")) return rc;
@@ -563,9 +575,14 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
   ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
   const int do_select = (sim + 1 < n_simulations ? 1 : 0) | (pdl_prewait() << 1) | ((pdl_tree_at() & 3) << 2);
   const float *cr = sc.r, *cp = sc.p, *cv = sc.v;
-  cudaError_t e = launch_pdl(2, g_tree_tl_search >= 0 ? search_backup_select<true> : search_backup_select<false>, dim3(search_grid(B)),
-                             dim3(kTreeThreads), 0, st, *s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth, sc.path, cr, cp, cv,
-                             do_select);
+#ifdef HMZ_NO_TRUST  // A/B switch (tools/sweep19.sh): per-operand range tests in the hot loop as well
+  constexpr bool kTrust = false;
+#else
+  constexpr bool kTrust = true;
+#endif
+  cudaError_t e = launch_pdl(2, g_tree_tl_search >= 0 ? search_backup_select<true, true> : search_backup_select<false, kTrust>,
+                             dim3(search_grid(B)), dim3(kTreeThreads), 0, st, *s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth,
+                             sc.path, sc.wild, cr, cp, cv, do_select);
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "search_backup_select launch: %s", cudaGetErrorString(e));
   return check_launch("search_backup_select");
 }

@@ -141,6 +141,15 @@ __device__ __forceinline__ double div_refine(double a, double b, double y) {
 __device__ __forceinline__ bool div_operand_ok(double a) {
   return (__double_as_longlong(a) == 0ll) | div_fast_ok(a);
 }
+// "Tame": +-0 or 2^-700 <= |a| < 2^700 (NaN / Inf are not).  The fused hot loop keeps a sticky per-search flag
+// "some W or Q written by a backup was not tame" instead of testing every operand of every walk: if all W and all
+//   Q = rwd + discount * W / N  (every one of which also went through the min/max update, so mn <= Q <= mx)
+// are tame, then W is a valid operand of the two-correction division, and so is  num = Q - mn:  0 <= num <=
+// mx - mn < 2^701, and a nonzero difference of two tame doubles is at least 2^-700 * 2^-52 > 2^-830.
+__device__ __forceinline__ bool is_tame(double a) {
+  const unsigned hi = (unsigned)__double2hiint(a) & 0x7FFFFFFFu;
+  return (__double_as_longlong(a) == 0ll) | ((hi - 0x14300000u) < (0x6BB00000u - 0x14300000u));
+}
 // a / n for a visit count n >= 1: the shortcut is evaluated unconditionally (straight-line code), the rare
 // operand outside its proven range takes the generic division afterwards
 __device__ __forceinline__ double div_by_count(double a, int n) {
@@ -204,15 +213,20 @@ __device__ __noinline__ float child_score_exact(double W, float rwd, int n, floa
 // (`active` masks the memory accesses of finished or out-of-range pairs), so the pair exchange is a plain
 // full-mask shuffle — a pair-masked shuffle inside a divergent loop costs a MATCH/REDUX/VOTE sequence per
 // call — and the walk needs no reconvergence bookkeeping.  ALL 32 lanes of the warp must call it.
-template <bool kTL = false>
+//   kTrusted / wild   hot loop only: the per-operand range tests are replaced by `wild` (the search's sticky flag or
+//                     untame persisted bounds) plus a per-launch test of the largest possible count; see is_tame()
+template <bool kTL = false, bool kTrusted = false>
 __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const double* __restrict__ root_prior64, double mn,
                                             double mx, int root_n, const double* __restrict__ ucb_table,
                                             double discount, int half, uint8_t* __restrict__ path_out, int path_cap,
-                                            uint4* __restrict__ path_elem, bool tl_on = false, bool active = true) {
+                                            uint4* __restrict__ path_elem, bool tl_on = false, bool active = true,
+                                            bool wild = false) {
   const bool normalise = mx > mn;  // MinMaxStats.normalize (MCTS/utils_mcts.py:12-16)
   const double range = __dsub_rn(mx, mn);
   const bool range_ok = normalise & rcp_usable(range);
   const double range_rcp = range_ok ? __drcp_rn(range) : 0.0;
+  // trusted mode: every count on the walk is <= root_n, the bounds persist from earlier searches (test them here)
+  const bool distrust = wild | (root_n + 1 > kRcpTable) | (normalise & (!range_ok | !is_tame(mn) | !is_tame(mx)));
   int e = 0, n_parent = root_n, depth = 0;
   Leaf leaf{0, 0, 0};
   uint4 q0 = make_uint4(0u, 0u, 0u, 0xFFFF0000u), q1 = q0, q2 = q0, q3 = make_uint4(0u, 0u, 0u, 0u);
@@ -253,7 +267,7 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
       yw[j] = __ldg(&g_rcp[min(c[j].n + 1, kRcpTable)]);
     }
     float score[3];
-    bool exact_needed = !div_operand_ok(tn);
+    bool exact_needed = !div_operand_ok(tn) | (kTrusted & distrust);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int n = c[j].n;
@@ -268,9 +282,13 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
       const float u = use64 ? __double2float_rn(__dmul_rn(rp64[j], w)) : __fmul_rn(prior[j], __double2float_rn(w));
       score[j] = __fadd_rn(qf, u);  // node.py:83 on float32 arrays
       // bitwise, not short-circuit: a data-dependent branch here would fence the three children's chains apart
-      exact_needed |= (n + 1 > kRcpTable) |
-                      ((n > 0) & (!div_operand_ok(c[j].W) | (normalise & (!range_ok | !div_operand_ok(num)))));
+      if (!kTrusted)
+        exact_needed |= (n + 1 > kRcpTable) |
+                        ((n > 0) & (!div_operand_ok(c[j].W) | (normalise & (!range_ok | !div_operand_ok(num)))));
     }
+#ifdef HMZ_EXPERIMENT_NOCHECK  // measurement only (tools/sweep19.sh): what the operand-range tests cost; NOT exact in general
+    exact_needed = false;
+#endif
     if (exact_needed & active) {
 #pragma unroll
       for (int j = 0; j < 3; ++j)
@@ -324,7 +342,7 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
 // node.expand bookkeeping on the parent slot + Node.backup (MCTS/node.py:53-70) from the leaf to
 // the root by walking parent links (any depth).  `value` enters as the network value of the new node.
 __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, int sim, float r, double value,
-                                            double discount, double& root_w, double& mn, double& mx) {
+                                            double discount, double& root_w, double& mn, double& mx, bool& wild) {
   int e = pe, a = pa;
   bool leaf = true;
   while (true) {
@@ -339,7 +357,9 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
     c.n += 1;                     // current.N += 1
     *sp = c.pack();
     const double rwd = (double)c.rwd;
-    minmax_update(__dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n))), mn, mx);
+    const double qv = __dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n)));
+    wild |= !is_tame(c.W) | !is_tame(qv);
+    minmax_update(qv, mn, mx);
     value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
     if (e == 0) break;
     a = nodes[e].h[0].parent_action;
@@ -347,7 +367,9 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
   }
   // the root itself: rwd = 0.0 (MCTS/mcts.py:69), N = sim + 1 after this backup
   root_w = __dadd_rn(root_w, value);
-  minmax_update(__dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1))), mn, mx);
+  const double q_root = __dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1)));
+  wild |= !is_tame(q_root);
+  minmax_update(q_root, mn, mx);
 }
 
 // Same backup for a path of depth <= kPathCap recorded by select_leaf as 32-byte path elements (slot + entry), four
@@ -369,7 +391,7 @@ __device__ __forceinline__ void load_batch4(const uint4* __restrict__ path_elem,
 }
 
 __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const PathBatch& pb, int k0, int depth, int sim, float r,
-                                              double& value, double discount, double& mn, double& mx) {
+                                              double& value, double discount, double& mn, double& mx, bool& wild) {
 #pragma unroll
   for (int j = 3; j >= 0; --j) {
     if (k0 + j < depth) {
@@ -382,7 +404,9 @@ __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const PathBatch
       c.n += 1;                     // current.N += 1
       *slot_ptr(nodes, (int)(pb.ent[j] & 0xFFFFu), (int)(pb.ent[j] >> 16)) = c.pack();
       const double rwd = (double)c.rwd;
-      minmax_update(__dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n))), mn, mx);
+      const double qv = __dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n)));
+      wild |= !is_tame(c.W) | !is_tame(qv);
+      minmax_update(qv, mn, mx);
       value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
     }
   }
@@ -390,20 +414,22 @@ __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const PathBatch
 
 // Levels >= 4, leaf side first (lane 1 of the pair): `pb` holds the leaf-side batch k_top = (depth - 1) & ~3 >= 4.
 __device__ __forceinline__ void backup_deep(hmz_node_t* nodes, const uint4* __restrict__ path_elem, PathBatch& pb, int depth, int sim,
-                                            float r, double& value, double discount, double& mn, double& mx) {
+                                            float r, double& value, double discount, double& mn, double& mx, bool& wild) {
 #pragma unroll 1
   for (int k0 = (depth - 1) & ~3; k0 >= 4; k0 -= 4) {
-    backup_batch4(nodes, pb, k0, depth, sim, r, value, discount, mn, mx);
+    backup_batch4(nodes, pb, k0, depth, sim, r, value, discount, mn, mx, wild);
     if (k0 >= 8) load_batch4(path_elem, k0 - 4, depth, pb);
   }
 }
 
 // Levels 0..3 and the root itself (lane 0 of the pair): rwd = 0.0 at the root (MCTS/mcts.py:69), N = sim + 1 after this backup.
 __device__ __forceinline__ void backup_top(hmz_node_t* nodes, const PathBatch& pb, int depth, int sim, float r, double value,
-                                           double discount, double& root_w, double& mn, double& mx) {
-  backup_batch4(nodes, pb, 0, depth, sim, r, value, discount, mn, mx);
+                                           double discount, double& root_w, double& mn, double& mx, bool& wild) {
+  backup_batch4(nodes, pb, 0, depth, sim, r, value, discount, mn, mx, wild);
   root_w = __dadd_rn(root_w, value);
-  minmax_update(__dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1))), mn, mx);
+  const double q_root = __dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1)));
+  wild |= !is_tame(q_root);
+  minmax_update(q_root, mn, mx);
 }
 
 }  // namespace hmz
