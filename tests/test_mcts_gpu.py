@@ -316,3 +316,49 @@ def test_fused_backup_deep_chains_bit_exact():
         torch.cuda.synchronize()
         assert np.array_equal(visits2.cpu().numpy(), o_visits[:groups_B]) and np.array_equal(q2.cpu().numpy(), o_q[:groups_B])
         assert np.array_equal(fused.store.minmax.cpu().numpy(), mm[:groups_B])
+
+
+def test_fused_untame_bounds_and_values_take_the_exact_path():
+    """The hot loop skips the per-operand range tests of the exact-division shortcut and trusts (a) the persisted
+    (min, max) bounds, tested once per launch, and (b) a sticky per-search flag kept by the backup.  (a) bounds far
+    outside the tame range (1e-300) must give the oracle's results bit for bit; (b) non-finite network values (NaN
+    weights in the value head) must give exactly what the split-phase kernels (per-operand tests) give."""
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    n, B, S = 3, 512, 40
+    env = VecHanoi(n, 200, B)
+    env.random_reset(seed=3)
+    # (a) untame persisted bounds on every second search
+    weights = PackedWeights(port.make_weights(n, 5), n)
+    mm0 = np.tile(np.array([[np.inf, -np.inf]]), (B, 1))
+    mm0[::2] = [1e-300, 3e-300]
+    mm0[1::4] = [-2.5, 1e-310]
+    mcts = BatchedMCTS(0.8, 0.0, S, B)
+    mcts.store.minmax.copy_(torch.from_numpy(mm0))
+    p0, r, p, v, depth = _split_search(mcts, weights, env.words, None)
+    _, _, q, visits = mcts.root_policy(0.0, True)
+    torch.cuda.synchronize()
+    mm = mm0.copy()
+    o_visits, o_q, _ = cport.search_injected(p0.cpu().numpy().astype(np.float64), False, mm, r.cpu().numpy(), p.cpu().numpy(),
+                                             v.cpu().numpy(), 0.8, port.ucb_table(S + 1), want_depth=True)
+    assert np.array_equal(visits.cpu().numpy(), o_visits) and np.array_equal(q.cpu().numpy(), o_q)
+    fused = BatchedMCTS(0.8, 0.0, S, B)
+    fused.store.minmax.copy_(torch.from_numpy(mm0))
+    _, _, q2, visits2 = fused.run_mcts(weights, words=env.words, temperature=0.0, deterministic=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(visits2.cpu().numpy(), o_visits) and np.array_equal(q2.cpu().numpy(), o_q)
+    assert np.array_equal(fused.store.minmax.cpu().numpy(), mm)
+    # (b) NaN values: fused == split phases, NaNs included
+    sd = {k: np.array(x, copy=True) for k, x in port.make_weights(n, 5).items()}
+    sd["value_net.2.bias"][:] = np.nan
+    bad = PackedWeights(sd, n)
+    split = BatchedMCTS(0.8, 0.0, S, B)
+    _split_search(split, bad, env.words, None)
+    _, _, q3, visits3 = split.root_policy(0.0, True)
+    fused = BatchedMCTS(0.8, 0.0, S, B)
+    _, _, q4, visits4 = fused.run_mcts(bad, words=env.words, temperature=0.0, deterministic=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(visits3.cpu().numpy(), visits4.cpu().numpy())
+    assert np.array_equal(q3.cpu().numpy(), q4.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(split.store.minmax.cpu().numpy(), fused.store.minmax.cpu().numpy(), equal_nan=True)
+    assert np.isnan(q4.cpu().numpy()).any()
