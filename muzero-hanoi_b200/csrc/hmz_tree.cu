@@ -348,7 +348,13 @@ static int ensure_rcp_table() {
   static double host[kRcpTable + 1];
   host[0] = 0.0;
   for (int k = 1; k <= kRcpTable; ++k) host[k] = 1.0 / (double)k;
-  if (cudaMemcpyToSymbol(g_rcp, host, sizeof(host)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+  static CountRow rows[kRcpTable];
+  for (int n = 0; n < kRcpTable; ++n) {
+    const double a = (double)(n > 0 ? n : 1), b = (double)(n + 1);
+    rows[n] = CountRow{1.0 / a, 1.0 / b, a, b};
+  }
+  if (cudaMemcpyToSymbol(g_rcp, host, sizeof(host)) != cudaSuccess || cudaMemcpyToSymbol(g_cnt, rows, sizeof(rows)) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess)
     return fail(HMZ_ERR_CUDA, "reciprocal table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   done_dev = dev;
   return HMZ_OK;

@@ -125,6 +125,13 @@ __device__ __forceinline__ void write_fresh_half(hmz_node_t* rec, int half, cons
 constexpr int kRcpTable = 4096;
 static __device__ double g_rcp[kRcpTable + 1];  // g_rcp[k] = RN(1 / k) for k >= 1 (filled by the host, IEEE division)
 
+// The walk needs, per child with visit count n: 1/max(n,1), 1/(n+1) and both divisors as doubles.  One 32-byte row
+// per count replaces two clamps, two table loads and two int -> float64 conversions (HMZ_NO_CNT_TABLE: the old form).
+struct __align__(32) CountRow {
+  double rcp_n, rcp_n1, dn, dn1;  // 1/max(n,1), 1/(n+1), (double)max(n,1), (double)(n+1)
+};
+static __device__ CountRow g_cnt[kRcpTable];  // n in [0, kRcpTable): n + 1 <= kRcpTable
+
 // |a| comfortably normal (2^-830 <= |a| < 2^830), tested on the exponent bits with integer instructions
 __device__ __forceinline__ bool div_fast_ok(double a) {
   const unsigned hi = (unsigned)__double2hiint(a) & 0x7FFFFFFFu;
@@ -260,24 +267,35 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
       if (active && c[j].child != (int)HMZ_NO_CHILD) prefetch_record(&nodes[c[j].child]);
 #endif
     const float prior[3] = {__uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z)};
-    double y[3], yw[3];
+    double y[3], yw[3], dn[3], dn1[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {  // reciprocals first: six independent L1 hits
+    for (int j = 0; j < 3; ++j) {  // reciprocals first: independent L1 hits
+#ifdef HMZ_NO_CNT_TABLE
       y[j] = __ldg(&g_rcp[min(max(c[j].n, 1), kRcpTable)]);
       yw[j] = __ldg(&g_rcp[min(c[j].n + 1, kRcpTable)]);
+      dn[j] = (double)max(c[j].n, 1);
+      dn1[j] = (double)(c[j].n + 1);
+#else  // counts beyond the table are flagged below (their results are discarded), so the clamp only keeps the load in range
+      const double2* row = reinterpret_cast<const double2*>(&g_cnt[min(c[j].n, kRcpTable - 1)]);
+      const double2 lo = __ldg(row), hi = __ldg(row + 1);
+      y[j] = lo.x;
+      yw[j] = lo.y;
+      dn[j] = hi.x;
+      dn1[j] = hi.y;
+#endif
     }
     float score[3];
     bool exact_needed = !div_operand_ok(tn) | (kTrusted & distrust);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int n = c[j].n;
-      const double t1 = div_refine(c[j].W, (double)max(n, 1), y[j]);
+      const double t1 = div_refine(c[j].W, dn[j], y[j]);
       const double q = __dadd_rn((double)c[j].rwd, __dmul_rn(discount, t1));
       const double num = __dsub_rn(q, mn);
       const double qn = normalise ? div_refine(num, range, range_rcp) : q;
       const float qf = n > 0 ? __double2float_rn(qn) : 0.0f;  // child_Q: 0 for unvisited children (node.py:98-102)
       // child_U: w = (log((N+c_base+1)/c_base) + c_init) * sqrt(N) / (child.N + 1)  (node.py:114-121)
-      const double w = div_refine(tn, (double)(n + 1), yw[j]);
+      const double w = div_refine(tn, dn1[j], yw[j]);
       // float64 prior (noised root): product in float64; float32 prior: weak scalar -> float32 product (node.py:122)
       const float u = use64 ? __double2float_rn(__dmul_rn(rp64[j], w)) : __fmul_rn(prior[j], __double2float_rn(w));
       score[j] = __fadd_rn(qf, u);  // node.py:83 on float32 arrays
