@@ -17,6 +17,7 @@
 //                           float64 product then rounded at a Dirichlet-noised root (:122);
 //   ties                  : lowest action index (the sanctioned replacement of :86).
 #pragma once
+#include <type_traits>
 #include <math.h>
 
 #include "hmz_common.cuh"
@@ -237,8 +238,11 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
   int e = 0, n_parent = root_n, depth = 0;
   Leaf leaf{0, 0, 0};
   uint4 q0 = make_uint4(0u, 0u, 0u, 0xFFFF0000u), q1 = q0, q2 = q0, q3 = make_uint4(0u, 0u, 0u, 0u);
-  while (__any_sync(0xffffffffu, active)) {
-    const bool use64 = (e == 0) & (root_prior64 != nullptr);
+  // One level of the walk.  The level body exists twice: the first level of a search whose root priors are float64
+  // (Dirichlet-noised) and every other level, which then carries none of the float64-prior work.
+  auto level = [&](auto root64_tag) {
+    constexpr bool kRoot64 = decltype(root64_tag)::value;
+    const bool use64 = kRoot64 && (e == 0) & (root_prior64 != nullptr);
     double rp64[3] = {0.0, 0.0, 0.0};
     double tn = 0.0;
     if (active) {
@@ -353,6 +357,18 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
         n_parent = best_n;
       }
     }
+  };
+  bool first = true;
+  while (__any_sync(0xffffffffu, active)) {
+#ifdef HMZ_NO_ROOT_PEEL  // A/B switch (tools/sweep21.sh): one level body with the float64-prior work in every level
+    level(std::true_type{});
+#else
+    if (first && root_prior64 != nullptr)  // uniform: every lane is at its root in the first iteration
+      level(std::true_type{});
+    else
+      level(std::false_type{});
+#endif
+    first = false;
   }
   return leaf;
 }
