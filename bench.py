@@ -347,9 +347,9 @@ def run_ours(args):
     net = MuZeroNet(3 * N_DISKS, 6, 0.002, "cpu", TD_return=True)  # random-init h / g / f
     weights = PackedWeights(net.state_dict(), N_DISKS, mode, dev)
     B, S = args.games, args.sims
-    _lib.check(lib.hmz_search_set_groups(args.groups))
     sp = SelfPlay(N_DISKS, MAX_STEPS, B, S, weights, DISCOUNT, ALPHA, EPS, TEMPERATURE, seed=1234 + rank,
                   ring_slots=4, device=dev, latent_dtype=latent_dtype)
+    sp.mcts.store.set_schedule(args.groups)
     gather_buf = torch.empty(world * B, 26, dtype=torch.uint8, device=dev) if world > 1 else None
 
     def step():
@@ -394,14 +394,14 @@ def run_ours(args):
 
     # ---- per-kernel device time over the same steps (CUDA-event pairs on the launch stream)
     barrier()
-    _lib.check(lib.hmz_search_set_groups(1))  # serial launches: clean, non-overlapped per-kernel durations
+    sp.mcts.store.set_schedule(1)  # serial launches: clean, non-overlapped per-kernel durations
     _lib.check(lib.hmz_prof_begin())
     for _ in range(args.steps):
         step()
     ms_cls = (C.c_double * 8)()
     n_cls = (C.c_int64 * 8)()
     _lib.check(lib.hmz_prof_end(ms_cls, n_cls))
-    _lib.check(lib.hmz_search_set_groups(args.groups))
+    sp.mcts.store.set_schedule(args.groups)
     # "backup_select" = the fused expansion + backup(sim) + selection(sim+1) kernel; "select" = the first selection of a move
     names = ["env_step", "select", "net_recurrent", "backup_select", "net_initial", "root_policy", "other", "-"]
     kern = {names[i]: {"ms_total": ms_cls[i], "launches": int(n_cls[i]),

@@ -14,7 +14,10 @@
  *     enqueued on `stream` (a cudaStream_t passed as void*, NULL = legacy default stream).
  *   - Every function returns HMZ_OK (0) or a negative HMZ_ERR_* code and never throws;
  *     hmz_last_error() returns a thread-local message for the last failure.
- *   - Re-entrant: no global mutable state apart from the thread-local error string.
+ *   - Re-entrant per descriptor: results depend only on the arguments of a call.  Process-wide state is
+ *     limited to the thread-local error string, the launch counter (hmz_launch_count), lazily created
+ *     per-thread helper streams / constant tables, and the TOOLING hooks hmz_prof_* / hmz_debug_* (one
+ *     profiling session per process at a time); none of it changes what a call computes.
  *   - There is NO CPU fallback: without a CUDA device every compute entry point fails
  *     with HMZ_ERR_CUDA.
  */
@@ -47,6 +50,9 @@ extern "C" {
 
 const char* hmz_last_error(void);
 int hmz_version(void);
+/* Names of the non-default compile-time tuning switches this library was built with ("" = the shipped
+ * configuration).  None of them changes results; tests assert a clean build. */
+const char* hmz_build_flags(void);
 /* Number of kernels this library has launched from the calling process (for bench.py's
  * gpu_launches claim). */
 int64_t hmz_launch_count(void);
@@ -163,12 +169,18 @@ typedef struct hmz_search {
   double* root_W;      /* [n_searches]   root.W                                           */
   double* minmax;      /* [n_searches][2] (min, max) of MinMaxStats; PERSISTS across calls */
   void* workspace;     /* hmz_search_workspace_bytes(n_searches) bytes of scratch          */
+  float* capture;      /* nullable [n_simulations][n_searches][8]: hmz_search_run records the network outputs
+                          p[6], r, v of every simulation here (parity tests replay them through the oracle) */
   int64_t n_searches;
   int32_t n_records;   /* >= n_simulations + 1                                           */
   int32_t latent_dtype;
   int32_t root_prior_is_f64; /* 1: noised root, U = f32(f64 prior * w) (node.py:122)      */
-  int32_t reserved;
+  int32_t schedule;    /* hmz_search_run scheduling, never changes results: 0 = automatic; k in [1, 16] = one
+                          launch pair per simulation with the batch cut into k concurrent stream groups;
+                          HMZ_SCHEDULE_PERSISTENT = one persistent role-specialised kernel per call        */
 } hmz_search_t;
+#define HMZ_SCHEDULE_AUTO 0
+#define HMZ_SCHEDULE_PERSISTENT 64
 
 /* Scratch needed by hmz_search_run (per-simulation leaf ids and network outputs). */
 int64_t hmz_search_workspace_bytes(int64_t n_searches);
@@ -214,10 +226,15 @@ int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, co
 
 /* MCTS/mcts.py:112-126: child_N, generate_play_policy (:154-176), arg-max or sampled action.
  *   uniforms nullable unless deterministic == 0 (one double in [0,1) per search; the draw of
- *   np.random.choice at :120 supplied as input);  outputs nullable individually. */
+ *   np.random.choice at :120 supplied as input);  outputs nullable individually.
+ *   pow_table nullable: float64 [n_simulations + 1], pow_table[n] = n ** clamp(1/T, 1, 5) as the caller's
+ *   NumPy evaluates np.power (:170-174) — NumPy's vectorised pow is not correctly rounded, so bit-exact
+ *   policies for non-integer exponents (or powers beyond 2^53) need the caller's own table.  NULL: the
+ *   device evaluates integer exponents by exact repeated multiplication (identical to NumPy while the
+ *   power stays below 2^53, i.e. counts < 1,552 at exponent 5) and others with CUDA's pow() (<= 2 ulp). */
 int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temperature, int deterministic,
-                           const double* uniforms, int32_t* visits, double* pi, double* root_q, int32_t* action,
-                           void* stream);
+                           const double* uniforms, const double* pow_table, int32_t* visits, double* pi, double* root_q,
+                           int32_t* action, void* stream);
 
 /* ------------------------------------------------------------------ networks -------
  * Packed weights: one device blob produced by hmz_weights_pack from the 20 tensors of
@@ -254,10 +271,7 @@ int hmz_net_recurrent(const void* weights, int mode, const void* latents_in, int
  * search in one launch sequence with no host round trips (MCTS.run_mcts, MCTS/mcts.py:71-109). */
 int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_simulations,
                    const double* ucb_table, double discount, void* stream);
-/* Scheduling knob of hmz_search_run: the batch is cut into `groups` independent slices whose
- * select -> MLP -> backup chains run concurrently on internal streams (forked from and joined back
- * to `stream`).  0 = automatic, 1 = strictly serial.  Never changes results. */
-int hmz_search_set_groups(int groups);
+/* (Scheduling is chosen per call by hmz_search_t.schedule.) */
 
 /* Tooling only: with HMZ_TC_TIMELINE=1 in the environment, CTA 0 of the tensor-core kernel records
  * clock64() at its phase boundaries; this copies the 96 marks of the last launch to the host. */
@@ -364,11 +378,14 @@ int hmz_episode_rows(const int32_t* ep_len, const double* returns, int64_t n_gam
  * of `capacity` rows with buffer.py's arrays (:29-39): states f32[3N], rwds f32[unroll], actions
  * i64[unroll], pi f32[unroll][6], returns f32[unroll], priority f32.  Step t of game g lands in row
  * (row_base[g] + t) % capacity; beyond the episode end the padding is reward 0, return 0, the uniform
- * policy and absorbing_action[g] (the reference draws ONE np.random.randint per episode, :300-303). */
+ * policy and absorbing_action[g] (the reference draws ONE np.random.randint per episode, :300-303).
+ * Rows with row_base[g] + t < first_row are skipped: when one call adds more rows than the ring holds, the
+ * reference's one-episode-at-a-time Buffer.add leaves only the LAST `capacity` rows, so the caller passes
+ * first_row = ptr + max(0, total - capacity) (0 otherwise). */
 int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const uint8_t* ep_flags, const uint16_t* ep_visits,
                        const double* returns, const float* priority, const int32_t* ep_len, const int64_t* row_base,
                        const uint8_t* absorbing_action, int64_t n_games, int t_max, int n_disks, int unroll, double temperature,
-                       int64_t capacity, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
+                       int64_t capacity, int64_t first_row, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
                        float* buf_returns, float* buf_priority, void* stream);
 
 /* ------------------------------------------------------------------ acting evaluation ------

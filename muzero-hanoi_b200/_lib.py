@@ -13,6 +13,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 FLAG_DONE, FLAG_ILLEGAL, FLAG_GOAL, FLAG_TRUNC = 1, 2, 4, 8
 N_ACTIONS, LATENT, HIDDEN, SUPPORT, MAX_DISKS, NO_CHILD = 6, 64, 256, 33, 12, 0xFFFF
 LATENT_F32, LATENT_BF16 = 0, 1
+SCHEDULE_AUTO, SCHEDULE_PERSISTENT = 0, 64
 MODE_FP32, MODE_BF16 = 0, 1
 
 
@@ -45,8 +46,8 @@ class SearchDesc(C.Structure):
     """hmz_search_t."""
 
     _fields_ = [("nodes", C.c_void_p), ("latents", C.c_void_p), ("root_prior", C.c_void_p), ("root_W", C.c_void_p),
-                ("minmax", C.c_void_p), ("workspace", C.c_void_p), ("n_searches", C.c_int64), ("n_records", C.c_int32),
-                ("latent_dtype", C.c_int32), ("root_prior_is_f64", C.c_int32), ("reserved", C.c_int32)]
+                ("minmax", C.c_void_p), ("workspace", C.c_void_p), ("capture", C.c_void_p), ("n_searches", C.c_int64),
+                ("n_records", C.c_int32), ("latent_dtype", C.c_int32), ("root_prior_is_f64", C.c_int32), ("schedule", C.c_int32)]
 
 
 assert C.sizeof(NodeRecord) == 128
@@ -70,6 +71,7 @@ _SD = C.POINTER(SearchDesc)
 SIGNATURES = {
     "hmz_last_error": (C.c_char_p, []),
     "hmz_version": (_I, []),
+    "hmz_build_flags": (C.c_char_p, []),
     "hmz_launch_count": (_L, []),
     "hmz_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "hmz_prof_begin": (_I, []),
@@ -91,7 +93,7 @@ SIGNATURES = {
     "hmz_search_select": (_I, [_SD, _I, _P, _D, _P, _P, _P, _P, _I, _P]),
     "hmz_search_child_scores": (_I, [_SD, _P, _P, _P, _D, _P, _P, _P, _P]),
     "hmz_search_expand_backup": (_I, [_SD, _I, _D, _P, _P, _P, _P, _P, _P]),
-    "hmz_search_root_policy": (_I, [_SD, _I, _D, _I, _P, _P, _P, _P, _P, _P]),
+    "hmz_search_root_policy": (_I, [_SD, _I, _D, _I, _P, _P, _P, _P, _P, _P, _P]),
     "hmz_weights_packed_bytes": (_L, [_I, _I]),
     "hmz_weights_pack": (_I, [C.POINTER(_P), _I, _I, _P]),
     "hmz_net_initial": (_I, [_P, _I, _I, _P, _P, _P, _L, _I, _P, _P, _L, _P]),
@@ -100,7 +102,6 @@ SIGNATURES = {
     "hmz_debug_tree_timeline": (_I, [C.c_longlong, _P]),
     "hmz_debug_div_check": (_I, [_U64, _U64, _P, _P]),
     "hmz_search_run": (_I, [_SD, _P, _I, _I, _P, _D, _P]),
-    "hmz_search_set_groups": (_I, [_I]),
     "hmz_rng_dirichlet": (_I, [_P, _L, _D, _U64, _U64, _P]),
     "hmz_rng_uniform": (_I, [_P, _L, _U64, _U64, _P]),
     "hmz_traj_record": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
@@ -116,7 +117,7 @@ SIGNATURES = {
     "hmz_episode_returns": (_I, [_P, _P, _P, _L, _I, _P, _I, _P, _P, _P]),
     "hmz_episode_mc_returns": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "hmz_episode_rows": (_I, [_P, _P, _L, _L, _I, _P, _P, _P]),
-    "hmz_episode_unroll": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _D, _L, _P, _P, _P, _P, _P, _P, _P]),
+    "hmz_episode_unroll": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _D, _L, _L, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lock = threading.Lock()

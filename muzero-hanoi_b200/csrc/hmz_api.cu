@@ -66,7 +66,7 @@ extern "C" {
 
 const char* hmz_last_error(void) { return hmz::error_buffer(); }
 
-int hmz_version(void) { return 100; }
+int hmz_version(void) { return 200; }
 
 int64_t hmz_launch_count(void) { return (int64_t)hmz::g_launches.load(); }
 

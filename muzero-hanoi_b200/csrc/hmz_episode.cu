@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) episode_unroll(
     const uint32_t* __restrict__ ep_state, const uint8_t* __restrict__ ep_action, const uint8_t* __restrict__ ep_flags,
     const uint16_t* __restrict__ ep_visits, const double* __restrict__ returns, const float* __restrict__ priority,
     const int32_t* __restrict__ ep_len, const int64_t* __restrict__ row_base, const uint8_t* __restrict__ absorbing_action,
-    int64_t n, int t_max, int n_disks, int unroll, int exponent, int64_t capacity, float* __restrict__ buf_states,
+    int64_t n, int t_max, int n_disks, int unroll, int exponent, int64_t capacity, int64_t first_row, float* __restrict__ buf_states,
     float* __restrict__ buf_rwds, int64_t* __restrict__ buf_actions, float* __restrict__ buf_pi, float* __restrict__ buf_returns,
     float* __restrict__ buf_priority) {
   const int64_t total = (int64_t)t_max * n;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) episode_unroll(
     const int64_t g = i % n;
     const int t = (int)(i / n), len = ep_len[g];
     const int64_t rb = row_base[g];
-    if (t >= len || rb < 0) continue;
+    if (t >= len || rb < 0 || rb + t < first_row) continue;  // rows a later row of this add overwrites are skipped
     const int64_t row = (rb + t) % capacity;  // buffer.py:47-62 wrap-around
     // state: utils.oneHot_encoding (utils.py:9-25) of the env word, float32 (buffer.py:29)
     const uint32_t w = ep_state[i];
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128) episode_unroll_warp(
     const uint32_t* __restrict__ ep_state, const uint8_t* __restrict__ ep_action, const uint8_t* __restrict__ ep_flags,
     const uint16_t* __restrict__ ep_visits, const double* __restrict__ returns, const float* __restrict__ priority,
     const int32_t* __restrict__ ep_len, const int64_t* __restrict__ row_base, const uint8_t* __restrict__ absorbing_action,
-    int64_t n, int t_max, int n_disks, int unroll, int exponent, int64_t capacity, float* __restrict__ buf_states,
+    int64_t n, int t_max, int n_disks, int unroll, int exponent, int64_t capacity, int64_t first_row, float* __restrict__ buf_states,
     float* __restrict__ buf_rwds, int64_t* __restrict__ buf_actions, float* __restrict__ buf_pi, float* __restrict__ buf_returns,
     float* __restrict__ buf_priority) {
   extern __shared__ StepStage stage_all[];
@@ -279,12 +279,15 @@ __global__ void __launch_bounds__(128) episode_unroll_warp(
     // states [len][3N]: utils.oneHot_encoding of the env word
     for (int w = lane; w < len * d_state; w += 32) {
       const int t = w / d_state, c = w - t * d_state, d = c / 3;
+      if (rb + t < first_row) continue;  // overwritten by a later row of this add (more rows than the ring holds)
       buf_states[((rb + t) % capacity) * d_state + c] = (((stage[t].state >> (2 * d)) & 3u) == (uint32_t)(c - 3 * d)) ? 1.0f : 0.0f;
     }
-    for (int t = lane; t < len; t += 32) buf_priority[(rb + t) % capacity] = stage[t].priority;
+    for (int t = lane; t < len; t += 32)
+      if (rb + t >= first_row) buf_priority[(rb + t) % capacity] = stage[t].priority;
     // [len][unroll] arrays: rewards, returns, actions; beyond the episode end the absorbing padding (Muzero.py:296-307)
     for (int w = lane; w < len * unroll; w += 32) {
       const int t = w / unroll, k = w - t * unroll, j = t + k;
+      if (rb + t < first_row) continue;
       const int64_t o = ((rb + t) % capacity) * unroll + k;
       buf_rwds[o] = j < len ? stage[j].reward : 0.0f;
       buf_returns[o] = j < len ? stage[j].ret : 0.0f;
@@ -292,6 +295,7 @@ __global__ void __launch_bounds__(128) episode_unroll_warp(
     }
     for (int w = lane; w < len * unroll * 6; w += 32) {
       const int t = w / (unroll * 6), r = w - t * unroll * 6, k = r / 6, a = r - k * 6, j = t + k;
+      if (rb + t < first_row) continue;
       buf_pi[((rb + t) % capacity) * unroll * 6 + r] = j < len ? stage[j].pi[a] : uniform;
     }
   }
@@ -361,7 +365,7 @@ int hmz_episode_rows(const int32_t* ep_len, const double* returns, int64_t n_gam
 int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const uint8_t* ep_flags, const uint16_t* ep_visits,
                        const double* returns, const float* priority, const int32_t* ep_len, const int64_t* row_base,
                        const uint8_t* absorbing_action, int64_t n_games, int t_max, int n_disks, int unroll, double temperature,
-                       int64_t capacity, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
+                       int64_t capacity, int64_t first_row, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
                        float* buf_returns, float* buf_priority, void* stream) {
   ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n_games == 0) return HMZ_OK;
@@ -382,12 +386,12 @@ int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const
   if (stage_bytes * 4 <= 48 * 1024 && !getenv("HMZ_UNROLL_SCALAR")) {  // warp-per-game form: staging fits the default shared memory
     episode_unroll_warp<<<grid_for(n_games, 4, 8), 128, stage_bytes * 4, (cudaStream_t)stream>>>(
         ep_state, ep_action, ep_flags, ep_visits, returns, priority, ep_len, row_base, absorbing_action, n_games, t_max, n_disks,
-        unroll, iex, capacity, buf_states, buf_rwds, buf_actions, buf_pi, buf_returns, buf_priority);
+        unroll, iex, capacity, first_row, buf_states, buf_rwds, buf_actions, buf_pi, buf_returns, buf_priority);
     return check_launch("episode_unroll_warp");
   }
   episode_unroll<<<grid_for(n_games * t_max, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       ep_state, ep_action, ep_flags, ep_visits, returns, priority, ep_len, row_base, absorbing_action, n_games, t_max, n_disks, unroll,
-      iex, capacity, buf_states, buf_rwds, buf_actions, buf_pi, buf_returns, buf_priority);
+      iex, capacity, first_row, buf_states, buf_rwds, buf_actions, buf_pi, buf_returns, buf_priority);
   return check_launch("episode_unroll");
 }
 

@@ -154,7 +154,7 @@ int hmz_selfplay_move(const hmz_selfplay_t* sp, uint64_t move_index, void* strea
   if (int rc = hmz_rng_uniform(sp->uniform, B, sp->seed, move_index, stream)) return rc;
   if (int rc = hmz_search_begin_p0(s, sp->p0, use_noise ? sp->noise : nullptr, sp->exploration_eps, stream)) return rc;
   if (int rc = hmz_search_run(s, sp->weights, sp->mode, sp->n_simulations, sp->ucb_table, sp->discount, stream)) return rc;
-  if (int rc = hmz_search_root_policy(s, sp->n_simulations, sp->temperature, 0, sp->uniform, sp->visits, nullptr, sp->root_q,
+  if (int rc = hmz_search_root_policy(s, sp->n_simulations, sp->temperature, 0, sp->uniform, nullptr, sp->visits, nullptr, sp->root_q,
                                       sp->action, stream))
     return rc;
   if (int rc = hmz_traj_record(sp->words, sp->action, sp->visits, sp->root_q, sp->traj_state, sp->traj_action, sp->traj_visits,

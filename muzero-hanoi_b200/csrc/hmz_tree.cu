@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
                                                                      double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
                                                                      uint16_t* leaf_depth, uint4* path_elem, uint8_t* wild_flags,
                                                                      const float* __restrict__ r, const float* __restrict__ p,
-                                                                     const float* __restrict__ v, int do_select) {
+                                                                     const float* __restrict__ v, int do_select, float* __restrict__ capture) {
   const int half = threadIdx.x & 1;
   const int64_t b_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
   const int signal_at = (do_select >> 2) & 3;  // HMZ_PDL_TREE_AT
@@ -135,6 +135,11 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
     r_leaf = r[b];
     value = (double)v[b];
     write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
+    if (capture != nullptr) {  // parity tests: the network outputs this backup consumed, [p0..p5, r, v] per search
+      float4* cap = reinterpret_cast<float4*>(capture + b * 8) + half;
+      *cap = half == 0 ? make_float4(p[b * 6], p[b * 6 + 1], p[b * 6 + 2], p[b * 6 + 3])
+                       : make_float4(p[b * 6 + 4], p[b * 6 + 5], r_leaf, v[b]);
+    }
     tree_mark<kTL>(6, tl, __float_as_uint(r_leaf));
     if (half == 1 && by_path && depth > 4) backup_deep(nodes, path, pb, depth, sim, r_leaf, value, discount, mn, mx, wild);
   }
@@ -168,7 +173,9 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
   }
   if (signal_at == 1) pdl_launch_dependents();
   if (!(do_select & 1)) return;
-  // lane 0's (min, max) to its partner; the shuffle also orders lane 0's record updates before the pair's next walk
+  // lane 0's slot stores must be visible to its partner's loads in the walk below (a shuffle orders nothing in memory)
+  __syncwarp();
+  // lane 0's (min, max) to its partner
   mn = __shfl_sync(0xffffffffu, mn, (threadIdx.x & 31) & ~1);
   mx = __shfl_sync(0xffffffffu, mx, (threadIdx.x & 31) & ~1);
   if (kTrusted) wild = __shfl_sync(0xffffffffu, (int)wild, (threadIdx.x & 31) & ~1) != 0;
@@ -235,6 +242,7 @@ __global__ void __launch_bounds__(128) search_child_scores(hmz_search_t s, const
 // MCTS/mcts.py:112-126 per search (one thread each; 52 bytes in, <= 76 bytes out).
 __global__ void __launch_bounds__(256) search_root_policy(hmz_search_t s, int n_sims, double temperature,
                                                          int deterministic, const double* __restrict__ uniforms,
+                                                         const double* __restrict__ pow_table, int pow_table_len,
                                                          int32_t* __restrict__ visits, double* __restrict__ pi,
                                                          double* __restrict__ root_q, int32_t* __restrict__ action) {
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < s.n_searches;
@@ -251,7 +259,9 @@ __global__ void __launch_bounds__(256) search_root_policy(hmz_search_t s, int n_
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
       double x = (double)n[a];
-      if ((double)iex == ex) {  // integer exponents 1..5: exact products while < 2^53
+      if (pow_table != nullptr && n[a] < pow_table_len) {  // visits ** exponent exactly as the caller's NumPy evaluates it
+        w[a] = pow_table[n[a]];
+      } else if ((double)iex == ex) {  // integer exponents 1..5: exact products while < 2^53
         double y = x;
         for (int k = 1; k < iex; ++k) y = __dmul_rn(y, x);
         w[a] = y;
@@ -414,6 +424,31 @@ int hmz_debug_tree_timeline(long long search, unsigned long long* host_out) {
   return HMZ_OK;
 }
 
+// Non-default compile-time tuning switches of this build ("" for a clean build), so that tests and bench lines can
+// tell a tuned library from the shipped one.  None of them changes results.
+const char* hmz_build_flags(void) {
+  return ""
+#if HMZ_TREE_THREADS != 128
+         " HMZ_TREE_THREADS"
+#endif
+#if HMZ_TREE_MIN_BLOCKS != (640 / HMZ_TREE_THREADS)
+         " HMZ_TREE_MIN_BLOCKS"
+#endif
+#if HMZ_PREFETCH_SECTORS != 0
+         " HMZ_PREFETCH_SECTORS"
+#endif
+#if HMZ_L2_HINTS != 0
+         " HMZ_L2_HINTS"
+#endif
+#ifdef HMZ_NO_LATENT_PREFETCH
+         " HMZ_NO_LATENT_PREFETCH"
+#endif
+#ifdef HMZ_TC_MAXNREG
+         " HMZ_TC_MAXNREG"
+#endif
+      ;
+}
+
 int64_t hmz_search_workspace_bytes(int64_t n_searches) {
   if (n_searches < 0) return -1;
   // p[6] r v, leaf_parent/action/depth, the sticky "wild" flag, kPathCap path elements of 32 B per search
@@ -484,13 +519,13 @@ int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, co
   // split-phase form: no recorded path, the backup walks the parent links
   search_backup_select<false, false><<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(
       *s, sim, nullptr, discount, const_cast<uint16_t*>(leaf_parent), const_cast<uint8_t*>(leaf_action), nullptr, nullptr,
-      nullptr, r, p, v, 0);
+      nullptr, r, p, v, 0, (float*)nullptr);
   return check_launch("search_expand_backup");
 }
 
 int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temperature, int deterministic,
-                           const double* uniforms, int32_t* visits, double* pi, double* root_q, int32_t* action,
-                           void* stream) {
+                           const double* uniforms, const double* pow_table, int32_t* visits, double* pi, double* root_q,
+                           int32_t* action, void* stream) {
   ProfScope prof_scope(HMZ_PROF_ROOT_POLICY, stream);
   if (int rc = check_search(s, "hmz_search_root_policy")) return rc;
   if (!(temperature >= 0.0 && temperature <= 1.0))  // MCTS/mcts.py:163-166 -> ValueError in the Python shim
@@ -498,18 +533,8 @@ int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temp
   if (s->n_searches == 0) return HMZ_OK;
   if (!deterministic && !uniforms) return fail(HMZ_ERR_INVALID, "hmz_search_root_policy: sampling needs uniforms");
   search_root_policy<<<grid_for(s->n_searches, 256, 4), 256, 0, (cudaStream_t)stream>>>(
-      *s, n_simulations, temperature, deterministic, uniforms, visits, pi, root_q, action);
+      *s, n_simulations, temperature, deterministic, uniforms, pow_table, n_simulations + 1, visits, pi, root_q, action);
   return check_launch("search_root_policy");
-}
-
-// Process-wide tuning knob: number of independent search groups hmz_search_run runs concurrently
-// on internal streams (0 = automatic).  Groups only change scheduling, never results.
-static std::atomic<int> g_search_groups{0};
-
-int hmz_search_set_groups(int groups) {
-  if (groups < 0 || groups > 16) return fail(HMZ_ERR_INVALID, "hmz_search_set_groups: %d outside [0, 16]", groups);
-  g_search_groups.store(groups);
-  return HMZ_OK;
 }
 
 namespace {
@@ -564,8 +589,10 @@ SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
 
 
 // One simulation of one group: [select (first simulation only)] -> g+f MLP -> fused backup + next select.
+// capture_stride / capture_lo: searches per capture row (the whole batch) and this group's first search in it.
 static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* weights, int mode, int sim,
-                       int n_simulations, const double* ucb_table, double discount, void* stream) {
+                       int n_simulations, const double* ucb_table, double discount, void* stream, int64_t capture_stride,
+                       int64_t capture_lo) {
   const int64_t B = s->n_searches;
   cudaStream_t st = (cudaStream_t)stream;
   if (sim == 0) {
@@ -581,14 +608,10 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
   ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
   const int do_select = (sim + 1 < n_simulations ? 1 : 0) | (pdl_prewait() << 1) | ((pdl_tree_at() & 3) << 2);
   const float *cr = sc.r, *cp = sc.p, *cv = sc.v;
-#ifdef HMZ_NO_TRUST  // A/B switch (tools/sweep19.sh): per-operand range tests in the hot loop as well
-  constexpr bool kTrust = false;
-#else
-  constexpr bool kTrust = true;
-#endif
-  cudaError_t e = launch_pdl(2, g_tree_tl_search >= 0 ? search_backup_select<true, true> : search_backup_select<false, kTrust>,
+  float* cap = s->capture ? s->capture + ((size_t)sim * (size_t)capture_stride + (size_t)capture_lo) * 8 : nullptr;
+  cudaError_t e = launch_pdl(2, g_tree_tl_search >= 0 ? search_backup_select<true, true> : search_backup_select<false, true>,
                              dim3(search_grid(B)), dim3(kTreeThreads), 0, st, *s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth,
-                             sc.path, sc.wild, cr, cp, cv, do_select);
+                             sc.path, sc.wild, cr, cp, cv, do_select, cap);
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "search_backup_select launch: %s", cudaGetErrorString(e));
   return check_launch("search_backup_select");
 }
@@ -606,14 +629,15 @@ static int search_run_direct(const hmz_search_t* s, const void* weights, int mod
   // Searches never interact, so the batch is cut into groups whose select -> MLP -> backup chains
   // run on separate streams: the latency-bound tree kernels of one group fill the issue slots the
   // tensor-core kernel of another leaves idle.  Group boundaries are multiples of 128 searches.
-  int groups = g_search_groups.load();
+  int groups = s->schedule;
+  if (groups < 0 || groups > 16) return fail(HMZ_ERR_INVALID, "hmz_search_run: schedule %d is not a group count in [0, 16]", groups);
   if (groups == 0) groups = B >= 32768 ? 4 : (B >= 8192 ? 2 : 1);
   const int64_t per = ((B + groups - 1) / groups + 127) / 128 * 128;
   groups = (int)((B + per - 1) / per);
   if (groups <= 1) {
     SimScratch sc = carve_scratch(s->workspace, Bp, 0);
     for (int sim = 0; sim < n_simulations; ++sim)
-      if (int rc = run_one_sim(s, sc, weights, mode, sim, n_simulations, ucb_table, discount, stream)) return rc;
+      if (int rc = run_one_sim(s, sc, weights, mode, sim, n_simulations, ucb_table, discount, stream, B, 0)) return rc;
     return HMZ_OK;
   }
   GroupStreams* gs = nullptr;
@@ -638,7 +662,7 @@ static int search_run_direct(const hmz_search_t* s, const void* weights, int mod
   int rc = HMZ_OK;
   for (int sim = 0; sim < n_simulations && rc == HMZ_OK; ++sim)
     for (int g = 0; g < groups && rc == HMZ_OK; ++g)
-      rc = run_one_sim(&sub[g], sc[g], weights, mode, sim, n_simulations, ucb_table, discount, (void*)gs->stream[g]);
+      rc = run_one_sim(&sub[g], sc[g], weights, mode, sim, n_simulations, ucb_table, discount, (void*)gs->stream[g], B, g * per);
   for (int g = 0; g < groups; ++g) {  // always join, even after an error, so the caller's stream stays ordered
     cudaEventRecord(gs->done[g], gs->stream[g]);
     cudaStreamWaitEvent(main_stream, gs->done[g], 0);
@@ -689,7 +713,7 @@ static int search_run_graph(const hmz_search_t* s, const void* weights, int mode
                                      (unsigned long long)(uintptr_t)ucb_table, dbits,
                                      (unsigned long long)s->n_records | ((unsigned long long)mode << 32) |
                                          ((unsigned long long)s->root_prior_is_f64 << 40) | ((unsigned long long)s->latent_dtype << 44) |
-                                         ((unsigned long long)g_search_groups.load() << 48)};
+                                         ((unsigned long long)s->schedule << 48) ^ (unsigned long long)(uintptr_t)s->capture};
   GraphEntry* hit = nullptr;
   for (auto& e : gc.entries)
     if (memcmp(e.key, key, sizeof(key)) == 0) hit = &e;

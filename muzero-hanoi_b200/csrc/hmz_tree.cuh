@@ -127,7 +127,7 @@ constexpr int kRcpTable = 4096;
 static __device__ double g_rcp[kRcpTable + 1];  // g_rcp[k] = RN(1 / k) for k >= 1 (filled by the host, IEEE division)
 
 // The walk needs, per child with visit count n: 1/max(n,1), 1/(n+1) and both divisors as doubles.  One 32-byte row
-// per count replaces two clamps, two table loads and two int -> float64 conversions (HMZ_NO_CNT_TABLE: the old form).
+// per count replaces two clamps, two table loads and two int -> float64 conversions.
 struct __align__(32) CountRow {
   double rcp_n, rcp_n1, dn, dn1;  // 1/max(n,1), 1/(n+1), (double)max(n,1), (double)(n+1)
 };
@@ -274,19 +274,13 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
     double y[3], yw[3], dn[3], dn1[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {  // reciprocals first: independent L1 hits
-#ifdef HMZ_NO_CNT_TABLE
-      y[j] = __ldg(&g_rcp[min(max(c[j].n, 1), kRcpTable)]);
-      yw[j] = __ldg(&g_rcp[min(c[j].n + 1, kRcpTable)]);
-      dn[j] = (double)max(c[j].n, 1);
-      dn1[j] = (double)(c[j].n + 1);
-#else  // counts beyond the table are flagged below (their results are discarded), so the clamp only keeps the load in range
+      // counts beyond the table are flagged below (their results are discarded), so the clamp only keeps the load in range
       const double2* row = reinterpret_cast<const double2*>(&g_cnt[min(c[j].n, kRcpTable - 1)]);
       const double2 lo = __ldg(row), hi = __ldg(row + 1);
       y[j] = lo.x;
       yw[j] = lo.y;
       dn[j] = hi.x;
       dn1[j] = hi.y;
-#endif
     }
     float score[3];
     bool exact_needed = !div_operand_ok(tn) | (kTrusted & distrust);
@@ -308,9 +302,6 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
         exact_needed |= (n + 1 > kRcpTable) |
                         ((n > 0) & (!div_operand_ok(c[j].W) | (normalise & (!range_ok | !div_operand_ok(num)))));
     }
-#ifdef HMZ_EXPERIMENT_NOCHECK  // measurement only (tools/sweep19.sh): what the operand-range tests cost; NOT exact in general
-    exact_needed = false;
-#endif
     if (exact_needed & active) {
 #pragma unroll
       for (int j = 0; j < 3; ++j)
@@ -360,14 +351,10 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
   };
   bool first = true;
   while (__any_sync(0xffffffffu, active)) {
-#ifdef HMZ_NO_ROOT_PEEL  // A/B switch (tools/sweep21.sh): one level body with the float64-prior work in every level
-    level(std::true_type{});
-#else
     if (first && root_prior64 != nullptr)  // uniform: every lane is at its root in the first iteration
       level(std::true_type{});
     else
       level(std::false_type{});
-#endif
     first = false;
   }
   return leaf;

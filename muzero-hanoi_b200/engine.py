@@ -181,11 +181,27 @@ class SearchStore:
         self.desc = _lib.SearchDesc(
             nodes=self.nodes.data_ptr(), latents=self.latents.data_ptr(), root_prior=self.root_prior.data_ptr(),
             root_W=self.root_W.data_ptr(), minmax=self.minmax.data_ptr(), workspace=self.workspace.data_ptr(),
-            n_searches=self.B, n_records=self.n_records, latent_dtype=latent_dtype, root_prior_is_f64=0, reserved=0)
+            capture=None, n_searches=self.B, n_records=self.n_records, latent_dtype=latent_dtype, root_prior_is_f64=0,
+            schedule=_lib.SCHEDULE_AUTO)
         self.reset_minmax()
 
     def reset_minmax(self):
         check(self.lib.hmz_search_minmax_reset(ptr(self.minmax), self.B, current_stream()))
+
+    def set_schedule(self, schedule):
+        """How hmz_search_run schedules its kernels (never changes results): 0 = automatic, k in [1, 16] = one launch
+        pair per simulation over k concurrent stream groups, _lib.SCHEDULE_PERSISTENT = one persistent kernel."""
+        self.desc.schedule = int(schedule)
+
+    def enable_capture(self, n_simulations):
+        """Parity tests: hmz_search_run records [p0..p5, r, v] of every simulation in the returned float32
+        [n_simulations, B, 8] tensor (until disable_capture)."""
+        self.capture = torch.zeros(int(n_simulations), self.B, 8, dtype=torch.float32, device=self.device)
+        self.desc.capture = self.capture.data_ptr()
+        return self.capture
+
+    def disable_capture(self):
+        self.capture, self.desc.capture = None, None
 
     def records(self):
         """Host copy of the node records as a dict of numpy arrays indexed [search, record, action]
@@ -223,6 +239,7 @@ class BatchedMCTS:
         self.pi = torch.zeros(self.B, 6, dtype=torch.float64, device=dev)
         self.root_q = torch.zeros(self.B, dtype=torch.float64, device=dev)
         self.action = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self._pow_cache = {}
 
     # -- split phases (used by the injected parity path and by tests) ---------------------------
     def begin(self, root_prior, prior_is_f64):
@@ -252,9 +269,23 @@ class BatchedMCTS:
             u = torch.as_tensor(uniforms, dtype=torch.float64, device=self.device).contiguous()
         n = self.n_simulations if n_simulations is None else n_simulations
         check(self.lib.hmz_search_root_policy(C.byref(self.store.desc), n, float(temperature), int(bool(deterministic)),
-                                              ptr(u), ptr(self.visits), ptr(self.pi), ptr(self.root_q),
-                                              ptr(self.action), current_stream()))
+                                              ptr(u), ptr(self._pow_table(temperature, n)), ptr(self.visits), ptr(self.pi),
+                                              ptr(self.root_q), ptr(self.action), current_stream()))
         return self.action, self.pi, self.root_q, self.visits
+
+    def _pow_table(self, temperature, n):
+        """visits ** clamp(1/T, 1, 5) for every possible count, evaluated by THIS process's NumPy exactly as
+        generate_play_policy does (MCTS/mcts.py:168-174: np.power on an int64 array); None when the device's exact
+        integer powers are identical (exponents 1..5 with every power below 2^53)."""
+        if temperature <= 0.0:
+            return None
+        ex = max(1.0, min(5.0, 1.0 / temperature))
+        if ex == int(ex) and float(n) ** ex < 2.0 ** 53:
+            return None
+        key = (ex, n)
+        if self._pow_cache.get("key") != key:
+            self._pow_cache = dict(key=key, table=torch.from_numpy(np.power(np.arange(n + 1, dtype=np.int64), ex)).to(self.device))
+        return self._pow_cache["table"]
 
     def run_injected(self, root_prior, prior_is_f64, r, p, v, want_paths=False):
         """Search with the network outputs of every simulation supplied (parity mode of

@@ -122,13 +122,15 @@ class ReplayRing:
         check(self.lib.hmz_episode_rows(ptr(store.ep_len), ptr(store.returns), store.B, self.ptr, int(bool(only_solved)),
                                         ptr(store.row_base), ptr(store.total), s))
         n = int(store.total.item())
-        if n > self.size:  # buffer.py:66 asserts n_transitions <= size for one episode; here for the batch
-            raise ValueError(f"{n} transitions do not fit a replay ring of {self.size} rows in one add")
+        # The reference adds one episode at a time (Muzero.py:98-101 -> buffer.py:47-83), so when the episodes finishing on
+        # this move hold more rows than the ring, the earlier rows are overwritten by the later ones: only the last
+        # `size` rows (in game order) survive, at the positions sequential adds would have left them.
+        first_row = self.ptr + max(0, n - self.size)
         if n:
             check(self.lib.hmz_episode_unroll(ptr(store.state), ptr(store.action), ptr(store.flags), ptr(store.visits),
                                               ptr(store.returns), ptr(store.priority), ptr(store.ep_len), ptr(store.row_base),
                                               ptr(ab), store.B, store.t_max, store.n_disks, self.unroll_n_steps,
-                                              float(temperature), self.size, ptr(self.states), ptr(self.rwds), ptr(self.actions),
+                                              float(temperature), self.size, first_row, ptr(self.states), ptr(self.rwds), ptr(self.actions),
                                               ptr(self.pi_probs), ptr(self.mc_returns), ptr(self.priorities), s))
             self._advance(n)
         return n

@@ -90,6 +90,10 @@ SEARCH_CONFIGS = {
     "n4_s200_lesion_t0": dict(N=4, S=200, alpha=0.0, T=0.0, det=False, wseed=3,
                               lesion=("policy_net", "value_net"), K=6),
     "n5_s100_noise_t05": dict(N=5, S=100, alpha=0.25, T=0.5, det=False, wseed=4, lesion=(), K=8),
+    # the temperature of episodes >= 750 (utils.py:89-96): exponent 5, np.power(int64, 5.0) (MCTS/mcts.py:170-174)
+    "n3_s50_noise_t01": dict(N=3, S=50, alpha=0.25, T=0.1, det=False, wseed=5, lesion=(), K=12),
+    # a non-integer exponent (1 / 0.4 = 2.5): NumPy's pow() on the visit counts
+    "n4_s60_noise_t04": dict(N=4, S=60, alpha=0.25, T=0.4, det=False, wseed=6, lesion=(), K=8),
 }
 DISCOUNT = 0.8
 

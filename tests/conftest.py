@@ -48,3 +48,18 @@ def lib():
     from muzero_hanoi_b200 import _lib
 
     return _lib.load()
+
+
+def record_metric(name, values):
+    """Achieved numbers of a GPU test (errors, fractions) appended to gpurun_out/test_metrics.jsonl so that a run on the
+    box leaves them behind for profiles/ (best effort: never fails a test)."""
+    import json
+
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "test_metrics.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: (float(v) if hasattr(v, "__float__") else v) for k, v in values.items()}}) + "\n")
+    except OSError:
+        pass
+    print(name, values)

@@ -89,6 +89,34 @@ def test_unroll_into_replay_ring_matches_organise_transitions(golden, capacity):
         row += T
 
 
+@pytest.mark.parametrize("capacity,scalar", [(100, False), (37, False), (100, True)])
+def test_more_rows_than_the_ring_holds_equals_sequential_adds(golden, capacity, scalar, monkeypatch):
+    """All eight fixture episodes (310 rows) finish on one move and that fit go into a ring of 100 / 37 rows (110 / 50 rows arrive).  The reference adds
+    episodes one at a time (Muzero.py:98-101 -> buffer.py:47-83), later rows overwriting earlier ones; the device-side
+    add of the whole batch must leave exactly the ring those sequential adds leave (ptr and is_full included)."""
+    from muzero_hanoi_b200.replay import ReplayRing
+
+    if scalar:
+        monkeypatch.setenv("HMZ_UNROLL_SCALAR", "1")
+    g = golden("episode_post.npz")
+    order = [k for k in range(int(g["n_episodes"])) if len(g[f"e{k}_returns"]) <= capacity]
+    st, words, ep_len = _fill_store(g, order=order)
+    st.post_process(int(g["n_step"]), float(g["discount"]))
+    absorbing = np.array([int(g[f"e{k}_absorbing"]) for k in order], np.uint8)
+    dev, seq = ReplayRing(capacity, int(g["unroll"]), 15, 6), ReplayRing(capacity, int(g["unroll"]), 15, 6)
+    dev.ptr = seq.ptr = 11
+    n = dev.add_episodes(st, temperature=1.0, only_solved=False, absorbing_action=absorbing)
+    assert n == int(ep_len.sum()) and n > capacity
+    for col, k in enumerate(order):  # the reference's order of operations, through the reference-shaped host add
+        T = ep_len[col]
+        onehot = np.stack([port.one_hot(port.packed_to_state(int(w), 5)) for w in words[:T, col]]).astype(np.float32)
+        seq.add(onehot, g[f"e{k}_o_r"], g[f"e{k}_o_a"], g[f"e{k}_o_p"], g[f"e{k}_o_g"], g[f"e{k}_priority"])
+    torch.cuda.synchronize()
+    assert dev.ptr == seq.ptr and dev.is_full and seq.is_full
+    for name in ("states", "rwds", "actions", "pi_probs", "mc_returns", "priorities"):
+        assert torch.equal(getattr(dev, name), getattr(seq, name)), name
+
+
 def test_only_solved_filter_and_row_bases(golden):
     """training_loop keeps an episode only if returns[-1, 0] > 0 (Muzero.py:98)."""
     from muzero_hanoi_b200.replay import ReplayRing

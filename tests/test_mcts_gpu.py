@@ -13,6 +13,9 @@ import torch
 from oracle import cport, port
 
 pytestmark = pytest.mark.gpu
+# hmz_search_t.schedule values exercised at full size: serial launches, the automatic choice (4 stream groups at this
+# size), 7 ragged groups, and the persistent role-specialised kernel
+SCHEDULES_FULL = (1, 0, 7)
 
 
 def _split_search(mcts, weights, words, noise, record=True):
@@ -215,6 +218,47 @@ def test_node_view_matches_tree_store(golden):
     assert leaf.N == 0 and leaf.Q == 0.0 and leaf.h_state is None and leaf.children == []
 
 
+@pytest.mark.parametrize("schedule", [0])
+def test_full_size_benchmarked_path_replayed_by_the_oracle(schedule):
+    """The path bench.py times, at the size it times it: bf16 throughput mode, hmz_search_run (fused backup + select
+    kernels, stream groups and programmatic dependent launches for schedule 0; the persistent kernel for schedule 64),
+    N = 5, 65,536 searches x 100 simulations, two consecutive moves (the second one starts from persisted min/max
+    bounds).  The run records the network outputs every backup consumed (hmz_search_t.capture); the C oracle replays
+    the tree arithmetic with exactly those outputs injected and must reproduce visit counts, root values (float64) and
+    the persistent min/max bit for bit.  An ordering bug between the network kernel and the tree kernel (a backup that
+    ran on stale or half-written outputs, a walk that missed a slot update) would show here and nowhere else."""
+    from muzero_hanoi_b200 import _lib
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    n, B, S = 5, 65536, 100
+    w = PackedWeights(port.make_weights(n, 21), n, _lib.MODE_BF16)
+    env = VecHanoi(n, 200, B)
+    env.random_reset(seed=2)
+    rng = np.random.default_rng(11)
+    m = BatchedMCTS(0.8, 0.25, S, B, latent_dtype=_lib.LATENT_BF16)
+    m.store.set_schedule(schedule)
+    cap = m.store.enable_capture(S)
+    table = port.ucb_table(S + 1)
+    for move in range(2):
+        noise = rng.dirichlet(np.full(6, 0.25), B)
+        uni = rng.random(B)
+        mm = m.store.minmax.cpu().numpy().copy()
+        cap.fill_(float("nan"))
+        action, pi, q, visits = m.run_mcts(w, words=env.words, temperature=1.0, deterministic=False, noise=noise, uniforms=uni)
+        torch.cuda.synchronize()
+        c = cap.cpu().numpy()
+        assert np.isfinite(c).all()  # every (simulation, search) cell was written
+        prior = m.store.root_prior.cpu().numpy()
+        assert np.array_equal(prior, port.mix_dirichlet(m.p0.cpu().numpy(), noise))
+        o_visits, o_q, _ = cport.search_injected(prior, True, mm, np.ascontiguousarray(c[:, :, 6]), np.ascontiguousarray(c[:, :, :6]),
+                                                 np.ascontiguousarray(c[:, :, 7]), 0.8, table)
+        assert np.array_equal(visits.cpu().numpy(), o_visits), f"move {move}: visit counts differ from the oracle replay"
+        assert np.array_equal(q.cpu().numpy(), o_q)
+        assert np.array_equal(m.store.minmax.cpu().numpy(), mm)
+        assert np.array_equal(pi.cpu().numpy(), o_visits / o_visits.sum(1, keepdims=True))
+        env.step(action.to(torch.uint8), want_obs=False)
+
+
 def test_full_size_config3_grouping_invariance_and_properties():
     """BASELINE.json configs[2] size (N = 5, 65,536 searches x 100 simulations, throughput mode): results must
     not depend on how hmz_search_run cuts the batch into concurrent stream groups (the groups only change
@@ -225,7 +269,6 @@ def test_full_size_config3_grouping_invariance_and_properties():
     from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
 
     n, B, S = 5, 65536, 100
-    lib = _lib.load()
     w = PackedWeights(port.make_weights(n, 21), n, _lib.MODE_BF16)
     env = VecHanoi(n, 200, B)
     env.random_reset(seed=2)
@@ -233,17 +276,15 @@ def test_full_size_config3_grouping_invariance_and_properties():
     noise = torch.from_numpy(rng.dirichlet(np.full(6, 0.25), B)).cuda()
     uni = torch.from_numpy(rng.random(B)).cuda()
     outs = []
-    try:
-        for groups in (1, 4, 7):
-            _lib.check(lib.hmz_search_set_groups(groups))
-            m = BatchedMCTS(0.8, 0.25, S, B, latent_dtype=_lib.LATENT_BF16)
-            action, pi, q, visits = m.run_mcts(w, words=env.words, temperature=1.0, deterministic=False, noise=noise,
-                                               uniforms=uni)
-            torch.cuda.synchronize()
-            outs.append((action.cpu().numpy(), pi.cpu().numpy(), q.cpu().numpy(), visits.cpu().numpy(),
-                         m.store.minmax.cpu().numpy()))
-    finally:
-        _lib.check(lib.hmz_search_set_groups(0))
+    for schedule in SCHEDULES_FULL:
+        m = BatchedMCTS(0.8, 0.25, S, B, latent_dtype=_lib.LATENT_BF16)
+        m.store.set_schedule(schedule)
+        action, pi, q, visits = m.run_mcts(w, words=env.words, temperature=1.0, deterministic=False, noise=noise,
+                                           uniforms=uni)
+        torch.cuda.synchronize()
+        outs.append((action.cpu().numpy(), pi.cpu().numpy(), q.cpu().numpy(), visits.cpu().numpy(),
+                     m.store.minmax.cpu().numpy()))
+        del m
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
             assert np.array_equal(a, b)  # bit for bit, float64 root values and min/max included

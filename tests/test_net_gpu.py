@@ -1,25 +1,41 @@
 """GPU parity: MuZeroNet inference kernels (through the C ABI) vs outputs recorded from the
 unmodified reference network (tests/golden/net_io.npz).
 
-Tolerances (HMZ_MODE_FP32, north_star: within 1e-5 relative in fp32):
-  latent h and policy p (both in [0, 1]):      |d| <= 1e-5            (relative to their unit scale)
+Tolerances (HMZ_MODE_FP32, north_star: within 1e-5 relative in fp32), all RELATIVE with a small absolute floor:
+  latent h and policy p:                       |d| <= 1e-5 * |ref| + 5e-7 (h) / 1e-7 (p)
   reward r and value v (support transform):    |d| <= 1e-5 * |ref| + 2.5e-4
-The absolute term for r/v is the float32 granularity of the reference's OWN signed-parabolic
-evaluation (networks.py:186-189 computes sqrt(..)/2/eps - 1/2/eps ~ 500.x - 500 in float32, i.e.
-its outputs live on a ~1.2e-4 grid near zero), so a 1-ulp difference in the softmax expectation
-moves the reference's result by one grid step; two grid steps are allowed."""
+The floor for h is the float32 rounding of normalize_h_state itself ((h - min) / (max - min + 1e-8), networks.py:191-196:
+every element is a difference of O(1) numbers, so elements near zero carry an absolute error of a few ulp(1) = 6e-8
+whatever the kernel does — the smallest element is exactly 0 in both).  The absolute term for r/v is the float32
+granularity of the reference's OWN signed-parabolic evaluation (networks.py:186-189 computes
+sqrt(..)/2/eps - 1/2/eps ~ 500.x - 500 in float32, i.e. its outputs live on a ~1.2e-4 grid near zero), so a 1-ulp
+difference in the softmax expectation moves the reference's result by one grid step; two grid steps are allowed.
+The achieved maxima are recorded by every test (conftest.record_metric -> gpurun_out/test_metrics.jsonl)."""
 import numpy as np
 import pytest
 import torch
 
+from conftest import record_metric
 from oracle import port
 
 pytestmark = pytest.mark.gpu
-H_TOL, RV_REL, RV_ABS = 1e-5, 1e-5, 2.5e-4
+REL, H_ABS, P_ABS, RV_REL, RV_ABS = 1e-5, 5e-7, 1e-7, 1e-5, 2.5e-4
+H_TOL = 1e-5  # drop-in surface checks (single rows through the Python shim)
+
+
+def _close(got, ref, atol):
+    return bool(np.all(np.abs(got - ref) <= REL * np.abs(ref) + atol))
 
 
 def _close_rv(got, ref):
     return np.all(np.abs(got - ref) <= RV_REL * np.abs(ref) + RV_ABS)
+
+
+def _errs(got, ref):
+    """(max absolute error, max relative error over elements with |ref| >= 1e-3)."""
+    d = np.abs(np.asarray(got, np.float64) - np.asarray(ref, np.float64))
+    big = np.abs(ref) >= 1e-3
+    return float(d.max()), float((d[big] / np.abs(ref)[big]).max()) if big.any() else 0.0
 
 
 def _weights(n, seed, mode=0):
@@ -40,9 +56,14 @@ def test_recurrent_matches_reference(golden, n, count):
     w.recurrent(count, latents_in=h_in, in_rows_per_item=1, in_row=None, actions=acts, latents_out=h,
                 out_rows_per_item=1, out_row=0, latent_dtype=0, r=r, p=p, v=v)
     torch.cuda.synchronize()
-    assert np.abs(h.cpu().numpy() - g[f"n{n}_h_out"][:count]).max() <= H_TOL
-    assert np.abs(p.cpu().numpy() - g[f"n{n}_p"][:count]).max() <= H_TOL
-    assert _close_rv(r.cpu().numpy(), g[f"n{n}_r"][:count]) and _close_rv(v.cpu().numpy(), g[f"n{n}_v"][:count])
+    hh, pp, rr, vv = h.cpu().numpy(), p.cpu().numpy(), r.cpu().numpy(), v.cpu().numpy()
+    eh, ep = _errs(hh, g[f"n{n}_h_out"][:count]), _errs(pp, g[f"n{n}_p"][:count])
+    er, ev = _errs(rr, g[f"n{n}_r"][:count]), _errs(vv, g[f"n{n}_v"][:count])
+    record_metric(f"fp32_recurrent_n{n}_x{count}", dict(h_abs=eh[0], h_rel=eh[1], p_abs=ep[0], p_rel=ep[1], r_abs=er[0], r_rel=er[1],
+                                                        v_abs=ev[0], v_rel=ev[1]))
+    assert _close(hh, g[f"n{n}_h_out"][:count], H_ABS)
+    assert _close(pp, g[f"n{n}_p"][:count], P_ABS)
+    assert _close_rv(rr, g[f"n{n}_r"][:count]) and _close_rv(vv, g[f"n{n}_v"][:count])
 
 
 @pytest.mark.parametrize("n", [3, 5, 10])
@@ -62,8 +83,10 @@ def test_initial_matches_reference_words_and_obs_paths(golden, n):
                   latents_out=h, out_rows_per_item=1, latent_dtype=0, p0=p0, v0=v0)
         torch.cuda.synchronize()
         outs.append((h.cpu().numpy(), p0.cpu().numpy(), v0.cpu().numpy()))
-        assert np.abs(outs[-1][0] - g[f"n{n}_h0"]).max() <= H_TOL
-        assert np.abs(outs[-1][1] - g[f"n{n}_p0"]).max() <= H_TOL
+        eh, ep, ev = _errs(outs[-1][0], g[f"n{n}_h0"]), _errs(outs[-1][1], g[f"n{n}_p0"]), _errs(outs[-1][2], g[f"n{n}_v0"])
+        record_metric(f"fp32_initial_n{n}_words{int(use_words)}", dict(h_abs=eh[0], h_rel=eh[1], p_abs=ep[0], p_rel=ep[1], v_abs=ev[0], v_rel=ev[1]))
+        assert _close(outs[-1][0], g[f"n{n}_h0"], H_ABS)
+        assert _close(outs[-1][1], g[f"n{n}_p0"], P_ABS)
         assert _close_rv(outs[-1][2], g[f"n{n}_v0"])
     for a, b in zip(*outs):  # packed-word and float-observation paths add the same terms in the same order
         assert np.array_equal(a, b)
@@ -198,5 +221,6 @@ def test_bf16_mode_search_runs_and_agrees_with_fp32_mode():
         assert (visits.sum(1) == S).all()
         out.append((pi.cpu().numpy(), q.cpu().numpy()))
     moved = np.abs(out[0][0] - out[1][0]).sum(1).mean() / 2
-    print("mean fraction of visits moved by bf16:", moved)
+    record_metric("bf16_vs_fp32_search_n5_1000x50", dict(mean_fraction_of_visits_moved=moved,
+                                                         max_abs_root_q_diff=np.abs(out[0][1] - out[1][1]).max()))
     assert moved < 0.10

@@ -6,7 +6,9 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-FIXTURES = ["n3_s50_noise_t1", "n3_s25_nonoise_t0", "n3_s25_det", "n4_s200_lesion_t0", "n5_s100_noise_t05"]
+FIXTURES = ["n3_s50_noise_t1", "n3_s25_nonoise_t0", "n3_s25_det", "n4_s200_lesion_t0", "n5_s100_noise_t05",
+            "n3_s50_noise_t01",   # T = 0.1 -> exponent 5 (utils.py:89-96 for episodes >= 750; np.power(int64, 5.0), mcts.py:170-174)
+            "n4_s60_noise_t04"]   # T = 0.4 -> exponent 2.5: NumPy's vectorised pow (host table through the ABI)
 INF = float("inf")
 
 
@@ -62,6 +64,51 @@ def test_minmax_persists_across_moves(golden, name):
         mcts.run_injected(g["prior"][k:k + 1], bool(g["prior_is_f64"]), g["r"][k][:, None], g["p"][k][:, None, :],
                           g["v"][k][:, None])
         _check_against_fixture(g, mcts, np.array([k]), None, None)
+
+
+@pytest.mark.parametrize("name", ["n3_s50_noise_t1", "n3_s25_det", "n4_s200_lesion_t0"])
+def test_return_latent_actions_equals_reference_last_path(golden, name):
+    """MCTS.return_latent_actions (MCTS/mcts.py:128-130; filled at :79,84-86) = the actions selected along the LAST
+    simulation's path.  Injected mode, so the tree is the reference's tree: the drop-in's list must equal the golden
+    path of simulation S - 1 exactly (values, not just shape)."""
+    from muzero_hanoi_b200.engine import BatchedMCTS
+    from muzero_hanoi_b200.MCTS.mcts import MCTS
+
+    g = golden(f"search_{name}.npz")
+    S, K = int(g["S"]), int(g["K"])
+    eng = BatchedMCTS(float(g["discount"]), float(g["alpha"]), S, 1)
+    shim = MCTS(float(g["discount"]), float(g["alpha"]), S, 1, "cpu")
+    shim._engine = eng
+    for k in range(K):
+        eng.run_injected(g["prior"][k:k + 1], bool(g["prior_is_f64"]), g["r"][k][:, None], g["p"][k][:, None, :], g["v"][k][:, None])
+        want = g["path"][k][S - 1, : int(g["depth"][k][S - 1])]
+        got = shim.return_latent_actions()
+        assert [int(t.item()) for t in got] == want.tolist()
+        assert all(t.dtype == torch.long and t.shape == (1,) for t in got) and got is shim.latent_actions
+
+
+def test_play_policy_powers_device_vs_numpy():
+    """generate_play_policy (MCTS/mcts.py:154-176) over every temperature of the reference's schedule and a few others:
+    the device's exact integer powers (no table) and the host-table path must both reproduce NumPy bit for bit."""
+    from muzero_hanoi_b200.engine import BatchedMCTS
+    from oracle import port
+
+    S, B = 1500, 64  # 1500 ** 5 < 2 ** 53: the largest counts for which exponent 5 is exact without a table
+    rng = np.random.default_rng(5)
+    mcts = BatchedMCTS(0.8, 0.0, S, B)
+    rec = mcts.store.nodes.view(torch.int16).reshape(B, S + 1, 64)
+    counts = rng.multinomial(S, rng.dirichlet(np.full(6, 0.3), B)).astype(np.int32)  # [B, 6], rows sum to S
+    counts[0] = [S, 0, 0, 0, 0, 0]
+    for a in range(6):  # child a lives in half a // 3, slot a % 3; N is the uint16 at byte 12 of the 16-byte slot
+        rec[:, 0, (a // 3) * 32 + (a % 3) * 8 + 6] = torch.from_numpy(counts[:, a].astype(np.int16)).cuda()
+    for T in (1.0, 0.5, 0.25, 0.2, 0.1, 0.05, 0.4, 0.3, 0.7, 0.0):
+        u = rng.random(B)
+        act, pi, _, visits = mcts.root_policy(T, False, uniforms=u)
+        torch.cuda.synchronize()
+        assert np.array_equal(visits.cpu().numpy(), counts)
+        want = np.stack([port.play_policy(c, T) for c in counts])
+        assert np.array_equal(pi.cpu().numpy(), want), f"T={T}"
+        assert act.cpu().numpy().tolist() == [port.sample_action(want[i], u[i]) for i in range(B)]
 
 
 def test_ragged_batch_and_record_layout(golden):

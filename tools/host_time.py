@@ -7,9 +7,9 @@ from muzero_hanoi_b200.engine import PackedWeights, SelfPlay
 from oracle import port
 B, S, n = 65536, 100, 5
 w = PackedWeights(port.make_weights(n, 3), n, 1)
-for groups in (1, 4):
-    _lib.load().hmz_search_set_groups(groups)
+for groups in (1, 4, _lib.SCHEDULE_PERSISTENT):
     sp = SelfPlay(n, 200, B, S, w, seed=1, latent_dtype=1)
+    sp.mcts.store.set_schedule(groups)
     for _ in range(3):
         sp.move()
     torch.cuda.synchronize()

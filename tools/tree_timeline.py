@@ -8,12 +8,12 @@ from oracle import port
 
 B, S, n = int(os.environ.get("B", 65536)), 100, 5
 lib = _lib.load()
-lib.hmz_search_set_groups(int(os.environ.get("GROUPS", 1)))
 w = PackedWeights(port.make_weights(n, 3), n, 1)
 env = VecHanoi(n, 200, B)
 env.reset()
 env.random_reset(seed=5)
 m = BatchedMCTS(0.8, 0.25, S, B, latent_dtype=1)
+m.store.set_schedule(int(os.environ.get("GROUPS", 1)))
 noise = torch.from_numpy(np.random.default_rng(0).dirichlet(np.full(6, 0.25), B)).cuda()
 uni = torch.rand(B, dtype=torch.float64, device="cuda")
 run = lambda: m.run_mcts(w, words=env.words, temperature=1.0, deterministic=False, noise=noise, uniforms=uni)
