@@ -286,29 +286,37 @@ int hmz_debug_tree_timeline(long long search, unsigned long long* host_out);
 int hmz_debug_div_check(uint64_t n_samples, uint64_t seed, unsigned long long* counters, void* stream);
 
 /* ------------------------------------------------------------------ self-play glue ---
- * Throughput-mode randomness, drawn on device with Philox4x32-10 keyed by (seed, item,
- * counter) so results do not depend on how games are sharded over GPUs.  Parity mode passes
- * the reference's own draws to hmz_search_begin_p0 / hmz_search_root_policy instead.
+ * Throughput-mode randomness, drawn on device with Philox4x32-10 keyed by (seed, GLOBAL item id, counter): item i of
+ * a call is keyed by item_offset + i, so results do not depend on how games are sharded over GPUs (rank r of G passes
+ * the global id of its first game).  Parity mode passes the reference's own draws to hmz_search_begin_p0 /
+ * hmz_search_root_policy instead.
  */
 /* np.random.dirichlet(alpha * ones(6)) (MCTS/mcts.py:148-149): out float64 [n][6]. */
-int hmz_rng_dirichlet(double* out, int64_t n, double alpha, uint64_t seed, uint64_t counter, void* stream);
+int hmz_rng_dirichlet(double* out, int64_t n, double alpha, uint64_t seed, uint64_t counter, uint64_t item_offset, void* stream);
 /* One uniform double in [0, 1) per item (the draw of np.random.choice, MCTS/mcts.py:120). */
-int hmz_rng_uniform(double* out, int64_t n, uint64_t seed, uint64_t counter, void* stream);
+int hmz_rng_uniform(double* out, int64_t n, uint64_t seed, uint64_t counter, uint64_t item_offset, void* stream);
+/* Tests only: n_blocks raw Philox4x32-10 blocks; counters_keys uint32 [n_blocks][6] = counter words 0..3, key words
+ * 0..1; out uint32 [n_blocks][4] (known-answer vectors of Salmon et al. 2011). */
+int hmz_debug_philox(const uint32_t* counters_keys, uint32_t* out, int n_blocks, void* stream);
 
-/* One trajectory record per game and move — the episode lists of Muzero._play_game
- * (Muzero.py:179-183) in struct-of-arrays form, slot `t` of a [n_slots][n_games] ring:
- *   state  uint32  env word BEFORE the move        action  uint8
- *   visits uint16[6] root child visit counts        root_q  float32 (root_node.Q)
- * (reward and flags of the move are written by hmz_env_step straight into their ring rows.) */
-int hmz_traj_record(const uint32_t* words, const int32_t* action, const int32_t* visits, const double* root_q,
-                    uint32_t* traj_state, uint8_t* traj_action, uint16_t* traj_visits, float* traj_root_q,
-                    uint8_t* action_u8_out, int64_t n_games, void* stream);
+/* One game-move — the episode lists of Muzero._play_game (Muzero.py:179-183) for one step — as a 32-byte record:
+ * the element of the trajectory ring AND the wire format of the NCCL all-gather towards the replay buffer. */
+typedef struct hmz_move_record {
+  double root_q;      /* root_node.Q (float64, so n-step returns computed downstream stay bit-exact)   */
+  uint32_t state;     /* env word BEFORE the move                                                      */
+  float reward;       /* 0, 100 or -0.1 (env/hanoi.py:62,66,72)                                        */
+  uint16_t visits[6]; /* root child visit counts                                                       */
+  uint8_t action;     /* sampled action                                                                */
+  uint8_t flags;      /* HMZ_FLAG_* of the move                                                        */
+  uint16_t game_lo;   /* low 16 bits of the global game id (ordering check after a gather)             */
+} hmz_move_record_t;
 
 /* One move of every game, fused on the host side of the ABI (the `hmz_selfplay_round` of SURVEY.md §8b): the loop body
- * of Muzero._play_game (Muzero.py:165-186) for all games — hmz_net_initial, hmz_rng_dirichlet / hmz_rng_uniform keyed by
- * (seed, game, move_index), hmz_search_begin_p0, hmz_search_run, hmz_search_root_policy (sampled action),
- * hmz_traj_record (+ hmz_episode_record / hmz_episode_close when the ep_* buffers are given), hmz_env_step with
- * auto-reset — enqueued on `stream` without any host synchronisation.  All pointers are caller-owned device buffers. */
+ * of Muzero._play_game (Muzero.py:165-186) for all games — hmz_net_initial; ONE kernel for the Dirichlet draw, its mix
+ * into the root prior (hmz_search_begin_p0) and the sampling uniform, keyed by (seed, game_offset + game, move_index);
+ * hmz_search_run; ONE kernel for the root policy + sampled action (hmz_search_root_policy), the move record, the
+ * episode store (hmz_episode_record / _close) and hmz_env_step with auto-reset — enqueued on `stream` without any host
+ * synchronisation.  All pointers are caller-owned device buffers. */
 typedef struct hmz_selfplay {
   hmz_search_t search;      /* root_prior_is_f64 must equal (dirichlet_alpha > 0 && exploration_eps > 0) */
   const void* weights;      /* hmz_weights_pack blob */
@@ -316,18 +324,12 @@ typedef struct hmz_selfplay {
   uint32_t* words;          /* [B] env words (stepped in place) */
   float* p0;                /* [B][6] root policy */
   float* v0;                /* [B] root value */
-  double* noise;            /* [B][6] Dirichlet draws (nullable when dirichlet_alpha == 0) */
-  double* uniform;          /* [B] sampling uniforms */
-  int32_t* visits;          /* [B][6] root child visit counts of the move */
-  double* root_q;           /* [B] root_node.Q */
-  int32_t* action;          /* [B] sampled action */
-  uint8_t* action_u8;       /* [B] the same, as the env kernel reads it */
-  float* step_reward;       /* [B] reward of the move (a trajectory-ring row) */
-  uint8_t* step_flags;      /* [B] HMZ_FLAG_* of the move (a trajectory-ring row) */
-  uint32_t* traj_state;     /* trajectory-ring rows, nullable individually (hmz_traj_record) */
-  uint8_t* traj_action;
-  uint16_t* traj_visits;
-  float* traj_root_q;
+  double* noise;            /* [B][6] receives the Dirichlet draws (nullable) */
+  double* uniform;          /* [B] receives the sampling uniforms */
+  int32_t* visits;          /* [B][6] root child visit counts of the move (nullable) */
+  double* root_q;           /* [B] root_node.Q (nullable) */
+  int32_t* action;          /* [B] sampled action (nullable) */
+  hmz_move_record_t* records; /* [B] this move's slot of the trajectory ring (nullable), 16-byte aligned */
   uint32_t* ep_state;       /* episode store (hmz_episode_record / _close), all NULL to skip */
   uint8_t* ep_action;
   uint8_t* ep_flags;
@@ -335,8 +337,10 @@ typedef struct hmz_selfplay {
   double* ep_root_q;
   int32_t* ep_cur_slot;
   int32_t* ep_len;
+  const double* pow_table;  /* as hmz_search_root_policy (nullable) */
   double discount, dirichlet_alpha, exploration_eps, temperature;
   uint64_t seed;
+  uint64_t game_offset;     /* global id of game 0 of this batch (Philox key, record.game_lo) */
   int32_t mode, n_disks, max_steps, goal_peg, n_simulations, ep_t_max;
   uint32_t reset_word;
   int32_t reserved;

@@ -53,16 +53,30 @@ class SearchDesc(C.Structure):
 assert C.sizeof(NodeRecord) == 128
 
 
+class MoveRecord(C.Structure):
+    """hmz_move_record_t — 32 bytes."""
+
+    _fields_ = [("root_q", C.c_double), ("state", C.c_uint32), ("reward", C.c_float), ("visits", C.c_uint16 * 6), ("action", C.c_uint8),
+                ("flags", C.c_uint8), ("game_lo", C.c_uint16)]
+
+
+assert C.sizeof(MoveRecord) == 32
+RECORD_BYTES = 32
+# numpy view of a record buffer (host copy): np.frombuffer(buf, RECORD_DTYPE)
+RECORD_DTYPE = [("root_q", "<f8"), ("state", "<u4"), ("reward", "<f4"), ("visits", "<u2", 6), ("action", "u1"), ("flags", "u1"),
+                ("game_lo", "<u2")]
+
+
 class SelfPlayDesc(C.Structure):
     """hmz_selfplay_t."""
 
     _fields_ = [("search", SearchDesc)] + [(name, C.c_void_p) for name in (
-        "weights", "ucb_table", "words", "p0", "v0", "noise", "uniform", "visits", "root_q", "action", "action_u8", "step_reward",
-        "step_flags", "traj_state", "traj_action", "traj_visits", "traj_root_q", "ep_state", "ep_action", "ep_flags", "ep_visits",
-        "ep_root_q", "ep_cur_slot", "ep_len")] + [
+        "weights", "ucb_table", "words", "p0", "v0", "noise", "uniform", "visits", "root_q", "action", "records", "ep_state",
+        "ep_action", "ep_flags", "ep_visits", "ep_root_q", "ep_cur_slot", "ep_len", "pow_table")] + [
         ("discount", C.c_double), ("dirichlet_alpha", C.c_double), ("exploration_eps", C.c_double), ("temperature", C.c_double),
-        ("seed", C.c_uint64), ("mode", C.c_int32), ("n_disks", C.c_int32), ("max_steps", C.c_int32), ("goal_peg", C.c_int32),
-        ("n_simulations", C.c_int32), ("ep_t_max", C.c_int32), ("reset_word", C.c_uint32), ("reserved", C.c_int32)]
+        ("seed", C.c_uint64), ("game_offset", C.c_uint64), ("mode", C.c_int32), ("n_disks", C.c_int32), ("max_steps", C.c_int32),
+        ("goal_peg", C.c_int32), ("n_simulations", C.c_int32), ("ep_t_max", C.c_int32), ("reset_word", C.c_uint32),
+        ("reserved", C.c_int32)]
 
 _P, _I, _L, _U32, _U64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
 _SD = C.POINTER(SearchDesc)
@@ -102,9 +116,9 @@ SIGNATURES = {
     "hmz_debug_tree_timeline": (_I, [C.c_longlong, _P]),
     "hmz_debug_div_check": (_I, [_U64, _U64, _P, _P]),
     "hmz_search_run": (_I, [_SD, _P, _I, _I, _P, _D, _P]),
-    "hmz_rng_dirichlet": (_I, [_P, _L, _D, _U64, _U64, _P]),
-    "hmz_rng_uniform": (_I, [_P, _L, _U64, _U64, _P]),
-    "hmz_traj_record": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "hmz_rng_dirichlet": (_I, [_P, _L, _D, _U64, _U64, _U64, _P]),
+    "hmz_rng_uniform": (_I, [_P, _L, _U64, _U64, _U64, _P]),
+    "hmz_debug_philox": (_I, [_P, _P, _I, _P]),
     "hmz_selfplay_move": (_I, [C.POINTER(SelfPlayDesc), _U64, _P]),
     "hmz_learner_param_count": (_L, [_I]),
     "hmz_learner_workspace_bytes": (_L, [_I, _I, _I]),

@@ -7,112 +7,43 @@
 // All kernels are HBM-streaming integer kernels: one env word per lane, 4 words per thread
 // through 128-bit loads/stores, grids sized in whole waves of the SM count.  No tensor cores:
 // there is no contraction here.
-#include "hmz_common.cuh"
+#include "hmz_env.cuh"
 
 namespace hmz {
 
-struct EnvCfg {
-  uint32_t even_mask;   // 0x55555555 restricted to the 2N state bits
-  uint32_t state_mask;  // (1 << 2N) - 1
-  uint32_t goal_word;   // goal_peg replicated on every disk
-  uint32_t reset_word;
-  uint32_t max_steps;
-  int shift;            // 2N: where the step counter starts
-  int auto_reset;
-};
-
-// Bit index (2*disk) of the top (smallest) disk on each peg, 0xFFFFFFFF if the peg is empty.
-__device__ __forceinline__ void peg_tops(uint32_t st, uint32_t even_mask, uint32_t& t0, uint32_t& t1, uint32_t& t2) {
-  uint32_t lo = st & even_mask, hi = (st >> 1) & even_mask;
-  t0 = (uint32_t)(__ffs((int)(even_mask & ~(lo | hi))) - 1);
-  t1 = (uint32_t)(__ffs((int)(lo & ~hi)) - 1);
-  t2 = (uint32_t)(__ffs((int)(hi & ~lo)) - 1);
-}
-
-// bit a = move a allowed; actions 0:(0,1) 1:(0,2) 2:(1,0) 3:(1,2) 4:(2,0) 5:(2,1)  (env/hanoi.py:39-41).
-// A move f->t is allowed iff peg f is non-empty and (peg t is empty or its top disk is larger),
-// i.e. top(f) < top(t) with "empty" = +inf (env/hanoi.py:123-139).
-__device__ __forceinline__ uint32_t legal_bits(uint32_t t0, uint32_t t1, uint32_t t2) {
-  return (uint32_t)(t0 < t1) | ((uint32_t)(t0 < t2) << 1) | ((uint32_t)(t1 < t0) << 2) | ((uint32_t)(t1 < t2) << 3) |
-         ((uint32_t)(t2 < t0) << 4) | ((uint32_t)(t2 < t1) << 5);
-}
-
-struct StepOut {
-  uint32_t word;      // new env word (state | counter << shift), after optional auto-reset
-  uint32_t obs_word;  // state the returned observation encodes
-  float reward;
-  uint32_t flags;
-};
-
-__device__ __forceinline__ StepOut step_word(uint32_t word, uint32_t action, const EnvCfg& c) {
-  uint32_t st = word & c.state_mask;
-  uint32_t ctr = (word >> c.shift) + 1u;  // env/hanoi.py:56 — counted for illegal moves too
-  uint32_t t0, t1, t2;
-  peg_tops(st, c.even_mask, t0, t1, t2);
-  uint32_t a = action > 5u ? 5u : action;
-  uint32_t legal = (action <= 5u) ? ((legal_bits(t0, t1, t2) >> a) & 1u) : 0u;
-  uint32_t f = a >> 1;
-  uint32_t t = (0x489u >> (2u * a)) & 3u;
-  uint32_t tf = f == 0u ? t0 : (f == 1u ? t1 : t2);
-  StepOut o;
-  o.flags = 0u;
-  uint32_t stored = st;
-  o.obs_word = st;
-  o.reward = 0.0f;
-  if (legal) {
-    uint32_t moved = st ^ ((f ^ t) << tf);  // env/hanoi.py:141-151: one digit changes
-    o.obs_word = moved;
-    if (moved == c.goal_word) {  // :65-69 — stored state is NOT updated, counter cleared
-      o.reward = 100.0f;
-      o.flags = HMZ_FLAG_DONE | HMZ_FLAG_GOAL;
-      ctr = 0u;
-    } else {
-      stored = moved;
-    }
-  } else {
-    o.reward = -0.1f;  // float32 image of the python double -100/1000 (:72)
-    o.flags = HMZ_FLAG_ILLEGAL;
-  }
-  if (ctr == c.max_steps) {  // :77-80
-    o.flags |= HMZ_FLAG_DONE | HMZ_FLAG_TRUNC;
-    ctr = 0u;
-  }
-  o.word = stored | (ctr << c.shift);
-  if (c.auto_reset && (o.flags & HMZ_FLAG_DONE)) o.word = c.reset_word;
-  return o;
-}
-
-// k-th (0-based) set bit of a mask with 2 or 3 bits set.
-__device__ __forceinline__ uint32_t kth_set_bit(uint32_t m, uint32_t k) {
-  uint32_t m1 = m & (m - 1u);
-  uint32_t m2 = m1 & (m1 - 1u);
-  uint32_t sel = k == 0u ? m : (k == 1u ? m1 : m2);
-  return (uint32_t)(__ffs((int)sel) - 1);
-}
-
-__device__ __forceinline__ uint32_t random_legal_action(uint32_t st, uint32_t rnd, const EnvCfg& c) {
-  uint32_t t0, t1, t2;
-  peg_tops(st, c.even_mask, t0, t1, t2);
-  uint32_t m = legal_bits(t0, t1, t2);
-  return kth_set_bit(m, __umulhi(rnd, (uint32_t)__popc(m)));
-}
-
 // ------------------------------------------------------------------------------ kernels
-template <bool kObs>
+// One thread owns U vec4 groups per grid-stride iteration, spaced a block apart so that every load / store instruction
+// of a warp covers one contiguous 512-byte (words, rewards) or 128-byte (actions, flags) span; all U groups' loads are
+// issued before the first use.  What bounds this kernel is bytes in flight per SM (5 B read per env against ~35 KB per
+// SM that HBM3e needs outstanding), so U = 4 keeps 80 B of loads in flight per thread instead of 20.
+template <bool kObs, int U>
 __global__ void __launch_bounds__(256) env_step_vec4(uint4* __restrict__ words, const uchar4* __restrict__ actions,
                                                     float4* __restrict__ rewards, uchar4* __restrict__ flags,
                                                     uint4* __restrict__ obs_words, int64_t n_vec, EnvCfg c) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    // every byte is touched exactly once per launch: streaming loads / stores keep it out of the way in L2
-    const uint4 w = __ldcs(words + i);
-    const uchar4 a = __ldcs(actions + i);
-    StepOut o0 = step_word(w.x, a.x, c), o1 = step_word(w.y, a.y, c), o2 = step_word(w.z, a.z, c),
-            o3 = step_word(w.w, a.w, c);
-    __stcs(words + i, make_uint4(o0.word, o1.word, o2.word, o3.word));
-    __stcs(rewards + i, make_float4(o0.reward, o1.reward, o2.reward, o3.reward));
-    __stcs(flags + i, make_uchar4((unsigned char)o0.flags, (unsigned char)o1.flags, (unsigned char)o2.flags,
-                                  (unsigned char)o3.flags));
-    if (kObs) __stcs(obs_words + i, make_uint4(o0.obs_word, o1.obs_word, o2.obs_word, o3.obs_word));
+  const int64_t tile = (int64_t)U * blockDim.x;
+  for (int64_t base = blockIdx.x * tile + threadIdx.x; base < n_vec; base += (int64_t)gridDim.x * tile) {
+    uint4 w[U];
+    uchar4 a[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t i = base + (int64_t)k * blockDim.x;
+      if (i < n_vec) {  // every byte is touched exactly once per launch: streaming loads / stores
+        w[k] = __ldcs(words + i);
+        a[k] = __ldcs(actions + i);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t i = base + (int64_t)k * blockDim.x;
+      if (i >= n_vec) continue;
+      const StepOut o0 = step_word(w[k].x, a[k].x, c), o1 = step_word(w[k].y, a[k].y, c), o2 = step_word(w[k].z, a[k].z, c),
+                    o3 = step_word(w[k].w, a[k].w, c);
+      __stcs(words + i, make_uint4(o0.word, o1.word, o2.word, o3.word));
+      __stcs(rewards + i, make_float4(o0.reward, o1.reward, o2.reward, o3.reward));
+      __stcs(flags + i, make_uchar4((unsigned char)o0.flags, (unsigned char)o1.flags, (unsigned char)o2.flags,
+                                    (unsigned char)o3.flags));
+      if (kObs) __stcs(obs_words + i, make_uint4(o0.obs_word, o1.obs_word, o2.obs_word, o3.obs_word));
+    }
   }
 }
 
@@ -130,22 +61,34 @@ __global__ void __launch_bounds__(256) env_step_scalar(uint32_t* __restrict__ wo
   }
 }
 
+template <int U>
 __global__ void __launch_bounds__(256) env_step_random_vec4(uint4* __restrict__ words, uchar4* __restrict__ actions,
                                                            float4* __restrict__ rewards, uchar4* __restrict__ flags,
                                                            int64_t n_vec, EnvCfg c, uint32_t seed_lo, uint32_t seed_hi,
                                                            uint32_t step_lo, uint32_t step_hi) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    uint4 w = words[i];
-    Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), step_lo, step_hi, seed_lo, seed_hi);
-    uint32_t a0 = random_legal_action(w.x & c.state_mask, r.x, c), a1 = random_legal_action(w.y & c.state_mask, r.y, c),
-             a2 = random_legal_action(w.z & c.state_mask, r.z, c), a3 = random_legal_action(w.w & c.state_mask, r.w, c);
-    StepOut o0 = step_word(w.x, a0, c), o1 = step_word(w.y, a1, c), o2 = step_word(w.z, a2, c),
-            o3 = step_word(w.w, a3, c);
-    words[i] = make_uint4(o0.word, o1.word, o2.word, o3.word);
-    actions[i] = make_uchar4((unsigned char)a0, (unsigned char)a1, (unsigned char)a2, (unsigned char)a3);
-    rewards[i] = make_float4(o0.reward, o1.reward, o2.reward, o3.reward);
-    flags[i] = make_uchar4((unsigned char)o0.flags, (unsigned char)o1.flags, (unsigned char)o2.flags,
-                           (unsigned char)o3.flags);
+  const int64_t tile = (int64_t)U * blockDim.x;
+  for (int64_t base = blockIdx.x * tile + threadIdx.x; base < n_vec; base += (int64_t)gridDim.x * tile) {
+    uint4 w[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t i = base + (int64_t)k * blockDim.x;
+      if (i < n_vec) w[k] = __ldcs(words + i);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t i = base + (int64_t)k * blockDim.x;
+      if (i >= n_vec) continue;
+      const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), step_lo, step_hi, seed_lo, seed_hi);
+      const uint32_t a0 = random_legal_action(w[k].x & c.state_mask, r.x, c), a1 = random_legal_action(w[k].y & c.state_mask, r.y, c),
+                     a2 = random_legal_action(w[k].z & c.state_mask, r.z, c), a3 = random_legal_action(w[k].w & c.state_mask, r.w, c);
+      const StepOut o0 = step_word(w[k].x, a0, c), o1 = step_word(w[k].y, a1, c), o2 = step_word(w[k].z, a2, c),
+                    o3 = step_word(w[k].w, a3, c);
+      __stcs(words + i, make_uint4(o0.word, o1.word, o2.word, o3.word));
+      __stcs(actions + i, make_uchar4((unsigned char)a0, (unsigned char)a1, (unsigned char)a2, (unsigned char)a3));
+      __stcs(rewards + i, make_float4(o0.reward, o1.reward, o2.reward, o3.reward));
+      __stcs(flags + i, make_uchar4((unsigned char)o0.flags, (unsigned char)o1.flags, (unsigned char)o2.flags,
+                                    (unsigned char)o3.flags));
+    }
   }
 }
 
@@ -269,7 +212,7 @@ __global__ void __launch_bounds__(256) env_solver(const uint32_t* __restrict__ w
 }
 
 // ------------------------------------------------------------------------------ host side
-static int make_cfg(EnvCfg& c, int n_disks, int max_steps, int goal_peg, int auto_reset, uint32_t reset_word) {
+int make_env_cfg(EnvCfg& c, int n_disks, int max_steps, int goal_peg, int auto_reset, uint32_t reset_word) {
   if (n_disks < 1 || n_disks > HMZ_MAX_DISKS)
     return fail(HMZ_ERR_UNSUPPORTED, "n_disks=%d outside [1, %d]", n_disks, HMZ_MAX_DISKS);
   if (goal_peg < 0 || goal_peg > 2) return fail(HMZ_ERR_INVALID, "goal_peg=%d outside [0, 2]", goal_peg);
@@ -285,6 +228,16 @@ static int make_cfg(EnvCfg& c, int n_disks, int max_steps, int goal_peg, int aut
   c.reset_word = reset_word;
   c.auto_reset = auto_reset;
   return HMZ_OK;
+}
+
+// Tuning switches (read once): vec4 groups per thread and iteration (1, 2 or 4) and resident CTAs per SM the grid is sized for.
+static int env_unroll() {
+  static const int u = getenv("HMZ_ENV_UNROLL") ? atoi(getenv("HMZ_ENV_UNROLL")) : 4;
+  return u == 1 || u == 2 ? u : 4;
+}
+static int env_ctas_per_sm() {
+  static const int v = getenv("HMZ_ENV_CTAS") ? atoi(getenv("HMZ_ENV_CTAS")) : 8;
+  return v >= 1 && v <= 8 ? v : 8;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -347,20 +300,27 @@ int hmz_env_step(uint32_t* words, const uint8_t* actions, float* rewards, uint8_
   if (n == 0) return HMZ_OK;
   if (!words || !actions || !rewards || !flags || n < 0) return fail(HMZ_ERR_INVALID, "hmz_env_step: null pointer");
   EnvCfg c;
-  if (int rc = make_cfg(c, n_disks, max_steps, goal_peg, auto_reset, reset_word)) return rc;
+  if (int rc = make_env_cfg(c, n_disks, max_steps, goal_peg, auto_reset, reset_word)) return rc;
   if (n == 0) return HMZ_OK;
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = aligned16(words) && aligned4(actions) && aligned16(rewards) && aligned4(flags) &&
              (!obs_words || aligned16(obs_words));
   int64_t n_vec = vec ? n / 4 : 0;
   if (n_vec > 0) {
-    unsigned grid = grid_for(n_vec, 256, 8);
-    if (obs_words)
-      env_step_vec4<true><<<grid, 256, 0, st>>>((uint4*)words, (const uchar4*)actions, (float4*)rewards, (uchar4*)flags,
-                                                (uint4*)obs_words, n_vec, c);
-    else
-      env_step_vec4<false><<<grid, 256, 0, st>>>((uint4*)words, (const uchar4*)actions, (float4*)rewards,
-                                                 (uchar4*)flags, nullptr, n_vec, c);
+    const int u = env_unroll();
+    unsigned grid = grid_for(n_vec, 256 * u, env_ctas_per_sm());
+    uint4* w4 = (uint4*)words;
+    const uchar4* a4 = (const uchar4*)actions;
+    float4* r4 = (float4*)rewards;
+    uchar4* f4 = (uchar4*)flags;
+    uint4* o4 = (uint4*)obs_words;
+#define HMZ_ENV_LAUNCH(OBS, U) env_step_vec4<OBS, U><<<grid, 256, 0, st>>>(w4, a4, r4, f4, o4, n_vec, c)
+    if (obs_words) {
+      if (u == 1) HMZ_ENV_LAUNCH(true, 1); else if (u == 2) HMZ_ENV_LAUNCH(true, 2); else HMZ_ENV_LAUNCH(true, 4);
+    } else {
+      if (u == 1) HMZ_ENV_LAUNCH(false, 1); else if (u == 2) HMZ_ENV_LAUNCH(false, 2); else HMZ_ENV_LAUNCH(false, 4);
+    }
+#undef HMZ_ENV_LAUNCH
     if (int rc = check_launch("env_step_vec4")) return rc;
   }
   if (n_vec * 4 < n) {
@@ -410,12 +370,18 @@ int hmz_env_step_random(uint32_t* words, uint8_t* actions, float* rewards, uint8
   if (!words || !actions || !rewards || !flags || n < 0)
     return fail(HMZ_ERR_INVALID, "hmz_env_step_random: null pointer");
   EnvCfg c;
-  if (int rc = make_cfg(c, n_disks, max_steps, goal_peg, 1, reset_word)) return rc;
+  if (int rc = make_env_cfg(c, n_disks, max_steps, goal_peg, 1, reset_word)) return rc;
   if (n % 4 != 0 || !aligned16(words) || !aligned4(actions) || !aligned16(rewards) || !aligned4(flags))
     return fail(HMZ_ERR_INVALID, "hmz_env_step_random: n_envs must be a multiple of 4 and buffers 16-byte aligned");
-  env_step_random_vec4<<<grid_for(n / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      (uint4*)words, (uchar4*)actions, (float4*)rewards, (uchar4*)flags, n / 4, c, (uint32_t)seed,
-      (uint32_t)(seed >> 32), (uint32_t)step_index, (uint32_t)(step_index >> 32));
+  const int u = env_unroll();
+  const unsigned grid = grid_for(n / 4, 256 * u, env_ctas_per_sm());
+#define HMZ_ENV_LAUNCH(U)                                                                                              \
+  env_step_random_vec4<U><<<grid, 256, 0, (cudaStream_t)stream>>>((uint4*)words, (uchar4*)actions, (float4*)rewards, \
+                                                                  (uchar4*)flags, n / 4, c, (uint32_t)seed,          \
+                                                                  (uint32_t)(seed >> 32), (uint32_t)step_index,      \
+                                                                  (uint32_t)(step_index >> 32))
+  if (u == 1) HMZ_ENV_LAUNCH(1); else if (u == 2) HMZ_ENV_LAUNCH(2); else HMZ_ENV_LAUNCH(4);
+#undef HMZ_ENV_LAUNCH
   return check_launch("env_step_random_vec4");
 }
 
@@ -426,7 +392,7 @@ int hmz_env_rollout_random(uint32_t* words, int64_t n, int n_disks, int max_step
   if (n == 0) return HMZ_OK;
   if (!words || !counters || n < 0 || n_steps < 0) return fail(HMZ_ERR_INVALID, "hmz_env_rollout_random: bad arguments");
   EnvCfg c;
-  if (int rc = make_cfg(c, n_disks, max_steps, goal_peg, 1, reset_word)) return rc;
+  if (int rc = make_env_cfg(c, n_disks, max_steps, goal_peg, 1, reset_word)) return rc;
   if (n % 4 != 0 || !aligned16(words))
     return fail(HMZ_ERR_INVALID, "hmz_env_rollout_random: n_envs must be a multiple of 4 and words 16-byte aligned");
   if (n == 0 || n_steps == 0) return HMZ_OK;

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(128) search_child_scores(hmz_search_t s, const
   if (best_out) best_out[b] = best;
 }
 
-// MCTS/mcts.py:112-126 per search (one thread each; 52 bytes in, <= 76 bytes out).
+// MCTS/mcts.py:112-126 per search (one thread each; 52 bytes in, <= 76 bytes out); arithmetic in root_policy_eval().
 __global__ void __launch_bounds__(256) search_root_policy(hmz_search_t s, int n_sims, double temperature,
                                                          int deterministic, const double* __restrict__ uniforms,
                                                          const double* __restrict__ pow_table, int pow_table_len,
@@ -247,61 +247,18 @@ __global__ void __launch_bounds__(256) search_root_policy(hmz_search_t s, int n_
                                                          double* __restrict__ root_q, int32_t* __restrict__ action) {
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < s.n_searches;
        b += (int64_t)gridDim.x * blockDim.x) {
-    const hmz_node_t* root = s.nodes + b * s.n_records;
-    int n[6];
-    double w[6];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) n[a] = root->h[a / 3].c[a % 3].N;
-    // generate_play_policy (:154-176): visits ** clamp(1/T, 1, 5) when T > 0, raw counts when T == 0
-    double ex = 1.0;
-    if (temperature > 0.0) ex = fmax(1.0, fmin(5.0, __ddiv_rn(1.0, temperature)));
-    const int iex = (int)ex;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double x = (double)n[a];
-      if (pow_table != nullptr && n[a] < pow_table_len) {  // visits ** exponent exactly as the caller's NumPy evaluates it
-        w[a] = pow_table[n[a]];
-      } else if ((double)iex == ex) {  // integer exponents 1..5: exact products while < 2^53
-        double y = x;
-        for (int k = 1; k < iex; ++k) y = __dmul_rn(y, x);
-        w[a] = y;
-      } else {
-        w[a] = pow(x, ex);
-      }
-    }
-    // np.sum of 6 doubles: first element + (0 + the rest, left to right)
-    double rest = 0.0;
-#pragma unroll
-    for (int a = 1; a < 6; ++a) rest = __dadd_rn(rest, w[a]);
-    const double total = __dadd_rn(w[0], rest);
-    double prob[6];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) prob[a] = __ddiv_rn(w[a], total);
-    int act = 0;
-    if (deterministic) {  // np.argmax(child_visits): first maximum (:117)
-      for (int a = 1; a < 6; ++a)
-        if (n[a] > n[act]) act = a;
-    } else {  // np.random.choice(6, p=pi) with its uniform supplied (:120): cdf / cdf[-1], searchsorted right
-      double cdf[6];
-      cdf[0] = prob[0];
-#pragma unroll
-      for (int a = 1; a < 6; ++a) cdf[a] = __dadd_rn(cdf[a - 1], prob[a]);
-      const double u = uniforms[b], last = cdf[5];
-      act = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) act += (__ddiv_rn(cdf[a], last) <= u) ? 1 : 0;
-      if (act > 5) act = 5;
-    }
+    const RootPolicy rp = root_policy_eval(s.nodes + b * s.n_records, temperature, deterministic, deterministic ? 0.0 : uniforms[b],
+                                           pow_table, pow_table_len);
     if (visits) {
 #pragma unroll
-      for (int a = 0; a < 6; ++a) visits[b * 6 + a] = n[a];
+      for (int a = 0; a < 6; ++a) visits[b * 6 + a] = rp.n[a];
     }
     if (pi) {
 #pragma unroll
-      for (int a = 0; a < 6; ++a) pi[b * 6 + a] = prob[a];
+      for (int a = 0; a < 6; ++a) pi[b * 6 + a] = rp.prob[a];
     }
     if (root_q) root_q[b] = n_sims > 0 ? __ddiv_rn(s.root_W[b], (double)n_sims) : 0.0;  // Node.Q (node.py:125-131)
-    if (action) action[b] = act;
+    if (action) action[b] = rp.action;
   }
 }
 
@@ -335,7 +292,7 @@ __global__ void __launch_bounds__(256) div_check(uint64_t n_samples, uint64_t se
 static int ensure_rcp_table();
 static int ensure_tree_attrs();
 
-static int check_search(const hmz_search_t* s, const char* who) {
+int check_search(const hmz_search_t* s, const char* who) {
   if (!s) return fail(HMZ_ERR_INVALID, "%s: null search descriptor", who);
   if (s->n_searches < 0 || s->n_records < 1 || s->n_records > 65535)
     return fail(HMZ_ERR_INVALID, "%s: n_searches=%lld n_records=%d out of range", who, (long long)s->n_searches,

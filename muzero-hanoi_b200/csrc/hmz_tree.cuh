@@ -27,6 +27,9 @@ namespace hmz {
 static_assert(sizeof(hmz_child_t) == 16 && sizeof(hmz_half_t) == 64 && sizeof(hmz_node_t) == 128,
               "node record layout (include/hmz.h) must be 2 x 64-byte halves of 3 x 16-byte child slots");
 
+// Host: validates a search descriptor and makes sure the per-device constant tables / kernel attributes are in place.
+int check_search(const hmz_search_t* s, const char* who);
+
 constexpr int kPathCap = 32;  // path levels recorded for the backup (deeper paths walk parent links)
 
 // Tooling: clock64() marks of one lane pair (hmz_debug_tree_timeline), compiled only into the kTL = true
@@ -192,7 +195,7 @@ __device__ __forceinline__ void prefetch_record(const void* rec) {
 
 // Reference-order evaluation of one child (the slow, always-exact form): used when an operand falls
 // outside the range the straight-line form below is proven for.
-__device__ __noinline__ float child_score_exact(double W, float rwd, int n, float prior, double prior64, bool use64, double tn,
+static __device__ __noinline__ float child_score_exact(double W, float rwd, int n, float prior, double prior64, bool use64, double tn,
                                                 double discount, double mn, double range, bool normalise) {
   float qf = 0.0f;  // child_Q: 0 for unvisited children (node.py:98-102)
   if (n > 0) {
@@ -451,6 +454,63 @@ __device__ __forceinline__ void backup_top(hmz_node_t* nodes, const PathBatch& p
   const double q_root = __dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1)));
   wild |= !is_tame(q_root);
   minmax_update(q_root, mn, mx);
+}
+
+// MCTS/mcts.py:112-122 for one search: child_N of the root, generate_play_policy (:154-176: visits ** clamp(1/T, 1, 5)
+// for T > 0, raw counts for T == 0, divided by their np.sum) and the action — np.argmax(child_visits) (first maximum,
+// :117) or np.random.choice(6, p=pi) with its single uniform `u` supplied (:120: cdf / cdf[-1], searchsorted right).
+// pow_table (nullable): the caller's own NumPy powers of every possible count (see hmz_search_root_policy).
+struct RootPolicy {
+  int n[6];
+  double prob[6];
+  int action;
+};
+__device__ __forceinline__ RootPolicy root_policy_eval(const hmz_node_t* root, double temperature, int deterministic, double u,
+                                                       const double* __restrict__ pow_table, int pow_table_len) {
+  RootPolicy out;
+  double w[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) out.n[a] = root->h[a / 3].c[a % 3].N;
+  double ex = 1.0;
+  if (temperature > 0.0) ex = fmax(1.0, fmin(5.0, __ddiv_rn(1.0, temperature)));
+  const int iex = (int)ex;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    const double x = (double)out.n[a];
+    if (pow_table != nullptr && out.n[a] < pow_table_len) {  // visits ** exponent exactly as the caller's NumPy evaluates it
+      w[a] = pow_table[out.n[a]];
+    } else if ((double)iex == ex) {  // integer exponents 1..5: exact products while < 2^53
+      double y = x;
+      for (int k = 1; k < iex; ++k) y = __dmul_rn(y, x);
+      w[a] = y;
+    } else {
+      w[a] = pow(x, ex);
+    }
+  }
+  // np.sum of 6 doubles: first element + (0 + the rest, left to right)
+  double rest = 0.0;
+#pragma unroll
+  for (int a = 1; a < 6; ++a) rest = __dadd_rn(rest, w[a]);
+  const double total = __dadd_rn(w[0], rest);
+#pragma unroll
+  for (int a = 0; a < 6; ++a) out.prob[a] = __ddiv_rn(w[a], total);
+  int act = 0;
+  if (deterministic) {
+    for (int a = 1; a < 6; ++a)
+      if (out.n[a] > out.n[act]) act = a;
+  } else {
+    double cdf[6];
+    cdf[0] = out.prob[0];
+#pragma unroll
+    for (int a = 1; a < 6; ++a) cdf[a] = __dadd_rn(cdf[a - 1], out.prob[a]);
+    const double last = cdf[5];
+    act = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) act += (__ddiv_rn(cdf[a], last) <= u) ? 1 : 0;
+    if (act > 5) act = 5;
+  }
+  out.action = act;
+  return out;
 }
 
 }  // namespace hmz

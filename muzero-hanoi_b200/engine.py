@@ -403,24 +403,23 @@ class SelfPlay:
     records land in a [ring_slots, B] struct-of-arrays ring that `gather` all-gathers over NCCL."""
 
     def __init__(self, N, max_steps, B, n_simulations, weights: PackedWeights, discount=0.8, alpha=0.25, eps=0.25,
-                 temperature=1.0, seed=0, ring_slots=8, device="cuda", latent_dtype=_lib.LATENT_F32, episodes=False):
+                 temperature=1.0, seed=0, ring_slots=8, device="cuda", latent_dtype=_lib.LATENT_F32, episodes=False,
+                 game_offset=0):
         self.env = VecHanoi(N, max_steps, B, device)
         self.mcts = BatchedMCTS(discount, alpha, n_simulations, B, device, eps, latent_dtype)
         self.weights, self.temperature, self.seed = weights, float(temperature), int(seed)
         self.B, self.S, self.T = int(B), int(n_simulations), int(ring_slots)
+        # global id of this batch's first game: keys the Philox streams, so that a game draws the same noise and
+        # uniforms whichever rank (and whichever position in the rank's batch) plays it (SURVEY.md §8e)
+        self.game_offset = int(game_offset)
         self.lib, self.device = self.env.lib, self.env.device
         dev = self.device
         self.p0 = torch.empty(B, 6, dtype=torch.float32, device=dev)
         self.v0 = torch.empty(B, dtype=torch.float32, device=dev)
         self.noise = torch.empty(B, 6, dtype=torch.float64, device=dev)
         self.uniform = torch.empty(B, dtype=torch.float64, device=dev)
-        self.action_u8 = torch.empty(B, dtype=torch.uint8, device=dev)
-        self.traj_state = torch.zeros(self.T, B, dtype=torch.int32, device=dev)
-        self.traj_action = torch.zeros(self.T, B, dtype=torch.uint8, device=dev)
-        self.traj_reward = torch.zeros(self.T, B, dtype=torch.float32, device=dev)
-        self.traj_flags = torch.zeros(self.T, B, dtype=torch.uint8, device=dev)
-        self.traj_visits = torch.zeros(self.T, B, 6, dtype=torch.int16, device=dev)
-        self.traj_root_q = torch.zeros(self.T, B, dtype=torch.float32, device=dev)
+        # trajectory ring: [slot][game] 32-byte move records (hmz_move_record_t) = the wire format of dist.RecordGather
+        self.records = torch.zeros(self.T, B, _lib.RECORD_BYTES, dtype=torch.uint8, device=dev)
         self.moves_done = 0
         # episodes=True additionally keeps whole episodes (slot = the game's own step counter) for the
         # device-side post-processing of replay.EpisodeStore / ReplayRing (SURVEY §8f rows 1-2)
@@ -438,18 +437,19 @@ class SelfPlay:
         use_noise = m.root_dirichlet_alpha > 0.0 and m.root_exploration_eps > 0.0
         st.desc.root_prior_is_f64 = int(use_noise)
         ep = self.episodes
+        pw = m._pow_table(self.temperature, self.S)
         d = _lib.SelfPlayDesc(
             search=st.desc, weights=self.weights.ptr.value, ucb_table=m._table.data_ptr(), words=env.words.data_ptr(),
             p0=self.p0.data_ptr(), v0=self.v0.data_ptr(), noise=self.noise.data_ptr() if use_noise else None,
             uniform=self.uniform.data_ptr(), visits=m.visits.data_ptr(), root_q=m.root_q.data_ptr(), action=m.action.data_ptr(),
-            action_u8=self.action_u8.data_ptr(), step_reward=self.traj_reward[t].data_ptr(), step_flags=self.traj_flags[t].data_ptr(),
-            traj_state=self.traj_state[t].data_ptr(), traj_action=self.traj_action[t].data_ptr(),
-            traj_visits=self.traj_visits[t].data_ptr(), traj_root_q=self.traj_root_q[t].data_ptr(),
+            records=self.records[t].data_ptr(),
             ep_state=ep.state.data_ptr() if ep else None, ep_action=ep.action.data_ptr() if ep else None,
             ep_flags=ep.flags.data_ptr() if ep else None, ep_visits=ep.visits.data_ptr() if ep else None,
             ep_root_q=ep.root_q.data_ptr() if ep else None, ep_cur_slot=ep.cur_slot.data_ptr() if ep else None,
-            ep_len=ep.ep_len.data_ptr() if ep else None, discount=m.discount, dirichlet_alpha=float(m.root_dirichlet_alpha),
-            exploration_eps=float(m.root_exploration_eps), temperature=self.temperature, seed=self.seed, mode=self.weights.mode,
+            ep_len=ep.ep_len.data_ptr() if ep else None, pow_table=pw.data_ptr() if pw is not None else None,
+            discount=m.discount, dirichlet_alpha=float(m.root_dirichlet_alpha),
+            exploration_eps=float(m.root_exploration_eps), temperature=self.temperature, seed=self.seed,
+            game_offset=self.game_offset, mode=self.weights.mode,
             n_disks=env.discs, max_steps=env.max_steps, goal_peg=env.goal_peg, n_simulations=self.S,
             ep_t_max=ep.t_max if ep else 0, reset_word=env.reset_word, reserved=0)
         check(self.lib.hmz_selfplay_move(C.byref(d), ctr, current_stream()))
@@ -457,8 +457,8 @@ class SelfPlay:
         return t
 
     def record_bytes_per_game(self):
-        return 4 + 1 + 4 + 1 + 12 + 4  # state, action, reward, flags, visits, root_q
+        return _lib.RECORD_BYTES
 
     def slot(self, t):
-        return dict(state=self.traj_state[t], action=self.traj_action[t], reward=self.traj_reward[t],
-                    flags=self.traj_flags[t], visits=self.traj_visits[t], root_q=self.traj_root_q[t])
+        """The move records written by the move that returned ``t``: uint8 [B, 32] (decode with dist.unpack_records)."""
+        return self.records[t]

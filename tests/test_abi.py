@@ -39,7 +39,7 @@ def test_ctypes_structs_match_the_header_as_compiled_by_gcc(tmp_path):
 
     from muzero_hanoi_b200 import _lib
 
-    structs = {"hmz_child_t": _lib.ChildSlot, "hmz_half_t": _lib.NodeHalf, "hmz_node_t": _lib.NodeRecord,
+    structs = {"hmz_move_record_t": _lib.MoveRecord, "hmz_child_t": _lib.ChildSlot, "hmz_half_t": _lib.NodeHalf, "hmz_node_t": _lib.NodeRecord,
                "hmz_search_t": _lib.SearchDesc, "hmz_selfplay_t": _lib.SelfPlayDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hmz.h"', "int main(void) {"]
     for cname, ct in structs.items():

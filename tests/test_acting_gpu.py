@@ -51,6 +51,36 @@ def test_get_results_matches_oracle_episodes(heads):
     assert np.array_equal(det[0]["min_moves"], [port.hanoi_solver(port.index_to_state(int(i), n)) for i in starts])
 
 
+def test_get_results_shared_minmax_is_sequentially_consistent_with_the_reference():
+    """shared_minmax=True: ONE MinMaxStats threads through every episode of the run (MCTS/mcts.py:23,
+    acting_ablations.py:343), so an episode's searches are normalised with the extrema of all earlier episodes.  The
+    oracle plays the same episodes in the same order on one PortSearch object; also checks that the option matters
+    (the per-episode-stats default gives different bounds)."""
+    from muzero_hanoi_b200 import _lib, acting
+    from muzero_hanoi_b200.engine import PackedWeights
+
+    n, max_steps, B, n_sims, T = 3, 30, 10, 12, 0.0
+    sd = port.make_weights(n, 11)
+    rng = np.random.default_rng(8)
+    starts = rng.integers(0, 26, B)
+    uniforms = rng.random((max_steps, B))
+    _, det = acting.get_results(PackedWeights(sd, n, _lib.MODE_FP32), n, max_steps, B, [n_sims], T, start_indices=starts,
+                                uniforms=uniforms, return_details=True, shared_minmax=True)
+    net, search = port.PortNet(sd), port.PortSearch(0.8, n_sims)  # ONE MinMaxStats for all episodes
+    ref_steps = []
+    for g in range(B):
+        env = port.PortHanoi(n, max_steps, init_state_idx=int(starts[g]))
+        obs, done, steps = env.reset(), False, 0
+        while not done:
+            a, _, _, _, _ = port.run_mcts_port(obs, net, search, T, False, alpha=0.0, u=float(uniforms[steps, g]))
+            obs, _, done, _ = env.step(a)
+            steps += 1
+        ref_steps.append(steps)
+    same = det[0]["steps"] == np.array(ref_steps)
+    assert same.mean() >= 0.9, (det[0]["steps"], ref_steps)
+    assert np.array_equal(det[0]["errors"], det[0]["steps"] - det[0]["min_moves"])
+
+
 def test_compute_n_step_returns_dropin_matches_oracle():
     from muzero_hanoi_b200.utils import compute_n_step_returns
 

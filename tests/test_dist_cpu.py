@@ -22,7 +22,9 @@ def _fake_slot(rank, B):
     return dict(state=torch.randint(0, 1 << 20, (B,), dtype=torch.int32, generator=g),
                 action=torch.randint(0, 6, (B,), dtype=torch.uint8, generator=g),
                 reward=torch.rand(B, generator=g), flags=torch.randint(0, 16, (B,), dtype=torch.uint8, generator=g),
-                visits=torch.randint(0, 101, (B, 6), dtype=torch.int16, generator=g), root_q=torch.randn(B, generator=g))
+                visits=torch.randint(0, 101, (B, 6), dtype=torch.int16, generator=g),
+                root_q=torch.randn(B, generator=g, dtype=torch.float64),
+                game_lo=(torch.arange(B) + rank * B).to(torch.int16))
 
 
 def _worker(rank, world, port, B, out):
@@ -32,13 +34,22 @@ def _worker(rank, world, port, B, out):
 
     r, w, _ = hdist.init_from_env(backend="gloo")
     assert (r, w) == (rank, world)
-    gathered = hdist.all_gather_records(_fake_slot(rank, B))
-    assert gathered.shape == (world * B, 26)
+    gathered = hdist.all_gather_records(hdist.pack_records(_fake_slot(rank, B)))
+    assert gathered.shape == (world * B, 32)
     for src in range(world):
         want = _fake_slot(src, B)
         got = hdist.unpack_records(gathered[src * B:(src + 1) * B])
         for k in hdist.RECORD_FIELDS:
             assert torch.equal(got[k], want[k]), (src, k)
+    # the pipelined form the bench uses: three moves through a two-deep RecordGather
+    pipe = hdist.RecordGather(B, world, "cpu", depth=2)
+    for move in range(3):
+        i = pipe.submit(hdist.pack_records(_fake_slot(10 * move + rank, B)))
+        got = hdist.unpack_records(pipe.result(i))
+        for src in range(world):
+            want = _fake_slot(10 * move + src, B)
+            for k in hdist.RECORD_FIELDS:
+                assert torch.equal(got[k][src * B:(src + 1) * B], want[k]), (move, src, k)
     lo, hi = hdist.shard_range(10, rank, world)
     out[rank] = (lo, hi)
     dist.barrier()
@@ -68,8 +79,21 @@ def test_record_pack_roundtrip_single_process():
     from muzero_hanoi_b200 import dist as hdist
 
     slot = _fake_slot(0, 129)
-    buf = hdist.all_gather_records(slot)  # world 1: just the packed wire format
-    assert buf.dtype == torch.uint8 and buf.shape == (129, 26)
+    buf = hdist.all_gather_records(hdist.pack_records(slot))  # world 1: the wire records themselves
+    assert buf.dtype == torch.uint8 and buf.shape == (129, 32)
     back = hdist.unpack_records(buf)
     for k in hdist.RECORD_FIELDS:
         assert torch.equal(back[k], slot[k])
+
+
+def test_wire_record_layout_matches_the_c_struct():
+    """dist's byte offsets against the ctypes mirror of hmz_move_record_t (itself checked against the header by gcc)."""
+    import numpy as np
+
+    from muzero_hanoi_b200 import _lib
+    from muzero_hanoi_b200 import dist as hdist
+
+    for name, (lo, hi) in hdist._OFF.items():
+        f = getattr(_lib.MoveRecord, name)
+        assert (f.offset, f.offset + f.size) == (lo, hi), name
+    assert np.dtype(_lib.RECORD_DTYPE).itemsize == hdist.RECORD_BYTES == _lib.RECORD_BYTES

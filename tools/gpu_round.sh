@@ -1,0 +1,57 @@
+#!/bin/bash
+# One gpurun call = one round of GPU evidence.  Usage (from the repo root, under gpurun):
+#   bash tools/gpu_round.sh tests          GPU test-suite + a short default bench line
+#   bash tools/gpu_round.sh bench          default bench line only (20 steps)
+#   bash tools/gpu_round.sh envsweep       env kernels over HMZ_ENV_UNROLL x HMZ_ENV_CTAS
+#   bash tools/gpu_round.sh memcheck       compute-sanitizer --tool memcheck over smoke()
+#   bash tools/gpu_round.sh ncu            plain bench, ncu launch list of one step, ncu --set full of the hot kernels
+# Several stages may be given; every stage writes into gpurun_out/ (scratch) and never stops the others.
+# (At most one of ncu / compute-sanitizer per call: B200_PROFILING.md.)
+mkdir -p gpurun_out
+for stage in "$@"; do
+  echo "=== stage $stage"
+  case "$stage" in
+    tests)
+      rm -f gpurun_out/test_metrics.jsonl
+      timeout 900 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+      echo "pytest rc=$?"; tail -n 25 gpurun_out/pytest_gpu.log
+      timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/smoke.log
+      ;;
+    bench)
+      timeout 900 python bench.py --steps ${STEPS:-20} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench_default.json 2> gpurun_out/bench_default.log
+      echo "bench rc=$?"; tail -n 12 gpurun_out/bench_default.log; head -c 600 gpurun_out/bench_default.json
+      ;;
+    benchquick)
+      timeout 600 python bench.py --steps 4 --warmup 3 --cpu-seconds 3 ${BENCH_ARGS} > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.log
+      echo "bench rc=$?"; tail -n 12 gpurun_out/bench_quick.log; head -c 600 gpurun_out/bench_quick.json
+      ;;
+    reference)
+      timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.log
+      echo "reference rc=$?"; head -c 400 gpurun_out/bench_reference.json
+      ;;
+    envsweep)
+      : > gpurun_out/env_sweep.txt
+      for u in 1 2 4; do for c in 3 4 8; do
+        echo "HMZ_ENV_UNROLL=$u HMZ_ENV_CTAS=$c" >> gpurun_out/env_sweep.txt
+        HMZ_ENV_UNROLL=$u HMZ_ENV_CTAS=$c timeout 120 python tools/env_probe.py >> gpurun_out/env_sweep.txt 2>&1
+      done; done
+      cat gpurun_out/env_sweep.txt
+      ;;
+    memcheck)
+      timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/memcheck_smoke.log 2>&1
+      echo "memcheck rc=$?"; tail -n 15 gpurun_out/memcheck_smoke.log
+      ;;
+    ncu)
+      CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-env --no-configs ${BENCH_ARGS}"
+      $CMD > gpurun_out/plain.json 2> gpurun_out/plain.log || { echo "plain run failed"; tail gpurun_out/plain.log; continue; }
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+      echo "ncu list rc=$?"
+      ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNEL:-search_persistent|search_backup_select}" -s ${NCU_SKIP:-40} -c 2 -o gpurun_out/prof_search -f $CMD > gpurun_out/ncu_search.log 2>&1
+      echo "ncu search rc=$?"
+      ncu --set full --clock-control none --import-source on -k regex:env_step -c 4 -o gpurun_out/prof_env -f python tools/env_probe.py > gpurun_out/ncu_env.log 2>&1
+      echo "ncu env rc=$?"
+      ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
+ls -la gpurun_out | tail -n 30
