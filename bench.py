@@ -333,10 +333,11 @@ def mean_leaf_depth(sp, sample=4096):
     """Mean leaf depth of the move just searched, measured from the trees themselves: a simulation whose leaf sits at
     depth d adds one visit to each of the d child slots on its path, so sum(child N over all records) / S = mean depth."""
     import numpy as np
+    import torch
 
     st = sp.mcts.store
     b = min(sample, st.B)
-    raw = st.nodes[: b * st.n_records * 128].view(-1, 8).cpu().numpy()  # 16-byte child slots and prior blocks, 8 x u16 each
+    raw = st.nodes[: b * st.n_records * 128].view(torch.int16).cpu().numpy().view(np.uint16)  # 16-byte blocks = 8 x u16 each
     slots = raw.reshape(b, st.n_records, 2, 4, 8)[:, : sp.S + 1, :, :3, 6]  # N = u16 at byte 12 of child slots 0..2 of each half
     return float(slots.astype(np.int64).sum() / (b * sp.S))
 

@@ -69,6 +69,7 @@ int hmz_device_info(int* sm_count, int* cc_major, int* cc_minor);
 #define HMZ_PROF_NET_INITIAL 4
 #define HMZ_PROF_ROOT_POLICY 5
 #define HMZ_PROF_OTHER 6
+#define HMZ_PROF_SEARCH_PERSISTENT 7 /* the one-launch-per-move search kernel (HMZ_SCHEDULE_PERSISTENT) */
 #define HMZ_PROF_CLASSES 8
 int hmz_prof_begin(void);
 int hmz_prof_end(double* ms_by_class, int64_t* launches_by_class);
@@ -227,11 +228,13 @@ int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, co
 /* MCTS/mcts.py:112-126: child_N, generate_play_policy (:154-176), arg-max or sampled action.
  *   uniforms nullable unless deterministic == 0 (one double in [0,1) per search; the draw of
  *   np.random.choice at :120 supplied as input);  outputs nullable individually.
- *   pow_table nullable: float64 [n_simulations + 1], pow_table[n] = n ** clamp(1/T, 1, 5) as the caller's
- *   NumPy evaluates np.power (:170-174) — NumPy's vectorised pow is not correctly rounded, so bit-exact
- *   policies for non-integer exponents (or powers beyond 2^53) need the caller's own table.  NULL: the
- *   device evaluates integer exponents by exact repeated multiplication (identical to NumPy while the
- *   power stays below 2^53, i.e. counts < 1,552 at exponent 5) and others with CUDA's pow() (<= 2 ulp). */
+ *   pow_table nullable: float64 [n_simulations + 1][6], pow_table[n][a] = element a of
+ *   np.power(int64 array of six n, clamp(1/T, 1, 5)) as the caller's NumPy evaluates it (:170-174).  NumPy's
+ *   vectorised pow is not correctly rounded and differs between its SIMD body and its scalar tail (so by
+ *   position in the 6-element array) and between CPUs; bit-exact policies for non-integer exponents (or powers
+ *   beyond 2^53) therefore need the caller's own table.  NULL: the device evaluates integer exponents by exact
+ *   repeated multiplication (identical to NumPy while the power stays below 2^53, i.e. counts < 1,552 at
+ *   exponent 5) and others with CUDA's pow() (<= 2 ulp). */
 int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temperature, int deterministic,
                            const double* uniforms, const double* pow_table, int32_t* visits, double* pi, double* root_q,
                            int32_t* action, void* stream);

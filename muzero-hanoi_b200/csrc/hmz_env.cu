@@ -14,8 +14,9 @@ namespace hmz {
 // ------------------------------------------------------------------------------ kernels
 // One thread owns U vec4 groups per grid-stride iteration, spaced a block apart so that every load / store instruction
 // of a warp covers one contiguous 512-byte (words, rewards) or 128-byte (actions, flags) span; all U groups' loads are
-// issued before the first use.  What bounds this kernel is bytes in flight per SM (5 B read per env against ~35 KB per
-// SM that HBM3e needs outstanding), so U = 4 keeps 80 B of loads in flight per thread instead of 20.
+// issued before the first use.  Measured on the B200 (tools/gpu_round.sh envsweep, 2^24 envs): U = 1 4.19-4.26 TB/s,
+// U = 2 4.0, U = 4 3.9 — more bytes in flight per thread do not help (2,048 resident threads per SM already cover the
+// latency-bandwidth product), so U = 1 is the default (HMZ_ENV_UNROLL / HMZ_ENV_CTAS are tuning switches).
 template <bool kObs, int U>
 __global__ void __launch_bounds__(256) env_step_vec4(uint4* __restrict__ words, const uchar4* __restrict__ actions,
                                                     float4* __restrict__ rewards, uchar4* __restrict__ flags,
@@ -79,10 +80,9 @@ __global__ void __launch_bounds__(256) env_step_random_vec4(uint4* __restrict__ 
       const int64_t i = base + (int64_t)k * blockDim.x;
       if (i >= n_vec) continue;
       const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), step_lo, step_hi, seed_lo, seed_hi);
-      const uint32_t a0 = random_legal_action(w[k].x & c.state_mask, r.x, c), a1 = random_legal_action(w[k].y & c.state_mask, r.y, c),
-                     a2 = random_legal_action(w[k].z & c.state_mask, r.z, c), a3 = random_legal_action(w[k].w & c.state_mask, r.w, c);
-      const StepOut o0 = step_word(w[k].x, a0, c), o1 = step_word(w[k].y, a1, c), o2 = step_word(w[k].z, a2, c),
-                    o3 = step_word(w[k].w, a3, c);
+      uint32_t a0, a1, a2, a3;
+      const StepOut o0 = step_random_word(w[k].x, r.x, c, a0), o1 = step_random_word(w[k].y, r.y, c, a1),
+                    o2 = step_random_word(w[k].z, r.z, c, a2), o3 = step_random_word(w[k].w, r.w, c, a3);
       __stcs(words + i, make_uint4(o0.word, o1.word, o2.word, o3.word));
       __stcs(actions + i, make_uchar4((unsigned char)a0, (unsigned char)a1, (unsigned char)a2, (unsigned char)a3));
       __stcs(rewards + i, make_float4(o0.reward, o1.reward, o2.reward, o3.reward));
@@ -104,10 +104,9 @@ __global__ void __launch_bounds__(256) env_rollout_random_vec4(uint4* __restrict
     for (int k = 0; k < n_steps; ++k) {
       uint64_t sidx = step_index + (uint64_t)k;
       Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)sidx, (uint32_t)(sidx >> 32), seed_lo, seed_hi);
-      StepOut o0 = step_word(w.x, random_legal_action(w.x & c.state_mask, r.x, c), c);
-      StepOut o1 = step_word(w.y, random_legal_action(w.y & c.state_mask, r.y, c), c);
-      StepOut o2 = step_word(w.z, random_legal_action(w.z & c.state_mask, r.z, c), c);
-      StepOut o3 = step_word(w.w, random_legal_action(w.w & c.state_mask, r.w, c), c);
+      uint32_t a0, a1, a2, a3;
+      const StepOut o0 = step_random_word(w.x, r.x, c, a0), o1 = step_random_word(w.y, r.y, c, a1),
+                    o2 = step_random_word(w.z, r.z, c, a2), o3 = step_random_word(w.w, r.w, c, a3);
       w = make_uint4(o0.word, o1.word, o2.word, o3.word);
       uint32_t fl = o0.flags | (o1.flags << 8) | (o2.flags << 16) | (o3.flags << 24);
       goals += __popc(fl & 0x04040404u);
@@ -232,8 +231,8 @@ int make_env_cfg(EnvCfg& c, int n_disks, int max_steps, int goal_peg, int auto_r
 
 // Tuning switches (read once): vec4 groups per thread and iteration (1, 2 or 4) and resident CTAs per SM the grid is sized for.
 static int env_unroll() {
-  static const int u = getenv("HMZ_ENV_UNROLL") ? atoi(getenv("HMZ_ENV_UNROLL")) : 4;
-  return u == 1 || u == 2 ? u : 4;
+  static const int u = getenv("HMZ_ENV_UNROLL") ? atoi(getenv("HMZ_ENV_UNROLL")) : 1;
+  return u == 2 || u == 4 ? u : 1;
 }
 static int env_ctas_per_sm() {
   static const int v = getenv("HMZ_ENV_CTAS") ? atoi(getenv("HMZ_ENV_CTAS")) : 8;

@@ -39,11 +39,11 @@ struct StepOut {
   uint32_t flags;
 };
 
-__device__ __forceinline__ StepOut step_word(uint32_t word, uint32_t action, const EnvCfg& c) {
+// TowersOfHanoi.step with the peg tops of the state already known (the random-move kernels need them to pick the action).
+__device__ __forceinline__ StepOut step_word_tops(uint32_t word, uint32_t action, uint32_t t0, uint32_t t1, uint32_t t2,
+                                                  const EnvCfg& c) {
   uint32_t st = word & c.state_mask;
   uint32_t ctr = (word >> c.shift) + 1u;  // env/hanoi.py:56 — counted for illegal moves too
-  uint32_t t0, t1, t2;
-  peg_tops(st, c.even_mask, t0, t1, t2);
   uint32_t a = action > 5u ? 5u : action;
   uint32_t legal = (action <= 5u) ? ((legal_bits(t0, t1, t2) >> a) & 1u) : 0u;
   uint32_t f = a >> 1;
@@ -77,6 +77,12 @@ __device__ __forceinline__ StepOut step_word(uint32_t word, uint32_t action, con
   return o;
 }
 
+__device__ __forceinline__ StepOut step_word(uint32_t word, uint32_t action, const EnvCfg& c) {
+  uint32_t t0, t1, t2;
+  peg_tops(word & c.state_mask, c.even_mask, t0, t1, t2);
+  return step_word_tops(word, action, t0, t1, t2, c);
+}
+
 // k-th (0-based) set bit of a mask with 2 or 3 bits set.
 __device__ __forceinline__ uint32_t kth_set_bit(uint32_t m, uint32_t k) {
   uint32_t m1 = m & (m - 1u);
@@ -90,6 +96,15 @@ __device__ __forceinline__ uint32_t random_legal_action(uint32_t st, uint32_t rn
   peg_tops(st, c.even_mask, t0, t1, t2);
   uint32_t m = legal_bits(t0, t1, t2);
   return kth_set_bit(m, __umulhi(rnd, (uint32_t)__popc(m)));
+}
+
+// One step on a uniformly random LEGAL move (the peg tops are computed once for the choice and the step).
+__device__ __forceinline__ StepOut step_random_word(uint32_t word, uint32_t rnd, const EnvCfg& c, uint32_t& action) {
+  uint32_t t0, t1, t2;
+  peg_tops(word & c.state_mask, c.even_mask, t0, t1, t2);
+  const uint32_t m = legal_bits(t0, t1, t2);
+  action = kth_set_bit(m, __umulhi(rnd, (uint32_t)__popc(m)));
+  return step_word_tops(word, action, t0, t1, t2, c);
 }
 
 // Host: fills an EnvCfg after validating the shape (HMZ_ERR_* with a message on failure).

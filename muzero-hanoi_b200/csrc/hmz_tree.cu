@@ -78,129 +78,16 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
   }
 }
 
-// Phases 2b + 3 of simulation `sim` (expansion with the network outputs, backup), optionally followed
-// at once by the selection of simulation `sim + 1` — the fused hot-loop form: the path just updated
-// is still in this SM's L1 and the next walk usually shares its prefix.  With path elements (slot + entry
-// per level, recorded by the previous walk) the backup needs one round trip for its inputs; without them
-// (split-phase API) it walks the parent links.
+// The fused hot-loop kernel of the launch-per-simulation schedule: tree_phase() (hmz_tree.cuh) for one lane pair per
+// search, launched as a programmatic dependent of the network kernel.
 #ifndef HMZ_TREE_MIN_BLOCKS
 #define HMZ_TREE_MIN_BLOCKS (640 / HMZ_TREE_THREADS)  // 20 warps per SM (96 registers)
 #endif
-// kTrusted (hmz_search_run only): `wild_flags[search]` is the sticky "a backup wrote an untame W or Q" flag of
-// is_tame(); the walk then skips its per-operand range tests.  The split-phase API keeps the tests.
 template <bool kTL, bool kTrusted>
 __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
-                                                                     double discount, uint16_t* leaf_parent, uint8_t* leaf_action,
-                                                                     uint16_t* leaf_depth, uint4* path_elem, uint8_t* wild_flags,
-                                                                     const float* __restrict__ r, const float* __restrict__ p,
-                                                                     const float* __restrict__ v, int do_select, float* __restrict__ capture) {
-  const int half = threadIdx.x & 1;
-  const int64_t b_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
-  const int signal_at = (do_select >> 2) & 3;  // HMZ_PDL_TREE_AT
-  if (signal_at == 0) pdl_launch_dependents();
-  if (!(do_select & 2)) pdl_wait();  // HMZ_PDL bit 2 off: nothing is read before the wait
-  const bool valid = b_raw < s.n_searches;  // out-of-range pairs stay for the warp-uniform walk, masked
-  const int64_t b = valid ? b_raw : s.n_searches - 1;
-  const bool tl = kTL && valid && b == (g_tree_timeline_search & 0xFFFFFFFFll) && sim == (int)(g_tree_timeline_search >> 32) && half == 0;
-  tree_mark<kTL>(0, tl);
-  hmz_node_t* nodes = s.nodes + b * s.n_records;
-  uint4* path = path_elem ? path_elem + b * (2 * kPathCap) : nullptr;
-  // Before waiting for the network kernel: everything the backup needs that the PREVIOUS tree kernel wrote
-  // (leaf scalars, min/max, the root's W, and the path elements = slot + entry per level, at addresses that
-  // depend only on the search index: ONE round trip for paths of up to four levels).  The network kernel only
-  // signals its dependents after its own wait, so that kernel has completed by the time this one runs.
-  // Lane 0 of the pair owns levels 0..3 and the root, lane 1 the levels from 4 on (leaf side first).
-  double mn = 0.0, mx = 0.0, root_w = 0.0;
-  int pe = 0, pa = 0, depth = kPathCap + 1;
-  PathBatch pb;
-  pb.slot[0] = make_uint4(0u, 0u, 0u, 0u);
-  bool wild = false, was_wild = false;
-  if (valid) {
-    if (kTrusted && half == 0) was_wild = wild = wild_flags[b] != 0;
-    if (half == 0 && path != nullptr) load_batch4(path, 0, 4, pb);  // unconditionally: the depth is not known yet
-    pe = leaf_parent[b];
-    pa = leaf_action[b];
-    if (path != nullptr && leaf_depth != nullptr) depth = (int)leaf_depth[b];
-    mn = s.minmax[2 * b];
-    mx = s.minmax[2 * b + 1];
-    if (half == 0) root_w = s.root_W[b];
-    if (half == 1 && depth > 4 && depth <= kPathCap) load_batch4(path, (depth - 1) & ~3, depth, pb);
-  }
-  tree_mark<kTL>(1, tl, (uint32_t)(pe + pa) ^ pb.slot[0].w);
-  pdl_wait();  // everything below reads what the network kernel wrote
-  float r_leaf = 0.f;
-  double value = 0.0;
-  const bool by_path = depth <= kPathCap;
-  if (valid) {
-    r_leaf = r[b];
-    value = (double)v[b];
-    write_fresh_half(&nodes[sim + 1], half, p + b * 6, pe, pa);
-    if (capture != nullptr) {  // parity tests: the network outputs this backup consumed, [p0..p5, r, v] per search
-      float4* cap = reinterpret_cast<float4*>(capture + b * 8) + half;
-      *cap = half == 0 ? make_float4(p[b * 6], p[b * 6 + 1], p[b * 6 + 2], p[b * 6 + 3])
-                       : make_float4(p[b * 6 + 4], p[b * 6 + 5], r_leaf, v[b]);
-    }
-    tree_mark<kTL>(6, tl, __float_as_uint(r_leaf));
-    if (half == 1 && by_path && depth > 4) backup_deep(nodes, path, pb, depth, sim, r_leaf, value, discount, mn, mx, wild);
-  }
-  {  // lane 1's running (value, min, max) to lane 0
-    const int src = (threadIdx.x & 31) | 1;
-    const double v1 = __shfl_sync(0xffffffffu, value, src);
-    const double mn1 = __shfl_sync(0xffffffffu, mn, src);
-    const double mx1 = __shfl_sync(0xffffffffu, mx, src);
-    const bool wild1 = __shfl_sync(0xffffffffu, (int)wild, src) != 0;
-    if (half == 0 && by_path && depth > 4) {
-      value = v1;
-      mn = mn1;
-      mx = mx1;
-      wild |= wild1;
-    }
-  }
-  if (valid && half == 0) {
-    tree_mark<kTL>(7, tl, (uint32_t)__double2loint(root_w) ^ (uint32_t)__double2loint(mn));
-    if (by_path)
-      backup_top(nodes, pb, depth, sim, r_leaf, value, discount, root_w, mn, mx, wild);
-    else
-      backup_walk(nodes, pe, pa, sim, r_leaf, value, discount, root_w, mn, mx, wild);
-    if (kTrusted && wild && !was_wild) wild_flags[b] = 1;
-    s.root_W[b] = root_w;
-    s.minmax[2 * b] = mn;
-    s.minmax[2 * b + 1] = mx;
-    if (tl) {
-      g_tree_timeline[2] = (unsigned long long)depth;
-      tree_mark<kTL>(3, tl, (uint32_t)__double2loint(mn));
-    }
-  }
-  if (signal_at == 1) pdl_launch_dependents();
-  if (!(do_select & 1)) return;
-  // lane 0's slot stores must be visible to its partner's loads in the walk below (a shuffle orders nothing in memory)
-  __syncwarp();
-  // lane 0's (min, max) to its partner
-  mn = __shfl_sync(0xffffffffu, mn, (threadIdx.x & 31) & ~1);
-  mx = __shfl_sync(0xffffffffu, mx, (threadIdx.x & 31) & ~1);
-  if (kTrusted) wild = __shfl_sync(0xffffffffu, (int)wild, (threadIdx.x & 31) & ~1) != 0;
-  const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
-  const Leaf leaf = select_leaf<kTL, kTrusted>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path, tl, valid, wild);
-  if (signal_at == 2) pdl_launch_dependents();
-  if (half == 0 && valid) {
-    leaf_parent[b] = (uint16_t)leaf.parent;
-    leaf_action[b] = (uint8_t)leaf.action;
-    leaf_depth[b] = (uint16_t)leaf.depth;
-#ifndef HMZ_NO_LATENT_PREFETCH
-    // The network kernel that follows gathers the parent's latent row (written many simulations ago, long gone
-    // from L2): ask for it now, a whole kernel launch ahead of its use.
-    if (s.latents != nullptr) {
-      const size_t row_bytes = s.latent_dtype == HMZ_LATENT_F32 ? 256 : 128;
-      const char* row = reinterpret_cast<const char*>(s.latents) + ((size_t)b * s.n_records + leaf.parent) * row_bytes;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-      if (row_bytes == 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
-    }
-#endif
-    if (tl) {
-      g_tree_timeline[4] = (unsigned long long)leaf.depth;
-      tree_mark<kTL>(5, tl);
-    }
-  }
+                                                                     double discount, TreeScratch sc, int do_select) {
+  tree_phase<kTL, kTrusted, true>(s, sim, ucb_table, discount, sc, do_select, (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1,
+                                  (int)(threadIdx.x & 1), GlobalTables());
 }
 
 // Node.child_Q / child_U of one node per search (inspection; same arithmetic as select_leaf).
@@ -350,6 +237,27 @@ static int ensure_tree_attrs() {
   return HMZ_OK;
 }
 
+// hmz_persist.cu
+int64_t persist_ctl_bytes(int64_t n_searches);
+bool persist_supported(const hmz_search_t* s, int mode, int n_simulations);
+int persist_launch(const hmz_search_t* s, const void* weights, int n_simulations, const double* ucb_table, double discount,
+                   const CountRow* cnt_table, const TreeScratch& scratch, void* ctl_mem, cudaStream_t stream);
+
+// Device address of this translation unit's count-row table (filled by ensure_rcp_table).
+static const CountRow* count_table_address() {
+  static thread_local const CountRow* addr = nullptr;
+  static thread_local int addr_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (addr_dev != dev) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_cnt) != cudaSuccess) return nullptr;
+    addr = (const CountRow*)p;
+    addr_dev = dev;
+  }
+  return addr;
+}
+
 static unsigned search_grid(int64_t n_searches) {
   return (unsigned)((n_searches + kSearchesPerBlock - 1) / kSearchesPerBlock);
 }
@@ -409,7 +317,8 @@ const char* hmz_build_flags(void) {
 int64_t hmz_search_workspace_bytes(int64_t n_searches) {
   if (n_searches < 0) return -1;
   // p[6] r v, leaf_parent/action/depth, the sticky "wild" flag, kPathCap path elements of 32 B per search
-  return ((n_searches + 63) / 64) * 64 * (40 + 32 * kPathCap) + 512;
+  // ... and the hand-off block of the persistent schedule (ticket counter, per-pair counters, item queue)
+  return ((n_searches + 63) / 64) * 64 * (40 + 32 * kPathCap) + 1024 + persist_ctl_bytes(n_searches);
 }
 
 int hmz_search_minmax_reset(double* minmax, int64_t n, void* stream) {
@@ -474,9 +383,8 @@ int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, co
   if (!leaf_parent || !leaf_action || !r || !p || !v || sim < 0 || sim + 1 >= s->n_records)
     return fail(HMZ_ERR_INVALID, "hmz_search_expand_backup: bad arguments (sim=%d, n_records=%d)", sim, s->n_records);
   // split-phase form: no recorded path, the backup walks the parent links
-  search_backup_select<false, false><<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(
-      *s, sim, nullptr, discount, const_cast<uint16_t*>(leaf_parent), const_cast<uint8_t*>(leaf_action), nullptr, nullptr,
-      nullptr, r, p, v, 0, (float*)nullptr);
+  TreeScratch sc{const_cast<uint16_t*>(leaf_parent), const_cast<uint8_t*>(leaf_action), nullptr, nullptr, nullptr, r, p, v, nullptr};
+  search_backup_select<false, false><<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(*s, sim, nullptr, discount, sc, 0);
   return check_launch("search_expand_backup");
 }
 
@@ -492,6 +400,12 @@ int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temp
   search_root_policy<<<grid_for(s->n_searches, 256, 4), 256, 0, (cudaStream_t)stream>>>(
       *s, n_simulations, temperature, deterministic, uniforms, pow_table, n_simulations + 1, visits, pi, root_q, action);
   return check_launch("search_root_policy");
+}
+
+// Tuning switch: HMZ_PERSIST_AUTO=0 keeps the automatic schedule on the launch-per-simulation path.
+static int persist_auto() {
+  static const int v = getenv("HMZ_PERSIST_AUTO") ? atoi(getenv("HMZ_PERSIST_AUTO")) : 0;
+  return v;
 }
 
 namespace {
@@ -565,10 +479,10 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
   ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
   const int do_select = (sim + 1 < n_simulations ? 1 : 0) | (pdl_prewait() << 1) | ((pdl_tree_at() & 3) << 2);
   const float *cr = sc.r, *cp = sc.p, *cv = sc.v;
-  float* cap = s->capture ? s->capture + ((size_t)sim * (size_t)capture_stride + (size_t)capture_lo) * 8 : nullptr;
+  TreeScratch ts{sc.lp, sc.la, sc.depth, sc.path, sc.wild, cr, cp, cv,
+                 s->capture ? s->capture + ((size_t)sim * (size_t)capture_stride + (size_t)capture_lo) * 8 : nullptr};
   cudaError_t e = launch_pdl(2, g_tree_tl_search >= 0 ? search_backup_select<true, true> : search_backup_select<false, true>,
-                             dim3(search_grid(B)), dim3(kTreeThreads), 0, st, *s, sim, ucb_table, discount, sc.lp, sc.la, sc.depth,
-                             sc.path, sc.wild, cr, cp, cv, do_select, cap);
+                             dim3(search_grid(B)), dim3(kTreeThreads), 0, st, *s, sim, ucb_table, discount, ts, do_select);
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "search_backup_select launch: %s", cudaGetErrorString(e));
   return check_launch("search_backup_select");
 }
@@ -583,11 +497,27 @@ static int search_run_direct(const hmz_search_t* s, const void* weights, int mod
                 s->n_records);
   const int64_t B = s->n_searches;
   const int64_t Bp = (B + 63) / 64 * 64;
+  // ONE persistent role-specialised kernel for the whole search (hmz_persist.cu): on request, or as the automatic choice
+  // where it is supported (throughput mode) unless HMZ_PERSIST_AUTO=0
+  const bool can_persist = persist_supported(s, mode, n_simulations);
+  if (s->schedule == HMZ_SCHEDULE_PERSISTENT && !can_persist)
+    return fail(HMZ_ERR_UNSUPPORTED, "hmz_search_run: the persistent schedule needs HMZ_MODE_BF16 and n_simulations <= 2046");
+  if (s->schedule == HMZ_SCHEDULE_PERSISTENT || (s->schedule == HMZ_SCHEDULE_AUTO && can_persist && persist_auto() && g_tree_tl_search < 0)) {
+    ProfScope prof_scope(HMZ_PROF_SEARCH_PERSISTENT, stream);
+    SimScratch sc = carve_scratch(s->workspace, Bp, 0);
+    if (cudaMemsetAsync(sc.wild, 0, (size_t)B, (cudaStream_t)stream) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaMemsetAsync(wild flags) failed");
+    const CountRow* cnt = count_table_address();
+    if (!cnt) return fail(HMZ_ERR_CUDA, "cudaGetSymbolAddress(count table) failed");
+    char* ws = (char*)(((uintptr_t)s->workspace + 255) & ~(uintptr_t)255);
+    void* ctl = ws + (((size_t)Bp * (40 + 32 * kPathCap) + 255) & ~(size_t)255);
+    TreeScratch ts{sc.lp, sc.la, sc.depth, sc.path, sc.wild, sc.r, sc.p, sc.v, nullptr};
+    return persist_launch(s, weights, n_simulations, ucb_table, discount, cnt, ts, ctl, (cudaStream_t)stream);
+  }
   // Searches never interact, so the batch is cut into groups whose select -> MLP -> backup chains
   // run on separate streams: the latency-bound tree kernels of one group fill the issue slots the
   // tensor-core kernel of another leaves idle.  Group boundaries are multiples of 128 searches.
   int groups = s->schedule;
-  if (groups < 0 || groups > 16) return fail(HMZ_ERR_INVALID, "hmz_search_run: schedule %d is not a group count in [0, 16]", groups);
+  if (groups < 0 || groups > 16) return fail(HMZ_ERR_INVALID, "hmz_search_run: schedule %d is neither a group count in [0, 16] nor HMZ_SCHEDULE_PERSISTENT", groups);
   if (groups == 0) groups = B >= 32768 ? 4 : (B >= 8192 ? 2 : 1);
   const int64_t per = ((B + groups - 1) / groups + 127) / 128 * 128;
   groups = (int)((B + per - 1) / per);

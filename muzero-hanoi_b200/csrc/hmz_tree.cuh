@@ -101,8 +101,8 @@ __device__ __forceinline__ uint4* slot_ptr(hmz_node_t* nodes, int e, int a) {
 
 // Node.expand (MCTS/node.py:30-51) of a fresh node: six children with priors `pr`, N = 0, W = 0,
 // rwd = 0, no expanded grandchildren.  Lane `half` of the pair writes its 64-byte half.
-__device__ __forceinline__ void write_fresh_half(hmz_node_t* rec, int half, const float* __restrict__ pr, int parent,
-                                                 int parent_action) {
+__device__ __forceinline__ void write_fresh_half_vals(hmz_node_t* rec, int half, float pr0, float pr1, float pr2, int parent,
+                                                      int parent_action) {
   uint4* dst = reinterpret_cast<uint4*>(&rec->h[half]);
   const uint4 empty = make_uint4(0u, 0u, 0u, 0xFFFF0000u);  // W = 0, rwd = 0, N = 0, child = HMZ_NO_CHILD
 #if HMZ_L2_HINTS & 2
@@ -112,8 +112,18 @@ __device__ __forceinline__ void write_fresh_half(hmz_node_t* rec, int half, cons
 #endif
   HMZ_ST_FRESH(dst, empty, empty);
   HMZ_ST_FRESH(dst + 2, empty,
-        make_uint4(__float_as_uint(pr[3 * half]), __float_as_uint(pr[3 * half + 1]), __float_as_uint(pr[3 * half + 2]),
+        make_uint4(__float_as_uint(pr0), __float_as_uint(pr1), __float_as_uint(pr2),
                    half == 0 ? ((uint32_t)parent | ((uint32_t)parent_action << 16)) : 0u));
+}
+__device__ __forceinline__ void write_fresh_half(hmz_node_t* rec, int half, const float* __restrict__ pr, int parent,
+                                                 int parent_action) {
+  write_fresh_half_vals(rec, half, pr[3 * half], pr[3 * half + 1], pr[3 * half + 2], parent, parent_action);
+}
+// A float the network kernel wrote: through the read-only path when that kernel has COMPLETED before this one reads
+// (stand-alone launches), a plain coherent load when it is written by other CTAs of the same kernel (persistent schedule).
+template <bool kReadOnly>
+__device__ __forceinline__ float ld_net_out(const float* p) {
+  return kReadOnly ? __ldg(p) : *p;
 }
 
 // ---- exact float64 division without the generic division routine ---------------------------------
@@ -135,6 +145,32 @@ struct __align__(32) CountRow {
   double rcp_n, rcp_n1, dn, dn1;  // 1/max(n,1), 1/(n+1), (double)max(n,1), (double)(n+1)
 };
 static __device__ CountRow g_cnt[kRcpTable];  // n in [0, kRcpTable): n + 1 <= kRcpTable
+
+// Where the walk and the backup read their constant tables from.  GlobalTables: the __device__ arrays above through the
+// read-only path (stand-alone kernels: L1-resident).  SmemTables: a shared-memory copy of the first `rows` count rows
+// and of the pUCT table — the persistent kernel's tree CTAs acquire at every hand-off, which invalidates L1, so global
+// tables would cost an L2 round trip per dependent lookup; `rows` must exceed every visit count of the search.
+struct GlobalTables {
+  __device__ __forceinline__ double rcp(int n) const { return __ldg(&g_rcp[min(n, kRcpTable)]); }
+  __device__ __forceinline__ void count_row(int n, double2& lo, double2& hi) const {
+    const double2* row = reinterpret_cast<const double2*>(&g_cnt[min(n, kRcpTable - 1)]);
+    lo = __ldg(row);
+    hi = __ldg(row + 1);
+  }
+  __device__ __forceinline__ double ucb(const double* __restrict__ ucb_table, int n) const { return ucb_table[n]; }
+};
+struct SmemTables {
+  const CountRow* cnt;  // shared memory, `rows` rows
+  const double* ucb_s;  // shared memory, `rows` entries
+  int rows;
+  __device__ __forceinline__ double rcp(int n) const { return cnt[min(n, rows - 1)].rcp_n; }  // 1 / n for n >= 1
+  __device__ __forceinline__ void count_row(int n, double2& lo, double2& hi) const {
+    const double2* row = reinterpret_cast<const double2*>(&cnt[min(n, rows - 1)]);
+    lo = row[0];
+    hi = row[1];
+  }
+  __device__ __forceinline__ double ucb(const double* __restrict__, int n) const { return ucb_s[min(n, rows - 1)]; }
+};
 
 // |a| comfortably normal (2^-830 <= |a| < 2^830), tested on the exponent bits with integer instructions
 __device__ __forceinline__ bool div_fast_ok(double a) {
@@ -163,11 +199,13 @@ __device__ __forceinline__ bool is_tame(double a) {
 }
 // a / n for a visit count n >= 1: the shortcut is evaluated unconditionally (straight-line code), the rare
 // operand outside its proven range takes the generic division afterwards
-__device__ __forceinline__ double div_by_count(double a, int n) {
-  const double q = div_refine(a, (double)n, __ldg(&g_rcp[min(n, kRcpTable)]));
+template <class TB>
+__device__ __forceinline__ double div_by_count(double a, int n, const TB& tb) {
+  const double q = div_refine(a, (double)n, tb.rcp(n));
   if ((n > kRcpTable) | !div_operand_ok(a)) return __ddiv_rn(a, (double)n);
   return q;
 }
+__device__ __forceinline__ double div_by_count(double a, int n) { return div_by_count(a, n, GlobalTables()); }
 // a / b with y = __drcp_rn(b) precomputed; y_ok = b is positive, comfortably normal and its significand is not all ones
 __device__ __forceinline__ double div_by_known(double a, double b, double y, bool y_ok) {
   if (y_ok && div_fast_ok(a)) return div_refine(a, b, y);
@@ -226,12 +264,12 @@ static __device__ __noinline__ float child_score_exact(double W, float rwd, int 
 // call — and the walk needs no reconvergence bookkeeping.  ALL 32 lanes of the warp must call it.
 //   kTrusted / wild   hot loop only: the per-operand range tests are replaced by `wild` (the search's sticky flag or
 //                     untame persisted bounds) plus a per-launch test of the largest possible count; see is_tame()
-template <bool kTL = false, bool kTrusted = false>
+template <bool kTL = false, bool kTrusted = false, class TB = GlobalTables>
 __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const double* __restrict__ root_prior64, double mn,
                                             double mx, int root_n, const double* __restrict__ ucb_table,
                                             double discount, int half, uint8_t* __restrict__ path_out, int path_cap,
                                             uint4* __restrict__ path_elem, bool tl_on = false, bool active = true,
-                                            bool wild = false) {
+                                            bool wild = false, const TB& tb = TB()) {
   const bool normalise = mx > mn;  // MinMaxStats.normalize (MCTS/utils_mcts.py:12-16)
   const double range = __dsub_rn(mx, mn);
   const bool range_ok = normalise & rcp_usable(range);
@@ -260,7 +298,7 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
         ld256(hp, q0, q1);
         ld256(hp + 2, q2, q3);
       }
-      tn = ucb_table[n_parent];
+      tn = tb.ucb(ucb_table, n_parent);
       if (use64) {  // only the (noised) root has float64 priors; requested together with the record
 #pragma unroll
         for (int j = 0; j < 3; ++j) rp64[j] = root_prior64[3 * half + j];
@@ -278,8 +316,8 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
 #pragma unroll
     for (int j = 0; j < 3; ++j) {  // reciprocals first: independent L1 hits
       // counts beyond the table are flagged below (their results are discarded), so the clamp only keeps the load in range
-      const double2* row = reinterpret_cast<const double2*>(&g_cnt[min(c[j].n, kRcpTable - 1)]);
-      const double2 lo = __ldg(row), hi = __ldg(row + 1);
+      double2 lo, hi;
+      tb.count_row(c[j].n, lo, hi);
       y[j] = lo.x;
       yw[j] = lo.y;
       dn[j] = hi.x;
@@ -365,8 +403,10 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
 
 // node.expand bookkeeping on the parent slot + Node.backup (MCTS/node.py:53-70) from the leaf to
 // the root by walking parent links (any depth).  `value` enters as the network value of the new node.
+template <class TB = GlobalTables>
 __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, int sim, float r, double value,
-                                            double discount, double& root_w, double& mn, double& mx, bool& wild) {
+                                            double discount, double& root_w, double& mn, double& mx, bool& wild,
+                                            const TB& tb = TB()) {
   int e = pe, a = pa;
   bool leaf = true;
   while (true) {
@@ -381,7 +421,7 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
     c.n += 1;                     // current.N += 1
     *sp = c.pack();
     const double rwd = (double)c.rwd;
-    const double qv = __dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n)));
+    const double qv = __dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n, tb)));
     wild |= !is_tame(c.W) | !is_tame(qv);
     minmax_update(qv, mn, mx);
     value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
@@ -391,7 +431,7 @@ __device__ __forceinline__ void backup_walk(hmz_node_t* nodes, int pe, int pa, i
   }
   // the root itself: rwd = 0.0 (MCTS/mcts.py:69), N = sim + 1 after this backup
   root_w = __dadd_rn(root_w, value);
-  const double q_root = __dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1)));
+  const double q_root = __dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1, tb)));
   wild |= !is_tame(q_root);
   minmax_update(q_root, mn, mx);
 }
@@ -414,8 +454,10 @@ __device__ __forceinline__ void load_batch4(const uint4* __restrict__ path_elem,
   }
 }
 
+template <class TB = GlobalTables>
 __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const PathBatch& pb, int k0, int depth, int sim, float r,
-                                              double& value, double discount, double& mn, double& mx, bool& wild) {
+                                              double& value, double discount, double& mn, double& mx, bool& wild,
+                                              const TB& tb = TB()) {
 #pragma unroll
   for (int j = 3; j >= 0; --j) {
     if (k0 + j < depth) {
@@ -428,7 +470,7 @@ __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const PathBatch
       c.n += 1;                     // current.N += 1
       *slot_ptr(nodes, (int)(pb.ent[j] & 0xFFFFu), (int)(pb.ent[j] >> 16)) = c.pack();
       const double rwd = (double)c.rwd;
-      const double qv = __dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n)));
+      const double qv = __dadd_rn(rwd, __dmul_rn(discount, div_by_count(c.W, c.n, tb)));
       wild |= !is_tame(c.W) | !is_tame(qv);
       minmax_update(qv, mn, mx);
       value = __dadd_rn(rwd, __dmul_rn(discount, value));  // value = rwd + discount * value
@@ -437,29 +479,184 @@ __device__ __forceinline__ void backup_batch4(hmz_node_t* nodes, const PathBatch
 }
 
 // Levels >= 4, leaf side first (lane 1 of the pair): `pb` holds the leaf-side batch k_top = (depth - 1) & ~3 >= 4.
+template <class TB = GlobalTables>
 __device__ __forceinline__ void backup_deep(hmz_node_t* nodes, const uint4* __restrict__ path_elem, PathBatch& pb, int depth, int sim,
-                                            float r, double& value, double discount, double& mn, double& mx, bool& wild) {
+                                            float r, double& value, double discount, double& mn, double& mx, bool& wild,
+                                            const TB& tb = TB()) {
 #pragma unroll 1
   for (int k0 = (depth - 1) & ~3; k0 >= 4; k0 -= 4) {
-    backup_batch4(nodes, pb, k0, depth, sim, r, value, discount, mn, mx, wild);
+    backup_batch4(nodes, pb, k0, depth, sim, r, value, discount, mn, mx, wild, tb);
     if (k0 >= 8) load_batch4(path_elem, k0 - 4, depth, pb);
   }
 }
 
 // Levels 0..3 and the root itself (lane 0 of the pair): rwd = 0.0 at the root (MCTS/mcts.py:69), N = sim + 1 after this backup.
+template <class TB = GlobalTables>
 __device__ __forceinline__ void backup_top(hmz_node_t* nodes, const PathBatch& pb, int depth, int sim, float r, double value,
-                                           double discount, double& root_w, double& mn, double& mx, bool& wild) {
-  backup_batch4(nodes, pb, 0, depth, sim, r, value, discount, mn, mx, wild);
+                                           double discount, double& root_w, double& mn, double& mx, bool& wild,
+                                           const TB& tb = TB()) {
+  backup_batch4(nodes, pb, 0, depth, sim, r, value, discount, mn, mx, wild, tb);
   root_w = __dadd_rn(root_w, value);
-  const double q_root = __dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1)));
+  const double q_root = __dadd_rn(0.0, __dmul_rn(discount, div_by_count(root_w, sim + 1, tb)));
   wild |= !is_tame(q_root);
   minmax_update(q_root, mn, mx);
 }
 
+// Scratch of hmz_search_run per search (hmz_search_workspace_bytes): the leaf of the pending simulation, the path
+// elements its walk recorded, the sticky tameness flag, and the network outputs of that simulation.
+struct TreeScratch {
+  uint16_t* leaf_parent;
+  uint8_t* leaf_action;
+  uint16_t* leaf_depth;
+  uint4* path_elem;
+  uint8_t* wild_flags;
+  const float* r;
+  const float* p;
+  const float* v;
+  float* capture;  // nullable: [n_searches][8] row of THIS simulation
+};
+
+// Phases 2b + 3 of simulation `sim` (expansion with the network outputs, backup), optionally followed at once by the
+// selection of simulation `sim + 1` — the fused hot-loop form: the path just updated is still close and the next walk
+// usually shares its prefix.  With path elements (slot + entry per level, recorded by the previous walk) the backup needs
+// one round trip for its inputs; without them (split-phase API) it walks the parent links.
+//   b_raw, half   the search this lane pair owns (b_raw >= n_searches: masked, but the lane stays for the warp-uniform walk)
+//   do_select     bit 0: select simulation sim + 1 afterwards; bits 1-3: programmatic-launch switches (kPdl only);
+//                 bit 4: no backup (with sim = -1: the first selection of a search)
+//   kTrusted      `wild_flags[search]` is the sticky "a backup wrote an untame W or Q" flag of is_tame(); the walk then
+//                 skips its per-operand range tests
+//   kPdl          stand-alone kernel launched as a programmatic dependent of the network kernel
+// ALL 32 lanes of the warp must call it.
+template <bool kTL, bool kTrusted, bool kPdl, class TB>
+__device__ __forceinline__ void tree_phase(const hmz_search_t& s, int sim, const double* __restrict__ ucb_table, double discount,
+                                           const TreeScratch& sc, int do_select, int64_t b_raw, int half, const TB& tb) {
+  uint16_t* leaf_parent = sc.leaf_parent;
+  uint8_t* leaf_action = sc.leaf_action;
+  uint16_t* leaf_depth = sc.leaf_depth;
+  uint4* path_elem = sc.path_elem;
+  uint8_t* wild_flags = sc.wild_flags;
+  const float* r = sc.r;
+  const float* p = sc.p;
+  const float* v = sc.v;
+  float* capture = sc.capture;
+  const int signal_at = (do_select >> 2) & 3;  // HMZ_PDL_TREE_AT
+  if (kPdl && signal_at == 0) pdl_launch_dependents();
+  if (kPdl && !(do_select & 2)) pdl_wait();  // HMZ_PDL bit 2 off: nothing is read before the wait
+  const bool valid = b_raw < s.n_searches;  // out-of-range pairs stay for the warp-uniform walk, masked
+  const int64_t b = valid ? b_raw : s.n_searches - 1;
+  const bool tl = kTL && valid && b == (g_tree_timeline_search & 0xFFFFFFFFll) && sim == (int)(g_tree_timeline_search >> 32) && half == 0;
+  tree_mark<kTL>(0, tl);
+  hmz_node_t* nodes = s.nodes + b * s.n_records;
+  uint4* path = path_elem ? path_elem + b * (2 * kPathCap) : nullptr;
+  // Before waiting for the network kernel: everything the backup needs that the PREVIOUS tree kernel wrote
+  // (leaf scalars, min/max, the root's W, and the path elements = slot + entry per level, at addresses that
+  // depend only on the search index: ONE round trip for paths of up to four levels).  The network kernel only
+  // signals its dependents after its own wait, so that kernel has completed by the time this one runs.
+  // Lane 0 of the pair owns levels 0..3 and the root, lane 1 the levels from 4 on (leaf side first).
+  double mn = 0.0, mx = 0.0, root_w = 0.0;
+  int pe = 0, pa = 0, depth = kPathCap + 1;
+  PathBatch pb;
+  pb.slot[0] = make_uint4(0u, 0u, 0u, 0u);
+  bool wild = false, was_wild = false;
+  const bool do_backup = !(do_select & 16);  // bit 4: selection only (the first selection of a search: sim = -1)
+  if (valid) {
+    if (kTrusted && half == 0) was_wild = wild = wild_flags[b] != 0;
+    mn = s.minmax[2 * b];
+    mx = s.minmax[2 * b + 1];
+  }
+  if (valid && do_backup) {
+    if (half == 0 && path != nullptr) load_batch4(path, 0, 4, pb);  // unconditionally: the depth is not known yet
+    pe = leaf_parent[b];
+    pa = leaf_action[b];
+    if (path != nullptr && leaf_depth != nullptr) depth = (int)leaf_depth[b];
+    if (half == 0) root_w = s.root_W[b];
+    if (half == 1 && depth > 4 && depth <= kPathCap) load_batch4(path, (depth - 1) & ~3, depth, pb);
+  }
+  tree_mark<kTL>(1, tl, (uint32_t)(pe + pa) ^ pb.slot[0].w);
+  if (kPdl) pdl_wait();  // everything below reads what the network kernel wrote
+  float r_leaf = 0.f;
+  double value = 0.0;
+  const bool by_path = depth <= kPathCap;
+  if (valid && do_backup) {
+    r_leaf = ld_net_out<kPdl>(r + b);
+    const float v_leaf = ld_net_out<kPdl>(v + b);
+    value = (double)v_leaf;
+    const float* pp = p + b * 6 + 3 * half;  // this lane's three priors
+    const float q0 = ld_net_out<kPdl>(pp), q1 = ld_net_out<kPdl>(pp + 1), q2 = ld_net_out<kPdl>(pp + 2);
+    write_fresh_half_vals(&nodes[sim + 1], half, q0, q1, q2, pe, pa);
+    if (capture != nullptr) {  // parity tests: the network outputs this backup consumed, [p0..p5, r, v] per search
+      float4* cap = reinterpret_cast<float4*>(capture + b * 8) + half;
+      *cap = half == 0 ? make_float4(q0, q1, q2, ld_net_out<kPdl>(pp + 3)) : make_float4(q1, q2, r_leaf, v_leaf);
+    }
+    tree_mark<kTL>(6, tl, __float_as_uint(r_leaf));
+    if (half == 1 && by_path && depth > 4) backup_deep(nodes, path, pb, depth, sim, r_leaf, value, discount, mn, mx, wild, tb);
+  }
+  {  // lane 1's running (value, min, max) to lane 0
+    const int src = (threadIdx.x & 31) | 1;
+    const double v1 = __shfl_sync(0xffffffffu, value, src);
+    const double mn1 = __shfl_sync(0xffffffffu, mn, src);
+    const double mx1 = __shfl_sync(0xffffffffu, mx, src);
+    const bool wild1 = __shfl_sync(0xffffffffu, (int)wild, src) != 0;
+    if (half == 0 && by_path && depth > 4) {
+      value = v1;
+      mn = mn1;
+      mx = mx1;
+      wild |= wild1;
+    }
+  }
+  if (valid && half == 0 && do_backup) {
+    tree_mark<kTL>(7, tl, (uint32_t)__double2loint(root_w) ^ (uint32_t)__double2loint(mn));
+    if (by_path)
+      backup_top(nodes, pb, depth, sim, r_leaf, value, discount, root_w, mn, mx, wild, tb);
+    else
+      backup_walk(nodes, pe, pa, sim, r_leaf, value, discount, root_w, mn, mx, wild, tb);
+    if (kTrusted && wild && !was_wild) wild_flags[b] = 1;
+    s.root_W[b] = root_w;
+    s.minmax[2 * b] = mn;
+    s.minmax[2 * b + 1] = mx;
+    if (tl) {
+      g_tree_timeline[2] = (unsigned long long)depth;
+      tree_mark<kTL>(3, tl, (uint32_t)__double2loint(mn));
+    }
+  }
+  if (kPdl && signal_at == 1) pdl_launch_dependents();
+  if (!(do_select & 1)) return;
+  // lane 0's slot stores must be visible to its partner's loads in the walk below (a shuffle orders nothing in memory)
+  __syncwarp();
+  // lane 0's (min, max) to its partner
+  mn = __shfl_sync(0xffffffffu, mn, (threadIdx.x & 31) & ~1);
+  mx = __shfl_sync(0xffffffffu, mx, (threadIdx.x & 31) & ~1);
+  if (kTrusted) wild = __shfl_sync(0xffffffffu, (int)wild, (threadIdx.x & 31) & ~1) != 0;
+  const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
+  const Leaf leaf = select_leaf<kTL, kTrusted, TB>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path, tl, valid, wild, tb);
+  if (kPdl && signal_at == 2) pdl_launch_dependents();
+  if (half == 0 && valid) {
+    leaf_parent[b] = (uint16_t)leaf.parent;
+    leaf_action[b] = (uint8_t)leaf.action;
+    leaf_depth[b] = (uint16_t)leaf.depth;
+#ifndef HMZ_NO_LATENT_PREFETCH
+    // The network kernel that follows gathers the parent's latent row (written many simulations ago, long gone
+    // from L2): ask for it now, a whole kernel launch ahead of its use.
+    if (s.latents != nullptr) {
+      const size_t row_bytes = s.latent_dtype == HMZ_LATENT_F32 ? 256 : 128;
+      const char* row = reinterpret_cast<const char*>(s.latents) + ((size_t)b * s.n_records + leaf.parent) * row_bytes;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+      if (row_bytes == 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+    }
+#endif
+    if (tl) {
+      g_tree_timeline[4] = (unsigned long long)leaf.depth;
+      tree_mark<kTL>(5, tl);
+    }
+  }
+}
+
+
 // MCTS/mcts.py:112-122 for one search: child_N of the root, generate_play_policy (:154-176: visits ** clamp(1/T, 1, 5)
 // for T > 0, raw counts for T == 0, divided by their np.sum) and the action — np.argmax(child_visits) (first maximum,
 // :117) or np.random.choice(6, p=pi) with its single uniform `u` supplied (:120: cdf / cdf[-1], searchsorted right).
-// pow_table (nullable): the caller's own NumPy powers of every possible count (see hmz_search_root_policy).
+// pow_table (nullable) [pow_table_len][6]: the caller's own NumPy powers of every possible count at every position of
+// the 6-element visit array (see hmz_search_root_policy).
 struct RootPolicy {
   int n[6];
   double prob[6];
@@ -478,7 +675,7 @@ __device__ __forceinline__ RootPolicy root_policy_eval(const hmz_node_t* root, d
   for (int a = 0; a < 6; ++a) {
     const double x = (double)out.n[a];
     if (pow_table != nullptr && out.n[a] < pow_table_len) {  // visits ** exponent exactly as the caller's NumPy evaluates it
-      w[a] = pow_table[out.n[a]];
+      w[a] = pow_table[out.n[a] * 6 + a];
     } else if ((double)iex == ex) {  // integer exponents 1..5: exact products while < 2^53
       double y = x;
       for (int k = 1; k < iex; ++k) y = __dmul_rn(y, x);

@@ -274,9 +274,10 @@ class BatchedMCTS:
         return self.action, self.pi, self.root_q, self.visits
 
     def _pow_table(self, temperature, n):
-        """visits ** clamp(1/T, 1, 5) for every possible count, evaluated by THIS process's NumPy exactly as
-        generate_play_policy does (MCTS/mcts.py:168-174: np.power on an int64 array); None when the device's exact
-        integer powers are identical (exponents 1..5 with every power below 2^53)."""
+        """visits ** clamp(1/T, 1, 5) for every possible count and every position of the 6-element visit array, evaluated
+        by THIS process's NumPy exactly as generate_play_policy does (MCTS/mcts.py:168-174: np.power on an int64 array of
+        six counts — NumPy's pow differs between its SIMD body and its scalar tail, hence per position); None when the
+        device's exact integer powers are identical (exponents 1..5 with every power below 2^53)."""
         if temperature <= 0.0:
             return None
         ex = max(1.0, min(5.0, 1.0 / temperature))
@@ -284,7 +285,8 @@ class BatchedMCTS:
             return None
         key = (ex, n)
         if self._pow_cache.get("key") != key:
-            self._pow_cache = dict(key=key, table=torch.from_numpy(np.power(np.arange(n + 1, dtype=np.int64), ex)).to(self.device))
+            table = np.stack([np.power(np.full(6, k, dtype=np.int64), ex) for k in range(n + 1)])  # [n + 1, 6]
+            self._pow_cache = dict(key=key, table=torch.from_numpy(np.ascontiguousarray(table)).to(self.device))
         return self._pow_cache["table"]
 
     def run_injected(self, root_prior, prior_is_f64, r, p, v, want_paths=False):

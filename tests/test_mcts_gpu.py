@@ -15,7 +15,7 @@ from oracle import cport, port
 pytestmark = pytest.mark.gpu
 # hmz_search_t.schedule values exercised at full size: serial launches, the automatic choice (4 stream groups at this
 # size), 7 ragged groups, and the persistent role-specialised kernel
-SCHEDULES_FULL = (1, 0, 7)
+SCHEDULES_FULL = (1, 0, 7, 64)
 
 
 def _split_search(mcts, weights, words, noise, record=True):
@@ -218,7 +218,7 @@ def test_node_view_matches_tree_store(golden):
     assert leaf.N == 0 and leaf.Q == 0.0 and leaf.h_state is None and leaf.children == []
 
 
-@pytest.mark.parametrize("schedule", [0])
+@pytest.mark.parametrize("schedule", [0, 64])
 def test_full_size_benchmarked_path_replayed_by_the_oracle(schedule):
     """The path bench.py times, at the size it times it: bf16 throughput mode, hmz_search_run (fused backup + select
     kernels, stream groups and programmatic dependent launches for schedule 0; the persistent kernel for schedule 64),
@@ -403,3 +403,44 @@ def test_fused_untame_bounds_and_values_take_the_exact_path():
     assert np.array_equal(q3.cpu().numpy(), q4.cpu().numpy(), equal_nan=True)
     assert np.array_equal(split.store.minmax.cpu().numpy(), fused.store.minmax.cpu().numpy(), equal_nan=True)
     assert np.isnan(q4.cpu().numpy()).any()
+
+
+@pytest.mark.parametrize("n,B,S,bias", [(5, 1, 8, 0.0), (5, 100, 1, 0.0), (3, 777, 30, 0.0), (4, 2048 + 17, 60, 12.0), (5, 8192, 100, 0.0)])
+def test_persistent_schedule_equals_serial_launches(n, B, S, bias):
+    """hmz_search_t.schedule = HMZ_SCHEDULE_PERSISTENT (one role-specialised kernel per search: tcgen05 MLP CTAs and tree
+    CTAs handing 256-search tile pairs to each other through release / acquire counters) against schedule 1 (one launch
+    pair per simulation, strictly serial): same arithmetic, so the whole search state must be identical bit for bit —
+    node records, latent rows, root values, persistent min/max — over ragged batches (1, 100, 777, 2,065 searches: partial
+    tiles, partial warps), 1 to 100 simulations, two consecutive moves, and deep chains (a dominant policy action drives
+    walks past the 4 / 8 / 32-level branches of the backup)."""
+    from muzero_hanoi_b200 import _lib
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    sd = {k: np.array(v, copy=True) for k, v in port.make_weights(n, 31).items()}
+    sd["policy_net.2.bias"][:] += np.array([bias, 0.0, bias / 2, 0.0, 0.0, 0.0], dtype=np.float32)
+    w = PackedWeights(sd, n, _lib.MODE_BF16)
+    rng = np.random.default_rng(B + S)
+    runs = []
+    for schedule in (1, _lib.SCHEDULE_PERSISTENT):
+        env = VecHanoi(n, 200, B)
+        env.random_reset(seed=9)
+        m = BatchedMCTS(0.8, 0.25, S, B, latent_dtype=_lib.LATENT_BF16)
+        m.store.set_schedule(schedule)
+        rng = np.random.default_rng(B + S)
+        out = []
+        for move in range(2):
+            noise, uni = rng.dirichlet(np.full(6, 0.25), B), rng.random(B)
+            action, pi, q, visits = m.run_mcts(w, words=env.words, temperature=1.0, deterministic=False, noise=noise, uniforms=uni)
+            torch.cuda.synchronize()
+            out.append([t.clone() for t in (action, pi, q, visits, m.store.minmax, m.store.root_W, m.store.nodes,
+                                            m.store.latents[:, : S + 1].contiguous())])
+            env.step(action.to(torch.uint8), want_obs=False)
+        runs.append(out)
+    names = ("action", "pi", "root_q", "visits", "minmax", "root_W", "node records", "latents")
+    for move in range(2):
+        for name, a, b in zip(names, runs[0][move], runs[1][move]):
+            assert torch.equal(a, b), f"move {move}: {name} differ between the serial and the persistent schedule"
+        assert (runs[1][move][3].sum(1) == S).all()
+    if bias:
+        depth_proxy = runs[1][1][3].max(1).values  # a dominant action concentrates the visits: chains well past 32 levels
+        assert int(depth_proxy.max()) >= S - 6

@@ -2,11 +2,12 @@
 unmodified reference network (tests/golden/net_io.npz).
 
 Tolerances (HMZ_MODE_FP32, north_star: within 1e-5 relative in fp32), all RELATIVE with a small absolute floor:
-  latent h and policy p:                       |d| <= 1e-5 * |ref| + 5e-7 (h) / 1e-7 (p)
+  latent h and policy p:                       |d| <= 1e-5 * |ref| + 1e-6 (h) / 1e-7 (p)
   reward r and value v (support transform):    |d| <= 1e-5 * |ref| + 2.5e-4
 The floor for h is the float32 rounding of normalize_h_state itself ((h - min) / (max - min + 1e-8), networks.py:191-196:
-every element is a difference of O(1) numbers, so elements near zero carry an absolute error of a few ulp(1) = 6e-8
-whatever the kernel does — the smallest element is exactly 0 in both).  The absolute term for r/v is the float32
+every element is a difference of O(1) numbers, so elements near zero carry an absolute error of a few ulp(1) = 1.2e-7
+whatever the kernel does — the smallest element is exactly 0 in both; measured on the B200: <= 4.9e-7 for h, <= 4.5e-8
+for p, r and v identical to the reference except for single grid steps, profiles/r02_net_errors.json).  The absolute term for r/v is the float32
 granularity of the reference's OWN signed-parabolic evaluation (networks.py:186-189 computes
 sqrt(..)/2/eps - 1/2/eps ~ 500.x - 500 in float32, i.e. its outputs live on a ~1.2e-4 grid near zero), so a 1-ulp
 difference in the softmax expectation moves the reference's result by one grid step; two grid steps are allowed.
@@ -19,7 +20,7 @@ from conftest import record_metric
 from oracle import port
 
 pytestmark = pytest.mark.gpu
-REL, H_ABS, P_ABS, RV_REL, RV_ABS = 1e-5, 5e-7, 1e-7, 1e-5, 2.5e-4
+REL, H_ABS, P_ABS, RV_REL, RV_ABS = 1e-5, 1e-6, 1e-7, 1e-5, 2.5e-4
 H_TOL = 1e-5  # drop-in surface checks (single rows through the Python shim)
 
 

@@ -19,7 +19,16 @@ def _check_against_fixture(g, mcts, ks, paths, depths):
     torch.cuda.synchronize()
     assert np.array_equal(visits.cpu().numpy(), g["child_N"][ks])
     assert np.array_equal(q.cpu().numpy(), g["root_q"][ks])  # float64, bit for bit
-    assert np.array_equal(pi.cpu().numpy(), g["pi"][ks])
+    ex = max(1.0, min(5.0, 1.0 / float(g["temperature"]))) if float(g["temperature"]) > 0 else 1.0
+    if ex == int(ex):
+        assert np.array_equal(pi.cpu().numpy(), g["pi"][ks])
+    else:
+        # NumPy's pow is not correctly rounded and depends on the CPU's SIMD dispatch: a fixture recorded on another
+        # machine pins a non-integer power to the last bit or two only; THIS machine's NumPy must be matched exactly
+        from oracle import port
+
+        assert np.allclose(pi.cpu().numpy(), g["pi"][ks], rtol=1e-15, atol=0.0)
+        assert np.array_equal(pi.cpu().numpy(), np.stack([port.play_policy(v, float(g["temperature"])) for v in g["child_N"][ks]]))
     assert np.array_equal(act.cpu().numpy(), g["action"][ks])
     mm = mcts.store.minmax.cpu().numpy()
     assert np.array_equal(mm[:, 0], g["mm_min"][ks]) and np.array_equal(mm[:, 1], g["mm_max"][ks])
