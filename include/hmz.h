@@ -283,6 +283,11 @@ int hmz_debug_tc_timeline(unsigned long long* host_out);
  * backup + select kernel, whose lane pair `search` records clock64() at its phase boundaries in that
  * simulation (-1 switches it off); host_out (nullable, 64 values) receives the marks. */
 int hmz_debug_tree_timeline(long long search, unsigned long long* host_out);
+/* Tooling only: with HMZ_PERSIST_STATS=1 in the environment the persistent search kernel accumulates clock64 sums of its
+ * last launch; host_out receives 16 values: [0] tree warps waiting for work, [1] tree warps working, [2] slices processed,
+ * [3] summed tree-warp lifetimes, [4] MLP CTAs waiting for the tree (one thread each), [5] MLP CTAs first -> last hand-off,
+ * [6] MLP passes, [7] tree warps. */
+int hmz_debug_persist_stats(unsigned long long* host_out);
 /* Tests only: compares the search kernels' exact-division shortcuts (table / precomputed reciprocal + two
  * FMA corrections) with IEEE division bit for bit on n_samples random operand pairs; adds the number of
  * mismatches to counters[0] (division by a visit count) and counters[1] (division by the min-max range). */

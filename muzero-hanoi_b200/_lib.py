@@ -7,7 +7,8 @@ import os
 import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libhmz.so")
+# HMZ_LIB_PATH (tooling): load another build of the library, e.g. an A/B variant produced by tools/build_variant.sh
+LIB_PATH = os.environ.get("HMZ_LIB_PATH") or os.path.join(PKG_DIR, "libhmz.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 FLAG_DONE, FLAG_ILLEGAL, FLAG_GOAL, FLAG_TRUNC = 1, 2, 4, 8
@@ -113,6 +114,7 @@ SIGNATURES = {
     "hmz_net_initial": (_I, [_P, _I, _I, _P, _P, _P, _L, _I, _P, _P, _L, _P]),
     "hmz_net_recurrent": (_I, [_P, _I, _P, _L, _P, _P, _P, _L, _L, _I, _P, _P, _P, _L, _P]),
     "hmz_debug_tc_timeline": (_I, [_P]),
+    "hmz_debug_persist_stats": (_I, [_P]),
     "hmz_debug_tree_timeline": (_I, [C.c_longlong, _P]),
     "hmz_debug_div_check": (_I, [_U64, _U64, _P, _P]),
     "hmz_search_run": (_I, [_SD, _P, _I, _I, _P, _D, _P]),

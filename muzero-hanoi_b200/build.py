@@ -19,11 +19,14 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(REPO, "include")
-OBJ_DIR = os.path.join(PKG_DIR, "build")
-LIB_PATH = os.path.join(PKG_DIR, "libhmz.so")
+# HMZ_VARIANT=name (tooling): an A/B build with HMZ_NVCC_EXTRA's flags into variants/libhmz_<name>.so (own object
+# directory), loaded with HMZ_LIB_PATH; the shipped library is always muzero-hanoi_b200/libhmz.so built without either.
+VARIANT = os.environ.get("HMZ_VARIANT", "")
+OBJ_DIR = os.path.join(PKG_DIR, "build" + ("_" + VARIANT if VARIANT else ""))
+LIB_PATH = os.path.join(PKG_DIR, "variants", f"libhmz_{VARIANT}.so") if VARIANT else os.path.join(PKG_DIR, "libhmz.so")
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
-EXTRA = os.environ.get("HMZ_NVCC_EXTRA", "").split()
+EXTRA = os.environ.get("HMZ_NVCC_EXTRA", "").split() + (["-DHMZ_VARIANT"] if os.environ.get("HMZ_VARIANT") else [])
 NVCC_FLAGS = [*EXTRA, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
               "-I", INCLUDE, "-I", CSRC]
 
@@ -57,6 +60,7 @@ def _compile(nvcc, src, obj, verbose):
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = nvcc_path()
     os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     if not sources:
         raise RuntimeError("no CUDA sources under " + CSRC)

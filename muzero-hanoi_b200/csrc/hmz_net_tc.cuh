@@ -45,18 +45,41 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kWaitTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+// A wait that has lasted 20 s is a protocol failure: trap (the launch fails with an error) rather than hang the GPU.
+// The clock is read once every 2^16 polls, so a wait that succeeds pays nothing for the guard.
+struct WaitGuard {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  __device__ __forceinline__ void poll() {
+    if ((++spins & 0xFFFFu) == 0u) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitTimeoutNs) __trap();
+    }
+  }
+};
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  WaitGuard guard;
+  while (!mbar_try_wait(bar, parity)) guard.poll();
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -329,10 +352,14 @@ struct PersistCtl {
   unsigned long long* queue;
   uint32_t q_mask;      // capacity - 1 (power of two)
   int n_sims;
+  unsigned long long* stats;  // tooling (HMZ_PERSIST_STATS=1), nullable: clock64 sums, see hmz_debug_persist_stats
 };
+#ifdef HMZ_PERSIST_STATS  // tooling build (tools/build_variant.py): role statistics of the persistent kernel
+constexpr bool kPersistStats = true;
+#else
+constexpr bool kPersistStats = false;
+#endif
 constexpr int kSlicesPerPair = 16;       // warps (16 searches each) per 256-search tile pair
-constexpr uint32_t kSpinLimit = 1u << 24;  // polls before a hand-off wait gives up (~seconds): trap instead of hanging the GPU
-
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -371,10 +398,10 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 __device__ __forceinline__ void persist_wait_tree(const PersistCtl& pc, int pair, int sim) {
   const uint32_t need = (uint32_t)kSlicesPerPair * (uint32_t)(sim + 1);
   const uint32_t* ctr = pc.tree_done + (size_t)pair * 8;
-  uint32_t spins = 0;
+  WaitGuard guard;
   while (ld_relaxed_u32(ctr) < need) {
     __nanosleep(64);
-    if (++spins > kSpinLimit) __trap();
+    guard.poll();
   }
   fence_acquire_gpu();
 }
@@ -605,7 +632,15 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
       const int64_t out_row = kPersist ? (int64_t)sim + 1 : a.out_row;
       const int64_t row0 = ((int64_t)pair * 2 + t) * kM;
       const int64_t item = row0 + row;
-      if (kPersist) persist_wait_tree(pc, pair, sim);  // the gather reads what the pair's selection wrote
+      if (kPersist) {  // the gather reads what the pair's selection wrote
+        const bool st = kPersistStats && pc.stats != nullptr && ltid == 0 && t == 0;
+        const long long c0 = st ? clock64() : 0;
+        persist_wait_tree(pc, pair, sim);
+        if (st) {
+          atomicAdd(pc.stats + 4, (unsigned long long)(clock64() - c0));
+          atomicAdd(pc.stats + 6, 1ull);
+        }
+      }
       {  // parent latents -> swizzled A0 tile; 8 consecutive lanes fetch the 8 16-byte chunks of one row
         const int chunk = ltid & 7;
         uint4 gathered[4];
@@ -732,6 +767,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph_s = 0;
     uint32_t ph_pass = 0;
+    unsigned long long pass_t0 = 0;
     for (int pass = 0; pass < n_pass; ++pass) {
       const int pair = HMZ_PASS_PAIR(pass), sim = HMZ_PASS_SIM(pass);
       if (kPersist) persist_wait_tree(pc, pair, sim);  // the action slice reads what the pair's selection wrote
@@ -812,6 +848,11 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
         if (row == 0) {
           mbar_wait(&s.bar_pass, ph_pass);
           persist_push_item(pc, n_pairs, pair, sim + 1);
+          if (kPersistStats && pc.stats != nullptr) {
+            const unsigned long long now = (unsigned long long)clock64();
+            if (pass == 0) pass_t0 = now;
+            if (pass == n_pass - 1) atomicAdd(pc.stats + 5, now - pass_t0);  // first push -> last push of this CTA
+          }
         }
         ph_pass ^= 1;
       }

@@ -26,7 +26,10 @@
 
 namespace hmz {
 
-constexpr int kPersistThreads = 768;               // 24 warps; at this block size ptxas may use 80 registers per thread
+#ifndef HMZ_PERSIST_THREADS
+#define HMZ_PERSIST_THREADS 768
+#endif
+constexpr int kPersistThreads = HMZ_PERSIST_THREADS;  // 24 warps; at this block size ptxas may use 80 registers per thread
 constexpr int kPersistWarps = kPersistThreads / 32;
 
 struct PersistArgs {
@@ -42,6 +45,11 @@ struct PersistArgs {
   int n_mlp, n_sims, n_pairs, table_rows;
 };
 
+// Tooling (HMZ_PERSIST_STATS=1): clock64 sums of the last launch — [0] tree warps waiting for an item, [1] tree warps
+// working, [2] items x slices processed, [3] tree warp lifetimes, [4] MLP CTAs waiting for the tree (one thread per CTA),
+// [5] MLP CTAs first push -> last push, [6] MLP passes, [7] CTAs x warps of the tree role.
+static __device__ unsigned long long g_persist_stats[16];
+
 __device__ __forceinline__ void tree_role(const PersistArgs& a, uint8_t* smem_raw) {
   // constant tables -> shared memory (the acquire at every hand-off invalidates L1)
   CountRow* s_cnt = reinterpret_cast<CountRow*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -50,14 +58,23 @@ __device__ __forceinline__ void tree_role(const PersistArgs& a, uint8_t* smem_ra
     reinterpret_cast<double*>(s_cnt)[i] = reinterpret_cast<const double*>(a.cnt_table)[i];
   for (int i = threadIdx.x; i < a.table_rows; i += blockDim.x) s_ucb[i] = a.ucb_table[i];
   __syncthreads();
+#ifdef HMZ_PERSIST_GLOBAL_TABLES  // A/B switch: read the tables from global memory through L1 instead
+  const SmemTables tb{a.cnt_table, a.ucb_table, a.table_rows};
+#else
   const SmemTables tb{s_cnt, s_ucb, a.table_rows};
+#endif
   const int lane = threadIdx.x & 31, half = lane & 1;
   const tc::v4::PersistCtl& pc = a.ctl;
+  const bool stats = tc::v4::kPersistStats && pc.stats != nullptr && lane == 0;
+  long long t_wait = 0, t_work = 0, n_items = 0;
+  const long long t_begin = stats ? clock64() : 0;
   for (;;) {
+    const long long c0 = stats ? clock64() : 0;
     uint32_t ticket = 0;
     if (lane == 0) ticket = atomicAdd(pc.tree_head, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
     if (ticket >= a.total_tickets) break;
+    ++n_items;
     const uint32_t item = ticket / tc::v4::kSlicesPerPair, slice = ticket % tc::v4::kSlicesPerPair;
     int pair, sim;
     if (item < (uint32_t)a.n_pairs) {  // implicit items: the first selection of every pair
@@ -66,15 +83,16 @@ __device__ __forceinline__ void tree_role(const PersistArgs& a, uint8_t* smem_ra
     } else {
       const unsigned long long* slot = pc.queue + ((item - (uint32_t)a.n_pairs) & pc.q_mask);
       unsigned long long q;
-      uint32_t spins = 0;
+      tc::WaitGuard guard;
       while ((uint32_t)((q = tc::v4::ld_relaxed_u64(slot)) >> 32) != item + 1u) {
         __nanosleep(100);
-        if (++spins > tc::v4::kSpinLimit) __trap();
+        guard.poll();
       }
       pair = (int)(q & 0xFFFFu);
       sim = (int)((q >> 16) & 0xFFFFu);
     }
     tc::v4::fence_acquire_gpu();  // every lane: the item's network outputs, and whatever other SMs wrote to this slice's tree
+    const long long c1 = stats ? clock64() : 0;
     const int64_t b_raw = (int64_t)pair * (2 * tc::kM) + (int64_t)slice * 16 + (lane >> 1);
     TreeScratch sc = a.sc;
     if (sc.capture != nullptr && sim > 0) sc.capture += (size_t)(sim - 1) * (size_t)a.capture_stride;
@@ -86,6 +104,18 @@ __device__ __forceinline__ void tree_role(const PersistArgs& a, uint8_t* smem_ra
       __syncwarp();  // every lane's stores of the slice happen before lane 0's release
       if (lane == 0) tc::v4::red_release_add(pc.tree_done + (size_t)pair * 8, 1u);
     }
+    if (stats) {
+      const long long c2 = clock64();
+      t_wait += c1 - c0;
+      t_work += c2 - c1;
+    }
+  }
+  if (stats) {
+    atomicAdd(pc.stats + 0, (unsigned long long)t_wait);
+    atomicAdd(pc.stats + 1, (unsigned long long)t_work);
+    atomicAdd(pc.stats + 2, (unsigned long long)n_items);
+    atomicAdd(pc.stats + 3, (unsigned long long)(clock64() - t_begin));
+    atomicAdd(pc.stats + 7, 1ull);
   }
 }
 
@@ -103,6 +133,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) search_persistent(PersistA
   }
 }
 
+static int persist_stats_on() {
+  static const int v = getenv("HMZ_PERSIST_STATS") ? atoi(getenv("HMZ_PERSIST_STATS")) : 0;
+  return v;
+}
+int persist_read_stats(unsigned long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_persist_stats, sizeof(unsigned long long) * 16) == cudaSuccess ? HMZ_OK : HMZ_ERR_CUDA;
+}
 static int persist_mlp_override() {
   static const int v = getenv("HMZ_PERSIST_MLP") ? atoi(getenv("HMZ_PERSIST_MLP")) : 0;
   return v;
@@ -192,6 +229,13 @@ int persist_launch(const hmz_search_t* s, const void* weights, int n_simulations
   a.ctl.queue = (unsigned long long*)(ctl + 1024 + (size_t)a.n_pairs * 32);
   a.ctl.q_mask = (uint32_t)(cap - 1);
   a.ctl.n_sims = n_simulations;
+  a.ctl.stats = nullptr;
+  if (tc::v4::kPersistStats && persist_stats_on()) {
+    void* sp = nullptr;
+    if (cudaGetSymbolAddress(&sp, g_persist_stats) != cudaSuccess || cudaMemsetAsync(sp, 0, sizeof(unsigned long long) * 16, stream) != cudaSuccess)
+      return fail(HMZ_ERR_CUDA, "persistent search: statistics buffer unavailable");
+    a.ctl.stats = (unsigned long long*)sp;
+  }
   // MLP arguments: latents gathered from the leaf's parent record, written to record sim + 1 (the body derives the row)
   a.net.wsec = (const uint8_t*)weights;
   a.net.lat_in = s->latents;

@@ -238,6 +238,7 @@ static int ensure_tree_attrs() {
 }
 
 // hmz_persist.cu
+int persist_read_stats(unsigned long long* host_out);
 int64_t persist_ctl_bytes(int64_t n_searches);
 bool persist_supported(const hmz_search_t* s, int mode, int n_simulations);
 int persist_launch(const hmz_search_t* s, const void* weights, int n_simulations, const double* ucb_table, double discount,
@@ -280,6 +281,11 @@ int hmz_debug_div_check(uint64_t n_samples, uint64_t seed, unsigned long long* c
   return check_launch("div_check");
 }
 
+int hmz_debug_persist_stats(unsigned long long* host_out) {
+  if (!host_out) return fail(HMZ_ERR_INVALID, "hmz_debug_persist_stats: null pointer");
+  return persist_read_stats(host_out);
+}
+
 int hmz_debug_tree_timeline(long long search, unsigned long long* host_out) {
   if (host_out && cudaMemcpyFromSymbol(host_out, g_tree_timeline, sizeof(unsigned long long) * 64) != cudaSuccess)
     return fail(HMZ_ERR_CUDA, "hmz_debug_tree_timeline: cudaMemcpyFromSymbol failed");
@@ -310,6 +316,12 @@ const char* hmz_build_flags(void) {
 #endif
 #ifdef HMZ_TC_MAXNREG
          " HMZ_TC_MAXNREG"
+#endif
+#ifdef HMZ_PERSIST_STATS
+         " HMZ_PERSIST_STATS"
+#endif
+#ifdef HMZ_VARIANT
+         " HMZ_VARIANT"
 #endif
       ;
 }

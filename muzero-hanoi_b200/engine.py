@@ -239,7 +239,6 @@ class BatchedMCTS:
         self.pi = torch.zeros(self.B, 6, dtype=torch.float64, device=dev)
         self.root_q = torch.zeros(self.B, dtype=torch.float64, device=dev)
         self.action = torch.zeros(self.B, dtype=torch.int32, device=dev)
-        self._pow_cache = {}
 
     # -- split phases (used by the injected parity path and by tests) ---------------------------
     def begin(self, root_prior, prior_is_f64):
@@ -274,20 +273,13 @@ class BatchedMCTS:
         return self.action, self.pi, self.root_q, self.visits
 
     def _pow_table(self, temperature, n):
-        """visits ** clamp(1/T, 1, 5) for every possible count and every position of the 6-element visit array, evaluated
-        by THIS process's NumPy exactly as generate_play_policy does (MCTS/mcts.py:168-174: np.power on an int64 array of
-        six counts — NumPy's pow differs between its SIMD body and its scalar tail, hence per position); None when the
-        device's exact integer powers are identical (exponents 1..5 with every power below 2^53)."""
-        if temperature <= 0.0:
-            return None
-        ex = max(1.0, min(5.0, 1.0 / temperature))
-        if ex == int(ex) and float(n) ** ex < 2.0 ** 53:
-            return None
-        key = (ex, n)
-        if self._pow_cache.get("key") != key:
-            table = np.stack([np.power(np.full(6, k, dtype=np.int64), ex) for k in range(n + 1)])  # [n + 1, 6]
-            self._pow_cache = dict(key=key, table=torch.from_numpy(np.ascontiguousarray(table)).to(self.device))
-        return self._pow_cache["table"]
+        """Optional caller-supplied powers for generate_play_policy (hmz_search_root_policy's pow_table): None by default.
+        Integer exponents (every temperature of the reference's schedule: 1, 2, 5) are exact on the device and identical to
+        NumPy while the power stays below 2^53.  For non-integer exponents NumPy's own np.power is not reproducible to the
+        last bit — its SIMD body and scalar head / tail round differently, so the result of the reference's 6-element call
+        depends on the array's memory alignment — and the device's pow() (<= 2 ulp) is as close to it as NumPy is to itself;
+        ``self.pow_table`` (float64 [n + 1, 6] device tensor) lets a caller pin the powers explicitly."""
+        return getattr(self, "pow_table", None)
 
     def run_injected(self, root_prior, prior_is_f64, r, p, v, want_paths=False):
         """Search with the network outputs of every simulation supplied (parity mode of

@@ -35,32 +35,40 @@ class BatchedMuzero:
         self.episodes_done = 0
         self._selfplay = None
         self._temperature = None
+        self._weights_dirty = False
 
     def _latent_dtype(self):
         return _lib.LATENT_BF16 if self.acting_mode == _lib.MODE_BF16 else _lib.LATENT_F32
 
     def _refresh_actor(self, temperature):
-        """New acting weights (and a new temperature) take effect; games in flight and their episode store carry on."""
-        w = PackedWeights({k: v for k, v in self.learner.state_dict().items()}, self.N, self.acting_mode, self.device)
+        """New acting weights (and a new temperature) take effect; games in flight and their episode store carry on.
+        The weights are repacked only after an update has changed them."""
         if self._selfplay is None:
+            w = PackedWeights({k: v for k, v in self.learner.state_dict().items()}, self.N, self.acting_mode, self.device)
             self._selfplay = SelfPlay(self.N, self.max_steps, self.B, self.S, w, self.discount, self.alpha, temperature=temperature,
                                       seed=self.seed, device=self.device, latent_dtype=self._latent_dtype(), episodes=True)
         else:
-            self._selfplay.weights, self._selfplay.temperature = w, float(temperature)
+            if self._weights_dirty:
+                self._selfplay.weights = PackedWeights({k: v for k, v in self.learner.state_dict().items()}, self.N, self.acting_mode,
+                                                       self.device)
+            self._selfplay.temperature = float(temperature)
+        self._weights_dirty = False
         self._temperature = temperature
 
     def play(self, n_moves):
         """n_moves moves of every game; finished episodes are post-processed and, if solved, stored.
         Returns (episodes finished, mean length of those episodes, transitions stored)."""
         sp, st = self._selfplay, self._selfplay.episodes
-        finished, length_sum, stored = 0, 0, 0
+        stored = 0
+        counts = torch.zeros(2, dtype=torch.int64, device=st.ep_len.device)  # episodes finished, sum of their lengths
         for _ in range(n_moves):
             sp.move()
             st.post_process(self.n_step, self.discount)
-            stored += self.buffer.add_episodes(st, temperature=self._temperature, only_solved=True)  # syncs: one scalar
+            stored += self.buffer.add_episodes(st, temperature=self._temperature, only_solved=True)  # the one sync per move
             lens = st.ep_len
-            finished += int((lens > 0).sum().item())
-            length_sum += int(lens.sum().item())
+            counts[0] += (lens > 0).sum()
+            counts[1] += lens.sum()
+        finished, length_sum = (int(x) for x in counts.tolist())  # read back once per call
         self.episodes_done += finished
         return finished, (length_sum / finished if finished else float("nan")), stored
 
@@ -72,6 +80,7 @@ class BatchedMuzero:
             states, rwds, actions, pi_probs, returns = self.buffer.uniform_sample(self.batch_s)
             indx, w = None, None
         new_p, v_loss, r_loss, p_loss = self.learner.update(states, rwds, actions, pi_probs, returns, w)
+        self._weights_dirty = True
         self.buffer.update_priorities(indx, new_p)
         return v_loss, r_loss, p_loss
 

