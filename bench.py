@@ -796,9 +796,12 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[1] / configs[4] / fp32-mode sub-records")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the secondary fixed-games-per-GPU record")
     ap.add_argument("--extras", action="store_true", help="also time the SURVEY §8f rows (episode kernels, replay ring, acting harness)")
+    ap.add_argument("--moves-per-step", type=int, default=MOVES_PER_STEP, help="moves of every game per timed step (profiling runs use 1)")
     ap.add_argument("--schedule", default=os.environ.get("HMZ_BENCH_SCHEDULE", "auto"),
                     help="hmz_search_t.schedule: auto | persistent | k (stream groups, 1..16)")
     args = ap.parse_args()
+    global MOVES_PER_STEP
+    MOVES_PER_STEP = max(1, args.moves_per_step)
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)

@@ -153,7 +153,10 @@ def load():
                 f"{LIB_PATH} is missing: build it with `python muzero-hanoi_b200/build.py` "
                 "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
         lib = C.CDLL(LIB_PATH)
+        lenient = bool(os.environ.get("HMZ_LIB_PATH")) and os.environ.get("HMZ_LIB_LENIENT") == "1"  # tooling: older builds
         for name, (restype, argtypes) in SIGNATURES.items():
+            if lenient and not hasattr(lib, name):
+                continue
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = restype, argtypes
         _lib = lib

@@ -64,22 +64,20 @@ struct WaitGuard {
     }
   }
 };
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
+// (Intra-CTA waits stay an unguarded try_wait loop: a guard costs registers in every wait of the hot kernel; the waits
+// that depend on OTHER CTAs — the hand-offs of the persistent kernel, which everything else waits behind — are guarded.)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
       : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  WaitGuard guard;
-  while (!mbar_try_wait(bar, parity)) guard.poll();
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -359,6 +357,13 @@ constexpr bool kPersistStats = true;
 #else
 constexpr bool kPersistStats = false;
 #endif
+// Back-off between two polls of a hand-off word (ns; 0 = poll back to back).  Tuning switch.
+#ifndef HMZ_PERSIST_SLEEP_NS
+#define HMZ_PERSIST_SLEEP_NS 64
+#endif
+__device__ __forceinline__ void persist_backoff() {
+  if (HMZ_PERSIST_SLEEP_NS > 0) __nanosleep(HMZ_PERSIST_SLEEP_NS);
+}
 constexpr int kSlicesPerPair = 16;       // warps (16 searches each) per 256-search tile pair
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
@@ -400,7 +405,7 @@ __device__ __forceinline__ void persist_wait_tree(const PersistCtl& pc, int pair
   const uint32_t* ctr = pc.tree_done + (size_t)pair * 8;
   WaitGuard guard;
   while (ld_relaxed_u32(ctr) < need) {
-    __nanosleep(64);
+    persist_backoff();
     guard.poll();
   }
   fence_acquire_gpu();

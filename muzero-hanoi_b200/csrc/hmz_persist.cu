@@ -85,7 +85,7 @@ __device__ __forceinline__ void tree_role(const PersistArgs& a, uint8_t* smem_ra
       unsigned long long q;
       tc::WaitGuard guard;
       while ((uint32_t)((q = tc::v4::ld_relaxed_u64(slot)) >> 32) != item + 1u) {
-        __nanosleep(100);
+        tc::v4::persist_backoff();
         guard.poll();
       }
       pair = (int)(q & 0xFFFFu);
@@ -203,7 +203,10 @@ int persist_launch(const hmz_search_t* s, const void* weights, int n_simulations
   a.n_pairs = (int)((B + 2 * tc::kM - 1) / (2 * tc::kM));
   a.n_sims = n_simulations;
   a.n_mlp = choose_n_mlp(a.n_pairs, sms);
-  const int tree_want = (a.n_pairs * tc::v4::kSlicesPerPair + kPersistWarps - 1) / kPersistWarps;
+  // every remaining SM plays the tree role, but never more CTAs than there are slices per simulation: with few searches
+  // the slices spread one or two per SM (a warp alone on its scheduler runs its dependent chain fastest); warps that
+  // find no ticket left exit at once
+  const int tree_want = a.n_pairs * tc::v4::kSlicesPerPair;
   int n_tree = sms - a.n_mlp;
   if (n_tree > tree_want) n_tree = tree_want;
   if (n_tree < 1) return fail(HMZ_ERR_UNSUPPORTED, "persistent search needs at least 2 SMs");

@@ -45,6 +45,17 @@ for stage in "$@"; do
       done
       cat gpurun_out/persist_sweep.txt
       ;;
+    variant)
+      # VARIANT=name: the network and search tests plus the probe against variants/libhmz_<name>.so
+      export HMZ_LIB_PATH=muzero-hanoi_b200/variants/libhmz_${VARIANT}.so
+      timeout 900 python -m pytest tests/test_net_gpu.py tests/test_mcts_gpu.py tests/test_rng_gpu.py -m gpu -q --maxfail=10 -p no:cacheprovider > gpurun_out/pytest_${VARIANT}.log 2>&1
+      echo "variant $VARIANT pytest rc=$?"; tail -n 12 gpurun_out/pytest_${VARIANT}.log | cut -c1-240
+      cp gpurun_out/test_metrics.jsonl gpurun_out/test_metrics_${VARIANT}.jsonl 2>/dev/null
+      SCHEDULES=64,0,1 MOVES=8 timeout 120 python tools/persist_probe.py > gpurun_out/probe_${VARIANT}.txt 2>&1
+      B=8192 SCHEDULES=64,0,1 MOVES=8 timeout 120 python tools/persist_probe.py >> gpurun_out/probe_${VARIANT}.txt 2>&1
+      cat gpurun_out/probe_${VARIANT}.txt
+      unset HMZ_LIB_PATH
+      ;;
     reference)
       timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.log
       echo "reference rc=$?"; head -c 400 gpurun_out/bench_reference.json
@@ -62,14 +73,28 @@ for stage in "$@"; do
       echo "memcheck rc=$?"; tail -n 15 gpurun_out/memcheck_smoke.log
       ;;
     ncu)
-      CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-env --no-configs ${BENCH_ARGS}"
+      # launch list of a whole (short) bench run, then --set full of the two hot kernels, the persistent kernel and the env kernels
+      CMD="python bench.py --steps 1 --warmup 3 --moves-per-step 1 --no-cpu-baseline --no-env --no-configs"
       $CMD > gpurun_out/plain.json 2> gpurun_out/plain.log || { echo "plain run failed"; tail gpurun_out/plain.log; continue; }
-      ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
       echo "ncu list rc=$?"
-      ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNEL:-search_persistent|search_backup_select}" -s ${NCU_SKIP:-40} -c 2 -o gpurun_out/prof_search -f $CMD > gpurun_out/ncu_search.log 2>&1
-      echo "ncu search rc=$?"
-      ncu --set full --clock-control none --import-source on -k regex:env_step -c 4 -o gpurun_out/prof_env -f python tools/env_probe.py > gpurun_out/ncu_env.log 2>&1
+      ncu --set full --clock-control none --import-source on -k regex:search_backup_select -s 60 -c 2 -o gpurun_out/prof_tree -f $CMD > gpurun_out/ncu_tree.log 2>&1
+      echo "ncu tree rc=$?"
+      ncu --set full --clock-control none --import-source on -k regex:net_tc -s 61 -c 2 -o gpurun_out/prof_net -f $CMD > gpurun_out/ncu_net.log 2>&1
+      echo "ncu net rc=$?"
+      $CMD --schedule persistent > gpurun_out/plain_persist.json 2> gpurun_out/plain_persist.log &&
+      ncu --set full --clock-control none --import-source on -k regex:search_persistent -s 2 -c 1 -o gpurun_out/prof_persist -f $CMD --schedule persistent > gpurun_out/ncu_persist.log 2>&1
+      echo "ncu persistent rc=$?"
+      python tools/env_probe.py > gpurun_out/env_probe.txt 2>&1 &&
+      ncu --set full --clock-control none --import-source on -k regex:env_step -s 6 -c 4 -o gpurun_out/prof_env -f python tools/env_probe.py > gpurun_out/ncu_env.log 2>&1
       echo "ncu env rc=$?"
+      ;;
+    groupsweep)
+      : > gpurun_out/group_sweep.txt
+      for b in 8192 16384 32768 65536; do
+        B=$b SCHEDULES=1,2,3,4,6,8 MOVES=8 timeout 200 python tools/persist_probe.py >> gpurun_out/group_sweep.txt 2>&1
+      done
+      cat gpurun_out/group_sweep.txt
       ;;
     *) echo "unknown stage $stage" ;;
   esac
