@@ -782,6 +782,7 @@ def measure_extras(dev, weights, peaks, timed):
 
 
 def main():
+    global MOVES_PER_STEP
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -800,7 +801,6 @@ def main():
     ap.add_argument("--schedule", default=os.environ.get("HMZ_BENCH_SCHEDULE", "auto"),
                     help="hmz_search_t.schedule: auto | persistent | k (stream groups, 1..16)")
     args = ap.parse_args()
-    global MOVES_PER_STEP
     MOVES_PER_STEP = max(1, args.moves_per_step)
     claim_stdout()
     if args.impl == "reference":

@@ -345,6 +345,7 @@ typedef struct hmz_selfplay {
   double* ep_root_q;
   int32_t* ep_cur_slot;
   int32_t* ep_len;
+  uint8_t* ep_exp;          /* nullable: receives the move's integer play-policy exponent (see hmz_episode_unroll) */
   const double* pow_table;  /* as hmz_search_root_policy (nullable) */
   double discount, dirichlet_alpha, exploration_eps, temperature;
   uint64_t seed;
@@ -391,13 +392,16 @@ int hmz_episode_rows(const int32_t* ep_len, const double* returns, int64_t n_gam
  * i64[unroll], pi f32[unroll][6], returns f32[unroll], priority f32.  Step t of game g lands in row
  * (row_base[g] + t) % capacity; beyond the episode end the padding is reward 0, return 0, the uniform
  * policy and absorbing_action[g] (the reference draws ONE np.random.randint per episode, :300-303).
+ * ep_exp (nullable, uint8 [t_max][n_games]): the play-policy exponent clamp(1/T, 1, 5) that was in force when each move was
+ * PLAYED (written by hmz_selfplay_move) — the reference stores the pi_prob run_mcts returned at move time (Muzero.py:179-183),
+ * so an episode that spans a change of the temperature schedule keeps each move's own exponent; NULL: `temperature` for all.
  * Rows with row_base[g] + t < first_row are skipped: when one call adds more rows than the ring holds, the
  * reference's one-episode-at-a-time Buffer.add leaves only the LAST `capacity` rows, so the caller passes
  * first_row = ptr + max(0, total - capacity) (0 otherwise). */
 int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const uint8_t* ep_flags, const uint16_t* ep_visits,
                        const double* returns, const float* priority, const int32_t* ep_len, const int64_t* row_base,
-                       const uint8_t* absorbing_action, int64_t n_games, int t_max, int n_disks, int unroll, double temperature,
-                       int64_t capacity, int64_t first_row, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
+                       const uint8_t* absorbing_action, const uint8_t* ep_exp, int64_t n_games, int t_max, int n_disks, int unroll,
+                       double temperature, int64_t capacity, int64_t first_row, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
                        float* buf_returns, float* buf_priority, void* stream);
 
 /* ------------------------------------------------------------------ acting evaluation ------

@@ -73,7 +73,7 @@ class SelfPlayDesc(C.Structure):
 
     _fields_ = [("search", SearchDesc)] + [(name, C.c_void_p) for name in (
         "weights", "ucb_table", "words", "p0", "v0", "noise", "uniform", "visits", "root_q", "action", "records", "ep_state",
-        "ep_action", "ep_flags", "ep_visits", "ep_root_q", "ep_cur_slot", "ep_len", "pow_table")] + [
+        "ep_action", "ep_flags", "ep_visits", "ep_root_q", "ep_cur_slot", "ep_len", "ep_exp", "pow_table")] + [
         ("discount", C.c_double), ("dirichlet_alpha", C.c_double), ("exploration_eps", C.c_double), ("temperature", C.c_double),
         ("seed", C.c_uint64), ("game_offset", C.c_uint64), ("mode", C.c_int32), ("n_disks", C.c_int32), ("max_steps", C.c_int32),
         ("goal_peg", C.c_int32), ("n_simulations", C.c_int32), ("ep_t_max", C.c_int32), ("reset_word", C.c_uint32),
@@ -133,7 +133,7 @@ SIGNATURES = {
     "hmz_episode_returns": (_I, [_P, _P, _P, _L, _I, _P, _I, _P, _P, _P]),
     "hmz_episode_mc_returns": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "hmz_episode_rows": (_I, [_P, _P, _L, _L, _I, _P, _P, _P]),
-    "hmz_episode_unroll": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _D, _L, _L, _P, _P, _P, _P, _P, _P, _P]),
+    "hmz_episode_unroll": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _D, _L, _L, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lock = threading.Lock()

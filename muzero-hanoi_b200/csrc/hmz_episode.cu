@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) episode_unroll(
     const uint32_t* __restrict__ ep_state, const uint8_t* __restrict__ ep_action, const uint8_t* __restrict__ ep_flags,
     const uint16_t* __restrict__ ep_visits, const double* __restrict__ returns, const float* __restrict__ priority,
     const int32_t* __restrict__ ep_len, const int64_t* __restrict__ row_base, const uint8_t* __restrict__ absorbing_action,
-    int64_t n, int t_max, int n_disks, int unroll, int exponent, int64_t capacity, int64_t first_row, float* __restrict__ buf_states,
+    const uint8_t* __restrict__ ep_exp, int64_t n, int t_max, int n_disks, int unroll, int exponent, int64_t capacity, int64_t first_row, float* __restrict__ buf_states,
     float* __restrict__ buf_rwds, int64_t* __restrict__ buf_actions, float* __restrict__ buf_pi, float* __restrict__ buf_returns,
     float* __restrict__ buf_priority) {
   const int64_t total = (int64_t)t_max * n;
@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(256) episode_unroll(
         for (int a = 0; a < 6; ++a) {
           const double x = (double)ep_visits[at * 6 + a];
           double y = x;
-          for (int e = 1; e < exponent; ++e) y = __dmul_rn(y, x);
+          const int ex_at = ep_exp ? (int)ep_exp[at] : exponent;  // the exponent in force when the move was played
+          for (int e = 1; e < ex_at; ++e) y = __dmul_rn(y, x);
           wv[a] = y;
         }
         double rest = 0.0;  // np.sum of 6 doubles: first element + (0 + the rest, left to right)
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(128) episode_unroll_warp(
     const uint32_t* __restrict__ ep_state, const uint8_t* __restrict__ ep_action, const uint8_t* __restrict__ ep_flags,
     const uint16_t* __restrict__ ep_visits, const double* __restrict__ returns, const float* __restrict__ priority,
     const int32_t* __restrict__ ep_len, const int64_t* __restrict__ row_base, const uint8_t* __restrict__ absorbing_action,
-    int64_t n, int t_max, int n_disks, int unroll, int exponent, int64_t capacity, int64_t first_row, float* __restrict__ buf_states,
+    const uint8_t* __restrict__ ep_exp, int64_t n, int t_max, int n_disks, int unroll, int exponent, int64_t capacity, int64_t first_row, float* __restrict__ buf_states,
     float* __restrict__ buf_rwds, int64_t* __restrict__ buf_actions, float* __restrict__ buf_pi, float* __restrict__ buf_returns,
     float* __restrict__ buf_priority) {
   extern __shared__ StepStage stage_all[];
@@ -262,7 +263,8 @@ __global__ void __launch_bounds__(128) episode_unroll_warp(
       for (int a = 0; a < 6; ++a) {
         const double x = (double)ep_visits[at * 6 + a];
         double y = x;
-        for (int e = 1; e < exponent; ++e) y = __dmul_rn(y, x);
+        const int ex_at = ep_exp ? (int)ep_exp[at] : exponent;  // the exponent in force when the move was played
+        for (int e = 1; e < ex_at; ++e) y = __dmul_rn(y, x);
         wv[a] = y;
       }
       double rest = 0.0;  // np.sum of 6 doubles: first element + (0 + the rest, left to right)
@@ -364,8 +366,8 @@ int hmz_episode_rows(const int32_t* ep_len, const double* returns, int64_t n_gam
 
 int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const uint8_t* ep_flags, const uint16_t* ep_visits,
                        const double* returns, const float* priority, const int32_t* ep_len, const int64_t* row_base,
-                       const uint8_t* absorbing_action, int64_t n_games, int t_max, int n_disks, int unroll, double temperature,
-                       int64_t capacity, int64_t first_row, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
+                       const uint8_t* absorbing_action, const uint8_t* ep_exp, int64_t n_games, int t_max, int n_disks, int unroll,
+                       double temperature, int64_t capacity, int64_t first_row, float* buf_states, float* buf_rwds, int64_t* buf_actions, float* buf_pi,
                        float* buf_returns, float* buf_priority, void* stream) {
   ProfScope prof_scope(HMZ_PROF_OTHER, stream);
   if (n_games == 0) return HMZ_OK;
@@ -385,12 +387,12 @@ int hmz_episode_unroll(const uint32_t* ep_state, const uint8_t* ep_action, const
   const size_t stage_bytes = (size_t)t_max * sizeof(StepStage);
   if (stage_bytes * 4 <= 48 * 1024 && !getenv("HMZ_UNROLL_SCALAR")) {  // warp-per-game form: staging fits the default shared memory
     episode_unroll_warp<<<grid_for(n_games, 4, 8), 128, stage_bytes * 4, (cudaStream_t)stream>>>(
-        ep_state, ep_action, ep_flags, ep_visits, returns, priority, ep_len, row_base, absorbing_action, n_games, t_max, n_disks,
+        ep_state, ep_action, ep_flags, ep_visits, returns, priority, ep_len, row_base, absorbing_action, ep_exp, n_games, t_max, n_disks,
         unroll, iex, capacity, first_row, buf_states, buf_rwds, buf_actions, buf_pi, buf_returns, buf_priority);
     return check_launch("episode_unroll_warp");
   }
   episode_unroll<<<grid_for(n_games * t_max, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      ep_state, ep_action, ep_flags, ep_visits, returns, priority, ep_len, row_base, absorbing_action, n_games, t_max, n_disks, unroll,
+      ep_state, ep_action, ep_flags, ep_visits, returns, priority, ep_len, row_base, absorbing_action, ep_exp, n_games, t_max, n_disks, unroll,
       iex, capacity, first_row, buf_states, buf_rwds, buf_actions, buf_pi, buf_returns, buf_priority);
   return check_launch("episode_unroll");
 }

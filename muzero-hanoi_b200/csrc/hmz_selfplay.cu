@@ -159,9 +159,10 @@ struct FinishArgs {
   double* ep_root_q;
   int32_t* ep_cur_slot;
   int32_t* ep_len;
+  uint8_t* ep_exp;
   double temperature;
   uint64_t game_offset;
-  int n_sims, n_disks, ep_t_max;
+  int n_sims, n_disks, ep_t_max, exponent;
 };
 
 // End of a move for every game, one thread each: MCTS/mcts.py:112-126 (root_policy_eval), the move's record, the env step.
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(256) selfplay_finish(FinishArgs a) {
       a.ep_cur_slot[b] = t;
       a.ep_flags[at] = (uint8_t)o.flags;
       a.ep_len[b] = (o.flags & HMZ_FLAG_DONE) ? t + 1 : 0;
+      if (a.ep_exp) a.ep_exp[at] = (uint8_t)a.exponent;
     }
   }
 }
@@ -283,6 +285,14 @@ int hmz_selfplay_move(const hmz_selfplay_t* sp, uint64_t move_index, void* strea
   fa.ep_root_q = sp->ep_root_q;
   fa.ep_cur_slot = sp->ep_cur_slot;
   fa.ep_len = sp->ep_len;
+  fa.ep_exp = sp->ep_exp;
+  {  // clamp(1/T, 1, 5), MCTS/mcts.py:170-172 (1 for T == 0: raw counts); the episode store keeps integer exponents only
+    double ex = 1.0;
+    if (sp->temperature > 0.0) ex = 1.0 / sp->temperature < 1.0 ? 1.0 : (1.0 / sp->temperature > 5.0 ? 5.0 : 1.0 / sp->temperature);
+    fa.exponent = (int)ex;
+    if (sp->ep_exp && (double)fa.exponent != ex)
+      return fail(HMZ_ERR_UNSUPPORTED, "hmz_selfplay_move: the episode store keeps integer play-policy exponents; temperature %g gives %g", sp->temperature, ex);
+  }
   fa.temperature = sp->temperature;
   fa.game_offset = sp->game_offset;
   fa.n_sims = sp->n_simulations;

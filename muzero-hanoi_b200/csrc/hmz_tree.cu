@@ -530,7 +530,9 @@ static int search_run_direct(const hmz_search_t* s, const void* weights, int mod
   // tensor-core kernel of another leaves idle.  Group boundaries are multiples of 128 searches.
   int groups = s->schedule;
   if (groups < 0 || groups > 16) return fail(HMZ_ERR_INVALID, "hmz_search_run: schedule %d is neither a group count in [0, 16] nor HMZ_SCHEDULE_PERSISTENT", groups);
-  if (groups == 0) groups = B >= 32768 ? 4 : (B >= 8192 ? 2 : 1);
+  // measured on the B200 (tools/gpu_round.sh groupsweep, S = 100): 8,192 searches 2.08 / 2.12 / 2.17 ms per move with 1 / 2 / 4
+  // groups, 16,384: 2.26 / 2.25 / 2.29, 32,768: 2.53 / 2.52 / 2.58, 65,536: 4.70 / 4.15 / 4.10 (3 groups 4.07, 6: 4.12, 8: 4.17)
+  if (groups == 0) groups = B >= 49152 ? 4 : (B >= 12288 ? 2 : 1);
   const int64_t per = ((B + groups - 1) / groups + 127) / 128 * 128;
   groups = (int)((B + per - 1) / per);
   if (groups <= 1) {

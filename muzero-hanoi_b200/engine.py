@@ -422,6 +422,7 @@ class SelfPlay:
             from .replay import EpisodeStore
 
             self.episodes = EpisodeStore(B, max_steps, N, device)
+            self.episodes.exp = torch.ones(max_steps, B, dtype=torch.uint8, device=dev)
         self.env.reset()
 
     def move(self):
@@ -440,7 +441,7 @@ class SelfPlay:
             ep_state=ep.state.data_ptr() if ep else None, ep_action=ep.action.data_ptr() if ep else None,
             ep_flags=ep.flags.data_ptr() if ep else None, ep_visits=ep.visits.data_ptr() if ep else None,
             ep_root_q=ep.root_q.data_ptr() if ep else None, ep_cur_slot=ep.cur_slot.data_ptr() if ep else None,
-            ep_len=ep.ep_len.data_ptr() if ep else None, pow_table=pw.data_ptr() if pw is not None else None,
+            ep_len=ep.ep_len.data_ptr() if ep else None, ep_exp=ep.exp.data_ptr() if ep else None, pow_table=pw.data_ptr() if pw is not None else None,
             discount=m.discount, dirichlet_alpha=float(m.root_dirichlet_alpha),
             exploration_eps=float(m.root_exploration_eps), temperature=self.temperature, seed=self.seed,
             game_offset=self.game_offset, mode=self.weights.mode,

@@ -37,6 +37,8 @@ class EpisodeStore:
         self.root_q = torch.zeros(T, B, dtype=torch.float64, device=dev)
         self.cur_slot = torch.zeros(B, dtype=torch.int32, device=dev)
         self.ep_len = torch.zeros(B, dtype=torch.int32, device=dev)
+        # play-policy exponent in force when each move was played (SelfPlay fills it); None = use add_episodes' temperature
+        self.exp = None
         self.returns = torch.zeros(T, B, dtype=torch.float64, device=dev)
         self.priority = torch.zeros(T, B, dtype=torch.float32, device=dev)
         self.row_base = torch.full((B,), -1, dtype=torch.int64, device=dev)
@@ -129,7 +131,7 @@ class ReplayRing:
         if n:
             check(self.lib.hmz_episode_unroll(ptr(store.state), ptr(store.action), ptr(store.flags), ptr(store.visits),
                                               ptr(store.returns), ptr(store.priority), ptr(store.ep_len), ptr(store.row_base),
-                                              ptr(ab), store.B, store.t_max, store.n_disks, self.unroll_n_steps,
+                                              ptr(ab), ptr(store.exp), store.B, store.t_max, store.n_disks, self.unroll_n_steps,
                                               float(temperature), self.size, first_row, ptr(self.states), ptr(self.rwds), ptr(self.actions),
                                               ptr(self.pi_probs), ptr(self.mc_returns), ptr(self.priorities), s))
             self._advance(n)
