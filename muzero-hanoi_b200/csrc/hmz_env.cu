@@ -176,9 +176,9 @@ __global__ void __launch_bounds__(256) env_random_reset(uint32_t* __restrict__ w
 __global__ void __launch_bounds__(256) env_legal_mask(const uint32_t* __restrict__ words, uint8_t* __restrict__ mask,
                                                      int64_t n, uint32_t even_mask, uint32_t state_mask) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t t0, t1, t2;
-    peg_tops(words[i] & state_mask, even_mask, t0, t1, t2);
-    mask[i] = (uint8_t)legal_bits(t0, t1, t2);
+    uint32_t k0, k1, k2;
+    peg_keys(words[i] & state_mask, even_mask, k0, k1, k2);
+    mask[i] = (uint8_t)legal_bits(k0, k1, k2);
   }
 }
 

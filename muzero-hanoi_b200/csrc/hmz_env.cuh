@@ -16,20 +16,26 @@ struct EnvCfg {
   int auto_reset;
 };
 
-// Bit index (2*disk) of the top (smallest) disk on each peg, 0xFFFFFFFF if the peg is empty.
-__device__ __forceinline__ void peg_tops(uint32_t st, uint32_t even_mask, uint32_t& t0, uint32_t& t1, uint32_t& t2) {
-  uint32_t lo = st & even_mask, hi = (st >> 1) & even_mask;
-  t0 = (uint32_t)(__ffs((int)(even_mask & ~(lo | hi))) - 1);
-  t1 = (uint32_t)(__ffs((int)(lo & ~hi)) - 1);
-  t2 = (uint32_t)(__ffs((int)(hi & ~lo)) - 1);
+// The kernels are issue-bound, not memory-bound (ncu, round 2: 70 % issue-active at 0.65 of the HBM roofline with the
+// first, branchy form: ~85 SASS instructions per env, 13 divergent regions), so everything below is straight-line
+// select / logic code with no find-first-set and no data-dependent branch.
+//
+// "Key" of a peg: (lowest set bit of the mask of disks on the peg) - 1, i.e. 2^(2 * top disk) - 1, and 0xFFFFFFFF for an
+// empty peg: keys order the pegs exactly as their top disks do, with "empty" = +inf.
+__device__ __forceinline__ void peg_keys(uint32_t st, uint32_t even_mask, uint32_t& k0, uint32_t& k1, uint32_t& k2) {
+  const uint32_t lo = st & even_mask, hi = (st >> 1) & even_mask;
+  const uint32_t m0 = even_mask & ~(lo | hi), m1 = lo & ~hi, m2 = hi & ~lo;
+  k0 = (m0 & (0u - m0)) - 1u;
+  k1 = (m1 & (0u - m1)) - 1u;
+  k2 = (m2 & (0u - m2)) - 1u;
 }
 
 // bit a = move a allowed; actions 0:(0,1) 1:(0,2) 2:(1,0) 3:(1,2) 4:(2,0) 5:(2,1)  (env/hanoi.py:39-41).
 // A move f->t is allowed iff peg f is non-empty and (peg t is empty or its top disk is larger),
-// i.e. top(f) < top(t) with "empty" = +inf (env/hanoi.py:123-139).
-__device__ __forceinline__ uint32_t legal_bits(uint32_t t0, uint32_t t1, uint32_t t2) {
-  return (uint32_t)(t0 < t1) | ((uint32_t)(t0 < t2) << 1) | ((uint32_t)(t1 < t0) << 2) | ((uint32_t)(t1 < t2) << 3) |
-         ((uint32_t)(t2 < t0) << 4) | ((uint32_t)(t2 < t1) << 5);
+// i.e. key(f) < key(t) (env/hanoi.py:123-139).
+__device__ __forceinline__ uint32_t legal_bits(uint32_t k0, uint32_t k1, uint32_t k2) {
+  return (uint32_t)(k0 < k1) | ((uint32_t)(k0 < k2) << 1) | ((uint32_t)(k1 < k0) << 2) | ((uint32_t)(k1 < k2) << 3) |
+         ((uint32_t)(k2 < k0) << 4) | ((uint32_t)(k2 < k1) << 5);
 }
 
 struct StepOut {
@@ -39,48 +45,53 @@ struct StepOut {
   uint32_t flags;
 };
 
-// TowersOfHanoi.step with the peg tops of the state already known (the random-move kernels need them to pick the action).
-__device__ __forceinline__ StepOut step_word_tops(uint32_t word, uint32_t action, uint32_t t0, uint32_t t1, uint32_t t2,
-                                                  const EnvCfg& c) {
-  uint32_t st = word & c.state_mask;
-  uint32_t ctr = (word >> c.shift) + 1u;  // env/hanoi.py:56 — counted for illegal moves too
-  uint32_t a = action > 5u ? 5u : action;
-  uint32_t legal = (action <= 5u) ? ((legal_bits(t0, t1, t2) >> a) & 1u) : 0u;
-  uint32_t f = a >> 1;
-  uint32_t t = (0x489u >> (2u * a)) & 3u;
-  uint32_t tf = f == 0u ? t0 : (f == 1u ? t1 : t2);
+// The tail of TowersOfHanoi.step once the move's legality and the moved disk's bit are known (env/hanoi.py:56-80):
+//   legal, next != goal -> (next, 0, not done);  legal, next == goal -> (obs = goal, 100, done, STORED STATE UNCHANGED,
+//   counter 0);  illegal -> (same, -0.1, not done);  counter == max_steps -> done, counter 0 (can co-occur with illegal).
+__device__ __forceinline__ StepOut step_finish(uint32_t word, uint32_t st, bool legal, uint32_t moved, const EnvCfg& c) {
+  uint32_t ctr = (word >> c.shift) + 1u;  // :56 — counted for illegal moves too
+  const bool goal = legal & (moved == c.goal_word);
+  const uint32_t stored = (legal & !goal) ? moved : st;  // :65-69 — the goal state is returned but not stored
   StepOut o;
-  o.flags = 0u;
-  uint32_t stored = st;
-  o.obs_word = st;
-  o.reward = 0.0f;
-  if (legal) {
-    uint32_t moved = st ^ ((f ^ t) << tf);  // env/hanoi.py:141-151: one digit changes
-    o.obs_word = moved;
-    if (moved == c.goal_word) {  // :65-69 — stored state is NOT updated, counter cleared
-      o.reward = 100.0f;
-      o.flags = HMZ_FLAG_DONE | HMZ_FLAG_GOAL;
-      ctr = 0u;
-    } else {
-      stored = moved;
-    }
-  } else {
-    o.reward = -0.1f;  // float32 image of the python double -100/1000 (:72)
-    o.flags = HMZ_FLAG_ILLEGAL;
-  }
-  if (ctr == c.max_steps) {  // :77-80
-    o.flags |= HMZ_FLAG_DONE | HMZ_FLAG_TRUNC;
-    ctr = 0u;
-  }
-  o.word = stored | (ctr << c.shift);
-  if (c.auto_reset && (o.flags & HMZ_FLAG_DONE)) o.word = c.reset_word;
+  o.obs_word = legal ? moved : st;
+  o.reward = goal ? 100.0f : (legal ? 0.0f : -0.1f);  // -0.1f: float32 image of the python double -100/1000 (:72)
+  uint32_t flags = (goal ? (HMZ_FLAG_DONE | HMZ_FLAG_GOAL) : 0u) | (legal ? 0u : HMZ_FLAG_ILLEGAL);
+  ctr = goal ? 0u : ctr;
+  const bool trunc = ctr == c.max_steps;  // :77-80
+  flags |= trunc ? (HMZ_FLAG_DONE | HMZ_FLAG_TRUNC) : 0u;
+  ctr = trunc ? 0u : ctr;
+  uint32_t w = stored | (ctr << c.shift);
+  if (c.auto_reset) w = (flags & HMZ_FLAG_DONE) ? c.reset_word : w;
+  o.word = w;
+  o.flags = flags;
   return o;
 }
 
+// TowersOfHanoi.step for a GIVEN action: only the source and the target peg matter.  XOR-ing the state with the peg
+// number replicated over all disks turns "disk on that peg" into a zero digit, so one mask expression serves any peg.
 __device__ __forceinline__ StepOut step_word(uint32_t word, uint32_t action, const EnvCfg& c) {
-  uint32_t t0, t1, t2;
-  peg_tops(word & c.state_mask, c.even_mask, t0, t1, t2);
-  return step_word_tops(word, action, t0, t1, t2, c);
+  const uint32_t st = word & c.state_mask;
+  const uint32_t a = action > 5u ? 5u : action;
+  const uint32_t f = a >> 1, t = (0x489u >> (2u * a)) & 3u;  // moves[a] = (f, t) (env/hanoi.py:39-41)
+  const uint32_t xf = st ^ (f * c.even_mask), xt = st ^ (t * c.even_mask);
+  const uint32_t mf = ~(xf | (xf >> 1)) & c.even_mask, mt = ~(xt | (xt >> 1)) & c.even_mask;
+  const uint32_t lf = mf & (0u - mf);  // bit of the top disk of the source peg (0: the peg is empty)
+  // _move_allowed (:123-139): source non-empty and no disk of the target peg below its top disk
+  const bool legal = (action <= 5u) & (lf != 0u) & ((mt & (lf - 1u)) == 0u);
+  const uint32_t moved = st ^ ((f ^ t) * lf);  // _get_moved_state (:141-151): one digit changes from f to t
+  return step_finish(word, st, legal, moved, c);
+}
+
+// The same with the pegs' keys already known (the random-move kernels need all three to pick the action).
+__device__ __forceinline__ StepOut step_word_keys(uint32_t word, uint32_t action, uint32_t k0, uint32_t k1, uint32_t k2,
+                                                  const EnvCfg& c) {
+  const uint32_t st = word & c.state_mask;
+  const uint32_t a = action > 5u ? 5u : action;
+  const uint32_t f = a >> 1, t = (0x489u >> (2u * a)) & 3u;
+  const uint32_t kf = f == 0u ? k0 : (f == 1u ? k1 : k2);
+  const bool legal = (action <= 5u) & (((legal_bits(k0, k1, k2) >> a) & 1u) != 0u);
+  const uint32_t moved = st ^ ((f ^ t) * (kf + 1u));
+  return step_finish(word, st, legal, moved, c);
 }
 
 // k-th (0-based) set bit of a mask with 2 or 3 bits set.
@@ -91,20 +102,16 @@ __device__ __forceinline__ uint32_t kth_set_bit(uint32_t m, uint32_t k) {
   return (uint32_t)(__ffs((int)sel) - 1);
 }
 
-__device__ __forceinline__ uint32_t random_legal_action(uint32_t st, uint32_t rnd, const EnvCfg& c) {
-  uint32_t t0, t1, t2;
-  peg_tops(st, c.even_mask, t0, t1, t2);
-  uint32_t m = legal_bits(t0, t1, t2);
-  return kth_set_bit(m, __umulhi(rnd, (uint32_t)__popc(m)));
-}
-
-// One step on a uniformly random LEGAL move (the peg tops are computed once for the choice and the step).
+// One step on a uniformly random LEGAL move (the pegs' keys are computed once for the choice and the step).
 __device__ __forceinline__ StepOut step_random_word(uint32_t word, uint32_t rnd, const EnvCfg& c, uint32_t& action) {
-  uint32_t t0, t1, t2;
-  peg_tops(word & c.state_mask, c.even_mask, t0, t1, t2);
-  const uint32_t m = legal_bits(t0, t1, t2);
+  uint32_t k0, k1, k2;
+  peg_keys(word & c.state_mask, c.even_mask, k0, k1, k2);
+  const uint32_t m = legal_bits(k0, k1, k2);
   action = kth_set_bit(m, __umulhi(rnd, (uint32_t)__popc(m)));
-  return step_word_tops(word, action, t0, t1, t2, c);
+  const uint32_t st = word & c.state_mask;
+  const uint32_t f = action >> 1, t = (0x489u >> (2u * action)) & 3u;
+  const uint32_t kf = f == 0u ? k0 : (f == 1u ? k1 : k2);
+  return step_finish(word, st, true, st ^ ((f ^ t) * (kf + 1u)), c);  // the chosen move is legal by construction
 }
 
 // Host: fills an EnvCfg after validating the shape (HMZ_ERR_* with a message on failure).
