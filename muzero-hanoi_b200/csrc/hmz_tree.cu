@@ -320,6 +320,15 @@ const char* hmz_build_flags(void) {
 #ifdef HMZ_PERSIST_STATS
          " HMZ_PERSIST_STATS"
 #endif
+#ifdef HMZ_PERSIST_THREADS
+         " HMZ_PERSIST_THREADS"
+#endif
+#ifdef HMZ_PERSIST_SLEEP_NS
+         " HMZ_PERSIST_SLEEP_NS"
+#endif
+#ifdef HMZ_PERSIST_GLOBAL_TABLES
+         " HMZ_PERSIST_GLOBAL_TABLES"
+#endif
 #ifdef HMZ_VARIANT
          " HMZ_VARIANT"
 #endif

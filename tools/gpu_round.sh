@@ -74,7 +74,9 @@ for stage in "$@"; do
       ;;
     ncu)
       # launch list of a whole (short) bench run, then --set full of the two hot kernels, the persistent kernel and the env kernels
-      CMD="python bench.py --steps 1 --warmup 3 --moves-per-step 1 --no-cpu-baseline --no-env --no-configs"
+      # --schedule 1: one launch pair per simulation for the whole batch (ncu serialises launches anyway), so that the
+      # per-launch counters refer to 65,536 searches like the serial per-kernel profile of bench.py
+      CMD="python bench.py --steps 1 --warmup 3 --moves-per-step 1 --no-cpu-baseline --no-env --no-configs --schedule 1"
       $CMD > gpurun_out/plain.json 2> gpurun_out/plain.log || { echo "plain run failed"; tail gpurun_out/plain.log; continue; }
       ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
       echo "ncu list rc=$?"
@@ -82,8 +84,9 @@ for stage in "$@"; do
       echo "ncu tree rc=$?"
       ncu --set full --clock-control none --import-source on -k regex:net_tc -s 61 -c 2 -o gpurun_out/prof_net -f $CMD > gpurun_out/ncu_net.log 2>&1
       echo "ncu net rc=$?"
-      $CMD --schedule persistent > gpurun_out/plain_persist.json 2> gpurun_out/plain_persist.log &&
-      ncu --set full --clock-control none --import-source on -k regex:search_persistent -s 2 -c 1 -o gpurun_out/prof_persist -f $CMD --schedule persistent > gpurun_out/ncu_persist.log 2>&1
+      PCMD="python bench.py --steps 1 --warmup 3 --moves-per-step 1 --no-cpu-baseline --no-env --no-configs --schedule persistent"
+      $PCMD > gpurun_out/plain_persist.json 2> gpurun_out/plain_persist.log &&
+      ncu --set full --clock-control none --import-source on -k regex:search_persistent -s 2 -c 1 -o gpurun_out/prof_persist -f $PCMD > gpurun_out/ncu_persist.log 2>&1
       echo "ncu persistent rc=$?"
       python tools/env_probe.py > gpurun_out/env_probe.txt 2>&1 &&
       ncu --set full --clock-control none --import-source on -k regex:env_step -s 6 -c 4 -o gpurun_out/prof_env -f python tools/env_probe.py > gpurun_out/ncu_env.log 2>&1
