@@ -12,8 +12,9 @@ config says: "sharded over 1/2/4/8 B200"); the fixed-games-per-GPU number is car
 A "step" is MOVES_PER_STEP = 16 consecutive moves of every game, a move being
 root inference -> 100 x (select -> g+f MLP -> expand+backup) -> root policy -> record -> env step,
 so the default 20 timed steps cover more than a second of device time.
-`value` = MCTS simulations / s over all GPUs with the state resident in HBM; `e2e` = the same steps with, every move,
-the env words coming from pinned host memory and the move's 32-byte records read back to the host.
+`value` = MCTS simulations / s over all GPUs with the state resident in HBM; `e2e` = the same steps with, every step,
+the env words coming from pinned host memory and the step's results (the 32-byte records of its 16 moves, the new env
+words) read back to pinned host memory before the next step starts.
 One JSON line on stdout (rank 0); progress goes to stderr.
 """
 from __future__ import annotations
@@ -552,27 +553,30 @@ def run_ours(args):
         other = "backup_select" if dominant == "net_recurrent" else "net_recurrent"
         roofline, roofline_other = roofline_of(dominant), roofline_of(other)
 
-    # ---- end to end: env words from pinned host memory in, the move's records back to the host, every move
+    # ---- end to end, through the public API (SelfPlay.move) with HOST buffers: every step the env words of all games come
+    #      from pinned host memory (H2D) and the step's results — the 32-byte records of its 16 moves and the new env
+    #      words — are read back to pinned host memory (D2H), then the host waits for them; the next step starts from the
+    #      words the host just received.
     h_words = torch.empty(B, dtype=torch.int32).pin_memory()
     h_words.copy_(sp.env.words.cpu())
-    h_rec = torch.empty(B, _lib.RECORD_BYTES, dtype=torch.uint8).pin_memory()
+    h_rec = torch.empty(MOVES_PER_STEP, B, _lib.RECORD_BYTES, dtype=torch.uint8).pin_memory()
     h_next = torch.empty(B, dtype=torch.int32).pin_memory()
 
     def e2e_step():
-        for _ in range(MOVES_PER_STEP):
-            sp.env.words.copy_(h_words, non_blocking=True)
+        sp.env.words.copy_(h_words, non_blocking=True)
+        for k in range(MOVES_PER_STEP):
             t = sp.move()
-            h_rec.copy_(sp.slot(t), non_blocking=True)
-            h_next.copy_(sp.env.words, non_blocking=True)
+            h_rec[k].copy_(sp.slot(t), non_blocking=True)
             if gather is not None:
                 gather.submit(sp.slot(t))
-            torch.cuda.current_stream().synchronize()
-            h_words.copy_(h_next)  # the host owns the env state between moves
+        h_next.copy_(sp.env.words, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h_words.copy_(h_next)  # the host owns the env state between steps
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     e2e_rate = world * B * S * moves / (ms_e2e * 1e-3)
-    h2d, d2h = 4 * B * MOVES_PER_STEP, (_lib.RECORD_BYTES + 4) * B * MOVES_PER_STEP
+    h2d, d2h = 4 * B, _lib.RECORD_BYTES * B * MOVES_PER_STEP + 4 * B
     log(f"[bench] e2e {ms_e2e / args.steps:.2f} ms/step -> {e2e_rate:.3e} sims/s")
 
     # ---- weak-scaling record (N > 1): the fixed-games-per-GPU number of round 1, a few steps

@@ -59,15 +59,19 @@ struct PhiloxStream {  // sequential 32-bit draws from one (key, item) Philox st
 };
 
 // np.random.dirichlet(alpha * ones(6)) (MCTS/mcts.py:148-149) for global item `item`: six gamma draws, normalised.
-__device__ __forceinline__ void dirichlet6(uint64_t seed, uint64_t item, uint64_t counter, double alpha, double (&g)[6]) {
-  PhiloxStream rng(seed ^ 0x4449524943484C45ull, item, counter);
+// Every action draws from its OWN Philox stream (the key carries the action), so the six draws can be made by six
+// lanes at once (selfplay_begin) or one after another (rng_dirichlet) with identical results.
+__device__ __forceinline__ double dirichlet_gamma(uint64_t seed, uint64_t item, uint64_t counter, double alpha, int a) {
+  PhiloxStream rng(seed ^ 0x4449524943484C45ull ^ ((uint64_t)(a + 1) << 56), item, counter);
+  return rng.gamma(alpha);
+}
+// the six gammas -> the Dirichlet draw (left-to-right sum, as both callers must round identically)
+__device__ __forceinline__ void dirichlet_normalise(uint64_t seed, uint64_t item, uint64_t counter, double (&g)[6]) {
   double sum = 0.0;
 #pragma unroll
-  for (int a = 0; a < 6; ++a) {
-    g[a] = rng.gamma(alpha);
-    sum += g[a];
-  }
+  for (int a = 0; a < 6; ++a) sum += g[a];
   if (!(sum > 0.0)) {  // all six gammas underflowed (alpha tiny): fall back to one-hot on a random action
+    PhiloxStream rng(seed ^ 0x4449524943484C45ull ^ (7ull << 56), item, counter);
     const int pick = (int)(rng.uniform() * 6.0);
 #pragma unroll
     for (int a = 0; a < 6; ++a) g[a] = (a == pick) ? 1.0 : 0.0;
@@ -75,6 +79,11 @@ __device__ __forceinline__ void dirichlet6(uint64_t seed, uint64_t item, uint64_
   }
 #pragma unroll
   for (int a = 0; a < 6; ++a) g[a] = g[a] / sum;
+}
+__device__ __forceinline__ void dirichlet6(uint64_t seed, uint64_t item, uint64_t counter, double alpha, double (&g)[6]) {
+#pragma unroll 1
+  for (int a = 0; a < 6; ++a) g[a] = dirichlet_gamma(seed, item, counter, alpha, a);
+  dirichlet_normalise(seed, item, counter, g);
 }
 
 // One uniform double in [0, 1) for global item `item` (the draw of np.random.choice, MCTS/mcts.py:120).
@@ -115,31 +124,39 @@ __global__ void philox_blocks(const uint32_t* __restrict__ ctr_key, uint32_t* __
 // Start of a move for every game: prior = p0, or add_dirichlet_noise (MCTS/mcts.py:148-150) with the draw made here;
 // root_node.expand(prior, h, 0.0) (MCTS/mcts.py:52-69): record 0 <- priors, root.W <- 0; the move's sampling uniform.
 // Bit-identical to hmz_rng_dirichlet + hmz_rng_uniform + hmz_search_begin_p0 issued one after another.
-__global__ void __launch_bounds__(128) selfplay_begin(hmz_search_t s, const float* __restrict__ p0, double* __restrict__ noise_out,
+// EIGHT lanes per game: lanes 0..5 draw the six gammas in parallel (the rejection sampler in float64 is the whole cost
+// of this kernel), every lane then rebuilds the full draw from six shuffles and lanes 0 / 1 write the record halves.
+__global__ void __launch_bounds__(256) selfplay_begin(hmz_search_t s, const float* __restrict__ p0, double* __restrict__ noise_out,
                                                      double* __restrict__ uniform_out, double alpha, float one_minus_eps, double eps,
                                                      int use_noise, uint64_t seed, uint64_t counter, uint64_t game_offset) {
-  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (b >= s.n_searches) return;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int a8 = (int)(t & 7);
+  const bool valid = (t >> 3) < s.n_searches;  // whole 8-lane groups are valid or not: the shuffles below stay convergent
+  const int64_t b = valid ? (t >> 3) : s.n_searches - 1;
   const uint64_t game = game_offset + (uint64_t)b;
-  double g[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (use_noise) dirichlet6(seed, game, counter, alpha, g);
+  double mine = 0.0;
+  if (use_noise && a8 < 6) mine = dirichlet_gamma(seed, game, counter, alpha, a8);
+  double g[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) g[a] = __shfl_sync(0xffffffffu, mine, (threadIdx.x & 24) | a);
+  if (use_noise) dirichlet_normalise(seed, game, counter, g);
+  if (!valid) return;
   float pr[6];
 #pragma unroll
   for (int a = 0; a < 6; ++a) {
     const float q = p0[b * 6 + a];
     double p = (double)q;
-    if (use_noise) {  // (1-eps)*prob is a float32 product, the sum with eps*noise is float64
-      p = __dadd_rn((double)__fmul_rn(one_minus_eps, q), __dmul_rn(eps, g[a]));
-      if (noise_out) noise_out[b * 6 + a] = g[a];
-    }
-    s.root_prior[b * 6 + a] = p;
+    if (use_noise) p = __dadd_rn((double)__fmul_rn(one_minus_eps, q), __dmul_rn(eps, g[a]));  // f32 product, f64 sum
     pr[a] = (float)p;
+    if (a == a8) {
+      s.root_prior[b * 6 + a] = p;
+      if (use_noise && noise_out) noise_out[b * 6 + a] = g[a];
+    }
   }
   hmz_node_t* rec = &s.nodes[b * s.n_records];
-  write_fresh_half(rec, 0, pr, 0, 0);
-  write_fresh_half(rec, 1, pr, 0, 0);
-  s.root_W[b] = 0.0;
-  uniform_out[b] = uniform01(seed, game, counter);
+  if (a8 < 2) write_fresh_half(rec, a8, pr, 0, 0);
+  if (a8 == 6) s.root_W[b] = 0.0;
+  if (a8 == 7) uniform_out[b] = uniform01(seed, game, counter);
 }
 
 struct FinishArgs {
@@ -263,7 +280,7 @@ int hmz_selfplay_move(const hmz_selfplay_t* sp, uint64_t move_index, void* strea
   {
     ProfScope prof_scope(HMZ_PROF_OTHER, stream);
     if (int rc = check_search(s, "hmz_selfplay_move")) return rc;
-    selfplay_begin<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(*s, sp->p0, sp->noise, sp->uniform, sp->dirichlet_alpha,
+    selfplay_begin<<<(unsigned)((B * 8 + 255) / 256), 256, 0, st>>>(*s, sp->p0, sp->noise, sp->uniform, sp->dirichlet_alpha,
                                                                 (float)(1.0 - sp->exploration_eps), sp->exploration_eps,
                                                                 use_noise ? 1 : 0, sp->seed, move_index, sp->game_offset);
     if (int rc = check_launch("selfplay_begin")) return rc;
