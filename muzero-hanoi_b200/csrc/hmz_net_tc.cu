@@ -144,11 +144,19 @@ static int tc_prepare(int* smem_bytes) {
   return HMZ_OK;
 }
 
-static unsigned tc_grid(int64_t n, int* n_pairs) {
+// Tile pairs per CTA the recurrent launch aims for (tuning switch HMZ_TC_PASSES, default 1): with several search groups in
+// flight a CTA that runs two passes pays the kernel's prologue (barrier init, TMEM allocation, first weight blocks,
+// ~1.9 us of a ~12.5 us single-pass CTA) once for both, at the price of a longer launch.
+static int tc_passes() {
+  static const int v = getenv("HMZ_TC_PASSES") ? atoi(getenv("HMZ_TC_PASSES")) : 1;
+  return v < 1 ? 1 : v;
+}
+static unsigned tc_grid(int64_t n, int* n_pairs, int passes = 1) {
   const int64_t pairs = (n + 2 * tc::kM - 1) / (2 * tc::kM);
   const int sms = sm_count();
   *n_pairs = (int)pairs;
-  return (unsigned)(pairs < sms ? pairs : sms);
+  const int64_t want = (pairs + passes - 1) / passes;
+  return (unsigned)(want < sms ? want : sms);
 }
 
 int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
@@ -156,7 +164,7 @@ int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_pe
                      int latent_dtype, float* r, float* p, float* v, int64_t n, cudaStream_t stream) {
   int smem = 0, n_pairs = 0;
   if (int rc = tc_prepare(&smem)) return rc;
-  const unsigned grid = tc_grid(n, &n_pairs);
+  const unsigned grid = tc_grid(n, &n_pairs, tc_passes());
   tc::v4::TcArgs a{};
   a.wsec = (const uint8_t*)weights;
   a.lat_in = lat_in;
