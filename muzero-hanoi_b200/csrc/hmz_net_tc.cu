@@ -33,11 +33,11 @@ namespace v4 {
 #ifdef HMZ_TC_MAXNREG
 #define HMZ_TC_BOUNDS __maxnreg__(HMZ_TC_MAXNREG)
 #else
-#define HMZ_TC_BOUNDS __launch_bounds__(kThreads, 1)
+#define HMZ_TC_BOUNDS __launch_bounds__(kLaunchThreads, 1)
 #endif
 // The stand-alone kernels: one launch per network evaluation of a whole batch (grid = min(tile pairs, SMs)).
 template <bool kInitial>
-__global__ void HMZ_TC_BOUNDS net_tc(TcArgs a) {
+__global__ void HMZ_TC_BOUNDS net_tc(const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   net_tc_body<kInitial, false>(a, PersistCtl{}, smem_raw, (int)blockIdx.x, (int)gridDim.x);
 }
@@ -181,7 +181,7 @@ int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_pe
   a.n = n;
   a.n_pairs = n_pairs;
   a.timeline = tc_timeline_enabled() | (pdl_prewait() << 1) | ((pdl_net_at() + 1) << 2);
-  cudaError_t e = launch_pdl(1, tc::v4::net_tc<false>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream, a);
+  cudaError_t e = launch_pdl(1, tc::v4::net_tc<false>, dim3(grid), dim3(tc::v4::kLaunchThreads), (size_t)smem, stream, a);
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_tc<recurrent> launch: %s", cudaGetErrorString(e));
   return check_launch("net_tc<recurrent>");
 }
@@ -205,7 +205,7 @@ int tc_net_initial(const void* weights, int n_disks, const uint32_t* words, void
   a.n = n;
   a.n_pairs = n_pairs;
   a.timeline = (pdl_prewait() << 1) | ((pdl_net_at() + 1) << 2);
-  cudaError_t e = launch_pdl(1, tc::v4::net_tc<true>, dim3(grid), dim3(tc::v4::kThreads), (size_t)smem, stream, a);
+  cudaError_t e = launch_pdl(1, tc::v4::net_tc<true>, dim3(grid), dim3(tc::v4::kLaunchThreads), (size_t)smem, stream, a);
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_tc<initial> launch: %s", cudaGetErrorString(e));
   return check_launch("net_tc<initial>");
 }

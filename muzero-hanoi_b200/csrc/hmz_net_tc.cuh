@@ -222,6 +222,7 @@ namespace v4 {
 constexpr int kHidThreadsPerTile = 256;
 constexpr int kSmallWarp0 = 16, kMmaWarp = 20, kLoaderWarp = 21;
 constexpr int kThreads = 22 * 32;
+constexpr int kLaunchThreads = kThreads;
 constexpr uint32_t kColsPerTile = 256, kColH1 = 128, kColO = 64;
 
 struct __align__(1024) Tile {
@@ -295,7 +296,9 @@ __device__ __forceinline__ void hidden_chunk_tmem(uint32_t dst, const uint32_t (
 }
 // Hidden-layer epilogue of one column half: H[0:128) float32 -> relu -> bf16 -> A1 in H[0:64), in place.
 // Chunk c (columns 16c..16c+15) lands in columns 8c..8c+7, always behind the read pointer; the TMEM
-// load of chunk c+1 is in flight while chunk c is converted.  (tcgen05.wait::ld waits for EVERY outstanding
+// load of chunk c+1 is in flight while chunk c is converted.  (Round 2: re-dividing the CTA's registers with setmaxnreg so that these warps could hold 32-column batches does not
+// work from one function — ptxas 12.9 compiles the WHOLE kernel to the smallest setmaxnreg value it sees.)
+// (tcgen05.wait::ld waits for EVERY outstanding
 // load, so each chunk still exposes most of one TMEM load latency, ~170 clk; requesting 64 columns per wait
 // was measured SLOWER: the 64 live registers spill under the 80-register cap of a 704-thread CTA; 32 columns
 // per wait without double buffering was slower too, 30.8 vs 27.3 us per launch.  Pooling all 16 epilogue
@@ -624,6 +627,8 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     if (elect_one()) umma_commit(&s.bar_end);
     __syncwarp();
     mbar_wait(&s.bar_end, 0);
+  } else if (warp > kLoaderWarp) {
+    // spare warps (CTAs launched with 24 warps: register-split build, persistent kernel): nothing to do
   } else if (warp < kSmallWarp0) {
     // ============================== hidden-epilogue warps ==============================
     const int t = warp >> 3, ltid = tid & 255;

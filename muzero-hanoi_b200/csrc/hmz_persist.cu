@@ -119,15 +119,11 @@ __device__ __forceinline__ void tree_role(const PersistArgs& a, uint8_t* smem_ra
   }
 }
 
-__global__ void __launch_bounds__(kPersistThreads, 1) search_persistent(PersistArgs a) {
+__global__ void __launch_bounds__(kPersistThreads, 1) search_persistent(const __grid_constant__ PersistArgs a) {
   extern __shared__ uint8_t smem_raw[];
   if ((int)blockIdx.x < a.n_mlp) {
-    if (threadIdx.x < tc::v4::kThreads) {
-      tc::v4::net_tc_body<false, true>(a.net, a.ctl, smem_raw, (int)blockIdx.x, a.n_mlp);
-    } else {  // the two spare warps of an MLP CTA only take part in the body's two block-wide barriers
-      __syncthreads();
-      __syncthreads();
-    }
+    // all 24 warps: the body's roles use 22 of them, the two spare warps only take part in its block-wide barriers
+    tc::v4::net_tc_body<false, true>(a.net, a.ctl, smem_raw, (int)blockIdx.x, a.n_mlp);
   } else {
     tree_role(a, smem_raw);
   }
