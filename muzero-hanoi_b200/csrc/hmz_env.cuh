@@ -82,36 +82,28 @@ __device__ __forceinline__ StepOut step_word(uint32_t word, uint32_t action, con
   return step_finish(word, st, legal, moved, c);
 }
 
-// The same with the pegs' keys already known (the random-move kernels need all three to pick the action).
-__device__ __forceinline__ StepOut step_word_keys(uint32_t word, uint32_t action, uint32_t k0, uint32_t k1, uint32_t k2,
-                                                  const EnvCfg& c) {
-  const uint32_t st = word & c.state_mask;
-  const uint32_t a = action > 5u ? 5u : action;
-  const uint32_t f = a >> 1, t = (0x489u >> (2u * a)) & 3u;
-  const uint32_t kf = f == 0u ? k0 : (f == 1u ? k1 : k2);
-  const bool legal = (action <= 5u) & (((legal_bits(k0, k1, k2) >> a) & 1u) != 0u);
-  const uint32_t moved = st ^ ((f ^ t) * (kf + 1u));
-  return step_finish(word, st, legal, moved, c);
-}
-
-// k-th (0-based) set bit of a mask with 2 or 3 bits set.
-__device__ __forceinline__ uint32_t kth_set_bit(uint32_t m, uint32_t k) {
-  uint32_t m1 = m & (m - 1u);
-  uint32_t m2 = m1 & (m1 - 1u);
-  uint32_t sel = k == 0u ? m : (k == 1u ? m1 : m2);
-  return (uint32_t)(__ffs((int)sel) - 1);
-}
-
-// One step on a uniformly random LEGAL move (the pegs' keys are computed once for the choice and the step).
+// One step on a uniformly random LEGAL move.  Tower of Hanoi has exactly two or three legal moves in any state: the
+// smallest disk (disk 0, on peg p0) can always go to either of the other two pegs q1, q2; between those two pegs the
+// smaller of the two top disks can move onto the other (no third move when both are empty, i.e. when every disk sits
+// on p0).  So the legal set is known from disk 0's peg and one comparison — no mask over all six moves, no k-th-set-bit
+// search: the random-move kernels are integer-bound (ncu: the HBM roofline is not what limits them).
+// Index in the move table [(0,1),(0,2),(1,0),(1,2),(2,0),(2,1)] (env/hanoi.py:39-41): a = 2 f + (t > f ? t - 1 : t).
 __device__ __forceinline__ StepOut step_random_word(uint32_t word, uint32_t rnd, const EnvCfg& c, uint32_t& action) {
-  uint32_t k0, k1, k2;
-  peg_keys(word & c.state_mask, c.even_mask, k0, k1, k2);
-  const uint32_t m = legal_bits(k0, k1, k2);
-  action = kth_set_bit(m, __umulhi(rnd, (uint32_t)__popc(m)));
   const uint32_t st = word & c.state_mask;
-  const uint32_t f = action >> 1, t = (0x489u >> (2u * action)) & 3u;
-  const uint32_t kf = f == 0u ? k0 : (f == 1u ? k1 : k2);
-  return step_finish(word, st, true, st ^ ((f ^ t) * (kf + 1u)), c);  // the chosen move is legal by construction
+  const uint32_t p0 = st & 3u;
+  const uint32_t q1 = p0 == 2u ? 0u : p0 + 1u, q2 = p0 == 0u ? 2u : p0 - 1u;
+  const uint32_t x1 = st ^ (q1 * c.even_mask), x2 = st ^ (q2 * c.even_mask);
+  const uint32_t m1 = ~(x1 | (x1 >> 1)) & c.even_mask, m2 = ~(x2 | (x2 >> 1)) & c.even_mask;
+  const uint32_t l1 = m1 & (0u - m1), l2 = m2 & (0u - m2);  // bits of the top disks of q1 / q2 (0: empty peg)
+  const uint32_t k1 = l1 - 1u, k2 = l2 - 1u;                // keys: empty = 0xFFFFFFFF
+  const uint32_t n_legal = 2u + (uint32_t)(k1 != k2);
+  const uint32_t idx = __umulhi(rnd, n_legal);              // uniform over the legal moves
+  const bool first = k1 < k2;                               // the third move goes q1 -> q2, else q2 -> q1
+  const uint32_t f = idx < 2u ? p0 : (first ? q1 : q2);
+  const uint32_t t = idx == 0u ? q1 : (idx == 1u ? q2 : (first ? q2 : q1));
+  const uint32_t lf = idx < 2u ? 1u : (first ? l1 : l2);    // bit of the disk that moves (disk 0: bit 0)
+  action = 2u * f + t - (uint32_t)(t > f);
+  return step_finish(word, st, true, st ^ ((f ^ t) * lf), c);  // the chosen move is legal by construction
 }
 
 // Host: fills an EnvCfg after validating the shape (HMZ_ERR_* with a message on failure).

@@ -185,6 +185,24 @@ def test_step_random_matches_port_given_same_actions():
     assert len(set(acts.tolist())) >= 3
 
 
+def test_step_random_is_uniform_over_the_legal_moves():
+    """The on-device move choice (two moves of the smallest disk + at most one move between the other two pegs) must be
+    uniform over exactly the legal set: 600,000 envs in one state, chi-square-style 5-sigma bounds per action."""
+    from muzero_hanoi_b200.engine import VecHanoi
+
+    n, b = 4, 600_000
+    for state in ((0, 0, 0, 0), (1, 0, 2, 2), (2, 1, 1, 0), (0, 2, 2, 2), (1, 1, 1, 1), (2, 0, 1, 2)):
+        legal = [a for a in range(6) if port.move_allowed(state, port.MOVES[a])]
+        env = VecHanoi(n, 200, b)
+        env.set_state_indices(np.full(b, port.state_to_index(state), dtype=np.int32))
+        acts, _, flags = env.step_random(seed=3, step_index=17)
+        counts = np.bincount(acts.cpu().numpy(), minlength=6)
+        assert not (flags.cpu().numpy() & 2).any()
+        assert sorted(np.nonzero(counts)[0].tolist()) == legal, (state, counts)
+        p = 1.0 / len(legal)
+        assert (np.abs(counts[legal] - b * p) < 5 * np.sqrt(b * p * (1 - p))).all(), (state, counts)
+
+
 def test_fused_rollout_equals_stepwise_random():
     from muzero_hanoi_b200.engine import VecHanoi
 
