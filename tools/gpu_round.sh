@@ -80,6 +80,11 @@ for stage in "$@"; do
       $CMD > gpurun_out/plain.json 2> gpurun_out/plain.log || { echo "plain run failed"; tail gpurun_out/plain.log; continue; }
       ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
       echo "ncu list rc=$?"
+      # the strong-scaling point of 8 GPUs: 8,192 games per GPU
+      SCMD="python bench.py --steps 1 --warmup 3 --moves-per-step 1 --no-cpu-baseline --no-env --no-configs --games 8192"
+      $SCMD > gpurun_out/plain_8192.json 2> gpurun_out/plain_8192.log &&
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_8192.csv $SCMD > gpurun_out/ncu_list_8192.log 2>&1
+      echo "ncu list 8192 rc=$?"
       ncu --set full --clock-control none --import-source on -k regex:search_backup_select -s 60 -c 2 -o gpurun_out/prof_tree -f $CMD > gpurun_out/ncu_tree.log 2>&1
       echo "ncu tree rc=$?"
       ncu --set full --clock-control none --import-source on -k regex:net_tc -s 61 -c 2 -o gpurun_out/prof_net -f $CMD > gpurun_out/ncu_net.log 2>&1

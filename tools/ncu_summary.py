@@ -56,31 +56,33 @@ with open(os.path.join(DST, f"{R}_ncu_highlights.md"), "w") as f:
                 f.write(f"| `{h}` | " + " | ".join(f"{o[h][0]} {o[h][1]}" for o in out) + " |\n")
         f.write("| DRAM read + write | " + " | ".join(f"{o['dram_bytes'] / 1e6:.2f} MB" for o in out) + " |\n\n")
 # launch list: aggregated per kernel
-lst = os.path.join(SRC, "launches.csv")
-if os.path.exists(lst):
-    rows = [r for r in csv.reader(open(lst)) if len(r) > 10]
-    hdr = rows[0]
-    i_name, i_val, i_unit = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-    agg = collections.OrderedDict()
-    for r in rows[1:]:
-        try:
-            us = to_us(r[i_val], r[i_unit])
-        except (ValueError, KeyError):
-            continue
-        name = re.sub(r"\(.*", "", r[i_name]).strip()
-        a = agg.setdefault(name, [0, 0.0])
-        a[0] += 1
-        a[1] += us
-    tot = sum(a[1] for a in agg.values())
-    with open(os.path.join(DST, f"{R}_launches_step.csv"), "w") as f:
-        f.write("kernel,launches,avg_us,total_us,share\n")
-        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write(f"\"{k}\",{a[0]},{a[1] / a[0]:.3f},{a[1]:.1f},{a[1] / tot:.4f}\n")
+for lst_name, out_name in (("launches.csv", "launches_step.csv"), ("launches_8192.csv", "launches_step_8192games.csv")):
+  lst = os.path.join(SRC, lst_name)
+  if os.path.exists(lst):
+      rows = [r for r in csv.reader(open(lst)) if len(r) > 10]
+      hdr = rows[0]
+      i_name, i_val, i_unit = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+      agg = collections.OrderedDict()
+      for r in rows[1:]:
+          try:
+              us = to_us(r[i_val], r[i_unit])
+          except (ValueError, KeyError):
+              continue
+          name = re.sub(r"\(.*", "", r[i_name]).strip()
+          a = agg.setdefault(name, [0, 0.0])
+          a[0] += 1
+          a[1] += us
+      tot = sum(a[1] for a in agg.values())
+      with open(os.path.join(DST, f"{R}_{out_name}"), "w") as f:
+          f.write("kernel,launches,avg_us,total_us,share\n")
+          for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+              f.write(f"\"{k}\",{a[0]},{a[1] / a[0]:.3f},{a[1]:.1f},{a[1] / tot:.4f}\n")
 # bench lines, sweeps, test metrics
 for src, dst in (("bench_default.json", "bench_default_line.json"), ("bench_reference.json", "bench_reference_line.json"),
                  ("bench_2gpu.json", "bench_2gpu_line.json"), ("bench_extras.json", "bench_extras_line.json"),
                  ("bench_persist.json", "bench_persistent_line.json"), ("plain.json", "plain_bench_line.json"),
-                 ("plain_persist.json", "plain_persistent_bench_line.json"), ("persist_sweep.txt", "persist_sweep.txt"),
+                 ("plain_persist.json", "plain_persistent_bench_line.json"), ("plain_8192.json", "plain_8192games_bench_line.json"),
+                 ("bench_8gpu.json", "bench_8gpu_line.json"), ("persist_sweep.txt", "persist_sweep.txt"),
                  ("group_sweep.txt", "group_sweep.txt"), ("env_sweep.txt", "env_sweep.txt"), ("env_probe.txt", "env_probe.txt")):
     if os.path.exists(os.path.join(SRC, src)):
         shutil.copyfile(os.path.join(SRC, src), os.path.join(DST, f"{R}_{dst}"))
