@@ -220,8 +220,8 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return (uint32_t
 // 4 output warps shared by both tiles, one MMA-issuing warp, one loader warp.
 namespace v4 {
 constexpr int kHidThreadsPerTile = 256;
-constexpr int kSmallWarp0 = 16, kMmaWarp = 20, kLoaderWarp = 21;
-constexpr int kThreads = 22 * 32;
+constexpr int kSmallWarp0 = 16, kMmaWarp = 20, kLoaderWarp = 21, kMmaWarp1 = 22;  // one MMA-issuing warp per tile
+constexpr int kThreads = 23 * 32;
 constexpr int kLaunchThreads = kThreads;
 constexpr uint32_t kColsPerTile = 256, kColH1 = 128, kColO = 64;
 
@@ -250,8 +250,10 @@ struct __align__(1024) Smem {
   uint32_t tmem_base;
 };
 
-static __constant__ uint32_t c_block_off[8] = {kWg1, kWg2, kWr1, kWr2, kWp1, kWp2, kWv1, kWv2};
-static __constant__ uint32_t c_block_bytes[8] = {kBytesW1, kBytesWg2, kBytesW1, kBytesW48, kBytesW1, kBytesW16, kBytesW1, kBytesW48};
+// network order of a pass: dynamics, reward, VALUE, POLICY — the policy head's output (a 6-way softmax) is the cheapest,
+// so it goes last, where nothing overlaps the output warps' work
+static __constant__ uint32_t c_block_off[8] = {kWg1, kWg2, kWr1, kWr2, kWv1, kWv2, kWp1, kWp2};
+static __constant__ uint32_t c_block_bytes[8] = {kBytesW1, kBytesWg2, kBytesW1, kBytesW48, kBytesW1, kBytesW48, kBytesW1, kBytesW16};
 
 // D = A x B^T with A in TMEM (lane = row, one 32-bit column = two consecutive k)
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -469,9 +471,9 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     for (int k = 0; k < 2; ++k)
       for (int j = 0; j < 2; ++j) {
         mbar_init(&s.bar_wfull[k][j], 1);
-        mbar_init(&s.bar_wfree[k][j], 1);
+        mbar_init(&s.bar_wfree[k][j], 2);  // one commit per tile's MMA warp
       }
-    mbar_init(&s.bar_end, 1);
+    mbar_init(&s.bar_end, 2);
     mbar_init(&s.bar_pass, 2 * kHidThreadsPerTile + 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -506,7 +508,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
   const int signal_net = kPersist ? 8 : ((timeline >> 2) & 7) - 1;  // HMZ_PDL_NET_AT: -1 = here (8: never)
   if (!kPersist) {
     if (!late_signal && signal_net < 0) pdl_launch_dependents();
-    if (warp != kLoaderWarp && (late_signal || warp != kMmaWarp)) {
+    if (warp != kLoaderWarp && (late_signal || (warp != kMmaWarp && warp != kMmaWarp1))) {
       pdl_wait();
       if (late_signal && signal_net < 0) pdl_launch_dependents();
     }
@@ -533,57 +535,51 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
         use[kind] = u + 1u;
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ================================= MMA-issuing warp =================================
-    // One elected lane issues every tcgen05.mma of both tiles in the static ping-pong order
-    //   L1(T0) L1(T1) L2(T0) L2(T1)   per network,
-    // so that the tensor core always has the other tile's layer to run while one tile's epilogue
-    // warps drain TMEM.
+  } else if (warp == kMmaWarp || warp == kMmaWarp1) {
+    // ================================= MMA-issuing warps =================================
+    // One warp per tile; an elected lane issues the tile's tcgen05.mma instructions  L1 L2  per network.  Issuing is
+    // blocking (~50 clk per small second-layer instruction, tools/microbench/mma.cu), so with one warp per tile a
+    // tile's waits and issue slots never sit behind the other tile's; the tensor core interleaves the two streams.
+    const int t = warp == kMmaWarp ? 0 : 1;
     const uint32_t id256 = umma_idesc(256);
-    uint32_t use_f = 0, use_s = 0, ph_g = 0, ph_a = 0, ph_raw = 0, ph_hn = 0, ph_fin[2] = {0u, 0u};
+    const uint32_t T = tmem + kColsPerTile * t;
+    const uint32_t ax = smem_u32(s.t[t].ax);
+    uint32_t use_f = 0, use_s = 0, ph_g = 0, ph_a = 0, ph_raw = 0, ph_hn = 0, ph_fin = 0;
     bool first = true;
-    int ev = 0;
     for (int pass = 0; pass < n_pass; ++pass) {
 #pragma unroll 1
-      for (int net = 0; net < 4; ++net) {  // dynamics / representation, reward, policy, value
+      for (int net = 0; net < 4; ++net) {  // dynamics / representation, reward, value, policy
         if (kInitial && net == 1) continue;
-        if (net == signal_net && pass == n_pass - 1) pdl_launch_dependents();
+        if (t == 0 && net == signal_net && pass == n_pass - 1) pdl_launch_dependents();
         // ---- first layer: H[0:256) = [A | AX] x W1'^T
         {
           const uint32_t slot = use_f & 1u;
-          if (elect_one()) TL4(16 + net);
+          if (elect_one()) TL4(16 + net * 2 + t);
           mbar_wait(&s.bar_wfull[0][slot], (use_f >> 1) & 1u);
-          if (elect_one()) TL4(24 + net);
           const uint32_t wf = smem_u32(s.wf[slot]);
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const uint32_t T = tmem + kColsPerTile * t;
-            const uint32_t ax = smem_u32(s.t[t].ax);
-            const uint32_t a_in = net <= 1 ? smem_u32(s.t[t].a0) : smem_u32(s.t[t].ahn);
-            if (net == 0) mbar_wait(&s.bar_g[t], ph_g);
-            if (net == 1) mbar_wait(&s.bar_raw[t], ph_raw);  // raw latent tile written, O copied out
-            if (net == 2) mbar_wait(&s.bar_hn[t], ph_hn);    // normalised latent tile written
-            // O (inside H) must have been copied out: by the output warps after a head, by the latent epilogue
-            // (bar_raw / bar_hn above) after the first network
-            if (net == 3 || (net == 2 && !kInitial) || (net == 0 && !first)) {
-              mbar_wait(&s.bar_fin[t], ph_fin[t]);
-              ph_fin[t] ^= 1;
-            }
-            if (elect_one()) TL4(ev);
-            ++ev;
-            tc_fence_after();
-            if (elect_one()) {
-              // one N = 256 instruction per k-step: A is fetched from shared memory once for both column
-              // halves (two N = 128 instructions read it twice and saturate the shared-memory port)
-              const uint64_t a_base = desc_sw128(a_in), b_base = desc_sw128(wf);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma(T, a_base + (uint64_t)(kk * 2), b_base + (uint64_t)(kk * 2), id256, kk ? 1u : 0u);
-              umma(T, desc_plain(ax), desc_plain(wf + 256 * 128), id256, 1u);
-              umma_commit(&s.bar_d[t]);
-              if (t == 1) umma_commit(&s.bar_wfree[0][slot]);
-            }
-            __syncwarp();
+          const uint32_t a_in = net <= 1 ? smem_u32(s.t[t].a0) : smem_u32(s.t[t].ahn);
+          if (net == 0) mbar_wait(&s.bar_g[t], ph_g);
+          if (net == 1) mbar_wait(&s.bar_raw[t], ph_raw);  // raw latent tile written, O copied out
+          if (net == 2) mbar_wait(&s.bar_hn[t], ph_hn);    // normalised latent tile written
+          // O (inside H) must have been copied out: by the output warps after a head, by the latent epilogue
+          // (bar_raw / bar_hn above) after the first network
+          if (net == 3 || (net == 2 && !kInitial) || (net == 0 && !first)) {
+            mbar_wait(&s.bar_fin[t], ph_fin);
+            ph_fin ^= 1;
           }
+          if (elect_one()) TL4(net * 4 + t);
+          tc_fence_after();
+          if (elect_one()) {
+            // one N = 256 instruction per k-step: A is fetched from shared memory once for both column
+            // halves (two N = 128 instructions read it twice and saturate the shared-memory port)
+            const uint64_t a_base = desc_sw128(a_in), b_base = desc_sw128(wf);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma(T, a_base + (uint64_t)(kk * 2), b_base + (uint64_t)(kk * 2), id256, kk ? 1u : 0u);
+            umma(T, desc_plain(ax), desc_plain(wf + 256 * 128), id256, 1u);
+            umma_commit(&s.bar_d[t]);
+            umma_commit(&s.bar_wfree[0][slot]);
+          }
+          __syncwarp();
           if (net == 0) ph_g ^= 1;
           if (net == 1) ph_raw ^= 1;
           if (net == 2) ph_hn ^= 1;
@@ -591,33 +587,25 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
         }
         // ---- second layer: O = [A1 | AX] x W2'^T, A1 from TMEM
         {
-          const uint32_t n2 = net == 0 ? 64u : (net == 2 ? 16u : 48u);
+          const uint32_t n2 = net == 0 ? 64u : (net == 3 ? 16u : 48u);
           const uint32_t id2 = umma_idesc(n2);
           const uint32_t slot = use_s & 1u;
-          if (elect_one()) TL4(20 + net);
           mbar_wait(&s.bar_wfull[1][slot], (use_s >> 1) & 1u);
-          if (elect_one()) TL4(28 + net);
           const uint32_t ws = smem_u32(s.ws[slot]);
+          mbar_wait(&s.bar_a[t], ph_a);
+          if (elect_one()) TL4(net * 4 + 2 + t);
+          tc_fence_after();
+          if (elect_one()) {
+            umma(T + kColO, desc_plain(ax), desc_plain(ws + n2 * 128 * 4), id2, 0u);  // bias step clears O
+            const uint64_t b_base = desc_sw128(ws);
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const uint32_t T = tmem + kColsPerTile * t;
-            const uint32_t ax = smem_u32(s.t[t].ax);
-            mbar_wait(&s.bar_a[t], ph_a);
-            if (elect_one()) TL4(ev);
-            ++ev;
-            tc_fence_after();
-            if (elect_one()) {
-              umma(T + kColO, desc_plain(ax), desc_plain(ws + n2 * 128 * 4), id2, 0u);  // bias step clears O
-              const uint64_t b_base = desc_sw128(ws);
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                umma_ts(T + kColO, T + (j >> 3) * kColH1 + (j & 7) * 8,
-                        b_base + (uint64_t)(((j >> 2) * n2 * 128 + (j & 3) * 32) >> 4), id2, 1u);
-              umma_commit(net == 0 ? &s.bar_o[t] : &s.bar_s[t]);
-              if (t == 1) umma_commit(&s.bar_wfree[1][slot]);
-            }
-            __syncwarp();
+            for (int j = 0; j < 16; ++j)
+              umma_ts(T + kColO, T + (j >> 3) * kColH1 + (j & 7) * 8,
+                      b_base + (uint64_t)(((j >> 2) * n2 * 128 + (j & 3) * 32) >> 4), id2, 1u);
+            umma_commit(net == 0 ? &s.bar_o[t] : &s.bar_s[t]);
+            umma_commit(&s.bar_wfree[1][slot]);
           }
+          __syncwarp();
           ph_a ^= 1;
           ++use_s;
         }
@@ -627,8 +615,8 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     if (elect_one()) umma_commit(&s.bar_end);
     __syncwarp();
     mbar_wait(&s.bar_end, 0);
-  } else if (warp > kLoaderWarp) {
-    // spare warps (CTAs launched with 24 warps: register-split build, persistent kernel): nothing to do
+  } else if (warp > kMmaWarp1) {
+    // spare warp (CTAs launched with 24 warps: the persistent kernel): nothing to do
   } else if (warp < kSmallWarp0) {
     // ============================== hidden-epilogue warps ==============================
     const int t = warp >> 3, ltid = tid & 255;
@@ -637,6 +625,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
     const uint32_t T = tmem + kColsPerTile * t + lane_bits;
     uint32_t ph_d = 0, ph_o = 0;
+    bool copy_pending = false;
     for (int pass = 0; pass < n_pass; ++pass) {
       const int pair = HMZ_PASS_PAIR(pass), sim = HMZ_PASS_SIM(pass);
       const int64_t out_row = kPersist ? (int64_t)sim + 1 : a.out_row;
@@ -750,10 +739,15 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
           fence_proxy_async();
           mbar_arrive(&s.bar_hn[t]);
           if (ltid == 0) TL4(42 + t * 8);
+          copy_pending = true;  // the rows leave for HBM after the NEXT hidden drain (see below)
+        } else if (copy_pending) {
+          // ---- deferred copy-out of the new latent rows (bf16): issued after the first head's hidden drain, while this
+          // tile's second-layer MMA runs, so that it no longer delays that drain (it did, by ~1,400 clk per pass).
+          // The normalised tile is only read by the remaining heads' first layers, never rewritten within the pass.
+          copy_pending = false;
           if (latent_dtype != HMZ_LATENT_F32) {
-            // bf16 rows leave through the normalised tile so that 8 consecutive lanes write one 128-byte
-            // row: the two warps of a lane quarter copy out 16 rows each (off the critical path: the heads
-            // are already running).
+            // 8 consecutive lanes write one 128-byte row: the two warps of a lane quarter copy out 16 rows each,
+            // once both have written their column halves of the tile
             asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + quarter) : "memory");
             const int lane = tid & 31, chunk = lane & 7;
             if (ltid == 0) TL4(43 + t * 8);
@@ -796,7 +790,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
         mbar_arrive(&s.bar_g[t]);
       }
 #pragma unroll 1
-      for (int head = 0; head < 3; ++head) {  // reward, policy, value
+      for (int head = 0; head < 3; ++head) {  // reward, value, policy
         if (kInitial && head == 0) continue;
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
@@ -804,7 +798,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
           const uint32_t O = tmem + kColsPerTile * t + kColO + lane_bits;
           mbar_wait(&s.bar_s[t], ph_s);
           tc_fence_after();
-          if (head == 1) {  // F.softmax(pi_logits) (networks.py:109)
+          if (head == 2) {  // F.softmax(pi_logits) (networks.py:109)
             float lg[16];
             tmem_ld16(O, lg);
             tc_fence_before();

@@ -36,17 +36,11 @@ if os.environ.get("HMZ_TC_V3"):
         names[35 + ly * 3] = f"hid {nm}: saw second layer"
 else:  # v4: two tiles per CTA
     names = {60: "CTA: kernel entry", 61: "CTA: barriers + TMEM ready", 62: "CTA: past the PDL wait", 63: "CTA: all warps done"}
-    ev = 0
-    for net in "grpv":
-        for what in ["L1 inputs ready", "L2 inputs ready (A1 written)"]:
-            for t in range(2):
-                names[ev] = f"T{t} mma {net}: {what}"
-                ev += 1
-    for i, net in enumerate("grpv"):
-        names[16 + i] = f"mma {net}: L1 issue point reached (waiting W1)"
-        names[24 + i] = f"mma {net}: W1 landed"
-        names[20 + i] = f"mma {net}: L2 issue point reached (waiting W2)"
-        names[28 + i] = f"mma {net}: W2 landed"
+    for i, net in enumerate("grvp"):  # network order of a pass: dynamics, reward, value, policy
+        for t in range(2):
+            names[i * 4 + t] = f"T{t} mma {net}: L1 inputs ready"
+            names[i * 4 + 2 + t] = f"T{t} mma {net}: L2 inputs ready (A1 written)"
+            names[16 + i * 2 + t] = f"T{t} mma {net}: L1 issue point reached"
     for t in range(2):
         names[86 + t * 8] = f"T{t} hid: raw latent published"
         names[44 + t * 8] = f"T{t} hid: saw dynamics L2 complete"
@@ -55,10 +49,10 @@ else:  # v4: two tiles per CTA
         names[42 + t * 8] = f"T{t} hid: hn published"
         names[43 + t * 8] = f"T{t} hid: copy-out barrier passed"
         names[80 + t * 8] = f"T{t} hid: gather done"
-        for ly, nm in enumerate("grpv"):
+        for ly, nm in enumerate("grvp"):
             names[81 + t * 8 + ly] = f"T{t} hid {nm}: A1 half 0 written"
         names[85 + t * 8] = f"T{t} hid: latent done"
-        for hd, nm in enumerate("rpv"):
+        for hd, nm in enumerate("rvp"):
             names[70 + hd * 2 + t] = f"T{t} out {nm}: done"
 t0 = min(int(marks[k]) for k in names if marks[k] != 0)
 ev = sorted((int(marks[k] - t0), names[k]) for k in names if marks[k] != 0)
