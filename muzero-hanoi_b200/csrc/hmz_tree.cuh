@@ -298,6 +298,7 @@ __device__ __forceinline__ Leaf select_leaf(const hmz_node_t* nodes, const doubl
         ld256(hp, q0, q1);
         ld256(hp + 2, q2, q3);
       }
+      if (depth == 0) tree_mark<kTL>(41, tl_on);
       tn = tb.ucb(ucb_table, n_parent);
       if (use64) {  // only the (noised) root has float64 priors; requested together with the record
 #pragma unroll
@@ -627,6 +628,7 @@ __device__ __forceinline__ void tree_phase(const hmz_search_t& s, int sim, const
   mn = __shfl_sync(0xffffffffu, mn, (threadIdx.x & 31) & ~1);
   mx = __shfl_sync(0xffffffffu, mx, (threadIdx.x & 31) & ~1);
   if (kTrusted) wild = __shfl_sync(0xffffffffu, (int)wild, (threadIdx.x & 31) & ~1) != 0;
+  tree_mark<kTL>(40, tl, (uint32_t)__double2loint(mn));
   const double* rp = s.root_prior_is_f64 ? s.root_prior + b * 6 : nullptr;
   const Leaf leaf = select_leaf<kTL, kTrusted, TB>(nodes, rp, mn, mx, sim + 1, ucb_table, discount, half, nullptr, 0, path, tl, valid, wild, tb);
   if (kPdl && signal_at == 2) pdl_launch_dependents();

@@ -8,7 +8,12 @@ from oracle import port
 
 B, S, n = int(os.environ.get("B", 65536)), 100, 5
 lib = _lib.load()
-w = PackedWeights(port.make_weights(n, 3), n, 1)
+if os.environ.get("TORCH_INIT"):  # the bench's network: torch's default initialisation (shallower trees)
+    from muzero_hanoi_b200.networks import MuZeroNet
+    torch.manual_seed(0)
+    w = PackedWeights(MuZeroNet(3 * n, 6, 0.002, "cpu", TD_return=True).state_dict(), n, 1)
+else:
+    w = PackedWeights(port.make_weights(n, 3), n, 1)
 env = VecHanoi(n, 200, B)
 env.reset()
 env.random_reset(seed=5)
@@ -30,7 +35,7 @@ for search in [int(x) for x in os.environ.get("SEARCHES", "0,1,17,5000,30000,300
     print(f"search {search}: backed-up depth {t[2]}, next path depth {t[4]}")
     t0 = t[0]
     marks = [(0, "entry"), (1, "leaf scalars loaded"), (6, "fresh record written, r loaded"), (7, "root W / min-max loaded"),
-             (3, "backup done (stores issued)")]
+             (3, "backup done (stores issued)"), (40, "walk entered (min / max exchanged)"), (41, "level 0 loads issued")]
     for bt in range(4):
         marks += [(24 + 3 * bt, f"backup batch {bt}: path entries loaded"), (25 + 3 * bt, f"backup batch {bt}: slots loaded"),
                   (26 + 3 * bt, f"backup batch {bt}: recurrence done")]
