@@ -480,6 +480,11 @@ SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
 }  // namespace
 
 
+static int debug_skip() {
+  const char* e = getenv("HMZ_DEBUG_SKIP");
+  return e ? atoi(e) : 0;
+}
+
 // One simulation of one group: [select (first simulation only)] -> g+f MLP -> fused backup + next select.
 // capture_stride / capture_lo: searches per capture row (the whole batch) and this group's first search in it.
 static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* weights, int mode, int sim,
@@ -494,9 +499,14 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
                                                           sc.path);
     if (int rc = check_launch("search_select")) return rc;
   }
-  if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, sc.lp, sc.la, s->latents, s->n_records, sim + 1,
-                                 s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
-    return rc;
+  // tooling (tools/persist_probe.py): HMZ_DEBUG_SKIP=1 leaves out the network launches, =2 the tree launches — timing of
+  // one kernel family alone under the group schedule; the search results are meaningless then
+  const int skip = debug_skip();
+  if (!(skip & 1))
+    if (int rc = hmz_net_recurrent(weights, mode, s->latents, s->n_records, sc.lp, sc.la, s->latents, s->n_records, sim + 1,
+                                   s->latent_dtype, sc.r, sc.p, sc.v, B, stream))
+      return rc;
+  if (skip & 2) return HMZ_OK;
   ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, stream);
   const int do_select = (sim + 1 < n_simulations ? 1 : 0) | (pdl_prewait() << 1) | ((pdl_tree_at() & 3) << 2);
   const float *cr = sc.r, *cp = sc.p, *cv = sc.v;

@@ -19,6 +19,8 @@ for sched in [int(x) for x in os.environ.get("SCHEDULES", "64").split(",")]:
     for _ in range(4):
         sp.move()
     torch.cuda.synchronize()
+    if os.environ.get("SKIP"):  # time one kernel family alone (HMZ_DEBUG_SKIP, read by the library at every call)
+        os.environ["HMZ_DEBUG_SKIP"] = os.environ["SKIP"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(moves):
@@ -37,4 +39,5 @@ for sched in [int(x) for x in os.environ.get("SCHEDULES", "64").split(",")]:
                  f"life {st[3] / warps / 1.965e3:.0f} us; work per slice {st[1] / items / 1.965e3:.2f} us"
                  f"\n    mlp: {passes} passes; waiting for the tree {st[4] / passes / 1.965e3:.2f} us per pass; first->last hand-off per CTA {st[5] / 1.965e3:.0f} us summed over CTAs")
     print(line, flush=True)
+    os.environ.pop("HMZ_DEBUG_SKIP", None)
     del sp
