@@ -19,6 +19,7 @@ constexpr uint32_t kBytesW1 = w_bytes(256, 1);   // 40960
 constexpr uint32_t kBytesWg2 = w_bytes(64, 4);   // 34816
 constexpr uint32_t kBytesW48 = w_bytes(48, 4);   // 26112
 constexpr uint32_t kBytesW16 = w_bytes(16, 4);   // 8704
+constexpr uint32_t kBytesWs1 = (kBytesW48 + 1023) / 1024 * 1024;  // second-layer slot 1 holds at most a 48-row block
 // byte offsets inside the tensor-core section of the weight blob (all multiples of 1024)
 constexpr uint32_t kWg1 = 0, kWg2 = 40960, kWr1 = 75776, kWr2 = 116736, kWp1 = 142848 + 1024 - 512, kWp2 = kWp1 + 40960,
                    kWv1 = kWp2 + 9216, kWv2 = kWv1 + 40960, kWh1 = kWv2 + 26112 + 512, kWh2 = kWh1 + 40960,
@@ -232,8 +233,9 @@ struct __align__(1024) Tile {
 };
 struct __align__(1024) Smem {
   Tile t[2];
-  uint8_t wf[2][kBytesW1];   // first-layer weight blocks (+ extra slice), double-buffered
-  uint8_t ws[2][kBytesWg2];  // second-layer weight blocks (+ extra slice), double-buffered
+  uint8_t wf[2][kBytesW1];   // first-layer weight blocks (+ extra slice), double-buffered: slot = network & 1
+  uint8_t ws0[kBytesWg2];    // second-layer weight blocks (+ extra slice), slot 0: dynamics / representation, value
+  uint8_t ws1[kBytesWs1];    // slot 1: reward, policy (the smaller blocks: leaves room for a tree block's tables on the SM)
   float2 row_minmax[2][2][kM];
   uint64_t bar_wfull[2][2];  // [kind][slot] TMA landed
   uint64_t bar_wfree[2][2];  // [kind][slot] both tiles' MMAs reading the slot have completed
@@ -517,22 +519,25 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
 
   if (warp == kLoaderWarp) {
     // ================================= loader warp =================================
-    uint32_t use[2] = {0u, 0u};
+    // Block i = 2 * network + layer goes to slot (network & 1) of its kind, so that the second-layer slot 1 only ever
+    // holds the reward / policy blocks; cnt = loads issued into a slot so far (a reload waits for the previous use's MMAs).
+    uint32_t cnt[2][2] = {{0u, 0u}, {0u, 0u}};
     for (int pass = 0; pass < n_pass; ++pass) {
-#pragma unroll 1
+#pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (kInitial && (i >> 1) == 1) continue;  // no reward head at the root
         if (late_signal && i == 4 && pass == 0) {  // the first four blocks are in flight: now order after the preceding kernel
           pdl_wait();
           if (signal_net < 0) pdl_launch_dependents();
         }
-        const int kind = i & 1;
-        const uint32_t u = use[kind], slot = u & 1u;
-        if (u >= 2u) mbar_wait(&s.bar_wfree[kind][slot], ((u >> 1) - 1u) & 1u);
+        const int kind = i & 1, slot = (i >> 1) & 1;
+        const uint32_t u = cnt[kind][slot];
+        if (u >= 1u) mbar_wait(&s.bar_wfree[kind][slot], (u - 1u) & 1u);
         const uint32_t off = (kInitial && i < 2) ? (i == 0 ? kWh1 : kWh2) : c_block_off[i];  // representation_net at the root
-        if (elect_one()) tma_load(kind ? s.ws[slot] : s.wf[slot], wsec + off, c_block_bytes[i], &s.bar_wfull[kind][slot]);
+        uint8_t* dst = kind ? (slot ? s.ws1 : s.ws0) : s.wf[slot];
+        if (elect_one()) tma_load(dst, wsec + off, c_block_bytes[i], &s.bar_wfull[kind][slot]);
         __syncwarp();
-        use[kind] = u + 1u;
+        cnt[kind][slot] = u + 1u;
       }
     }
   } else if (warp == kMmaWarp || warp == kMmaWarp1) {
@@ -544,7 +549,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     const uint32_t id256 = umma_idesc(256);
     const uint32_t T = tmem + kColsPerTile * t;
     const uint32_t ax = smem_u32(s.t[t].ax);
-    uint32_t use_f = 0, use_s = 0, ph_g = 0, ph_a = 0, ph_raw = 0, ph_hn = 0, ph_fin = 0;
+    uint32_t use0 = 0, use1 = 0, ph_g = 0, ph_a = 0, ph_raw = 0, ph_hn = 0, ph_fin = 0;  // use0 / use1: networks done on weight slot 0 / 1
     bool first = true;
     for (int pass = 0; pass < n_pass; ++pass) {
 #pragma unroll 1
@@ -553,9 +558,9 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
         if (t == 0 && net == signal_net && pass == n_pass - 1) pdl_launch_dependents();
         // ---- first layer: H[0:256) = [A | AX] x W1'^T
         {
-          const uint32_t slot = use_f & 1u;
+          const uint32_t slot = (uint32_t)net & 1u, use = slot ? use1 : use0;  // both layers of a network use slot (net & 1)
           if (elect_one()) TL4(16 + net * 2 + t);
-          mbar_wait(&s.bar_wfull[0][slot], (use_f >> 1) & 1u);
+          mbar_wait(&s.bar_wfull[0][slot], use & 1u);
           const uint32_t wf = smem_u32(s.wf[slot]);
           const uint32_t a_in = net <= 1 ? smem_u32(s.t[t].a0) : smem_u32(s.t[t].ahn);
           if (net == 0) mbar_wait(&s.bar_g[t], ph_g);
@@ -583,15 +588,14 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
           if (net == 0) ph_g ^= 1;
           if (net == 1) ph_raw ^= 1;
           if (net == 2) ph_hn ^= 1;
-          ++use_f;
         }
         // ---- second layer: O = [A1 | AX] x W2'^T, A1 from TMEM
         {
           const uint32_t n2 = net == 0 ? 64u : (net == 3 ? 16u : 48u);
           const uint32_t id2 = umma_idesc(n2);
-          const uint32_t slot = use_s & 1u;
-          mbar_wait(&s.bar_wfull[1][slot], (use_s >> 1) & 1u);
-          const uint32_t ws = smem_u32(s.ws[slot]);
+          const uint32_t slot = (uint32_t)net & 1u, use = slot ? use1 : use0;
+          mbar_wait(&s.bar_wfull[1][slot], use & 1u);
+          const uint32_t ws = smem_u32(slot ? s.ws1 : s.ws0);
           mbar_wait(&s.bar_a[t], ph_a);
           if (elect_one()) TL4(net * 4 + 2 + t);
           tc_fence_after();
@@ -607,7 +611,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
           }
           __syncwarp();
           ph_a ^= 1;
-          ++use_s;
+          if (slot) ++use1; else ++use0;
         }
       }
       first = false;
