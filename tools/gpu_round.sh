@@ -4,6 +4,7 @@
 #   bash tools/gpu_round.sh bench          default bench line only (20 steps)
 #   bash tools/gpu_round.sh envsweep       env kernels over HMZ_ENV_UNROLL x HMZ_ENV_CTAS
 #   bash tools/gpu_round.sh memcheck       compute-sanitizer --tool memcheck over smoke()
+#   bash tools/gpu_round.sh microbench     TMEM / tcgen05.mma micro-benchmarks, kernel families alone, clock64 timelines
 #   bash tools/gpu_round.sh ncu            plain bench, ncu launch list of one step, ncu --set full of the hot kernels
 # Several stages may be given; every stage writes into gpurun_out/ (scratch) and never stops the others.
 # (At most one of ncu / compute-sanitizer per call: B200_PROFILING.md.)
@@ -96,6 +97,17 @@ for stage in "$@"; do
       python tools/env_probe.py > gpurun_out/env_probe.txt 2>&1 &&
       ncu --set full --clock-control none --import-source on -k regex:env_step -s 6 -c 4 -o gpurun_out/prof_env -f python tools/env_probe.py > gpurun_out/ncu_env.log 2>&1
       echo "ncu env rc=$?"
+      ;;
+    microbench)
+      # TMEM port / tcgen05.mma issue micro-benchmarks behind DESIGN.md's MLP model (make -C tools/microbench first, here)
+      timeout 60 ./tools/microbench/tmem > gpurun_out/tmem_bench.txt 2>&1; echo "tmem rc=$?"
+      timeout 60 ./tools/microbench/mma > gpurun_out/mma_bench.txt 2>&1; echo "mma rc=$?"
+      SKIP=1 SCHEDULES=1,2,4 MOVES=8 timeout 100 python tools/persist_probe.py > gpurun_out/family_alone.txt 2>&1
+      SKIP=2 SCHEDULES=1,2,4 MOVES=8 timeout 100 python tools/persist_probe.py >> gpurun_out/family_alone.txt 2>&1
+      SCHEDULES=4 MOVES=8 timeout 100 python tools/persist_probe.py >> gpurun_out/family_alone.txt 2>&1
+      cat gpurun_out/family_alone.txt
+      python tools/tc_timeline.py > gpurun_out/timeline_net_tc.txt 2>&1
+      TORCH_INIT=1 SEARCHES=17,30000,5000 timeout 120 python tools/tree_timeline.py > gpurun_out/timeline_tree.txt 2>&1
       ;;
     groupsweep)
       : > gpurun_out/group_sweep.txt
