@@ -288,6 +288,10 @@ int hmz_debug_tree_timeline(long long search, unsigned long long* host_out);
  * [3] summed tree-warp lifetimes, [4] MLP CTAs waiting for the tree (one thread each), [5] MLP CTAs first -> last hand-off,
  * [6] MLP passes, [7] tree warps. */
 int hmz_debug_persist_stats(unsigned long long* host_out);
+/* Tooling: launch Gantt of the hot-loop kernels.  enable = 1 starts recording; enable = 0 stops, synchronises the device
+ * and writes up to max_records records of four words {kind (0 = network kernel, 1 = fused tree kernel), tag = sim << 8 |
+ * group, first block's start, last block's end} (globaltimer ns) to host_out; *n_out = records written. */
+int hmz_debug_gantt(int enable, unsigned long long* host_out, int max_records, int* n_out);
 /* Tests only: compares the search kernels' exact-division shortcuts (table / precomputed reciprocal + two
  * FMA corrections) with IEEE division bit for bit on n_samples random operand pairs; adds the number of
  * mismatches to counters[0] (division by a visit count) and counters[1] (division by the min-max range). */

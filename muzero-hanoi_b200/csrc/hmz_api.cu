@@ -60,9 +60,61 @@ int sm_count() {
   return cached;
 }
 
+// ---- launch Gantt recorder (tooling) ----
+namespace {
+constexpr int kGanttSlots = 16384;
+std::mutex g_gantt_mu;
+unsigned long long* g_gantt_dev = nullptr;
+int g_gantt_on = 0, g_gantt_used = 0;
+int g_gantt_meta[kGanttSlots][2];
+thread_local int tl_gantt_tag = 0;
+}  // namespace
+unsigned long long* gantt_next(int kind, int tag) {
+  if (!g_gantt_on) return nullptr;
+  std::lock_guard<std::mutex> lk(g_gantt_mu);
+  if (!g_gantt_on || g_gantt_used >= kGanttSlots) return nullptr;
+  g_gantt_meta[g_gantt_used][0] = kind;
+  g_gantt_meta[g_gantt_used][1] = tag;
+  return g_gantt_dev + 2 * (size_t)(g_gantt_used++);
+}
+void gantt_set_context(int group, int sim) { tl_gantt_tag = (sim << 8) | (group & 0xFF); }
+int gantt_context_tag() { return tl_gantt_tag; }
+
 }  // namespace hmz
 
 extern "C" {
+
+// enable = 1: start recording (slots reset).  enable = 0: stop, synchronise the device and copy out up to max_records
+// records of four words {kind (0 = network, 1 = tree), tag = sim << 8 | group, start ns, end ns}; *n_out = records written.
+int hmz_debug_gantt(int enable, unsigned long long* host_out, int max_records, int* n_out) {
+  using namespace hmz;
+  std::lock_guard<std::mutex> lk(g_gantt_mu);
+  if (enable) {
+    if (!g_gantt_dev && cudaMalloc(&g_gantt_dev, sizeof(unsigned long long) * 2 * kGanttSlots) != cudaSuccess)
+      return fail(HMZ_ERR_CUDA, "hmz_debug_gantt: cudaMalloc failed");
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemset(g_gantt_dev, 0xFF, sizeof(unsigned long long) * 2 * kGanttSlots) != cudaSuccess)
+      return fail(HMZ_ERR_CUDA, "hmz_debug_gantt: reset failed");
+    g_gantt_used = 0;
+    g_gantt_on = 1;
+    return HMZ_OK;
+  }
+  g_gantt_on = 0;
+  if (n_out) *n_out = 0;
+  if (!g_gantt_dev || !host_out) return HMZ_OK;
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail(HMZ_ERR_CUDA, "hmz_debug_gantt: synchronise failed");
+  const int n = g_gantt_used < max_records ? g_gantt_used : max_records;
+  std::vector<unsigned long long> raw(2 * (size_t)(n > 0 ? n : 1));
+  if (n > 0 && cudaMemcpy(raw.data(), g_gantt_dev, sizeof(unsigned long long) * 2 * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(HMZ_ERR_CUDA, "hmz_debug_gantt: copy failed");
+  for (int i = 0; i < n; ++i) {
+    host_out[4 * i] = (unsigned long long)g_gantt_meta[i][0];
+    host_out[4 * i + 1] = (unsigned long long)g_gantt_meta[i][1];
+    host_out[4 * i + 2] = raw[2 * i];
+    host_out[4 * i + 3] = ~raw[2 * i + 1];
+  }
+  if (n_out) *n_out = n;
+  return HMZ_OK;
+}
 
 const char* hmz_last_error(void) { return hmz::error_buffer(); }
 

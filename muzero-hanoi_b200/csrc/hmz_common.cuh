@@ -82,6 +82,21 @@ inline cudaError_t launch_pdl(int kind_bit, void (*kernel)(KArgs...), dim3 grid,
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Tooling (hmz_debug_gantt): when recording is on, the next launch of a hot-loop kernel by this host thread gets a slot of
+// two device words — the globaltimer of its first block's start and (complemented, so that both are atomicMin) of its
+// last block's end.  gantt_next() hands out the slot and remembers (kind, tag); nullptr when recording is off.
+unsigned long long* gantt_next(int kind, int tag);
+__device__ __forceinline__ void gantt_mark(unsigned long long* slot, int which) {
+  if (slot != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(slot + which, which ? ~t : t);
+  }
+}
+// (kind, tag) of the launch being enqueued by this host thread: set by hmz_search_run around each launch
+void gantt_set_context(int group, int sim);
+int gantt_context_tag();
+
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
 
 // Grid for a grid-stride kernel: a whole number of waves of `ctas_per_sm` CTAs on every SM,

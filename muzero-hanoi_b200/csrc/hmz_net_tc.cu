@@ -181,6 +181,7 @@ int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_pe
   a.n = n;
   a.n_pairs = n_pairs;
   a.timeline = tc_timeline_enabled() | (pdl_prewait() << 1) | ((pdl_net_at() + 1) << 2);
+  a.gantt = gantt_next(0, gantt_context_tag());
   cudaError_t e = launch_pdl(1, tc::v4::net_tc<false>, dim3(grid), dim3(tc::v4::kLaunchThreads), (size_t)smem, stream, a);
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_tc<recurrent> launch: %s", cudaGetErrorString(e));
   return check_launch("net_tc<recurrent>");

@@ -342,6 +342,7 @@ struct TcArgs {
   int64_t n;                  // items
   int n_pairs;                // tile pairs = ceil(n / 256)
   int timeline;               // tooling / PDL switches of the stand-alone kernels
+  unsigned long long* gantt;  // tooling (hmz_debug_gantt), nullable
 };
 
 // Hand-off state of the persistent search kernel (hmz_persist.cu), in global memory; zeroed before every launch.
@@ -467,6 +468,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     }                                                                        \
   } while (0)
   TL4_CTA(60);
+  if (!kPersist && tid == 0) gantt_mark(a.gantt, 0);
 
   // barrier initialisation is spread over one lane of each of warps 1-3 while warp 0 allocates TMEM
   if (tid == 32) {
@@ -870,6 +872,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
   tc_fence_before();
   __syncthreads();
   TL4_CTA(63);
+  if (!kPersist && tid == 0) gantt_mark(a.gantt, 1);
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");

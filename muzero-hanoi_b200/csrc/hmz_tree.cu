@@ -86,8 +86,10 @@ __global__ void __launch_bounds__(kTreeThreads) search_select(hmz_search_t s, in
 template <bool kTL, bool kTrusted>
 __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_backup_select(hmz_search_t s, int sim, const double* __restrict__ ucb_table,
                                                                      double discount, TreeScratch sc, int do_select) {
+  if (threadIdx.x == 0) gantt_mark(sc.gantt, 0);
   tree_phase<kTL, kTrusted, true>(s, sim, ucb_table, discount, sc, do_select, (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1,
                                   (int)(threadIdx.x & 1), GlobalTables());
+  if ((threadIdx.x & 31) == 0) gantt_mark(sc.gantt, 1);
 }
 
 // Node.child_Q / child_U of one node per search (inspection; same arithmetic as select_leaf).
@@ -404,7 +406,7 @@ int hmz_search_expand_backup(const hmz_search_t* s, int sim, double discount, co
   if (!leaf_parent || !leaf_action || !r || !p || !v || sim < 0 || sim + 1 >= s->n_records)
     return fail(HMZ_ERR_INVALID, "hmz_search_expand_backup: bad arguments (sim=%d, n_records=%d)", sim, s->n_records);
   // split-phase form: no recorded path, the backup walks the parent links
-  TreeScratch sc{const_cast<uint16_t*>(leaf_parent), const_cast<uint8_t*>(leaf_action), nullptr, nullptr, nullptr, r, p, v, nullptr};
+  TreeScratch sc{const_cast<uint16_t*>(leaf_parent), const_cast<uint8_t*>(leaf_action), nullptr, nullptr, nullptr, r, p, v, nullptr, nullptr};
   search_backup_select<false, false><<<search_grid(s->n_searches), kTreeThreads, 0, (cudaStream_t)stream>>>(*s, sim, nullptr, discount, sc, 0);
   return check_launch("search_expand_backup");
 }
@@ -511,7 +513,8 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
   const int do_select = (sim + 1 < n_simulations ? 1 : 0) | (pdl_prewait() << 1) | ((pdl_tree_at() & 3) << 2);
   const float *cr = sc.r, *cp = sc.p, *cv = sc.v;
   TreeScratch ts{sc.lp, sc.la, sc.depth, sc.path, sc.wild, cr, cp, cv,
-                 s->capture ? s->capture + ((size_t)sim * (size_t)capture_stride + (size_t)capture_lo) * 8 : nullptr};
+                 s->capture ? s->capture + ((size_t)sim * (size_t)capture_stride + (size_t)capture_lo) * 8 : nullptr,
+                 gantt_next(1, gantt_context_tag())};
   cudaError_t e = launch_pdl(2, g_tree_tl_search >= 0 ? search_backup_select<true, true> : search_backup_select<false, true>,
                              dim3(search_grid(B)), dim3(kTreeThreads), 0, st, *s, sim, ucb_table, discount, ts, do_select);
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "search_backup_select launch: %s", cudaGetErrorString(e));
@@ -541,7 +544,7 @@ static int search_run_direct(const hmz_search_t* s, const void* weights, int mod
     if (!cnt) return fail(HMZ_ERR_CUDA, "cudaGetSymbolAddress(count table) failed");
     char* ws = (char*)(((uintptr_t)s->workspace + 255) & ~(uintptr_t)255);
     void* ctl = ws + (((size_t)Bp * (40 + 32 * kPathCap) + 255) & ~(size_t)255);
-    TreeScratch ts{sc.lp, sc.la, sc.depth, sc.path, sc.wild, sc.r, sc.p, sc.v, nullptr};
+    TreeScratch ts{sc.lp, sc.la, sc.depth, sc.path, sc.wild, sc.r, sc.p, sc.v, nullptr, nullptr};
     return persist_launch(s, weights, n_simulations, ucb_table, discount, cnt, ts, ctl, (cudaStream_t)stream);
   }
   // Searches never interact, so the batch is cut into groups whose select -> MLP -> backup chains
@@ -556,8 +559,10 @@ static int search_run_direct(const hmz_search_t* s, const void* weights, int mod
   groups = (int)((B + per - 1) / per);
   if (groups <= 1) {
     SimScratch sc = carve_scratch(s->workspace, Bp, 0);
-    for (int sim = 0; sim < n_simulations; ++sim)
+    for (int sim = 0; sim < n_simulations; ++sim) {
+      gantt_set_context(0, sim);
       if (int rc = run_one_sim(s, sc, weights, mode, sim, n_simulations, ucb_table, discount, stream, B, 0)) return rc;
+    }
     return HMZ_OK;
   }
   GroupStreams* gs = nullptr;
@@ -581,8 +586,10 @@ static int search_run_direct(const hmz_search_t* s, const void* weights, int mod
   }
   int rc = HMZ_OK;
   for (int sim = 0; sim < n_simulations && rc == HMZ_OK; ++sim)
-    for (int g = 0; g < groups && rc == HMZ_OK; ++g)
+    for (int g = 0; g < groups && rc == HMZ_OK; ++g) {
+      gantt_set_context(g, sim);
       rc = run_one_sim(&sub[g], sc[g], weights, mode, sim, n_simulations, ucb_table, discount, (void*)gs->stream[g], B, g * per);
+    }
   for (int g = 0; g < groups; ++g) {  // always join, even after an error, so the caller's stream stays ordered
     cudaEventRecord(gs->done[g], gs->stream[g]);
     cudaStreamWaitEvent(main_stream, gs->done[g], 0);

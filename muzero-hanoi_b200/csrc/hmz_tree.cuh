@@ -515,6 +515,7 @@ struct TreeScratch {
   const float* p;
   const float* v;
   float* capture;  // nullable: [n_searches][8] row of THIS simulation
+  unsigned long long* gantt;  // tooling (hmz_debug_gantt), nullable
 };
 
 // Phases 2b + 3 of simulation `sim` (expansion with the network outputs, backup), optionally followed at once by the
