@@ -178,10 +178,13 @@ typedef struct hmz_search {
   int32_t root_prior_is_f64; /* 1: noised root, U = f32(f64 prior * w) (node.py:122)      */
   int32_t schedule;    /* hmz_search_run scheduling, never changes results: 0 = automatic; k in [1, 16] = one
                           launch pair per simulation with the batch cut into k concurrent stream groups;
-                          HMZ_SCHEDULE_PERSISTENT = one persistent role-specialised kernel per call        */
+                          HMZ_SCHEDULE_PERSISTENT = one persistent role-specialised kernel per call;
+                          HMZ_SCHEDULE_SERVER | k = network CTAs resident for the whole call on a fixed share of the
+                          SMs, fed through memory flags by ordinary tree-kernel launches in k stream groups (0: 4) */
 } hmz_search_t;
 #define HMZ_SCHEDULE_AUTO 0
 #define HMZ_SCHEDULE_PERSISTENT 64
+#define HMZ_SCHEDULE_SERVER 128
 
 /* Scratch needed by hmz_search_run (per-simulation leaf ids and network outputs). */
 int64_t hmz_search_workspace_bytes(int64_t n_searches);

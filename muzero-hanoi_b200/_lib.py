@@ -14,7 +14,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 FLAG_DONE, FLAG_ILLEGAL, FLAG_GOAL, FLAG_TRUNC = 1, 2, 4, 8
 N_ACTIONS, LATENT, HIDDEN, SUPPORT, MAX_DISKS, NO_CHILD = 6, 64, 256, 33, 12, 0xFFFF
 LATENT_F32, LATENT_BF16 = 0, 1
-SCHEDULE_AUTO, SCHEDULE_PERSISTENT = 0, 64
+SCHEDULE_AUTO, SCHEDULE_PERSISTENT, SCHEDULE_SERVER = 0, 64, 128
 MODE_FP32, MODE_BF16 = 0, 1
 
 

@@ -57,11 +57,17 @@ constexpr unsigned long long kWaitTimeoutNs = 20ull * 1000ull * 1000ull * 1000ul
 struct WaitGuard {
   uint32_t spins = 0;
   unsigned long long t0 = 0;
+  bool expired = false;  // HMZ_WATCHDOG_SOFT (tooling build): the wait gives up after 2 s instead of trapping, so that the
+                         // kernels end and the caller of the wait can report what it was waiting for
   __device__ __forceinline__ void poll() {
     if ((++spins & 0xFFFFu) == 0u) {
       const unsigned long long now = globaltimer_ns();
       if (t0 == 0) t0 = now;
+#ifdef HMZ_WATCHDOG_SOFT
+      else if (now - t0 > 2000000000ull) expired = true;
+#else
       else if (now - t0 > kWaitTimeoutNs) __trap();
+#endif
     }
   }
 };
@@ -359,6 +365,8 @@ struct PersistCtl {
   uint32_t q_mask;      // capacity - 1 (power of two)
   int n_sims;
   unsigned long long* stats;  // tooling (HMZ_PERSIST_STATS=1), nullable: clock64 sums, see hmz_debug_persist_stats
+  uint32_t* mlp_done;         // server schedule (nullable; stride 8 words): mlp_done[pair] = simulations whose network outputs are
+                              // complete — the tree kernels' warps wait on it; when set, no item is pushed to the queue
 };
 #ifdef HMZ_PERSIST_STATS  // tooling build (tools/build_variant.py): role statistics of the persistent kernel
 constexpr bool kPersistStats = true;
@@ -415,12 +423,22 @@ __device__ __forceinline__ void persist_wait_tree(const PersistCtl& pc, int pair
   while (ld_relaxed_u32(ctr) < need) {
     persist_backoff();
     guard.poll();
+#ifdef HMZ_WATCHDOG_SOFT
+    if (guard.expired) {
+      if ((threadIdx.x & 127) == 0) printf("MLP cta %d thread %d: pair %d sim %d waits tree_done >= %u, sees %u\n", (int)blockIdx.x, (int)threadIdx.x, pair, sim, need, ld_relaxed_u32(ctr));
+      break;
+    }
+#endif
   }
   fence_acquire_gpu();
 }
 // One thread, after every output of (pair, sim) is in global memory and ordered before it at CTA scope: hands the pair
 // to the tree warps as work item (pair, sim + 1).
 __device__ __forceinline__ void persist_push_item(const PersistCtl& pc, int n_pairs, int pair, int sim_next) {
+  if (pc.mlp_done != nullptr) {  // server schedule: the pair's flag is the hand-off
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(pc.mlp_done + (size_t)pair * 8), "r"((uint32_t)sim_next) : "memory");
+    return;
+  }
   const uint32_t pos = atomicAdd(pc.q_tail, 1u);
   const unsigned long long item = (unsigned long long)n_pairs + pos;
   st_release_u64(pc.queue + (pos & pc.q_mask), ((item + 1ull) << 32) | (unsigned long long)((uint32_t)pair | ((uint32_t)sim_next << 16)));

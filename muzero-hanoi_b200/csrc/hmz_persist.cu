@@ -129,6 +129,75 @@ __global__ void __launch_bounds__(kPersistThreads, 1) search_persistent(const __
   }
 }
 
+// ---- server schedule (HMZ_SCHEDULE_SERVER): the MLP role alone stays resident (search_persistent launched with MLP CTAs
+// only), the tree phases are ORDINARY launches of the fused kernel below on the remaining SMs, one per simulation and
+// stream group.  Hand-off per 256-search tile pair, both ways through memory:
+//   tree -> MLP   every warp adds 1 to tree_done[pair] (release) after its 16 searches' selection of simulation `sim`
+//   MLP -> tree   mlp_done[pair] = sim (release) once the network outputs of simulation sim - 1 are stored; the warps of
+//                 the tree launch for `sim` poll it before their backup (acquire)
+// A network CTA needs a whole SM, so under the launch-per-simulation schedule the two kernel families take turns on the
+// machine; here the network CTAs keep their SMs and the tree blocks never wait for an SM to drain.
+static int server_mlp_ctas() {
+  static const int v = getenv("HMZ_SERVER_MLP") ? atoi(getenv("HMZ_SERVER_MLP")) : 64;
+  return v;
+}
+
+// Launches the resident MLP CTAs on `mlp_stream`; the caller then enqueues the tree launches (server_tree_launch).
+int server_mlp_launch(const hmz_search_t* s, const void* weights, int n_simulations, TreeScratch scratch, void* ctl_mem,
+                      cudaStream_t ctl_stream, cudaStream_t mlp_stream, ServerCtl* out) {
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed");
+  const int smem = (int)sizeof(tc::v4::Smem) + 1024;
+  if (attr_dev != dev) {
+    if (cudaFuncSetAttribute(search_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return fail(HMZ_ERR_CUDA, "cudaFuncSetAttribute(search_persistent): %s", cudaGetErrorString(cudaGetLastError()));
+    attr_dev = dev;
+  }
+  PersistArgs a{};
+  const int64_t B = s->n_searches;
+  a.n_pairs = (int)((B + 2 * tc::kM - 1) / (2 * tc::kM));
+  a.n_sims = n_simulations;
+  int n_mlp = server_mlp_ctas();
+  if (n_mlp > sm_count() - 8) n_mlp = sm_count() - 8;
+  if (n_mlp > a.n_pairs) n_mlp = a.n_pairs;
+  if (n_mlp < 1) return fail(HMZ_ERR_UNSUPPORTED, "server schedule needs at least 9 SMs");
+  a.n_mlp = n_mlp;
+  char* ctl = (char*)ctl_mem;
+  int64_t cap = 64;
+  while (cap < 2 * (int64_t)a.n_pairs) cap <<= 1;
+  // (the caller has zeroed the control block on ctl_stream and ordered both streams behind it)
+  (void)ctl_stream;
+  a.ctl.tree_head = (uint32_t*)ctl;
+  a.ctl.q_tail = (uint32_t*)(ctl + 256);
+  a.ctl.tree_done = (uint32_t*)(ctl + 1024);
+  a.ctl.queue = (unsigned long long*)(ctl + 1024 + (size_t)a.n_pairs * 32);
+  a.ctl.q_mask = (uint32_t)(cap - 1);
+  a.ctl.n_sims = n_simulations;
+  a.ctl.stats = nullptr;
+  a.ctl.mlp_done = (uint32_t*)(ctl + 1024 + (size_t)a.n_pairs * 32 + (size_t)cap * 8 + 256);
+  a.net.wsec = (const uint8_t*)weights;
+  a.net.lat_in = s->latents;
+  a.net.in_rows_per_item = s->n_records;
+  a.net.in_row = scratch.leaf_parent;
+  a.net.actions = scratch.leaf_action;
+  a.net.lat_out = s->latents;
+  a.net.out_rows_per_item = s->n_records;
+  a.net.out_row = 0;
+  a.net.latent_dtype = s->latent_dtype;
+  a.net.r_out = const_cast<float*>(scratch.r);
+  a.net.p_out = const_cast<float*>(scratch.p);
+  a.net.v_out = const_cast<float*>(scratch.v);
+  a.net.n = B;
+  a.net.n_pairs = a.n_pairs;
+  a.net.timeline = 0;
+  search_persistent<<<dim3((unsigned)n_mlp), dim3(kPersistThreads), (size_t)smem, mlp_stream>>>(a);
+  if (int rc = check_launch("search_persistent (server: MLP CTAs)")) return rc;
+  out->tree_done = a.ctl.tree_done;
+  out->mlp_done = a.ctl.mlp_done;
+  return HMZ_OK;
+}
+
 static int persist_stats_on() {
   static const int v = getenv("HMZ_PERSIST_STATS") ? atoi(getenv("HMZ_PERSIST_STATS")) : 0;
   return v;
@@ -171,7 +240,7 @@ int64_t persist_ctl_bytes(int64_t n_searches) {
   const int64_t n_pairs = (n_searches + 2 * tc::kM - 1) / (2 * tc::kM);
   int64_t cap = 64;
   while (cap < 2 * n_pairs) cap <<= 1;
-  return 1024 + n_pairs * 32 + cap * 8;
+  return 1024 + n_pairs * 32 + cap * 8 + 256 + n_pairs * 32;  // ... + the server schedule's per-pair flags
 }
 
 bool persist_supported(const hmz_search_t* s, int mode, int n_simulations) {

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "hmz_common.cuh"
+#include "hmz_net_tc.cuh"
 #include "hmz_tree.cuh"
 
 namespace hmz {
@@ -91,6 +92,46 @@ __global__ void __launch_bounds__(kTreeThreads, HMZ_TREE_MIN_BLOCKS) search_back
                                   (int)(threadIdx.x & 1), GlobalTables());
   if ((threadIdx.x & 31) == 0) gantt_mark(sc.gantt, 1);
 }
+
+// Server schedule (HMZ_SCHEDULE_SERVER, hmz_persist.cu): the fused tree phase as an ORDINARY launch whose warps hand
+// 256-search tile pairs to / from network CTAs that stay resident on their own SMs for the whole search:
+//   MLP -> tree   the warps poll mlp_done[pair] until the network outputs of the simulation they back up are stored (acquire)
+//   tree -> MLP   every warp adds 1 to tree_done[pair] (release) after its 16 searches' next selection
+template <bool kTrusted>
+__global__ void __launch_bounds__(128, 5) search_tree_served(hmz_search_t s, int sim, const double* __restrict__ ucb_table, double discount,
+                                                            TreeScratch sc, int flags, uint32_t* tree_done, const uint32_t* mlp_done,
+                                                            int pair_base) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int pair = pair_base + (int)(t >> 9);  // 512 threads = 256 searches per tile pair; a warp never straddles pairs
+  if (!(flags & 16)) {  // the backup consumes the network outputs of simulation `sim`: wait for the pair's pass
+    const uint32_t need = (uint32_t)sim + 1u;
+    const uint32_t* flag = mlp_done + (size_t)pair * 8;
+    if (lane == 0) {
+      tc::WaitGuard guard;
+      while (tc::v4::ld_relaxed_u32(flag) < need) {
+        tc::v4::persist_backoff();
+        guard.poll();
+#ifdef HMZ_WATCHDOG_SOFT
+        if (guard.expired) {
+          if ((t & 511) == 0) printf("tree block %d: pair %d sim %d waits mlp_done >= %u, sees %u (tree_done %u)\n", (int)blockIdx.x, pair, sim, need, tc::v4::ld_relaxed_u32(flag), tc::v4::ld_relaxed_u32(tree_done + (size_t)pair * 8));
+          break;
+        }
+#endif
+      }
+    }
+    __syncwarp();
+    tc::v4::fence_acquire_gpu();
+  }
+  if (threadIdx.x == 0) gantt_mark(sc.gantt, 0);
+  tree_phase<false, kTrusted, false>(s, sim, ucb_table, discount, sc, flags, t >> 1, lane & 1, GlobalTables());
+  if (flags & 1) {
+    __syncwarp();  // every lane's stores of the slice happen before lane 0's release
+    if (lane == 0) tc::v4::red_release_add(tree_done + (size_t)pair * 8, 1u);
+  }
+  if (lane == 0) gantt_mark(sc.gantt, 1);
+}
+
 
 // Node.child_Q / child_U of one node per search (inspection; same arithmetic as select_leaf).
 __global__ void __launch_bounds__(128) search_child_scores(hmz_search_t s, const uint16_t* __restrict__ record,
@@ -245,6 +286,8 @@ int64_t persist_ctl_bytes(int64_t n_searches);
 bool persist_supported(const hmz_search_t* s, int mode, int n_simulations);
 int persist_launch(const hmz_search_t* s, const void* weights, int n_simulations, const double* ucb_table, double discount,
                    const CountRow* cnt_table, const TreeScratch& scratch, void* ctl_mem, cudaStream_t stream);
+int server_mlp_launch(const hmz_search_t* s, const void* weights, int n_simulations, TreeScratch scratch, void* ctl_mem,
+                      cudaStream_t ctl_stream, cudaStream_t mlp_stream, ServerCtl* out);
 
 // Device address of this translation unit's count-row table (filled by ensure_rcp_table).
 static const CountRow* count_table_address() {
@@ -482,6 +525,18 @@ SimScratch carve_scratch(void* workspace, int64_t padded_total, int64_t lo) {
 }  // namespace
 
 
+// One tree launch of the server schedule for the searches of `s` (a slice that starts at tile pair `pair_base`):
+// item `sim_item` = expansion + backup of simulation sim_item - 1 (none for 0) and the selection of simulation sim_item
+// (none after the last one).
+static int server_tree_launch(const hmz_search_t* s, int sim_item, int n_simulations, const double* ucb_table, double discount,
+                       const TreeScratch& sc, const ServerCtl& ctl, int pair_base, cudaStream_t stream) {
+  const int64_t pairs = (s->n_searches + 2 * tc::kM - 1) / (2 * tc::kM);
+  const int flags = (sim_item < n_simulations ? 1 : 0) | (sim_item == 0 ? 16 : 0);
+  search_tree_served<true><<<dim3((unsigned)(pairs * 4)), dim3(128), 0, stream>>>(*s, sim_item - 1, ucb_table, discount, sc, flags,
+                                                                               ctl.tree_done, ctl.mlp_done, pair_base);
+  return check_launch("search_tree_served");
+}
+
 static int debug_skip() {
   const char* e = getenv("HMZ_DEBUG_SKIP");
   return e ? atoi(e) : 0;
@@ -521,6 +576,73 @@ static int run_one_sim(const hmz_search_t* s, const SimScratch& sc, const void* 
   return check_launch("search_backup_select");
 }
 
+// HMZ_SCHEDULE_SERVER | k: resident network CTAs + one ordinary tree launch per simulation and stream group (k groups of
+// whole tile pairs; 0 = 4).  Stream plan: the control block is zeroed on the caller's stream; the MLP stream and the k
+// tree streams fork from it; the caller's stream joins all of them.
+static int search_run_server(const hmz_search_t* s, const void* weights, int n_simulations, const double* ucb_table,
+                             double discount, void* stream) {
+  const int64_t B = s->n_searches;
+  const int64_t Bp = (B + 63) / 64 * 64;
+  int groups = s->schedule - HMZ_SCHEDULE_SERVER;
+  if (groups < 0 || groups > 15) return fail(HMZ_ERR_INVALID, "hmz_search_run: bad server schedule %d", s->schedule);
+  if (groups == 0) groups = 4;
+  const int64_t per = ((B + groups - 1) / groups + 255) / 256 * 256;  // whole tile pairs: the hand-offs are per pair
+  groups = (int)((B + per - 1) / per);
+  GroupStreams* gs = nullptr;
+  if (int rc = get_group_streams(groups + 1, &gs)) return rc;
+  cudaStream_t main_stream = (cudaStream_t)stream, mlp_stream = gs->stream[groups];
+  SimScratch sc0 = carve_scratch(s->workspace, Bp, 0);
+  char* ws = (char*)(((uintptr_t)s->workspace + 255) & ~(uintptr_t)255);
+  void* ctl = ws + (((size_t)Bp * (40 + 32 * kPathCap) + 255) & ~(size_t)255);
+  if (cudaMemsetAsync(sc0.wild, 0, (size_t)B, main_stream) != cudaSuccess ||
+      cudaMemsetAsync(ctl, 0, (size_t)persist_ctl_bytes(B), main_stream) != cudaSuccess)
+    return fail(HMZ_ERR_CUDA, "cudaMemsetAsync(server control block) failed");
+  if (cudaEventRecord(gs->fork, main_stream) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaEventRecord(fork) failed");
+  for (int g = 0; g <= groups; ++g)
+    if (cudaStreamWaitEvent(gs->stream[g], gs->fork, 0) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaStreamWaitEvent failed");
+  {  // CUDA loads kernels lazily, and loading one may wait for the device to go idle — which the resident network CTAs
+     // never let it: the tree kernel must be loaded BEFORE they are launched
+    static thread_local int loaded_dev = -1;
+    int dev = 0;
+    cudaFuncAttributes fa;
+    if (cudaGetDevice(&dev) != cudaSuccess || (loaded_dev != dev && cudaFuncGetAttributes(&fa, search_tree_served<true>) != cudaSuccess))
+      return fail(HMZ_ERR_CUDA, "hmz_search_run: loading the served tree kernel failed");
+    loaded_dev = dev;
+  }
+  ServerCtl sctl{};
+  TreeScratch whole{sc0.lp, sc0.la, sc0.depth, sc0.path, sc0.wild, sc0.r, sc0.p, sc0.v, nullptr, nullptr};
+  int rc = server_mlp_launch(s, weights, n_simulations, whole, ctl, main_stream, mlp_stream, &sctl);
+  hmz_search_t sub[16];
+  SimScratch sc[16];
+  const size_t lat_elem = s->latent_dtype == HMZ_LATENT_F32 ? 4 : 2;
+  for (int g = 0; g < groups; ++g) {
+    const int64_t lo = g * per, hi = (lo + per < B) ? lo + per : B;
+    sub[g] = *s;
+    sub[g].nodes = s->nodes + lo * s->n_records;
+    sub[g].latents = (char*)s->latents + (size_t)lo * s->n_records * kLatentWidth * lat_elem;
+    sub[g].root_prior = s->root_prior + lo * 6;
+    sub[g].root_W = s->root_W + lo;
+    sub[g].minmax = s->minmax + 2 * lo;
+    sub[g].n_searches = hi - lo;
+    sc[g] = carve_scratch(s->workspace, Bp, lo);
+  }
+  // item k: expansion + backup of simulation k - 1 (none for k = 0) and the selection of simulation k (none for k = S)
+  for (int k = 0; k <= n_simulations && rc == HMZ_OK; ++k)
+    for (int g = 0; g < groups && rc == HMZ_OK; ++g) {
+      ProfScope prof_scope(HMZ_PROF_EXPAND_BACKUP, (void*)gs->stream[g]);
+      gantt_set_context(g, k);
+      TreeScratch ts{sc[g].lp, sc[g].la, sc[g].depth, sc[g].path, sc[g].wild, sc[g].r, sc[g].p, sc[g].v,
+                     (s->capture && k > 0) ? s->capture + ((size_t)(k - 1) * (size_t)B + (size_t)(g * per)) * 8 : nullptr,
+                     gantt_next(1, gantt_context_tag())};
+      rc = server_tree_launch(&sub[g], k, n_simulations, ucb_table, discount, ts, sctl, (int)(g * per / 256), gs->stream[g]);
+    }
+  for (int g = 0; g <= groups; ++g) {  // always join, even after an error, so the caller's stream stays ordered
+    cudaEventRecord(gs->done[g], gs->stream[g]);
+    cudaStreamWaitEvent(main_stream, gs->done[g], 0);
+  }
+  return rc;
+}
+
 static int search_run_direct(const hmz_search_t* s, const void* weights, int mode, int n_simulations, const double* ucb_table,
                              double discount, void* stream) {
   if (int rc = check_search(s, "hmz_search_run")) return rc;
@@ -546,6 +668,10 @@ static int search_run_direct(const hmz_search_t* s, const void* weights, int mod
     void* ctl = ws + (((size_t)Bp * (40 + 32 * kPathCap) + 255) & ~(size_t)255);
     TreeScratch ts{sc.lp, sc.la, sc.depth, sc.path, sc.wild, sc.r, sc.p, sc.v, nullptr, nullptr};
     return persist_launch(s, weights, n_simulations, ucb_table, discount, cnt, ts, ctl, (cudaStream_t)stream);
+  }
+  if (s->schedule >= HMZ_SCHEDULE_SERVER) {
+    if (!can_persist) return fail(HMZ_ERR_UNSUPPORTED, "hmz_search_run: the server schedule needs HMZ_MODE_BF16 and n_simulations <= 2046");
+    return search_run_server(s, weights, n_simulations, ucb_table, discount, stream);
   }
   // Searches never interact, so the batch is cut into groups whose select -> MLP -> backup chains
   // run on separate streams: the latency-bound tree kernels of one group fill the issue slots the

@@ -518,6 +518,12 @@ struct TreeScratch {
   unsigned long long* gantt;  // tooling (hmz_debug_gantt), nullable
 };
 
+// Hand-off words of the server schedule (hmz_persist.cu), one 32-byte sector per 256-search tile pair each.
+struct ServerCtl {
+  uint32_t* tree_done;  // warps that have finished the pair's selections: 16 per simulation
+  uint32_t* mlp_done;   // simulations whose network outputs are complete for the pair
+};
+
 // Phases 2b + 3 of simulation `sim` (expansion with the network outputs, backup), optionally followed at once by the
 // selection of simulation `sim + 1` — the fused hot-loop form: the path just updated is still close and the next walk
 // usually shares its prefix.  With path elements (slot + entry per level, recorded by the previous walk) the backup needs

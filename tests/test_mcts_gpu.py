@@ -421,7 +421,7 @@ def test_persistent_schedule_equals_serial_launches(n, B, S, bias):
     w = PackedWeights(sd, n, _lib.MODE_BF16)
     rng = np.random.default_rng(B + S)
     runs = []
-    for schedule in (1, _lib.SCHEDULE_PERSISTENT):
+    for schedule in (1, _lib.SCHEDULE_PERSISTENT, _lib.SCHEDULE_SERVER, _lib.SCHEDULE_SERVER | 1):
         env = VecHanoi(n, 200, B)
         env.random_reset(seed=9)
         m = BatchedMCTS(0.8, 0.25, S, B, latent_dtype=_lib.LATENT_BF16)
@@ -438,8 +438,9 @@ def test_persistent_schedule_equals_serial_launches(n, B, S, bias):
         runs.append(out)
     names = ("action", "pi", "root_q", "visits", "minmax", "root_W", "node records", "latents")
     for move in range(2):
-        for name, a, b in zip(names, runs[0][move], runs[1][move]):
-            assert torch.equal(a, b), f"move {move}: {name} differ between the serial and the persistent schedule"
+        for other, label in ((1, "persistent"), (2, "server (4 groups)"), (3, "server (1 group)")):
+            for name, a, b in zip(names, runs[0][move], runs[other][move]):
+                assert torch.equal(a, b), f"move {move}: {name} differ between the serial and the {label} schedule"
         assert (runs[1][move][3].sum(1) == S).all()
     if bias:
         depth_proxy = runs[1][1][3].max(1).values  # a dominant action concentrates the visits: chains well past 32 levels
