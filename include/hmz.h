@@ -291,6 +291,9 @@ int hmz_debug_tree_timeline(long long search, unsigned long long* host_out);
  * [3] summed tree-warp lifetimes, [4] MLP CTAs waiting for the tree (one thread each), [5] MLP CTAs first -> last hand-off,
  * [6] MLP passes, [7] tree warps. */
 int hmz_debug_persist_stats(unsigned long long* host_out);
+/* Tooling: clock64 phase marks (96 words) of MLP CTA 0 of the persistent / server schedules for the pass named by
+ * HMZ_TC_TIMELINE=1 HMZ_TC_TIMELINE_PASS=p (same slots as hmz_debug_tc_timeline). */
+int hmz_debug_persist_timeline(unsigned long long* host_out);
 /* Tooling: launch Gantt of the hot-loop kernels.  enable = 1 starts recording; enable = 0 stops, synchronises the device
  * and writes up to max_records records of four words {kind (0 = network kernel, 1 = fused tree kernel), tag = sim << 8 |
  * group, first block's start, last block's end} (globaltimer ns) to host_out; *n_out = records written. */

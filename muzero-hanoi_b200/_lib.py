@@ -115,6 +115,7 @@ SIGNATURES = {
     "hmz_net_recurrent": (_I, [_P, _I, _P, _L, _P, _P, _P, _L, _L, _I, _P, _P, _P, _L, _P]),
     "hmz_debug_tc_timeline": (_I, [_P]),
     "hmz_debug_persist_stats": (_I, [_P]),
+    "hmz_debug_persist_timeline": (_I, [_P]),
     "hmz_debug_gantt": (_I, [_I, _P, _I, _P]),
     "hmz_debug_tree_timeline": (_I, [C.c_longlong, _P]),
     "hmz_debug_div_check": (_I, [_U64, _U64, _P, _P]),

@@ -330,7 +330,7 @@ __device__ __forceinline__ void hidden_epilogue_tmem(uint32_t h) {
   tmem_st_wait();
 }
 
-#define TL4(slot) do { if ((timeline & 1) && cta == 0 && pass == 0) g_timeline[slot] = clock64(); } while (0)
+#define TL4(slot) do { if ((timeline & 1) && cta == 0 && pass == (timeline >> 8)) g_timeline[slot] = clock64(); } while (0)  // bits 8+: the traced pass
 
 // Arguments of one network pass set (the stand-alone kernels' parameter list).
 struct TcArgs {
@@ -468,7 +468,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
   float* __restrict__ v_out = a.v_out;
   const int64_t n = a.n;
   const int n_pairs = a.n_pairs;
-  const int timeline = kPersist ? 0 : a.timeline;
+  const int timeline = a.timeline;  // (persistent passes: only the tooling bits 0 and 8+ are set)
   // passes of this CTA: its tile pairs, once (stand-alone) or once per simulation (persistent)
   const int own = cta < n_pairs ? (n_pairs - cta + n_cta - 1) / n_cta : 0;
   const int n_pass = kPersist ? own * pc.n_sims : own;
@@ -655,6 +655,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
       const int64_t out_row = kPersist ? (int64_t)sim + 1 : a.out_row;
       const int64_t row0 = ((int64_t)pair * 2 + t) * kM;
       const int64_t item = row0 + row;
+      if (ltid == 0 && t == 0) TL4(64);
       if (kPersist) {  // the gather reads what the pair's selection wrote
         const bool st = kPersistStats && pc.stats != nullptr && ltid == 0 && t == 0;
         const long long c0 = st ? clock64() : 0;
@@ -876,6 +877,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
         if (row == 0) {
           mbar_wait(&s.bar_pass, ph_pass);
           persist_push_item(pc, n_pairs, pair, sim + 1);
+          TL4(66);
           if (kPersistStats && pc.stats != nullptr) {
             const unsigned long long now = (unsigned long long)clock64();
             if (pass == 0) pass_t0 = now;

@@ -190,7 +190,10 @@ int server_mlp_launch(const hmz_search_t* s, const void* weights, int n_simulati
   a.net.v_out = const_cast<float*>(scratch.v);
   a.net.n = B;
   a.net.n_pairs = a.n_pairs;
-  a.net.timeline = 0;
+  // tooling: HMZ_TC_TIMELINE=1 HMZ_TC_TIMELINE_PASS=p records the phase marks of CTA 0's pass p (hmz_debug_persist_timeline)
+  a.net.timeline = (getenv("HMZ_TC_TIMELINE") && atoi(getenv("HMZ_TC_TIMELINE")))
+                       ? (1 | ((getenv("HMZ_TC_TIMELINE_PASS") ? atoi(getenv("HMZ_TC_TIMELINE_PASS")) : 0) << 8))
+                       : 0;
   search_persistent<<<dim3((unsigned)n_mlp), dim3(kPersistThreads), (size_t)smem, mlp_stream>>>(a);
   if (int rc = check_launch("search_persistent (server: MLP CTAs)")) return rc;
   out->tree_done = a.ctl.tree_done;
@@ -201,6 +204,9 @@ int server_mlp_launch(const hmz_search_t* s, const void* weights, int n_simulati
 static int persist_stats_on() {
   static const int v = getenv("HMZ_PERSIST_STATS") ? atoi(getenv("HMZ_PERSIST_STATS")) : 0;
   return v;
+}
+int persist_read_timeline(unsigned long long* host_out) {  // this translation unit's copy of the MLP body's phase marks
+  return cudaMemcpyFromSymbol(host_out, tc::g_timeline, sizeof(unsigned long long) * 96) == cudaSuccess ? HMZ_OK : HMZ_ERR_CUDA;
 }
 int persist_read_stats(unsigned long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, g_persist_stats, sizeof(unsigned long long) * 16) == cudaSuccess ? HMZ_OK : HMZ_ERR_CUDA;

@@ -282,6 +282,7 @@ static int ensure_tree_attrs() {
 
 // hmz_persist.cu
 int persist_read_stats(unsigned long long* host_out);
+int persist_read_timeline(unsigned long long* host_out);
 int64_t persist_ctl_bytes(int64_t n_searches);
 bool persist_supported(const hmz_search_t* s, int mode, int n_simulations);
 int persist_launch(const hmz_search_t* s, const void* weights, int n_simulations, const double* ucb_table, double discount,
@@ -324,6 +325,11 @@ int hmz_debug_div_check(uint64_t n_samples, uint64_t seed, unsigned long long* c
   if (int rc = ensure_rcp_table()) return rc;
   div_check<<<grid_for((int64_t)n_samples, 256 * 64, 8), 256, 0, (cudaStream_t)stream>>>(n_samples, seed, counters);
   return check_launch("div_check");
+}
+
+int hmz_debug_persist_timeline(unsigned long long* host_out) {
+  if (!host_out) return fail(HMZ_ERR_INVALID, "hmz_debug_persist_timeline: null pointer");
+  return persist_read_timeline(host_out);
 }
 
 int hmz_debug_persist_stats(unsigned long long* host_out) {

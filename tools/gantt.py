@@ -61,6 +61,8 @@ span = t1[steady].max() - t0[steady].min()
 print(f"\nsteady state (simulations 10..{S - 6}): {span / 1e3 / (S - 15):.2f} us per round")
 for k, nm in ((0, "network"), (1, "tree")):
     m = steady & (kind == k)
+    if not m.any():  # (server / persistent schedules: the network CTAs are one resident launch, not recorded)
+        continue
     d = (t1[m] - t0[m]) / 1e3
     print(f"  {nm:8s}: {m.sum()} launches, duration mean {d.mean():.2f} us (min {d.min():.2f}, max {d.max():.2f}); "
           f"some {nm} kernel in flight {100 * union(m) / span:.1f} % of the time; sum of durations / span = {d.sum() * 1e3 / span:.2f} kernels in flight on average")
@@ -73,5 +75,9 @@ for g in sorted(set(grp[steady])):
     k_, s0, s1 = kind[mg][order], t0[mg][order], t1[mg][order]
     gaps_tn = [(s0[i + 1] - s1[i]) / 1e3 for i in range(len(k_) - 1) if k_[i] == 1 and k_[i + 1] == 0]
     gaps_nt = [(s0[i + 1] - s1[i]) / 1e3 for i in range(len(k_) - 1) if k_[i] == 0 and k_[i + 1] == 1]
+    if not gaps_tn:
+        gaps_tt = [(s0[i + 1] - s1[i]) / 1e3 for i in range(len(k_) - 1)]
+        print(f"  group {g}: tree launch end -> next tree launch's first block {np.mean(gaps_tt):6.2f} us")
+        continue
     print(f"  group {g}: tree end -> next network start {np.mean(gaps_tn):6.2f} us (first block), network end -> tree start {np.mean(gaps_nt):6.2f} us "
           f"(negative = the dependent was already resident, waiting)")

@@ -14,12 +14,23 @@ h_in = torch.rand(n, 64, device="cuda").to(torch.bfloat16)
 acts = torch.randint(0, 6, (n,), dtype=torch.uint8, device="cuda")
 h = torch.empty(n, 64, device="cuda", dtype=torch.bfloat16)
 r, v, p = torch.empty(n, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, 6, device="cuda")
-for _ in range(3):
+if os.environ.get("SERVER"):  # phase marks of one steady-state pass of MLP CTA 0 under the server schedule
+    from muzero_hanoi_b200.engine import SelfPlay
+    os.environ.setdefault("HMZ_TC_TIMELINE_PASS", "203")
+    sp = SelfPlay(5, 200, 65536, 100, w, seed=1, ring_slots=4, latent_dtype=_lib.LATENT_BF16)
+    sp.mcts.store.set_schedule(int(os.environ["SERVER"]))
+    for _ in range(3):
+        sp.move()
+    torch.cuda.synchronize()
+    READ = _lib.load().hmz_debug_persist_timeline
+else:
+    READ = _lib.load().hmz_debug_tc_timeline
+for _ in range(0 if os.environ.get("SERVER") else 3):
     w.recurrent(n, latents_in=h_in, in_rows_per_item=1, in_row=None, actions=acts, latents_out=h, out_rows_per_item=1,
                 out_row=0, latent_dtype=1, r=r, p=p, v=v)
 torch.cuda.synchronize()
 buf = (C.c_ulonglong * 96)()
-_lib.check(_lib.load().hmz_debug_tc_timeline(buf))
+_lib.check(READ(buf))
 marks = np.array(list(buf), dtype=np.int64)
 if os.environ.get("HMZ_TC_V3"):
     names = {0: "ctl start", 1: "ctl gather seen", 2: "ctl Wg1 landed", 3: "ctl L1 issued", 4: "ctl L1 complete", 5: "ctl Wg2 landed",
@@ -35,7 +46,8 @@ if os.environ.get("HMZ_TC_V3"):
         names[34 + ly * 3] = f"hid {nm}: epilogue done"
         names[35 + ly * 3] = f"hid {nm}: saw second layer"
 else:  # v4: two tiles per CTA
-    names = {60: "CTA: kernel entry", 61: "CTA: barriers + TMEM ready", 62: "CTA: past the PDL wait", 63: "CTA: all warps done"}
+    names = {60: "CTA: kernel entry", 61: "CTA: barriers + TMEM ready", 62: "CTA: past the PDL wait", 63: "CTA: all warps done",
+             64: "T0 hid: pass start", 66: "out: pass published"}
     for i, net in enumerate("grvp"):  # network order of a pass: dynamics, reward, value, policy
         for t in range(2):
             names[i * 4 + t] = f"T{t} mma {net}: L1 inputs ready"
@@ -54,6 +66,9 @@ else:  # v4: two tiles per CTA
         names[85 + t * 8] = f"T{t} hid: latent done"
         for hd, nm in enumerate("rvp"):
             names[70 + hd * 2 + t] = f"T{t} out {nm}: done"
+if os.environ.get("SERVER"):
+    for k in (60, 61, 62, 63):
+        names.pop(k, None)
 t0 = min(int(marks[k]) for k in names if marks[k] != 0)
 ev = sorted((int(marks[k] - t0), names[k]) for k in names if marks[k] != 0)
 prev = 0
