@@ -420,7 +420,7 @@ def run_ours(args):
     if args.games % world:
         raise SystemExit(f"--games {args.games} is not divisible by {world} ranks")
     B, S = args.games // world, args.sims
-    schedule = {"auto": _lib.SCHEDULE_AUTO, "persistent": _lib.SCHEDULE_PERSISTENT}.get(args.schedule, None)
+    schedule = {"auto": _lib.SCHEDULE_AUTO, "persistent": _lib.SCHEDULE_PERSISTENT, "server": _lib.SCHEDULE_SERVER}.get(args.schedule, None)
     if schedule is None:
         schedule = int(args.schedule)
 
@@ -803,7 +803,7 @@ def main():
     ap.add_argument("--extras", action="store_true", help="also time the SURVEY §8f rows (episode kernels, replay ring, acting harness)")
     ap.add_argument("--moves-per-step", type=int, default=MOVES_PER_STEP, help="moves of every game per timed step (profiling runs use 1)")
     ap.add_argument("--schedule", default=os.environ.get("HMZ_BENCH_SCHEDULE", "auto"),
-                    help="hmz_search_t.schedule: auto | persistent | k (stream groups, 1..16)")
+                    help="hmz_search_t.schedule: auto | persistent | server | k (stream groups, 1..16; 128 + k = server with k tree groups)")
     args = ap.parse_args()
     MOVES_PER_STEP = max(1, args.moves_per_step)
     claim_stdout()

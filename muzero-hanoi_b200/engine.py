@@ -190,7 +190,8 @@ class SearchStore:
 
     def set_schedule(self, schedule):
         """How hmz_search_run schedules its kernels (never changes results): 0 = automatic, k in [1, 16] = one launch
-        pair per simulation over k concurrent stream groups, _lib.SCHEDULE_PERSISTENT = one persistent kernel."""
+        pair per simulation over k concurrent stream groups, _lib.SCHEDULE_PERSISTENT = one persistent kernel,
+        _lib.SCHEDULE_SERVER | k = resident network CTAs fed by ordinary tree-kernel launches in k stream groups."""
         self.desc.schedule = int(schedule)
 
     def enable_capture(self, n_simulations):

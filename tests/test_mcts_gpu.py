@@ -15,7 +15,7 @@ from oracle import cport, port
 pytestmark = pytest.mark.gpu
 # hmz_search_t.schedule values exercised at full size: serial launches, the automatic choice (4 stream groups at this
 # size), 7 ragged groups, and the persistent role-specialised kernel
-SCHEDULES_FULL = (1, 0, 7, 64)
+SCHEDULES_FULL = (1, 0, 7, 64, 128)
 
 
 def _split_search(mcts, weights, words, noise, record=True):
@@ -218,10 +218,11 @@ def test_node_view_matches_tree_store(golden):
     assert leaf.N == 0 and leaf.Q == 0.0 and leaf.h_state is None and leaf.children == []
 
 
-@pytest.mark.parametrize("schedule", [0, 64])
+@pytest.mark.parametrize("schedule", [0, 64, 128])
 def test_full_size_benchmarked_path_replayed_by_the_oracle(schedule):
     """The path bench.py times, at the size it times it: bf16 throughput mode, hmz_search_run (fused backup + select
-    kernels, stream groups and programmatic dependent launches for schedule 0; the persistent kernel for schedule 64),
+    kernels, stream groups and programmatic dependent launches for schedule 0; the persistent kernel for schedule 64;
+    resident network CTAs fed by ordinary tree launches through release / acquire flags for schedule 128),
     N = 5, 65,536 searches x 100 simulations, two consecutive moves (the second one starts from persisted min/max
     bounds).  The run records the network outputs every backup consumed (hmz_search_t.capture); the C oracle replays
     the tree arithmetic with exactly those outputs injected and must reproduce visit counts, root values (float64) and
