@@ -374,7 +374,9 @@ constexpr bool kPersistStats = true;
 constexpr bool kPersistStats = false;
 #endif
 // Back-off between two polls of a hand-off word (ns; 0 = poll back to back).  Tuning switch.
-#ifndef HMZ_PERSIST_SLEEP_NS
+#ifdef HMZ_PERSIST_SLEEP_NS
+#define HMZ_PERSIST_SLEEP_NS_SET 1  // (hmz_build_flags reports a non-default value)
+#else
 #define HMZ_PERSIST_SLEEP_NS 64
 #endif
 __device__ __forceinline__ void persist_backoff() {

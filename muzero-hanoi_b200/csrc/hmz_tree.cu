@@ -374,7 +374,7 @@ const char* hmz_build_flags(void) {
 #ifdef HMZ_PERSIST_THREADS
          " HMZ_PERSIST_THREADS"
 #endif
-#ifdef HMZ_PERSIST_SLEEP_NS
+#ifdef HMZ_PERSIST_SLEEP_NS_SET
          " HMZ_PERSIST_SLEEP_NS"
 #endif
 #ifdef HMZ_PERSIST_GLOBAL_TABLES
