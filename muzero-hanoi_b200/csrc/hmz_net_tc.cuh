@@ -367,6 +367,11 @@ struct PersistCtl {
   unsigned long long* stats;  // tooling (HMZ_PERSIST_STATS=1), nullable: clock64 sums, see hmz_debug_persist_stats
   uint32_t* mlp_done;         // server schedule (nullable; stride 8 words): mlp_done[pair] = simulations whose network outputs are
                               // complete — the tree kernels' warps wait on it; when set, no item is pushed to the queue
+  uint32_t* group_done;       // server schedule (nullable): group_done[pair / pairs_per_group] += 1 per finished pass (release): the
+                              // stream of the group's tree launches waits on it (cuStreamWaitValue32)
+  int pairs_per_group;
+  int rotate;                 // 1: a CTA's residue class of tile pairs rotates by n_pairs % n_cta per simulation, so that with a CTA
+                              // count that does not divide the pair count every CTA gets the extra pass equally often
 };
 #ifdef HMZ_PERSIST_STATS  // tooling build (tools/build_variant.py): role statistics of the persistent kernel
 constexpr bool kPersistStats = true;
@@ -439,6 +444,7 @@ __device__ __forceinline__ void persist_wait_tree(const PersistCtl& pc, int pair
 __device__ __forceinline__ void persist_push_item(const PersistCtl& pc, int n_pairs, int pair, int sim_next) {
   if (pc.mlp_done != nullptr) {  // server schedule: the pair's flag is the hand-off
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(pc.mlp_done + (size_t)pair * 8), "r"((uint32_t)sim_next) : "memory");
+    if (pc.group_done != nullptr) red_release_add(pc.group_done + (size_t)(pair / pc.pairs_per_group) * 8, 1u);
     return;
   }
   const uint32_t pos = atomicAdd(pc.q_tail, 1u);
@@ -472,10 +478,32 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
   const int n_pairs = a.n_pairs;
   const int timeline = a.timeline;  // (persistent passes: only the tooling bits 0 and 8+ are set)
   // passes of this CTA: its tile pairs, once (stand-alone) or once per simulation (persistent)
-  const int own = cta < n_pairs ? (n_pairs - cta + n_cta - 1) / n_cta : 0;
-  const int n_pass = kPersist ? own * pc.n_sims : own;
-#define HMZ_PASS_PAIR(pass) (cta + (kPersist ? (pass) % own : (pass)) * n_cta)
-#define HMZ_PASS_SIM(pass) (kPersist ? (pass) / own : 0)
+  // (pair, sim) sequence of this CTA: in simulation s it owns the pairs first_pair(s), first_pair(s) + n_cta, ...
+  const int rot = (kPersist && pc.rotate) ? n_pairs % n_cta : 0;
+  auto first_pair = [&](int sim) {
+    int f = cta - (int)(((long long)sim * rot) % n_cta);
+    return f < 0 ? f + n_cta : f;
+  };
+  int n_pass = 0;
+  if (kPersist && rot != 0) {
+    for (int sm = 0; sm < pc.n_sims; ++sm) {
+      const int f = first_pair(sm);
+      if (f < n_pairs) n_pass += (n_pairs - f - 1) / n_cta + 1;
+    }
+  } else {
+    const int own = cta < n_pairs ? (n_pairs - cta + n_cta - 1) / n_cta : 0;
+    n_pass = kPersist ? own * pc.n_sims : own;
+  }
+  struct PassIter {
+    int pair, sim;
+  };
+  auto next_item = [&](PassIter& it) {
+    it.pair += n_cta;
+    while (it.pair >= n_pairs && it.sim + 1 < (kPersist ? pc.n_sims : 1)) {
+      ++it.sim;
+      it.pair = first_pair(it.sim);
+    }
+  };
   Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5;
 // (the clock is read through an asm with a memory clobber so that it cannot be scheduled above a barrier)
@@ -652,8 +680,9 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     const uint32_t T = tmem + kColsPerTile * t + lane_bits;
     uint32_t ph_d = 0, ph_o = 0;
     bool copy_pending = false;
-    for (int pass = 0; pass < n_pass; ++pass) {
-      const int pair = HMZ_PASS_PAIR(pass), sim = HMZ_PASS_SIM(pass);
+    PassIter item_it{first_pair(0), 0};
+    for (int pass = 0; pass < n_pass; ++pass, next_item(item_it)) {
+      const int pair = item_it.pair, sim = item_it.sim;
       const int64_t out_row = kPersist ? (int64_t)sim + 1 : a.out_row;
       const int64_t row0 = ((int64_t)pair * 2 + t) * kM;
       const int64_t item = row0 + row;
@@ -799,8 +828,9 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     uint32_t ph_s = 0;
     uint32_t ph_pass = 0;
     unsigned long long pass_t0 = 0;
-    for (int pass = 0; pass < n_pass; ++pass) {
-      const int pair = HMZ_PASS_PAIR(pass), sim = HMZ_PASS_SIM(pass);
+    PassIter item_it{first_pair(0), 0};
+    for (int pass = 0; pass < n_pass; ++pass, next_item(item_it)) {
+      const int pair = item_it.pair, sim = item_it.sim;
       if (kPersist) persist_wait_tree(pc, pair, sim);  // the action slice reads what the pair's selection wrote
 #pragma unroll
       for (int t = 0; t < 2; ++t) {  // the extra A slice of this row: one-hot(action) at k = 0..5, the constant 1 at k = 6
@@ -900,8 +930,6 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
-#undef HMZ_PASS_PAIR
-#undef HMZ_PASS_SIM
 #undef TL4_CTA
 
 #undef TL4

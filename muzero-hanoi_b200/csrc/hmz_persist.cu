@@ -138,13 +138,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) search_persistent(const __
 // A network CTA needs a whole SM, so under the launch-per-simulation schedule the two kernel families take turns on the
 // machine; here the network CTAs keep their SMs and the tree blocks never wait for an SM to drain.
 static int server_mlp_ctas() {
-  static const int v = getenv("HMZ_SERVER_MLP") ? atoi(getenv("HMZ_SERVER_MLP")) : 64;
+  static const int v = getenv("HMZ_SERVER_MLP") ? atoi(getenv("HMZ_SERVER_MLP")) : 72;
   return v;
 }
 
 // Launches the resident MLP CTAs on `mlp_stream`; the caller then enqueues the tree launches (server_tree_launch).
 int server_mlp_launch(const hmz_search_t* s, const void* weights, int n_simulations, TreeScratch scratch, void* ctl_mem,
-                      cudaStream_t ctl_stream, cudaStream_t mlp_stream, ServerCtl* out) {
+                      int pairs_per_group, cudaStream_t mlp_stream, ServerCtl* out) {
   static thread_local int attr_dev = -1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed");
@@ -166,8 +166,7 @@ int server_mlp_launch(const hmz_search_t* s, const void* weights, int n_simulati
   char* ctl = (char*)ctl_mem;
   int64_t cap = 64;
   while (cap < 2 * (int64_t)a.n_pairs) cap <<= 1;
-  // (the caller has zeroed the control block on ctl_stream and ordered both streams behind it)
-  (void)ctl_stream;
+  // (the caller has zeroed the control block and ordered every stream behind that)
   a.ctl.tree_head = (uint32_t*)ctl;
   a.ctl.q_tail = (uint32_t*)(ctl + 256);
   a.ctl.tree_done = (uint32_t*)(ctl + 1024);
@@ -176,6 +175,9 @@ int server_mlp_launch(const hmz_search_t* s, const void* weights, int n_simulati
   a.ctl.n_sims = n_simulations;
   a.ctl.stats = nullptr;
   a.ctl.mlp_done = (uint32_t*)(ctl + 1024 + (size_t)a.n_pairs * 32 + (size_t)cap * 8 + 256);
+  a.ctl.group_done = (uint32_t*)(ctl + 1024 + (size_t)a.n_pairs * 32 + (size_t)cap * 8 + 256 + (size_t)a.n_pairs * 32 + 256);
+  a.ctl.pairs_per_group = pairs_per_group;
+  a.ctl.rotate = 1;
   a.net.wsec = (const uint8_t*)weights;
   a.net.lat_in = s->latents;
   a.net.in_rows_per_item = s->n_records;
@@ -198,6 +200,7 @@ int server_mlp_launch(const hmz_search_t* s, const void* weights, int n_simulati
   if (int rc = check_launch("search_persistent (server: MLP CTAs)")) return rc;
   out->tree_done = a.ctl.tree_done;
   out->mlp_done = a.ctl.mlp_done;
+  out->group_done = a.ctl.group_done;
   return HMZ_OK;
 }
 
@@ -246,7 +249,7 @@ int64_t persist_ctl_bytes(int64_t n_searches) {
   const int64_t n_pairs = (n_searches + 2 * tc::kM - 1) / (2 * tc::kM);
   int64_t cap = 64;
   while (cap < 2 * n_pairs) cap <<= 1;
-  return 1024 + n_pairs * 32 + cap * 8 + 256 + n_pairs * 32;  // ... + the server schedule's per-pair flags
+  return 1024 + n_pairs * 32 + cap * 8 + 256 + n_pairs * 32 + 1024;  // ... + the server schedule's per-pair flags and group counters
 }
 
 bool persist_supported(const hmz_search_t* s, int mode, int n_simulations) {

@@ -288,7 +288,7 @@ bool persist_supported(const hmz_search_t* s, int mode, int n_simulations);
 int persist_launch(const hmz_search_t* s, const void* weights, int n_simulations, const double* ucb_table, double discount,
                    const CountRow* cnt_table, const TreeScratch& scratch, void* ctl_mem, cudaStream_t stream);
 int server_mlp_launch(const hmz_search_t* s, const void* weights, int n_simulations, TreeScratch scratch, void* ctl_mem,
-                      cudaStream_t ctl_stream, cudaStream_t mlp_stream, ServerCtl* out);
+                      int pairs_per_group, cudaStream_t mlp_stream, ServerCtl* out);
 
 // Device address of this translation unit's count-row table (filled by ensure_rcp_table).
 static const CountRow* count_table_address() {
@@ -617,7 +617,23 @@ static int search_run_server(const hmz_search_t* s, const void* weights, int n_s
   }
   ServerCtl sctl{};
   TreeScratch whole{sc0.lp, sc0.la, sc0.depth, sc0.path, sc0.wild, sc0.r, sc0.p, sc0.v, nullptr, nullptr};
-  int rc = server_mlp_launch(s, weights, n_simulations, whole, ctl, main_stream, mlp_stream, &sctl);
+  int rc = server_mlp_launch(s, weights, n_simulations, whole, ctl, (int)(per / 256), mlp_stream, &sctl);
+  // A tree launch that is resident before its pairs' network outputs exist holds its SM slots spinning: the group's
+  // stream waits (cuStreamWaitValue32, resolved through the runtime so that libcuda is not a link dependency) until the
+  // network CTAs have finished every pair of the group for the previous simulation.  HMZ_SERVER_GATE=0: spin only.
+  typedef int (*WaitValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+  static WaitValue32 wait_value = nullptr;
+  static int gate = -1;
+  if (gate < 0) {
+    gate = getenv("HMZ_SERVER_GATE") ? atoi(getenv("HMZ_SERVER_GATE")) : 1;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (gate && (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn)) {
+      gate = 0;
+      cudaGetLastError();
+    }
+    wait_value = (WaitValue32)fn;
+  }
   hmz_search_t sub[16];
   SimScratch sc[16];
   const size_t lat_elem = s->latent_dtype == HMZ_LATENT_F32 ? 4 : 2;
@@ -640,7 +656,13 @@ static int search_run_server(const hmz_search_t* s, const void* weights, int n_s
       TreeScratch ts{sc[g].lp, sc[g].la, sc[g].depth, sc[g].path, sc[g].wild, sc[g].r, sc[g].p, sc[g].v,
                      (s->capture && k > 0) ? s->capture + ((size_t)(k - 1) * (size_t)B + (size_t)(g * per)) * 8 : nullptr,
                      gantt_next(1, gantt_context_tag())};
-      rc = server_tree_launch(&sub[g], k, n_simulations, ucb_table, discount, ts, sctl, (int)(g * per / 256), gs->stream[g]);
+      if (gate && k > 0) {
+        const unsigned int pairs_g = (unsigned int)((sub[g].n_searches + 255) / 256);
+        if (wait_value(gs->stream[g], (unsigned long long)(uintptr_t)(sctl.group_done + (size_t)g * 8), pairs_g * (unsigned int)k, 0u /* >= */) != 0)
+          rc = fail(HMZ_ERR_CUDA, "cuStreamWaitValue32 failed");
+      }
+      if (rc == HMZ_OK)
+        rc = server_tree_launch(&sub[g], k, n_simulations, ucb_table, discount, ts, sctl, (int)(g * per / 256), gs->stream[g]);
     }
   for (int g = 0; g <= groups; ++g) {  // always join, even after an error, so the caller's stream stays ordered
     cudaEventRecord(gs->done[g], gs->stream[g]);

@@ -522,6 +522,7 @@ struct TreeScratch {
 struct ServerCtl {
   uint32_t* tree_done;  // warps that have finished the pair's selections: 16 per simulation
   uint32_t* mlp_done;   // simulations whose network outputs are complete for the pair
+  uint32_t* group_done; // (one sector per stream group) passes the network CTAs have finished for the group's pairs
 };
 
 // Phases 2b + 3 of simulation `sim` (expansion with the network outputs, backup), optionally followed at once by the
