@@ -107,6 +107,12 @@ for stage in "$@"; do
       SCHEDULES=4 MOVES=8 timeout 100 python tools/persist_probe.py >> gpurun_out/family_alone.txt 2>&1
       cat gpurun_out/family_alone.txt
       python tools/tc_timeline.py > gpurun_out/timeline_net_tc.txt 2>&1
+      timeout 200 python tools/gantt.py > gpurun_out/gantt_4groups.txt 2>&1
+      SCHEDULE=128 timeout 200 python tools/gantt.py > gpurun_out/gantt_server.txt 2>&1
+      SERVER=128 timeout 200 python tools/tc_timeline.py > gpurun_out/timeline_net_tc_server.txt 2>&1
+      SCHEDULES=0,64,128,136 MOVES=10 timeout 200 python tools/persist_probe.py > gpurun_out/schedules.txt 2>&1
+      for m in 64 68 72 76 80; do HMZ_SERVER_MLP=$m SCHEDULES=128 MOVES=8 timeout 200 python tools/persist_probe.py 2>&1 | sed "s/^/HMZ_SERVER_MLP=$m /" >> gpurun_out/schedules.txt; done
+      timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-env --no-configs --schedule server > gpurun_out/bench_server.json 2> gpurun_out/bench_server.log
       TORCH_INIT=1 SEARCHES=17,30000,5000 timeout 120 python tools/tree_timeline.py > gpurun_out/timeline_tree.txt 2>&1
       ;;
     groupsweep)

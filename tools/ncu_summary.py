@@ -85,7 +85,10 @@ for src, dst in (("bench_default.json", "bench_default_line.json"), ("bench_refe
                  ("bench_8gpu.json", "bench_8gpu_line.json"), ("persist_sweep.txt", "persist_sweep.txt"),
                  ("group_sweep.txt", "group_sweep.txt"), ("env_sweep.txt", "env_sweep.txt"), ("env_probe.txt", "env_probe.txt"),
                  ("tmem_bench.txt", "microbench_tmem.txt"), ("mma_bench.txt", "microbench_mma.txt"), ("family_alone.txt", "kernel_families_alone.txt"),
-                 ("timeline_net_tc.txt", "timeline_net_tc.txt"), ("timeline_tree.txt", "timeline_tree.txt")):
+                 ("timeline_net_tc.txt", "timeline_net_tc.txt"), ("timeline_tree.txt", "timeline_tree.txt"),
+                 ("gantt_4groups.txt", "gantt_4groups.txt"), ("gantt_server.txt", "gantt_server.txt"),
+                 ("timeline_net_tc_server.txt", "timeline_net_tc_server.txt"), ("schedules.txt", "schedules.txt"),
+                 ("bench_server.json", "bench_server_line.json")):
     if os.path.exists(os.path.join(SRC, src)):
         shutil.copyfile(os.path.join(SRC, src), os.path.join(DST, f"{R}_{dst}"))
 tm = os.path.join(SRC, "test_metrics.jsonl")
