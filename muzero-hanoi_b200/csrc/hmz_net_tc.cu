@@ -164,8 +164,12 @@ int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_pe
                      int latent_dtype, float* r, float* p, float* v, int64_t n, cudaStream_t stream) {
   int smem = 0, n_pairs = 0;
   if (int rc = tc_prepare(&smem)) return rc;
-  const unsigned grid = tc_grid(n, &n_pairs, tc_passes());
+  unsigned grid = tc_grid(n, &n_pairs, tc_passes());
   tc::v4::TcArgs a{};
+  // small batches: three CTAs per tile pair, one head each (TcArgs::head_split); HMZ_TC_SPLIT=0 switches it off
+  static const int split_on = getenv("HMZ_TC_SPLIT") ? atoi(getenv("HMZ_TC_SPLIT")) : 1;
+  a.head_split = (split_on && 3 * n_pairs <= sm_count()) ? 3 : 1;
+  if (a.head_split == 3) grid = 3u * (unsigned)n_pairs;
   a.wsec = (const uint8_t*)weights;
   a.lat_in = lat_in;
   a.in_rows_per_item = in_rows_per_item;
@@ -205,6 +209,7 @@ int tc_net_initial(const void* weights, int n_disks, const uint32_t* words, void
   a.v_out = v0;
   a.n = n;
   a.n_pairs = n_pairs;
+  a.head_split = 1;
   a.timeline = (pdl_prewait() << 1) | ((pdl_net_at() + 1) << 2);
   cudaError_t e = launch_pdl(1, tc::v4::net_tc<true>, dim3(grid), dim3(tc::v4::kLaunchThreads), (size_t)smem, stream, a);
   if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "net_tc<initial> launch: %s", cudaGetErrorString(e));

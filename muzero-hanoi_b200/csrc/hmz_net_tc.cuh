@@ -347,6 +347,9 @@ struct TcArgs {
   float *r_out, *p_out, *v_out;
   int64_t n;                  // items
   int n_pairs;                // tile pairs = ceil(n / 256)
+  int head_split;             // 3: small batches (3 x tile pairs <= SMs) — CTAs 3 p, 3 p + 1, 3 p + 2 all run the dynamics network
+                              // of pair p and then ONE head each (reward + the latent rows / value / policy): the per-simulation
+                              // chain of a pass shrinks from four networks to two while idle SMs do the redundant work; else 1
   int timeline;               // tooling / PDL switches of the stand-alone kernels
   unsigned long long* gantt;  // tooling (hmz_debug_gantt), nullable
 };
@@ -460,7 +463,12 @@ __device__ __forceinline__ void persist_push_item(const PersistCtl& pc, int n_pa
 // The network index `net` keeps the recurrent numbering (0 = g / h, 1 = reward, 2 = policy, 3 = value);
 // the root inference simply skips net 1.
 template <bool kInitial, bool kPersist>
-__device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& pc, uint8_t* smem_raw, int cta, int n_cta) {
+__device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& pc, uint8_t* smem_raw, int cta_raw, int n_cta_raw) {
+  // head split (TcArgs::head_split): `cta` / `n_cta` below count tile-pair owners; role -1 = all networks
+  const int split = (!kInitial && !kPersist && a.head_split == 3) ? 3 : 1;
+  const int role = split == 3 ? cta_raw % 3 : -1;
+  const int cta = cta_raw / split, n_cta = n_cta_raw / split;
+  auto runs = [&](int net) { return net == 0 || split == 1 || net == role + 1; };
   const uint8_t* __restrict__ wsec = a.wsec;
   const void* __restrict__ lat_in = a.lat_in;
   const int64_t in_rows_per_item = a.in_rows_per_item;
@@ -572,14 +580,17 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
     // Block i = 2 * network + layer goes to slot (network & 1) of its kind, so that the second-layer slot 1 only ever
     // holds the reward / policy blocks; cnt = loads issued into a slot so far (a reload waits for the previous use's MMAs).
     uint32_t cnt[2][2] = {{0u, 0u}, {0u, 0u}};
+    int issued = 0;
     for (int pass = 0; pass < n_pass; ++pass) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (kInitial && (i >> 1) == 1) continue;  // no reward head at the root
-        if (late_signal && i == 4 && pass == 0) {  // the first four blocks are in flight: now order after the preceding kernel
+        if (!runs(i >> 1)) continue;
+        if (late_signal && pass == 0 && issued == (split == 1 ? 4 : 2)) {  // the first blocks are in flight: now order after the preceding kernel
           pdl_wait();
           if (signal_net < 0) pdl_launch_dependents();
         }
+        ++issued;
         const int kind = i & 1, slot = (i >> 1) & 1;
         const uint32_t u = cnt[kind][slot];
         if (u >= 1u) mbar_wait(&s.bar_wfree[kind][slot], (u - 1u) & 1u);
@@ -605,6 +616,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
 #pragma unroll 1
       for (int net = 0; net < 4; ++net) {  // dynamics / representation, reward, value, policy
         if (kInitial && net == 1) continue;
+        if (!runs(net)) continue;
         if (t == 0 && net == signal_net && pass == n_pass - 1) pdl_launch_dependents();
         // ---- first layer: H[0:256) = [A | AX] x W1'^T
         {
@@ -615,10 +627,10 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
           const uint32_t a_in = net <= 1 ? smem_u32(s.t[t].a0) : smem_u32(s.t[t].ahn);
           if (net == 0) mbar_wait(&s.bar_g[t], ph_g);
           if (net == 1) mbar_wait(&s.bar_raw[t], ph_raw);  // raw latent tile written, O copied out
-          if (net == 2) mbar_wait(&s.bar_hn[t], ph_hn);    // normalised latent tile written
+          if (net == 2 || (net == 3 && split == 3)) mbar_wait(&s.bar_hn[t], ph_hn);  // normalised latent tile written
           // O (inside H) must have been copied out: by the output warps after a head, by the latent epilogue
-          // (bar_raw / bar_hn above) after the first network
-          if (net == 3 || (net == 2 && !kInitial) || (net == 0 && !first)) {
+          // (bar_raw / bar_hn above) after the first network.  (Head split: one head and one pass per CTA — nothing to wait for.)
+          if (split == 1 && (net == 3 || (net == 2 && !kInitial) || (net == 0 && !first))) {
             mbar_wait(&s.bar_fin[t], ph_fin);
             ph_fin ^= 1;
           }
@@ -732,6 +744,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
 #pragma unroll 1
       for (int layer = 0; layer < 4; ++layer) {
         if (kInitial && layer == 1) continue;
+        if (!runs(layer)) continue;
         mbar_wait(&s.bar_d[t], ph_d);
         ph_d ^= 1;
         tc_fence_after();
@@ -785,7 +798,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
 #pragma unroll
             for (int j = 0; j < 4; ++j) ph[j] = pack_bf16(hn[2 * j], hn[2 * j + 1]);
             *reinterpret_cast<uint4*>(tile.ahn + sw128(row, half * 4 + c)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            if (latent_dtype == HMZ_LATENT_F32 && item < n) {  // parity-mode stores keep the per-row form
+            if (latent_dtype == HMZ_LATENT_F32 && item < n && role <= 0) {  // parity-mode stores keep the per-row form
               float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(lat_out) + orow * kLatent + half * 32 + c * 8);
               __stcs(dst, make_float4(hn[0], hn[1], hn[2], hn[3]));
               __stcs(dst + 1, make_float4(hn[4], hn[5], hn[6], hn[7]));
@@ -812,7 +825,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
               const int r2 = quarter * 32 + half * 16 + i * 4 + (lane >> 3);
               const int64_t it2 = row0 + r2;
               const uint4 val = *reinterpret_cast<const uint4*>(tile.ahn + sw128(r2, chunk));
-              if (it2 < n)
+              if (it2 < n && role <= 0)  // (head split: the reward CTA stores the rows)
                 __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(lat_out) + (it2 * out_rows_per_item + out_row) * kLatent + chunk * 8), val);
             }
           }
@@ -849,6 +862,7 @@ __device__ __forceinline__ void net_tc_body(const TcArgs& a, const PersistCtl& p
 #pragma unroll 1
       for (int head = 0; head < 3; ++head) {  // reward, value, policy
         if (kInitial && head == 0) continue;
+        if (!runs(head + 1)) continue;
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
           const int64_t item = ((int64_t)pair * 2 + t) * kM + row;
