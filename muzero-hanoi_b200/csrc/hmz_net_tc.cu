@@ -159,6 +159,10 @@ static unsigned tc_grid(int64_t n, int* n_pairs, int passes = 1) {
   return (unsigned)(want < sms ? want : sms);
 }
 
+// hmz_search_run with several stream groups: the launches of the other groups want the idle SMs — no head split then
+static thread_local int tl_split_allowed = 1;
+void tc_allow_head_split(int allow) { tl_split_allowed = allow; }
+
 int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
                      const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row,
                      int latent_dtype, float* r, float* p, float* v, int64_t n, cudaStream_t stream) {
@@ -168,7 +172,7 @@ int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_pe
   tc::v4::TcArgs a{};
   // small batches: three CTAs per tile pair, one head each (TcArgs::head_split); HMZ_TC_SPLIT=0 switches it off
   static const int split_on = getenv("HMZ_TC_SPLIT") ? atoi(getenv("HMZ_TC_SPLIT")) : 1;
-  a.head_split = (split_on && 3 * n_pairs <= sm_count()) ? 3 : 1;
+  a.head_split = (split_on && tl_split_allowed && 3 * n_pairs <= sm_count()) ? 3 : 1;
   if (a.head_split == 3) grid = 3u * (unsigned)n_pairs;
   a.wsec = (const uint8_t*)weights;
   a.lat_in = lat_in;

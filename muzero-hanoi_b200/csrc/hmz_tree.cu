@@ -739,11 +739,13 @@ static int search_run_direct(const hmz_search_t* s, const void* weights, int mod
     if (cudaStreamWaitEvent(gs->stream[g], gs->fork, 0) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaStreamWaitEvent failed");
   }
   int rc = HMZ_OK;
+  tc_allow_head_split(0);  // the groups' launches share the machine
   for (int sim = 0; sim < n_simulations && rc == HMZ_OK; ++sim)
     for (int g = 0; g < groups && rc == HMZ_OK; ++g) {
       gantt_set_context(g, sim);
       rc = run_one_sim(&sub[g], sc[g], weights, mode, sim, n_simulations, ucb_table, discount, (void*)gs->stream[g], B, g * per);
     }
+  tc_allow_head_split(1);
   for (int g = 0; g < groups; ++g) {  // always join, even after an error, so the caller's stream stays ordered
     cudaEventRecord(gs->done[g], gs->stream[g]);
     cudaStreamWaitEvent(main_stream, gs->done[g], 0);
