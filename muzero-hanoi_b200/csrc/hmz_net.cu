@@ -336,6 +336,7 @@ int64_t hmz_weights_packed_bytes(int n_disks, int mode) {
   if (n_disks < 1 || n_disks > HMZ_MAX_DISKS) return -1;
   if (mode == HMZ_MODE_FP32) return (int64_t)Fp32Layout::total(n_disks) * 4;
   if (mode == HMZ_MODE_BF16) return tc_packed_bytes(n_disks);
+  if (mode == HMZ_MODE_FP32X3) return x3::packed_bytes(n_disks);
   return -1;
 }
 
@@ -352,6 +353,10 @@ int hmz_weights_pack(const float* const* host_tensors, int n_disks, int mode, vo
     tc_pack(host_tensors, n_disks, host_out);
     return HMZ_OK;
   }
+  if (mode == HMZ_MODE_FP32X3) {
+    x3::pack(host_tensors, n_disks, host_out);
+    return HMZ_OK;
+  }
   return fail(HMZ_ERR_INVALID, "hmz_weights_pack: unknown mode %d", mode);
 }
 
@@ -363,17 +368,16 @@ int hmz_net_initial(const void* weights, int mode, int n_disks, const uint32_t* 
   if (!weights || (!words && !obs) || !latents_out || !p0 || !v0 || n < 0 || n_disks < 1 || n_disks > HMZ_MAX_DISKS ||
       out_rows_per_item < 1 || (latent_dtype != HMZ_LATENT_F32 && latent_dtype != HMZ_LATENT_BF16))
     return fail(HMZ_ERR_INVALID, "hmz_net_initial: bad arguments");
-  // HMZ_MODE_BF16 blobs embed a float32 copy of the weights behind the tensor-core section.
-  if (mode != HMZ_MODE_FP32 && mode != HMZ_MODE_BF16) return fail(HMZ_ERR_INVALID, "hmz_net_initial: unknown mode %d", mode);
+  // HMZ_MODE_BF16 / HMZ_MODE_FP32X3 blobs embed a float32 copy of the weights behind the tensor-core section.
+  if (mode != HMZ_MODE_FP32 && mode != HMZ_MODE_BF16 && mode != HMZ_MODE_FP32X3) return fail(HMZ_ERR_INVALID, "hmz_net_initial: unknown mode %d", mode);
   // throughput mode with packed env words: the tcgen05 kernel (bf16 representation + policy + value);
   // float observations (drop-in B = 1 views, arbitrary input vectors) keep the float32 kernel below
   if (mode == HMZ_MODE_BF16 && words != nullptr)
     return tc_net_initial(weights, n_disks, words, latents_out, out_rows_per_item, latent_dtype, p0, v0, n, (cudaStream_t)stream);
   if (int rc = ensure_smem_optin()) return rc;
   const unsigned grid = (unsigned)((n + kRows - 1) / kRows);
-  const float* w32 = mode == HMZ_MODE_BF16
-                         ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(weights) + tc_fp32_offset_bytes())
-                         : reinterpret_cast<const float*>(weights);
+  const int64_t w32_off = mode == HMZ_MODE_BF16 ? tc_fp32_offset_bytes() : (mode == HMZ_MODE_FP32X3 ? x3::fp32_offset_bytes() : 0);
+  const float* w32 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(weights) + w32_off);
   net_initial_fp32<<<grid, kNetThreads, sizeof(NetSmem), (cudaStream_t)stream>>>(
       w32, n_disks, words, obs, latents_out, out_rows_per_item, latent_dtype, p0, v0, n);
   return check_launch("net_initial_fp32");
@@ -391,6 +395,9 @@ int hmz_net_recurrent(const void* weights, int mode, const void* latents_in, int
   if (mode == HMZ_MODE_BF16)
     return tc_net_recurrent(weights, latents_in, in_rows_per_item, in_row, actions, latents_out, out_rows_per_item,
                             out_row, latent_dtype, r, p, v, n, (cudaStream_t)stream);
+  if (mode == HMZ_MODE_FP32X3)
+    return x3::net_recurrent(weights, latents_in, in_rows_per_item, in_row, actions, latents_out, out_rows_per_item, out_row,
+                             latent_dtype, r, p, v, n, (cudaStream_t)stream);
   if (mode != HMZ_MODE_FP32) return fail(HMZ_ERR_INVALID, "hmz_net_recurrent: unknown mode %d", mode);
   if (int rc = ensure_smem_optin()) return rc;
   const unsigned grid = (unsigned)((n + kRows - 1) / kRows);

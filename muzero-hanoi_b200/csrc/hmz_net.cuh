@@ -53,6 +53,16 @@ int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_pe
                      const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row,
                      int latent_dtype, float* r, float* p, float* v, int64_t n, cudaStream_t stream);
 
+// float32-accurate tensor-core path (hmz_net_x3.cu, HMZ_MODE_FP32X3): split section + the float32 blob behind it
+namespace x3 {
+int64_t packed_bytes(int n_disks);
+int64_t fp32_offset_bytes();
+void pack(const float* const* tensors, int n_disks, void* out);
+int net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
+                  const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row, int latent_dtype,
+                  float* r, float* p, float* v, int64_t n, cudaStream_t stream);
+}  // namespace x3
+
 // ---- epilogue math, float32, in the reference's operation order ---------------------------
 
 // MuZeroNet._signed_parabolic (networks.py:186-189) applied to the support expectation x:

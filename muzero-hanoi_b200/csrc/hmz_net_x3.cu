@@ -1,0 +1,544 @@
+// MuZeroNet recurrent_inference (networks.py:96-116) at float32 accuracy ON THE TENSOR CORES (HMZ_MODE_FP32X3):
+// the fast parity mode.  Every float32 operand is split into three bf16 parts, x = x0 + x1 + x2 with
+// x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1) (the residuals are exact in float32), and a product
+// x w is evaluated as the seven bf16 x bf16 products x0 w0, x1 w0, x2 w0, x0 w1, x1 w1, x2 w1, x0 w2 — each
+// exact in the float32 accumulator; the dropped x1 w2, x2 w2 are <= 2^-25 |x w|.  Per Linear layer that is
+//     D[:, 0:n)  = (x0 + x1 + x2) w0^T          tcgen05.mma kind::f16, one N = 2n instruction per part and k-step
+//     D[:, n:2n) = (x0 + x1 + x2) w1^T + x0 w2^T    (+ one N = n instruction per k-step for the w2 term)
+// with the weight parts stacked along N in shared memory ([w0; w1; w2] rows of one SWIZZLE_128B K-atom), and the
+// epilogue adds the two accumulator blocks.  The small terms accumulate apart from the large one, so the
+// accumulator's rounding acts on them at their own scale.
+//
+// One CTA = one tile of 128 rows (UMMA M = 128), persistent over tiles.  A network is processed in four CHUNKS
+// of 64 hidden units: first layer of chunk c -> TMEM accumulator (128 columns, double-buffered) -> the epilogue
+// warps add the blocks, apply relu, split into three bf16 parts and write them back IN PLACE -> the second layer
+// accumulates the chunk's K = 64 slice with its A operand taken from TMEM (the .ts form).  The first layer of
+// chunk c + 1 is issued before the second layer of chunk c, so the tensor core works while a chunk is drained.
+// Bias and the one-hot action columns of dynamic_net.0 ride in an extra K = 16 step as in the bf16 kernel
+// (hmz_net_tc.cuh).  Weights stream from L2 per chunk with 1-D TMA bulk copies into double-buffered slots.
+// Epilogue math (normalize_h_state :191-196, support transform :152-189, softmax) is the float32 code of the
+// FFMA kernel (hmz_net.cu).
+#include <cstring>
+
+#include "hmz_net_tc.cuh"
+
+namespace hmz {
+namespace x3 {
+using namespace tc;
+using tc::v4::tmem_ld16_issue;
+using tc::v4::tmem_ld16_wait;
+using tc::v4::tmem_st8;
+using tc::v4::tmem_st_wait;
+using tc::v4::umma_ts;
+
+constexpr int kEpiThreads = 256;  // 8 epilogue warps: warp -> TMEM lane quarter (w & 3), column half (w >> 2)
+constexpr int kMmaWarp = 8, kLoaderWarp = 9;
+constexpr int kThreads = 10 * 32;
+constexpr uint32_t kW1Main = 192 * 128;            // [w0; w1; w2] rows of a 64-unit chunk, K = 64
+constexpr uint32_t kW1Bytes = 192 * 160;           // + the extra K = 16 slice
+constexpr uint32_t kSlot = 30720;                  // both layer kinds: 192 x 160 >= 3 n2 x 160
+constexpr uint32_t kBlockStride = 2 * kSlot;       // one (network, chunk) block of the weight section
+constexpr uint32_t kSectionBytes = 16 * kBlockStride;
+constexpr uint32_t kColD2 = 256;                   // TMEM: D1[2] at columns 0 / 128, D2 at 256
+// second-layer width per network in pass order dynamics, reward, value, policy (33 support logits -> 48, 6 -> 16)
+__host__ __device__ constexpr uint32_t n2_of(int net) { return net == 0 ? 64u : (net == 3 ? 16u : 48u); }
+
+struct __align__(1024) Smem {
+  uint8_t t0[3][kAtomA];  // parts of the input latent tile, later of the raw new latent (reward head input)
+  uint8_t t1[3][kAtomA];  // parts of the normalised new latent (value / policy head input)
+  uint8_t w1[2][kSlot];   // first-layer chunk blocks, slot = chunk counter & 1
+  uint8_t w2[2][kSlot];   // second-layer chunk blocks
+  uint8_t ax[kM * 32];    // extra A slice [onehot(action) (6), 1, 0 x 9] per row (exact in bf16: one part)
+  float2 row_minmax[2][kM];
+  uint64_t bar_w1full[2], bar_w1free[2], bar_w2full[2], bar_w2free[2];
+  uint64_t bar_g;         // input tile + extra slice written (256 arrivals)
+  uint64_t bar_d[2];      // first-layer accumulator of the buffer complete
+  uint64_t bar_a[2];      // hidden parts written back (256 arrivals)
+  uint64_t bar_o;         // second layer of a network complete
+  uint64_t bar_out;       // D2 drained (and, after the dynamics network, both latent tiles written) (256 arrivals)
+  uint32_t tmem_base;
+};
+
+struct Args {
+  const uint8_t* wsec;
+  const void* lat_in;
+  int64_t in_rows_per_item;
+  const uint16_t* in_row;
+  const uint8_t* actions;
+  void* lat_out;
+  int64_t out_rows_per_item, out_row;
+  int latent_dtype;
+  float *r_out, *p_out, *v_out;
+  int64_t n;
+  int n_tiles;
+};
+
+// Every wait of this kernel is time-bounded (2 s: a launch lasts well under a millisecond): a protocol failure traps —
+// the launch fails with an error — instead of hanging the GPU.  (Registers are plentiful here: 320 threads per SM.)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0xFFFu) == 0u) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
+// three bf16 parts of two floats (a in the low half-words)
+__device__ __forceinline__ void split3(float a, float b, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  p0 = pack_bf16(a, b);
+  a = __fsub_rn(a, bf_lo(p0));
+  b = __fsub_rn(b, bf_hi(p0));
+  p1 = pack_bf16(a, b);
+  a = __fsub_rn(a, bf_lo(p1));
+  b = __fsub_rn(b, bf_hi(p1));
+  p2 = pack_bf16(a, b);
+}
+// eight floats -> the 16-byte chunk `chunk` of row `row` in the three part tiles
+__device__ __forceinline__ void store_parts8(uint8_t (*tile)[kAtomA], int row, int chunk, const float (&x)[8]) {
+  uint32_t p[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split3(x[2 * j], x[2 * j + 1], p[0][j], p[1][j], p[2][j]);
+  const uint32_t off = sw128(row, chunk);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) *reinterpret_cast<uint4*>(tile[i] + off) = make_uint4(p[i][0], p[i][1], p[i][2], p[i][3]);
+}
+// out[j] = block 0 column j + block 1 column j for 16 columns (the two accumulator blocks of a layer)
+__device__ __forceinline__ void ld_sum16(uint32_t t0, uint32_t t1, float (&out)[16]) {
+  uint32_t a[16], b[16];
+  tmem_ld16_issue(t0, a);
+  tmem_ld16_issue(t1, b);
+  tmem_ld16_wait(a);
+  tmem_ld16_wait(b);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out[j] = __fadd_rn(__uint_as_float(a[j]), __uint_as_float(b[j]));
+}
+
+// Hidden epilogue of one chunk for this thread's row and column half: units 32 half .. 32 half + 31 of the chunk.
+// Batch b (16 units) reads columns [16b, 16b + 16) of both blocks and leaves h0 in [16b, 16b + 8), h1 in
+// [16b + 8, 16b + 16) and h2 in [64 + 16b, 64 + 16b + 8): always inside the columns it has just read.
+__device__ __forceinline__ void hidden_epilogue(uint32_t D, int half) {
+  uint32_t a[2][16], b[2][16];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    tmem_ld16_issue(D + 32 * half + 16 * j, a[j]);
+    tmem_ld16_issue(D + 64 + 32 * half + 16 * j, b[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    tmem_ld16_wait(a[j]);
+    tmem_ld16_wait(b[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint32_t p0[8], p1[8], p2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float lo = fmaxf(__fadd_rn(__uint_as_float(a[j][2 * i]), __uint_as_float(b[j][2 * i])), 0.f);
+      const float hi = fmaxf(__fadd_rn(__uint_as_float(a[j][2 * i + 1]), __uint_as_float(b[j][2 * i + 1])), 0.f);
+      split3(lo, hi, p0[i], p1[i], p2[i]);
+    }
+    const uint32_t c = D + 32 * half + 16 * j;
+    tmem_st8(c, p0);
+    tmem_st8(c + 8, p1);
+    tmem_st8(c + 64, p2);
+  }
+  tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_constant__ Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int cta = (int)blockIdx.x, n_cta = (int)gridDim.x;
+  const int n_tiles = a.n_tiles;
+  const int64_t n = a.n;
+
+  if (tid == 32) {
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(&s.bar_w1full[j], 1);
+      mbar_init(&s.bar_w1free[j], 1);
+      mbar_init(&s.bar_w2full[j], 1);
+      mbar_init(&s.bar_w2free[j], 1);
+      mbar_init(&s.bar_d[j], 1);
+      mbar_init(&s.bar_a[j], kEpiThreads);
+    }
+    mbar_init(&s.bar_g, kEpiThreads);
+    mbar_init(&s.bar_o, 1);
+    mbar_init(&s.bar_out, kEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+
+  if (warp == kLoaderWarp) {
+    // ================================= loader warp =================================
+    uint32_t G = 0;  // chunk counter of this CTA: slot G & 1, use G >> 1
+    for (int tile = cta; tile < n_tiles; tile += n_cta) {
+      for (int g = 0; g < 16; ++g, ++G) {
+        const uint32_t slot = G & 1u, use = G >> 1;
+        const uint8_t* blk = a.wsec + (size_t)g * kBlockStride;
+        if (use >= 1u) mbar_wait(&s.bar_w1free[slot], (use - 1u) & 1u);
+        if (elect_one()) tma_load(s.w1[slot], blk, kW1Bytes, &s.bar_w1full[slot]);
+        __syncwarp();
+        if (use >= 1u) mbar_wait(&s.bar_w2free[slot], (use - 1u) & 1u);
+        if (elect_one()) tma_load(s.w2[slot], blk + kSlot, 3u * n2_of(g >> 2) * 160u, &s.bar_w2full[slot]);
+        __syncwarp();
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================= MMA-issuing warp =================================
+    const uint32_t id128 = umma_idesc(128), id64 = umma_idesc(64);
+    const uint32_t ax = smem_u32(s.ax);
+    uint32_t G0 = 0, ph_g = 0, ph_out = 0;
+    bool first_tile = true;
+    // first layer of chunk g (network g >> 2) into accumulator buffer Gc & 1
+    auto layer1 = [&](int g, uint32_t Gc) {
+      const uint32_t slot = Gc & 1u, use = Gc >> 1;
+      mbar_wait(&s.bar_w1full[slot], use & 1u);
+      if (g == 0) {
+        mbar_wait(&s.bar_g, ph_g);
+        ph_g ^= 1u;
+      }
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t D1 = tmem + 128u * slot;
+        const uint32_t a_in = (g >> 2) <= 1 ? smem_u32(s.t0[0]) : smem_u32(s.t1[0]);
+        const uint32_t w = smem_u32(s.w1[slot]);
+        const uint64_t b01 = desc_sw128(w), b2 = desc_sw128(w + 128u * 128u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            umma(D1, desc_sw128(a_in + (uint32_t)i * kAtomA) + (uint64_t)(kk * 2), b01 + (uint64_t)(kk * 2), id128, (kk | i) ? 1u : 0u);
+          umma(D1 + 64u, desc_sw128(a_in) + (uint64_t)(kk * 2), b2 + (uint64_t)(kk * 2), id64, 1u);
+        }
+        umma(D1, desc_plain(ax), desc_plain(w + kW1Main), id128, 1u);
+        umma(D1 + 64u, desc_plain(ax), desc_plain(w + kW1Main + plain_off(128, 0)), id64, 1u);
+        umma_commit(&s.bar_d[slot]);
+        umma_commit(&s.bar_w1free[slot]);
+      }
+      __syncwarp();
+    };
+    // second layer: the chunk's K = 64 slice, A = the three hidden parts in TMEM
+    auto layer2 = [&](int g, uint32_t Gc) {
+      const uint32_t slot = Gc & 1u, use = Gc >> 1;
+      const int net = g >> 2, c = g & 3;
+      mbar_wait(&s.bar_w2full[slot], use & 1u);
+      mbar_wait(&s.bar_a[slot], use & 1u);
+      // D2 must have been drained by the previous network's output epilogue (the dynamics network's was waited for
+      // before the reward head's first layer)
+      if (c == 0 && (net >= 2 || (net == 0 && !first_tile))) {
+        mbar_wait(&s.bar_out, ph_out);
+        ph_out ^= 1u;
+      }
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t n2 = n2_of(net);
+        const uint32_t ida = umma_idesc(2u * n2), idb = umma_idesc(n2);
+        const uint32_t D1 = tmem + 128u * slot, D2 = tmem + kColD2;
+        const uint32_t w = smem_u32(s.w2[slot]);
+        const uint64_t b01 = desc_sw128(w), b2 = desc_sw128(w + 2u * n2 * 128u);
+        if (c == 0) {  // bias step clears D2
+          umma(D2, desc_plain(ax), desc_plain(w + 3u * n2 * 128u), ida, 0u);
+          umma(D2 + n2, desc_plain(ax), desc_plain(w + 3u * n2 * 128u + plain_off((int)(2u * n2), 0)), idb, 1u);
+        }
+#pragma unroll
+        for (int b4 = 0; b4 < 4; ++b4) {
+          const uint32_t h0 = D1 + 16u * b4, h1 = h0 + 8u, h2 = h0 + 64u;
+          umma_ts(D2, h0, b01 + (uint64_t)(b4 * 2), ida, 1u);
+          umma_ts(D2, h1, b01 + (uint64_t)(b4 * 2), ida, 1u);
+          umma_ts(D2, h2, b01 + (uint64_t)(b4 * 2), ida, 1u);
+          umma_ts(D2 + n2, h0, b2 + (uint64_t)(b4 * 2), idb, 1u);
+        }
+        if (c == 3) umma_commit(&s.bar_o);
+        umma_commit(&s.bar_w2free[slot]);
+      }
+      __syncwarp();
+    };
+    for (int tile = cta; tile < n_tiles; tile += n_cta) {
+      layer1(0, G0);
+#pragma unroll 1
+      for (int g = 0; g < 16; ++g) {
+        // (the reward head's input is the dynamics network's output: its first layer cannot be issued ahead)
+        if (g + 1 < 16 && g + 1 != 4) layer1(g + 1, G0 + (uint32_t)g + 1u);
+        layer2(g, G0 + (uint32_t)g);
+        if (g == 3) {
+          mbar_wait(&s.bar_out, ph_out);  // raw and normalised latent tiles written, D2 drained
+          ph_out ^= 1u;
+          layer1(4, G0 + 4u);
+        }
+      }
+      G0 += 16u;
+      first_tile = false;
+    }
+  } else {
+    // ================================= epilogue warps =================================
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + (tid & 31);
+    const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
+    const uint32_t T = tmem + lane_bits;
+    uint32_t G = 0, ph_o = 0;
+    for (int tile = cta; tile < n_tiles; tile += n_cta) {
+      const int64_t row0 = (int64_t)tile * kM;
+      const int64_t item = row0 + row;
+      {  // parent latents -> the three part tiles; 8 consecutive lanes fetch the 8 chunks of one row
+        const int chunk = tid & 7;
+        float x[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int grow = (tid >> 3) + 32 * i;
+          const int64_t it = (row0 + grow) < n ? (row0 + grow) : n - 1;
+          const int64_t irow = it * a.in_rows_per_item + (a.in_row ? (int64_t)a.in_row[it] : 0);
+          if (a.latent_dtype == HMZ_LATENT_F32) {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.lat_in) + irow * kLatent + chunk * 8);
+            const float4 u0 = __ldcs(src), u1 = __ldcs(src + 1);
+            x[i][0] = u0.x; x[i][1] = u0.y; x[i][2] = u0.z; x[i][3] = u0.w;
+            x[i][4] = u1.x; x[i][5] = u1.y; x[i][6] = u1.z; x[i][7] = u1.w;
+          } else {
+            const uint4 q = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.lat_in) + irow * kLatent + chunk * 8));
+            const uint32_t pk[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              x[i][2 * j] = bf_lo(pk[j]);
+              x[i][2 * j + 1] = bf_hi(pk[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store_parts8(s.t0, (tid >> 3) + 32 * i, chunk, x[i]);
+        if (tid < kM) {  // extra A slice of row tid: one-hot(action) at k = 0..5, the constant 1 at k = 6
+          const int64_t it = (row0 + tid) < n ? (row0 + tid) : n - 1;
+          int act = (int)a.actions[it];
+          act = act < kActions ? act : kActions - 1;
+          uint32_t w[4] = {0u, 0u, 0u, 0x3F80u};
+          w[act >> 1] |= 0x3F80u << ((act & 1) * 16);
+          *reinterpret_cast<uint4*>(s.ax + plain_off(tid, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(s.ax + plain_off(tid, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async();
+        mbar_arrive(&s.bar_g);
+      }
+#pragma unroll 1
+      for (int net = 0; net < 4; ++net) {  // dynamics, reward, value, policy
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c, ++G) {
+          const uint32_t slot = G & 1u, use = G >> 1;
+          mbar_wait(&s.bar_d[slot], use & 1u);
+          tc_fence_after();
+          hidden_epilogue(T + 128u * slot, half);
+          tc_fence_before();
+          mbar_arrive(&s.bar_a[slot]);
+        }
+        mbar_wait(&s.bar_o, ph_o);
+        ph_o ^= 1u;
+        tc_fence_after();
+        const uint32_t D2 = T + kColD2;
+        if (net == 0) {
+          // ---- new latent: thread (row, half) owns columns [32 half, 32 half + 32)
+          float raw[32];
+          ld_sum16(D2 + 32 * half, D2 + 64 + 32 * half, *reinterpret_cast<float(*)[16]>(&raw[0]));
+          ld_sum16(D2 + 32 * half + 16, D2 + 64 + 32 * half + 16, *reinterpret_cast<float(*)[16]>(&raw[16]));
+          tc_fence_before();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) store_parts8(s.t0, row, half * 4 + c, *reinterpret_cast<float(*)[8]>(&raw[c * 8]));
+          float mn = raw[0], mx = raw[0];
+#pragma unroll
+          for (int i = 1; i < 32; ++i) {
+            mn = fminf(mn, raw[i]);
+            mx = fmaxf(mx, raw[i]);
+          }
+          s.row_minmax[half][row] = make_float2(mn, mx);
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+          const float2 m0 = s.row_minmax[0][row], m1 = s.row_minmax[1][row];
+          mn = fminf(m0.x, m1.x);
+          mx = fmaxf(m0.y, m1.y);
+          const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-8f);  // normalize_h_state (networks.py:191-196)
+          const int64_t orow = item * a.out_rows_per_item + a.out_row;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float hn[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hn[j] = __fdiv_rn(__fsub_rn(raw[c * 8 + j], mn), den);
+            store_parts8(s.t1, row, half * 4 + c, hn);
+            if (item < n) {
+              if (a.latent_dtype == HMZ_LATENT_F32) {
+                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.lat_out) + orow * kLatent + half * 32 + c * 8);
+                __stcs(dst, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                __stcs(dst + 1, make_float4(hn[4], hn[5], hn[6], hn[7]));
+              } else {
+                __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.lat_out) + orow * kLatent + half * 32 + c * 8),
+                       make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7])));
+              }
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(&s.bar_out);
+        } else if (half != 0) {
+          mbar_arrive(&s.bar_out);  // the heads' outputs are one thread per row
+        } else if (net == 3) {      // F.softmax(pi_logits) (networks.py:109)
+          float lg[16];
+          ld_sum16(D2, D2 + 16, lg);
+          tc_fence_before();
+          mbar_arrive(&s.bar_out);
+          float mx = lg[0], den = 0.f;
+#pragma unroll
+          for (int k = 1; k < kActions; ++k) mx = fmaxf(mx, lg[k]);
+#pragma unroll
+          for (int k = 0; k < kActions; ++k) {
+            lg[k] = expf(lg[k] - mx);
+            den += lg[k];
+          }
+          if (item < n) {
+#pragma unroll
+            for (int k = 0; k < kActions; ++k) a.p_out[item * kActions + k] = __fdiv_rn(lg[k], den);
+          }
+        } else {  // support transform (networks.py:152-189) of the 33 logits
+          float lg[48];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) ld_sum16(D2 + 16 * j, D2 + 48 + 16 * j, *reinterpret_cast<float(*)[16]>(&lg[16 * j]));
+          tc_fence_before();
+          mbar_arrive(&s.bar_out);
+          const float x = support_to_scalar([&](int i) { return lg[i]; });
+          if (item < n) (net == 1 ? a.r_out : a.v_out)[item] = x;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---- host-side packing ----------------------------------------------------------------
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40u);
+  return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+static float bf2f(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+static uint16_t part_of(float w, int part) {
+  uint16_t h = f2bf(w);
+  for (int p = 0; p < part; ++p) {
+    w = w - bf2f(h);  // exact: the residual of a bf16 rounding fits float32
+    h = f2bf(w);
+  }
+  return h;
+}
+// rows [part * n_rows + r] of one SWIZZLE_128B K-atom (K = 64) followed by the extra K = 16 slice; get(r, k) is the
+// float32 weight of output row r and input column k (k < 64 main, 64 + j = column j of the extra slice), 0 when absent
+template <typename F>
+static void pack_block(uint8_t* dst, int n_rows, F get) {
+  const int rows = 3 * n_rows;
+  for (int part = 0; part < 3; ++part)
+    for (int r = 0; r < n_rows; ++r) {
+      const int row = part * n_rows + r;
+      for (int k = 0; k < 64; ++k)
+        *reinterpret_cast<uint16_t*>(dst + (size_t)row * 128 + (((k >> 3) ^ (row & 7)) << 4) + (k & 7) * 2) = part_of(get(r, k), part);
+      for (int k = 0; k < 16; ++k)
+        *reinterpret_cast<uint16_t*>(dst + (size_t)rows * 128 + plain_off(row, k >> 3) + (k & 7) * 2) = part_of(get(r, 64 + k), part);
+    }
+}
+
+int64_t fp32_offset_bytes() { return (int64_t)kSectionBytes; }
+int64_t packed_bytes(int n_disks) { return fp32_offset_bytes() + (int64_t)Fp32Layout::total(n_disks) * 4; }
+
+void pack(const float* const* t, int n_disks, void* out) {
+  std::memset(out, 0, (size_t)packed_bytes(n_disks));
+  // the root inference (1/S of the work) runs on the float32 copy behind the section (FFMA kernel)
+  pack_fp32(t, n_disks, (float*)((uint8_t*)out + fp32_offset_bytes()));
+  uint8_t* sec = (uint8_t*)out;
+  // state_dict order: rep(0-3) dyn(4-7) rwd(8-11) pol(12-15) val(16-19), each {w1, b1, w2, b2}; pass order dyn, rwd, val, pol
+  const int first[4] = {4, 8, 16, 12};
+  const int out2[4] = {kLatent, kSupport, kSupport, kActions};
+  for (int net = 0; net < 4; ++net) {
+    const float *w1 = t[first[net]], *b1 = t[first[net] + 1], *w2 = t[first[net] + 2], *b2 = t[first[net] + 3];
+    const int in1 = net == 0 ? kLatent + kActions : kLatent;
+    const int n2 = (int)n2_of(net);
+    for (int c = 0; c < 4; ++c) {
+      uint8_t* blk = sec + (size_t)(net * 4 + c) * kBlockStride;
+      pack_block(blk, 64, [&](int r, int k) -> float {
+        const int unit = 64 * c + r;
+        if (k < 64) return w1[(size_t)unit * in1 + k];
+        const int j = k - 64;
+        if (net == 0 && j < kActions) return w1[(size_t)unit * in1 + kLatent + j];
+        return j == kBiasK ? b1[unit] : 0.f;
+      });
+      pack_block(blk + kSlot, n2, [&](int r, int k) -> float {
+        if (r >= out2[net]) return 0.f;
+        if (k < 64) return w2[(size_t)r * kHidden + 64 * c + k];
+        return (c == 0 && k - 64 == kBiasK) ? b2[r] : 0.f;
+      });
+    }
+  }
+}
+
+int net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
+                  const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row, int latent_dtype,
+                  float* r, float* p, float* v, int64_t n, cudaStream_t stream) {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)");
+  const int smem = (int)sizeof(Smem) + 1024;
+  if (done_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(net_x3_recurrent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaFuncSetAttribute(net_x3_recurrent): %s", cudaGetErrorString(e));
+    done_dev = dev;
+  }
+  Args a{};
+  a.wsec = (const uint8_t*)weights;
+  a.lat_in = lat_in;
+  a.in_rows_per_item = in_rows_per_item;
+  a.in_row = in_row;
+  a.actions = actions;
+  a.lat_out = lat_out;
+  a.out_rows_per_item = out_rows_per_item;
+  a.out_row = out_row;
+  a.latent_dtype = latent_dtype;
+  a.r_out = r;
+  a.p_out = p;
+  a.v_out = v;
+  a.n = n;
+  a.n_tiles = (int)((n + kM - 1) / kM);
+  const int sms = sm_count();
+  const unsigned grid = (unsigned)(a.n_tiles < sms ? a.n_tiles : sms);
+  net_x3_recurrent<<<grid, kThreads, (size_t)smem, stream>>>(a);
+  return check_launch("net_x3_recurrent");
+}
+
+}  // namespace x3
+}  // namespace hmz

@@ -45,11 +45,12 @@ def _weights(n, seed, mode=0):
     return PackedWeights(port.make_weights(n, seed), n, mode)
 
 
+@pytest.mark.parametrize("mode", [0, 2])  # 0: FFMA kernel, 2: HMZ_MODE_FP32X3 (tcgen05, three bf16 parts per operand)
 @pytest.mark.parametrize("n", [3, 5, 10])
 @pytest.mark.parametrize("count", [96, 33, 1])
-def test_recurrent_matches_reference(golden, n, count):
+def test_recurrent_matches_reference(golden, n, count, mode):
     g = golden("net_io.npz")
-    w = _weights(n, int(g[f"n{n}_weight_seed"]))
+    w = _weights(n, int(g[f"n{n}_weight_seed"]), mode)
     h_in = torch.from_numpy(g[f"n{n}_h_in"][:count]).cuda()
     acts = torch.from_numpy(g[f"n{n}_action"][:count].astype(np.uint8)).cuda()
     h = torch.empty(count, 64, device="cuda")
@@ -60,20 +61,60 @@ def test_recurrent_matches_reference(golden, n, count):
     hh, pp, rr, vv = h.cpu().numpy(), p.cpu().numpy(), r.cpu().numpy(), v.cpu().numpy()
     eh, ep = _errs(hh, g[f"n{n}_h_out"][:count]), _errs(pp, g[f"n{n}_p"][:count])
     er, ev = _errs(rr, g[f"n{n}_r"][:count]), _errs(vv, g[f"n{n}_v"][:count])
-    record_metric(f"fp32_recurrent_n{n}_x{count}", dict(h_abs=eh[0], h_rel=eh[1], p_abs=ep[0], p_rel=ep[1], r_abs=er[0], r_rel=er[1],
+    record_metric(f"{'fp32x3' if mode else 'fp32'}_recurrent_n{n}_x{count}", dict(h_abs=eh[0], h_rel=eh[1], p_abs=ep[0], p_rel=ep[1], r_abs=er[0], r_rel=er[1],
                                                         v_abs=ev[0], v_rel=ev[1]))
     assert _close(hh, g[f"n{n}_h_out"][:count], H_ABS)
     assert _close(pp, g[f"n{n}_p"][:count], P_ABS)
     assert _close_rv(rr, g[f"n{n}_r"][:count]) and _close_rv(vv, g[f"n{n}_v"][:count])
 
 
+def test_fp32x3_many_tiles_against_the_ffma_kernel(golden):
+    """HMZ_MODE_FP32X3 at a batch that gives every CTA several 128-row tiles (40,000 + a ragged tail), gathered through
+    in_row and scattered to out_row like the search does, float32 and bf16 latent stores: same gate against the FFMA
+    kernel's outputs as both have against the reference (the FFMA kernel is pinned to the reference above)."""
+    g = golden("net_io.npz")
+    n, count, E = 5, 40000 + 77, 3
+    sd_seed = int(g[f"n{n}_weight_seed"])
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 96, count)
+    rows = rng.integers(0, E, count)
+    lat = torch.zeros(count, E, 64, device="cuda")
+    lat[torch.arange(count), torch.from_numpy(rows)] = torch.from_numpy(g[f"n{n}_h_in"][src]).cuda()
+    acts = torch.from_numpy(rng.integers(0, 6, count).astype(np.uint8)).cuda()
+    in_row = torch.from_numpy(rows.astype(np.int16)).cuda()
+    outs = []
+    for mode in (0, 2):
+        w = _weights(n, sd_seed, mode)
+        out = torch.zeros(count, E + 1, 64, device="cuda")
+        r, v, p = torch.empty(count, device="cuda"), torch.empty(count, device="cuda"), torch.empty(count, 6, device="cuda")
+        w.recurrent(count, latents_in=lat, in_rows_per_item=E, in_row=in_row, actions=acts, latents_out=out,
+                    out_rows_per_item=E + 1, out_row=E, latent_dtype=0, r=r, p=p, v=v)
+        torch.cuda.synchronize()
+        assert float(out[:, :E].abs().max()) == 0.0
+        outs.append((out[:, E].cpu().numpy(), p.cpu().numpy(), r.cpu().numpy(), v.cpu().numpy()))
+    (h0, p0, r0, v0), (h2, p2, r2, v2) = outs
+    eh, ep, er, ev = _errs(h2, h0), _errs(p2, p0), _errs(r2, r0), _errs(v2, v0)
+    record_metric("fp32x3_vs_ffma_n5_x40077", dict(h_abs=eh[0], h_rel=eh[1], p_abs=ep[0], p_rel=ep[1], r_abs=er[0], r_rel=er[1],
+                                                   v_abs=ev[0], v_rel=ev[1]))
+    assert _close(h2, h0, H_ABS) and _close(p2, p0, P_ABS) and _close_rv(r2, r0) and _close_rv(v2, v0)
+    # bf16 latents in and out (the kernel accepts both dtypes): one part is then non-zero
+    w = _weights(n, sd_seed, 2)
+    outb = torch.zeros(count, 64, dtype=torch.bfloat16, device="cuda")
+    r, v, p = torch.empty(count, device="cuda"), torch.empty(count, device="cuda"), torch.empty(count, 6, device="cuda")
+    w.recurrent(count, latents_in=lat.to(torch.bfloat16), in_rows_per_item=E, in_row=in_row, actions=acts, latents_out=outb,
+                out_rows_per_item=1, out_row=0, latent_dtype=1, r=r, p=p, v=v)
+    torch.cuda.synchronize()
+    assert np.abs(outb.float().cpu().numpy() - h0).max() <= 2e-2
+
+
+@pytest.mark.parametrize("mode", [0, 2])
 @pytest.mark.parametrize("n", [3, 5, 10])
-def test_initial_matches_reference_words_and_obs_paths(golden, n):
+def test_initial_matches_reference_words_and_obs_paths(golden, n, mode):
     from muzero_hanoi_b200.engine import VecHanoi
 
     g = golden("net_io.npz")
     count = 96
-    w = _weights(n, int(g[f"n{n}_weight_seed"]))
+    w = _weights(n, int(g[f"n{n}_weight_seed"]), mode)  # (mode 2: the FFMA kernel on the blob's embedded float32 copy)
     env = VecHanoi(n, 200, count)
     env.set_state_indices(g[f"n{n}_state_idx"].astype(np.int32))
     outs = []
@@ -85,7 +126,7 @@ def test_initial_matches_reference_words_and_obs_paths(golden, n):
         torch.cuda.synchronize()
         outs.append((h.cpu().numpy(), p0.cpu().numpy(), v0.cpu().numpy()))
         eh, ep, ev = _errs(outs[-1][0], g[f"n{n}_h0"]), _errs(outs[-1][1], g[f"n{n}_p0"]), _errs(outs[-1][2], g[f"n{n}_v0"])
-        record_metric(f"fp32_initial_n{n}_words{int(use_words)}", dict(h_abs=eh[0], h_rel=eh[1], p_abs=ep[0], p_rel=ep[1], v_abs=ev[0], v_rel=ev[1]))
+        record_metric(f"{'fp32x3' if mode else 'fp32'}_initial_n{n}_words{int(use_words)}", dict(h_abs=eh[0], h_rel=eh[1], p_abs=ep[0], p_rel=ep[1], v_abs=ev[0], v_rel=ev[1]))
         assert _close(outs[-1][0], g[f"n{n}_h0"], H_ABS)
         assert _close(outs[-1][1], g[f"n{n}_p0"], P_ABS)
         assert _close_rv(outs[-1][2], g[f"n{n}_v0"])
