@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native MuZero/Hanoi acting engine.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|fp32|fp32x3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
@@ -363,7 +363,8 @@ def network_accuracy(net, n, dev, rows=4096):
         logits, v = net64.prediction(h2)
         ref = dict(h=h2, r=r.reshape(-1), p=torch.softmax(logits, -1), v=v.reshape(-1))
     out = {}
-    for name, md, ld in (("fp32", _lib.MODE_FP32, _lib.LATENT_F32), ("bf16", _lib.MODE_BF16, _lib.LATENT_F32)):
+    for name, md, ld in (("fp32", _lib.MODE_FP32, _lib.LATENT_F32), ("fp32x3", _lib.MODE_FP32X3, _lib.LATENT_F32),
+                         ("bf16", _lib.MODE_BF16, _lib.LATENT_F32)):
         w = PackedWeights(net.state_dict(), n, md, dev)
         h = torch.empty(rows, 64, device=dev)
         rr, vv, pp = torch.empty(rows, device=dev), torch.empty(rows, device=dev), torch.empty(rows, 6, device=dev)
@@ -378,7 +379,7 @@ def network_accuracy(net, n, dev, rows=4096):
             rec[k + "_max_abs"] = float(d.max())
             rec[k + "_max_rel"] = float((d[big] / ref[k].abs()[big]).max()) if bool(big.any()) else 0.0
         out[name] = rec
-    out["reference"] = f"float64 evaluation of the same weights on {rows} random latents; tolerance gates: 1e-5 relative (fp32), 2e-2 (bf16)"
+    out["reference"] = f"float64 evaluation of the same weights on {rows} random latents; tolerance gates: 1e-5 relative (fp32 = FFMA kernel, fp32x3 = tcgen05 with three bf16 parts per operand), 2e-2 (bf16)"
     return out
 
 
@@ -412,7 +413,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     lib = _lib.load()
     flags = lib.hmz_build_flags().decode()
-    mode = _lib.MODE_BF16 if args.mode == "bf16" else _lib.MODE_FP32
+    mode = {"bf16": _lib.MODE_BF16, "fp32": _lib.MODE_FP32, "fp32x3": _lib.MODE_FP32X3}[args.mode]
     latent_dtype = _lib.LATENT_BF16 if args.mode == "bf16" else _lib.LATENT_F32
     torch.manual_seed(0)
     net = MuZeroNet(3 * N_DISKS, 6, 0.002, "cpu", TD_return=True)  # random-init h / g / f
@@ -538,7 +539,7 @@ def run_ours(args):
             tr, src = traffic_of(name, B)
             if name == "net_recurrent":
                 ach = FLOP_PER_SIM * B / per_launch_s / 1e12
-                return {"kernel": "net_tc<recurrent> (fused g + reward/policy/value heads, tcgen05)" if args.mode == "bf16" else "net_recurrent_fp32 (FFMA)",
+                return {"kernel": "net_tc<recurrent> (fused g + reward/policy/value heads, tcgen05)" if args.mode == "bf16" else ("net_recurrent_fp32 (FFMA)" if args.mode == "fp32" else "net_x3_recurrent (tcgen05, three bf16 parts per float32 operand)"),
                         "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": tr, "traffic_source": src,
                         "peak_source": peaks["source"] + ", sustained bf16", "algorithmic": f"{FLOP_PER_SIM} FLOP/sim x {B} sims per launch"}
@@ -653,26 +654,29 @@ def run_ours(args):
             rec = {"workload": name, "n_disks": n, "games": games, "n_simulations": sims, "dirichlet_alpha": alpha, "temperature": temp,
                    "lesioned_heads": list(heads)}
             for m_name in modes:
-                md = _lib.MODE_BF16 if m_name == "bf16" else _lib.MODE_FP32
+                md = {"bf16": _lib.MODE_BF16, "fp32": _lib.MODE_FP32, "fp32x3": _lib.MODE_FP32X3}[m_name]
                 ld = _lib.LATENT_BF16 if m_name == "bf16" else _lib.LATENT_F32
                 w_ = PackedWeights(net_.state_dict(), n, md, dev)
                 sp_ = SelfPlay(n, MAX_STEPS, games, sims, w_, DISCOUNT, alpha, EPS, temp, seed=7, ring_slots=4, device=dev, latent_dtype=ld)
                 sp_.env.random_reset(seed=3)
                 sp_.mcts.store.set_schedule(schedule if m_name == "bf16" else _lib.SCHEDULE_AUTO)
-                ms_move = time_moves(sp_, n_moves if m_name == "bf16" else max(2, n_moves // 8))
+                ms_move = time_moves(sp_, n_moves if m_name == "bf16" else max(2, n_moves // (8 if m_name == "fp32" else 2)))
                 rec[m_name] = {"ms_per_step": ms_move, "step": "one move of every game", "value": games * sims / (ms_move * 1e-3), "unit": UNIT,
                                "mean_leaf_depth": mean_leaf_depth(sp_)}
                 del sp_, w_
             return rec
 
         sub["configs_1"] = sub_record("hanoi3_4096searches_x50sims (BASELINE.json configs[1]; fp32 = the bit-exact-gated parity mode)",
-                                      3, 4096, 50, ALPHA, 1.0, (), ("fp32", "bf16"), 64)
+                                      3, 4096, 50, ALPHA, 1.0, (), ("fp32", "fp32x3", "bf16"), 64)
         sub["configs_4"] = sub_record("hanoi4_lesion_16384searches_x200sims_T0 (BASELINE.json configs[4], acting_ablations.py lesion mode)",
-                                      4, 16384, 200, 0.0, 0.0, ("policy_net", "value_net", "rwd_net"), ("fp32", "bf16"), 16)
+                                      4, 16384, 200, 0.0, 0.0, ("policy_net", "value_net", "rwd_net"), ("fp32", "fp32x3", "bf16"), 16)
         fp = sub_record("hanoi5_65536games_x100sims in fp32 parity mode (configs[2] workload)", N_DISKS, args.games, S, ALPHA, 1.0, (),
-                        ("fp32",), 16)
-        sub["fp32_mode"] = {"value": fp["fp32"]["value"], "unit": UNIT, "ms_per_step": fp["fp32"]["ms_per_step"],
-                            "step": "one move of every game", "mean_leaf_depth": fp["fp32"]["mean_leaf_depth"],
+                        ("fp32", "fp32x3"), 16)
+        # the parity mode's number is the tensor-core kernel's (HMZ_MODE_FP32X3, same 1e-5 gate); the FFMA kernel's stays beside it
+        sub["fp32_mode"] = {"value": fp["fp32x3"]["value"], "unit": UNIT, "ms_per_step": fp["fp32x3"]["ms_per_step"],
+                            "kernel": "net_x3_recurrent (tcgen05, every float32 operand as three bf16 parts, fp32 accumulate)",
+                            "step": "one move of every game", "mean_leaf_depth": fp["fp32x3"]["mean_leaf_depth"],
+                            "ffma_kernel": {"value": fp["fp32"]["value"], "ms_per_step": fp["fp32"]["ms_per_step"]},
                             "accuracy": network_accuracy(net, N_DISKS, dev)}
 
     # ---- §8f rows (episode post-processing, replay ring, acting harness): measured only on request
@@ -792,7 +796,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--mode", choices=["bf16", "fp32"], default=os.environ.get("HMZ_BENCH_MODE", "bf16"))
+    ap.add_argument("--mode", choices=["bf16", "fp32", "fp32x3"], default=os.environ.get("HMZ_BENCH_MODE", "bf16"))
     ap.add_argument("--games", type=int, default=GLOBAL_GAMES, help="GLOBAL number of games (sharded over the ranks)")
     ap.add_argument("--sims", type=int, default=N_SIMS)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

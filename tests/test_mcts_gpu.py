@@ -147,7 +147,8 @@ def test_dropin_mcts_close_to_reference_episode(golden, name):
         mcts.run_mcts(g["obs"][0], net, 1.5, True)
 
 
-def test_config5_lesion_mode_bit_exact_vs_oracle():
+@pytest.mark.parametrize("mode", [0, 2])  # parity mode on the FFMA kernel / on the tensor cores (HMZ_MODE_FP32X3)
+def test_config5_lesion_mode_bit_exact_vs_oracle(mode):
     """BASELINE.json config 5 semantics (acting_ablations.py lesion mode): N=4, random non-goal starts,
     policy and value heads re-initialised U(-1/8, 1/8) (networks.py:201-205), no root noise, S=200,
     temperature 0 with sampling (deterministic=False) — 16,384 searches replayed by the C oracle."""
@@ -155,7 +156,7 @@ def test_config5_lesion_mode_bit_exact_vs_oracle():
 
     n, B, S = 4, 16384, 200
     sd = port.lesion_weights(port.make_weights(n, 3), ("policy_net", "value_net"), seed=103)
-    weights = PackedWeights(sd, n)
+    weights = PackedWeights(sd, n, mode)
     env = VecHanoi(n, 200, B)
     env.random_reset(seed=5)
     mcts = BatchedMCTS(0.8, 0.0, S, B)
@@ -216,6 +217,41 @@ def test_node_view_matches_tree_store(golden):
     with pytest.raises(ValueError, match="Expand leaf node first"):
         leaf.best_child(mcts, mm)
     assert leaf.N == 0 and leaf.Q == 0.0 and leaf.h_state is None and leaf.children == []
+
+
+@pytest.mark.parametrize("n,B,S,schedule", [(3, 4096, 50, 0), (5, 32768 + 300, 100, 0), (5, 20000, 60, 3)])
+def test_fast_parity_mode_search_run_replayed_by_the_oracle(n, B, S, schedule):
+    """HMZ_MODE_FP32X3 through hmz_search_run (configs[1] size and two larger ragged batches; float32 latents, stream
+    groups): the network outputs every backup consumed are captured and the C oracle must reproduce visit counts, root
+    values and min/max from them bit for bit, over two moves."""
+    from muzero_hanoi_b200 import _lib
+    from muzero_hanoi_b200.engine import BatchedMCTS, PackedWeights, VecHanoi
+
+    w = PackedWeights(port.make_weights(n, 8), n, _lib.MODE_FP32X3)
+    env = VecHanoi(n, 200, B)
+    env.random_reset(seed=4)
+    rng = np.random.default_rng(12)
+    m = BatchedMCTS(0.8, 0.25, S, B, latent_dtype=_lib.LATENT_F32)
+    m.store.set_schedule(schedule)
+    cap = m.store.enable_capture(S)
+    table = port.ucb_table(S + 1)
+    for move in range(2):
+        noise = rng.dirichlet(np.full(6, 0.25), B)
+        uni = rng.random(B)
+        mm = m.store.minmax.cpu().numpy().copy()
+        cap.fill_(float("nan"))
+        action, pi, q, visits = m.run_mcts(w, words=env.words, temperature=1.0, deterministic=False, noise=noise, uniforms=uni)
+        torch.cuda.synchronize()
+        c = cap.cpu().numpy()
+        assert np.isfinite(c).all()
+        prior = m.store.root_prior.cpu().numpy()
+        assert np.array_equal(prior, port.mix_dirichlet(m.p0.cpu().numpy(), noise))
+        o_visits, o_q, _ = cport.search_injected(prior, True, mm, np.ascontiguousarray(c[:, :, 6]), np.ascontiguousarray(c[:, :, :6]),
+                                                 np.ascontiguousarray(c[:, :, 7]), 0.8, table)
+        assert np.array_equal(visits.cpu().numpy(), o_visits), f"move {move}: visit counts differ from the oracle replay"
+        assert np.array_equal(q.cpu().numpy(), o_q)
+        assert np.array_equal(m.store.minmax.cpu().numpy(), mm)
+        env.step(action.to(torch.uint8), want_obs=False)
 
 
 @pytest.mark.parametrize("schedule", [0, 64, 128])
