@@ -114,6 +114,7 @@ SIGNATURES = {
     "hmz_net_initial": (_I, [_P, _I, _I, _P, _P, _P, _L, _I, _P, _P, _L, _P]),
     "hmz_net_recurrent": (_I, [_P, _I, _P, _L, _P, _P, _P, _L, _L, _I, _P, _P, _P, _L, _P]),
     "hmz_debug_tc_timeline": (_I, [_P]),
+    "hmz_debug_x3_timeline": (_I, [_P]),
     "hmz_debug_persist_stats": (_I, [_P]),
     "hmz_debug_persist_timeline": (_I, [_P]),
     "hmz_debug_gantt": (_I, [_I, _P, _I, _P]),

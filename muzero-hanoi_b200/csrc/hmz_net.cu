@@ -331,6 +331,7 @@ using namespace hmz;
 extern "C" {
 
 int hmz_debug_tc_timeline(unsigned long long* host_out) { return tc_debug_read_timeline(host_out); }
+int hmz_debug_x3_timeline(unsigned long long* host_out) { return x3::debug_read_timeline(host_out); }
 
 int64_t hmz_weights_packed_bytes(int n_disks, int mode) {
   if (n_disks < 1 || n_disks > HMZ_MAX_DISKS) return -1;

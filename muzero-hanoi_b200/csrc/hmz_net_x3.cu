@@ -18,6 +18,7 @@
 // (hmz_net_tc.cuh).  Weights stream from L2 per chunk with 1-D TMA bulk copies into double-buffered slots.
 // Epilogue math (normalize_h_state :191-196, support transform :152-189, softmax) is the float32 code of the
 // FFMA kernel (hmz_net.cu).
+#include <cstdlib>
 #include <cstring>
 
 #include "hmz_net_tc.cuh"
@@ -32,8 +33,8 @@ using tc::v4::tmem_st_wait;
 using tc::v4::umma_ts;
 
 constexpr int kEpiThreads = 256;  // 8 epilogue warps: warp -> TMEM lane quarter (w & 3), column half (w >> 2)
-constexpr int kMmaWarp = 8, kLoaderWarp = 9;
-constexpr int kThreads = 10 * 32;
+constexpr int kMma1Warp = 8, kMma2Warp = 9, kLoaderWarp = 10;
+constexpr int kThreads = 11 * 32;
 constexpr uint32_t kW1Main = 192 * 128;            // [w0; w1; w2] rows of a 64-unit chunk, K = 64
 constexpr uint32_t kW1Bytes = 192 * 160;           // + the extra K = 16 slice
 constexpr uint32_t kSlot = 30720;                  // both layer kinds: 192 x 160 >= 3 n2 x 160
@@ -55,7 +56,9 @@ struct __align__(1024) Smem {
   uint64_t bar_d[2];      // first-layer accumulator of the buffer complete
   uint64_t bar_a[2];      // hidden parts written back (256 arrivals)
   uint64_t bar_o;         // second layer of a network complete
-  uint64_t bar_out;       // D2 drained (and, after the dynamics network, both latent tiles written) (256 arrivals)
+  uint64_t bar_raw;       // dynamics output: D2 drained and the raw latent tile written (256 arrivals)
+  uint64_t bar_hn;        // dynamics output: normalised latent tile written (256 arrivals)
+  uint64_t bar_out;       // a head's output: D2 drained (256 arrivals)
   uint32_t tmem_base;
 };
 
@@ -71,7 +74,18 @@ struct Args {
   float *r_out, *p_out, *v_out;
   int64_t n;
   int n_tiles;
+  int timeline;  // tooling (HMZ_X3_TIMELINE=1): CTA 0 records clock64() at the phase boundaries of its first tile
 };
+
+static __device__ unsigned long long g_x3_timeline[128];
+#define X3_TL(slot)                                                   \
+  do {                                                                \
+    if (tl_on) {                                                      \
+      unsigned long long now_;                                        \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_)::"memory");  \
+      g_x3_timeline[slot] = now_;                                     \
+    }                                                                 \
+  } while (0)
 
 // Every wait of this kernel is time-bounded (2 s: a launch lasts well under a millisecond): a protocol failure traps —
 // the launch fails with an error — instead of hanging the GPU.  (Registers are plentiful here: 320 threads per SM.)
@@ -116,9 +130,12 @@ __device__ __forceinline__ void store_parts8(uint8_t (*tile)[kAtomA], int row, i
   uint32_t p[3][4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) split3(x[2 * j], x[2 * j + 1], p[0][j], p[1][j], p[2][j]);
-  const uint32_t off = sw128(row, chunk);
+  const uint32_t addr = smem_u32(tile[0]) + sw128(row, chunk);  // (explicit st.shared: the pointer form compiles to generic stores)
 #pragma unroll
-  for (int i = 0; i < 3; ++i) *reinterpret_cast<uint4*>(tile[i] + off) = make_uint4(p[i][0], p[i][1], p[i][2], p[i][3]);
+  for (int i = 0; i < 3; ++i)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr + (uint32_t)i * kAtomA), "r"(p[i][0]), "r"(p[i][1]), "r"(p[i][2]),
+                 "r"(p[i][3])
+                 : "memory");
 }
 // out[j] = block 0 column j + block 1 column j for 16 columns (the two accumulator blocks of a layer)
 __device__ __forceinline__ void ld_sum16(uint32_t t0, uint32_t t1, float (&out)[16]) {
@@ -170,6 +187,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
   const int cta = (int)blockIdx.x, n_cta = (int)gridDim.x;
   const int n_tiles = a.n_tiles;
   const int64_t n = a.n;
+  bool tl_on = a.timeline != 0 && cta == 0 && (tid & 31) == 0;  // (switched off after the first tile)
+  if (tid == 0) X3_TL(110);
 
   if (tid == 32) {
     for (int j = 0; j < 2; ++j) {
@@ -183,6 +202,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     mbar_init(&s.bar_g, kEpiThreads);
     mbar_init(&s.bar_o, 1);
     mbar_init(&s.bar_out, kEpiThreads);
+    mbar_init(&s.bar_raw, kEpiThreads);
+    mbar_init(&s.bar_hn, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -194,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
+  if (tid == 0) X3_TL(111);
 
   if (warp == kLoaderWarp) {
     // ================================= loader warp =================================
@@ -210,91 +232,98 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
         __syncwarp();
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ================================= MMA-issuing warp =================================
+  } else if (warp == kMma1Warp) {
+    // ========================= first-layer issuing warp =========================
+    // Two issuing warps, one per layer kind: issuing a tcgen05.mma blocks for about its execution time, so a single warp
+    // would serialise the second layer of chunk g behind the issue of the first layer of chunk g + 1 (and behind its own
+    // waits); the tensor core takes the two streams in arrival order.  The write-after-read hazard on an accumulator
+    // buffer — the first layer of chunk G + 2 overwrites what the second layer of chunk G reads as its A operand —
+    // is then ordered by an mbarrier (bar_w2free: second layer of chunk G complete) instead of by issue order.
     const uint32_t id128 = umma_idesc(128), id64 = umma_idesc(64);
     const uint32_t ax = smem_u32(s.ax);
-    uint32_t G0 = 0, ph_g = 0, ph_out = 0;
-    bool first_tile = true;
-    // first layer of chunk g (network g >> 2) into accumulator buffer Gc & 1
-    auto layer1 = [&](int g, uint32_t Gc) {
-      const uint32_t slot = Gc & 1u, use = Gc >> 1;
-      mbar_wait(&s.bar_w1full[slot], use & 1u);
-      if (g == 0) {
-        mbar_wait(&s.bar_g, ph_g);
-        ph_g ^= 1u;
-      }
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t D1 = tmem + 128u * slot;
-        const uint32_t a_in = (g >> 2) <= 1 ? smem_u32(s.t0[0]) : smem_u32(s.t1[0]);
-        const uint32_t w = smem_u32(s.w1[slot]);
-        const uint64_t b01 = desc_sw128(w), b2 = desc_sw128(w + 128u * 128u);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-            umma(D1, desc_sw128(a_in + (uint32_t)i * kAtomA) + (uint64_t)(kk * 2), b01 + (uint64_t)(kk * 2), id128, (kk | i) ? 1u : 0u);
-          umma(D1 + 64u, desc_sw128(a_in) + (uint64_t)(kk * 2), b2 + (uint64_t)(kk * 2), id64, 1u);
-        }
-        umma(D1, desc_plain(ax), desc_plain(w + kW1Main), id128, 1u);
-        umma(D1 + 64u, desc_plain(ax), desc_plain(w + kW1Main + plain_off(128, 0)), id64, 1u);
-        umma_commit(&s.bar_d[slot]);
-        umma_commit(&s.bar_w1free[slot]);
-      }
-      __syncwarp();
-    };
-    // second layer: the chunk's K = 64 slice, A = the three hidden parts in TMEM
-    auto layer2 = [&](int g, uint32_t Gc) {
-      const uint32_t slot = Gc & 1u, use = Gc >> 1;
-      const int net = g >> 2, c = g & 3;
-      mbar_wait(&s.bar_w2full[slot], use & 1u);
-      mbar_wait(&s.bar_a[slot], use & 1u);
-      // D2 must have been drained by the previous network's output epilogue (the dynamics network's was waited for
-      // before the reward head's first layer)
-      if (c == 0 && (net >= 2 || (net == 0 && !first_tile))) {
-        mbar_wait(&s.bar_out, ph_out);
-        ph_out ^= 1u;
-      }
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t n2 = n2_of(net);
-        const uint32_t ida = umma_idesc(2u * n2), idb = umma_idesc(n2);
-        const uint32_t D1 = tmem + 128u * slot, D2 = tmem + kColD2;
-        const uint32_t w = smem_u32(s.w2[slot]);
-        const uint64_t b01 = desc_sw128(w), b2 = desc_sw128(w + 2u * n2 * 128u);
-        if (c == 0) {  // bias step clears D2
-          umma(D2, desc_plain(ax), desc_plain(w + 3u * n2 * 128u), ida, 0u);
-          umma(D2 + n2, desc_plain(ax), desc_plain(w + 3u * n2 * 128u + plain_off((int)(2u * n2), 0)), idb, 1u);
-        }
-#pragma unroll
-        for (int b4 = 0; b4 < 4; ++b4) {
-          const uint32_t h0 = D1 + 16u * b4, h1 = h0 + 8u, h2 = h0 + 64u;
-          umma_ts(D2, h0, b01 + (uint64_t)(b4 * 2), ida, 1u);
-          umma_ts(D2, h1, b01 + (uint64_t)(b4 * 2), ida, 1u);
-          umma_ts(D2, h2, b01 + (uint64_t)(b4 * 2), ida, 1u);
-          umma_ts(D2 + n2, h0, b2 + (uint64_t)(b4 * 2), idb, 1u);
-        }
-        if (c == 3) umma_commit(&s.bar_o);
-        umma_commit(&s.bar_w2free[slot]);
-      }
-      __syncwarp();
-    };
+    uint32_t G = 0, ph_tile = 0;
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
-      layer1(0, G0);
 #pragma unroll 1
-      for (int g = 0; g < 16; ++g) {
-        // (the reward head's input is the dynamics network's output: its first layer cannot be issued ahead)
-        if (g + 1 < 16 && g + 1 != 4) layer1(g + 1, G0 + (uint32_t)g + 1u);
-        layer2(g, G0 + (uint32_t)g);
-        if (g == 3) {
-          mbar_wait(&s.bar_out, ph_out);  // raw and normalised latent tiles written, D2 drained
-          ph_out ^= 1u;
-          layer1(4, G0 + 4u);
+      for (int g = 0; g < 16; ++g, ++G) {
+        const uint32_t slot = G & 1u, use = G >> 1;
+        mbar_wait(&s.bar_w1full[slot], use & 1u);
+        if (use >= 1u) mbar_wait(&s.bar_w2free[slot], (use - 1u) & 1u);  // accumulator buffer no longer read
+        if (g == 0) mbar_wait(&s.bar_g, ph_tile);    // input tile gathered
+        if (g == 4) mbar_wait(&s.bar_raw, ph_tile);  // raw latent tile written (reward head input)
+        if (g == 8) mbar_wait(&s.bar_hn, ph_tile);   // normalised latent tile written (value / policy head input)
+        tc_fence_after();
+        X3_TL(g);
+        if (elect_one()) {
+          const uint32_t D1 = tmem + 128u * slot;
+          const uint32_t a_in = (g >> 2) <= 1 ? smem_u32(s.t0[0]) : smem_u32(s.t1[0]);
+          const uint32_t w = smem_u32(s.w1[slot]);
+          const uint64_t b01 = desc_sw128(w), b2 = desc_sw128(w + 128u * 128u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              umma(D1, desc_sw128(a_in + (uint32_t)i * kAtomA) + (uint64_t)(kk * 2), b01 + (uint64_t)(kk * 2), id128, (kk | i) ? 1u : 0u);
+            umma(D1 + 64u, desc_sw128(a_in) + (uint64_t)(kk * 2), b2 + (uint64_t)(kk * 2), id64, 1u);
+          }
+          umma(D1, desc_plain(ax), desc_plain(w + kW1Main), id128, 1u);
+          umma(D1 + 64u, desc_plain(ax), desc_plain(w + kW1Main + plain_off(128, 0)), id64, 1u);
+          umma_commit(&s.bar_d[slot]);
+          umma_commit(&s.bar_w1free[slot]);
         }
+        __syncwarp();
+        X3_TL(16 + g);
       }
-      G0 += 16u;
+      ph_tile ^= 1u;
+      tl_on = false;
+    }
+  } else if (warp == kMma2Warp) {
+    // ========================= second-layer issuing warp =========================
+    // the chunk's K = 64 slice, A = the three hidden parts in TMEM
+    const uint32_t ax = smem_u32(s.ax);
+    uint32_t G = 0, ph_tile = 0, ph_out = 0;
+    bool first_tile = true;
+    for (int tile = cta; tile < n_tiles; tile += n_cta) {
+#pragma unroll 1
+      for (int g = 0; g < 16; ++g, ++G) {
+        const uint32_t slot = G & 1u, use = G >> 1;
+        const int net = g >> 2, c = g & 3;
+        mbar_wait(&s.bar_w2full[slot], use & 1u);
+        mbar_wait(&s.bar_a[slot], use & 1u);
+        // D2 must have been drained by the previous network's output epilogue
+        if (g == 4) mbar_wait(&s.bar_raw, ph_tile);
+        if (c == 0 && (net >= 2 || (net == 0 && !first_tile))) {
+          mbar_wait(&s.bar_out, ph_out);
+          ph_out ^= 1u;
+        }
+        tc_fence_after();
+        X3_TL(32 + g);
+        if (elect_one()) {
+          const uint32_t n2 = n2_of(net);
+          const uint32_t ida = umma_idesc(2u * n2), idb = umma_idesc(n2);
+          const uint32_t D1 = tmem + 128u * slot, D2 = tmem + kColD2;
+          const uint32_t w = smem_u32(s.w2[slot]);
+          const uint64_t b01 = desc_sw128(w), b2 = desc_sw128(w + 2u * n2 * 128u);
+          if (c == 0) {  // bias step clears D2
+            umma(D2, desc_plain(ax), desc_plain(w + 3u * n2 * 128u), ida, 0u);
+            umma(D2 + n2, desc_plain(ax), desc_plain(w + 3u * n2 * 128u + plain_off((int)(2u * n2), 0)), idb, 1u);
+          }
+#pragma unroll
+          for (int b4 = 0; b4 < 4; ++b4) {
+            const uint32_t h0 = D1 + 16u * b4, h1 = h0 + 8u, h2 = h0 + 64u;
+            umma_ts(D2, h0, b01 + (uint64_t)(b4 * 2), ida, 1u);
+            umma_ts(D2, h1, b01 + (uint64_t)(b4 * 2), ida, 1u);
+            umma_ts(D2, h2, b01 + (uint64_t)(b4 * 2), ida, 1u);
+            umma_ts(D2 + n2, h0, b2 + (uint64_t)(b4 * 2), idb, 1u);
+          }
+          if (c == 3) umma_commit(&s.bar_o);
+          umma_commit(&s.bar_w2free[slot]);
+        }
+        __syncwarp();
+        X3_TL(48 + g);
+      }
+      ph_tile ^= 1u;
       first_tile = false;
+      tl_on = false;
     }
   } else {
     // ================================= epilogue warps =================================
@@ -303,9 +332,11 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
     const uint32_t T = tmem + lane_bits;
     uint32_t G = 0, ph_o = 0;
+    tl_on = tl_on && tid == 0;
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
       const int64_t row0 = (int64_t)tile * kM;
       const int64_t item = row0 + row;
+      X3_TL(104);
       {  // parent latents -> the three part tiles; 8 consecutive lanes fetch the 8 chunks of one row
         const int chunk = tid & 7;
         float x[4][8];
@@ -342,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
         }
         fence_proxy_async();
         mbar_arrive(&s.bar_g);
+        X3_TL(105);
       }
 #pragma unroll 1
       for (int net = 0; net < 4; ++net) {  // dynamics, reward, value, policy
@@ -350,13 +382,16 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
           const uint32_t slot = G & 1u, use = G >> 1;
           mbar_wait(&s.bar_d[slot], use & 1u);
           tc_fence_after();
+          X3_TL(64 + net * 4 + c);
           hidden_epilogue(T + 128u * slot, half);
           tc_fence_before();
           mbar_arrive(&s.bar_a[slot]);
+          X3_TL(80 + net * 4 + c);
         }
         mbar_wait(&s.bar_o, ph_o);
         ph_o ^= 1u;
         tc_fence_after();
+        X3_TL(96 + net);
         const uint32_t D2 = T + kColD2;
         if (net == 0) {
           // ---- new latent: thread (row, half) owns columns [32 half, 32 half + 32)
@@ -364,8 +399,11 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
           ld_sum16(D2 + 32 * half, D2 + 64 + 32 * half, *reinterpret_cast<float(*)[16]>(&raw[0]));
           ld_sum16(D2 + 32 * half + 16, D2 + 64 + 32 * half + 16, *reinterpret_cast<float(*)[16]>(&raw[16]));
           tc_fence_before();
+          // the raw latent feeds the reward head: publish it first so that head's first layers overlap the rest
 #pragma unroll
           for (int c = 0; c < 4; ++c) store_parts8(s.t0, row, half * 4 + c, *reinterpret_cast<float(*)[8]>(&raw[c * 8]));
+          fence_proxy_async();
+          mbar_arrive(&s.bar_raw);
           float mn = raw[0], mx = raw[0];
 #pragma unroll
           for (int i = 1; i < 32; ++i) {
@@ -377,13 +415,16 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
           const float2 m0 = s.row_minmax[0][row], m1 = s.row_minmax[1][row];
           mn = fminf(m0.x, m1.x);
           mx = fmaxf(m0.y, m1.y);
-          const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-8f);  // normalize_h_state (networks.py:191-196)
+          // normalize_h_state (networks.py:191-196); the quotient as a product with the correctly rounded reciprocal
+          // (<= 1.5 ulp from the division, far inside the gate; 32 IEEE divisions per thread sat on the chain that the
+          // reward head's first chunk waits behind)
+          const float inv = __frcp_rn(__fadd_rn(__fsub_rn(mx, mn), 1e-8f));
           const int64_t orow = item * a.out_rows_per_item + a.out_row;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float hn[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hn[j] = __fdiv_rn(__fsub_rn(raw[c * 8 + j], mn), den);
+            for (int j = 0; j < 8; ++j) hn[j] = __fmul_rn(__fsub_rn(raw[c * 8 + j], mn), inv);
             store_parts8(s.t1, row, half * 4 + c, hn);
             if (item < n) {
               if (a.latent_dtype == HMZ_LATENT_F32) {
@@ -397,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
             }
           }
           fence_proxy_async();
-          mbar_arrive(&s.bar_out);
+          mbar_arrive(&s.bar_hn);
         } else if (half != 0) {
           mbar_arrive(&s.bar_out);  // the heads' outputs are one thread per row
         } else if (net == 3) {      // F.softmax(pi_logits) (networks.py:109)
@@ -426,7 +467,9 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
           const float x = support_to_scalar([&](int i) { return lg[i]; });
           if (item < n) (net == 1 ? a.r_out : a.v_out)[item] = x;
         }
+        X3_TL(100 + net);
       }
+      tl_on = false;
     }
   }
 
@@ -534,10 +577,16 @@ int net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_i
   a.v_out = v;
   a.n = n;
   a.n_tiles = (int)((n + kM - 1) / kM);
+  static const int tl = getenv("HMZ_X3_TIMELINE") ? atoi(getenv("HMZ_X3_TIMELINE")) : 0;
+  a.timeline = tl;
   const int sms = sm_count();
   const unsigned grid = (unsigned)(a.n_tiles < sms ? a.n_tiles : sms);
   net_x3_recurrent<<<grid, kThreads, (size_t)smem, stream>>>(a);
   return check_launch("net_x3_recurrent");
+}
+
+int debug_read_timeline(unsigned long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_x3_timeline, sizeof(g_x3_timeline)) == cudaSuccess ? HMZ_OK : HMZ_ERR_CUDA;
 }
 
 }  // namespace x3
