@@ -32,15 +32,16 @@ using tc::v4::tmem_st8;
 using tc::v4::tmem_st_wait;
 using tc::v4::umma_ts;
 
-constexpr int kEpiThreads = 256;  // 8 epilogue warps: warp -> TMEM lane quarter (w & 3), column half (w >> 2)
-constexpr int kMma1Warp = 8, kMma2Warp = 9, kLoaderWarp = 10;
-constexpr int kThreads = 11 * 32;
+constexpr int kEpiThreads = 256;  // 8 hidden-epilogue warps: warp -> TMEM lane quarter (w & 3), column half (w >> 2)
+constexpr int kOutThreads = 128;  // 4 output warps: thread = row
+constexpr int kOutWarp0 = 8, kMma1Warp = 12, kMma2Warp = 13, kLoader1Warp = 14, kLoader2Warp = 15;
+constexpr int kThreads = 16 * 32;
 constexpr uint32_t kW1Main = 192 * 128;            // [w0; w1; w2] rows of a 64-unit chunk, K = 64
 constexpr uint32_t kW1Bytes = 192 * 160;           // + the extra K = 16 slice
 constexpr uint32_t kSlot = 30720;                  // both layer kinds: 192 x 160 >= 3 n2 x 160
 constexpr uint32_t kBlockStride = 2 * kSlot;       // one (network, chunk) block of the weight section
 constexpr uint32_t kSectionBytes = 16 * kBlockStride;
-constexpr uint32_t kColD2 = 256;                   // TMEM: D1[2] at columns 0 / 128, D2 at 256
+constexpr uint32_t kColD2 = 384;                   // TMEM: D1[3] at columns 0 / 128 / 256, D2 at 384 (all 512 columns)
 // second-layer width per network in pass order dynamics, reward, value, policy (33 support logits -> 48, 6 -> 16)
 __host__ __device__ constexpr uint32_t n2_of(int net) { return net == 0 ? 64u : (net == 3 ? 16u : 48u); }
 
@@ -50,15 +51,15 @@ struct __align__(1024) Smem {
   uint8_t w1[2][kSlot];   // first-layer chunk blocks, slot = chunk counter & 1
   uint8_t w2[2][kSlot];   // second-layer chunk blocks
   uint8_t ax[kM * 32];    // extra A slice [onehot(action) (6), 1, 0 x 9] per row (exact in bf16: one part)
-  float2 row_minmax[2][kM];
   uint64_t bar_w1full[2], bar_w1free[2], bar_w2full[2], bar_w2free[2];
-  uint64_t bar_g;         // input tile + extra slice written (256 arrivals)
-  uint64_t bar_d[2];      // first-layer accumulator of the buffer complete
-  uint64_t bar_a[2];      // hidden parts written back (256 arrivals)
+  uint64_t bar_g;         // input tile + extra slice written (128 arrivals: the output warps)
+  uint64_t bar_d[3];      // first-layer accumulator of the buffer complete
+  uint64_t bar_a[3];      // hidden parts written back (256 arrivals)
+  uint64_t bar_hfree[3];  // the second layer that read the buffer's hidden parts has completed
   uint64_t bar_o;         // second layer of a network complete
-  uint64_t bar_raw;       // dynamics output: D2 drained and the raw latent tile written (256 arrivals)
-  uint64_t bar_hn;        // dynamics output: normalised latent tile written (256 arrivals)
-  uint64_t bar_out;       // a head's output: D2 drained (256 arrivals)
+  uint64_t bar_raw;       // dynamics output: D2 drained and the raw latent tile written (128 arrivals)
+  uint64_t bar_hn;        // dynamics output: normalised latent tile written (128 arrivals)
+  uint64_t bar_out;       // a head's output: D2 drained (128 arrivals)
   uint32_t tmem_base;
 };
 
@@ -196,14 +197,17 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
       mbar_init(&s.bar_w1free[j], 1);
       mbar_init(&s.bar_w2full[j], 1);
       mbar_init(&s.bar_w2free[j], 1);
+    }
+    for (int j = 0; j < 3; ++j) {
       mbar_init(&s.bar_d[j], 1);
       mbar_init(&s.bar_a[j], kEpiThreads);
+      mbar_init(&s.bar_hfree[j], 1);
     }
-    mbar_init(&s.bar_g, kEpiThreads);
+    mbar_init(&s.bar_g, kOutThreads);
     mbar_init(&s.bar_o, 1);
-    mbar_init(&s.bar_out, kEpiThreads);
-    mbar_init(&s.bar_raw, kEpiThreads);
-    mbar_init(&s.bar_hn, kEpiThreads);
+    mbar_init(&s.bar_out, kOutThreads);
+    mbar_init(&s.bar_raw, kOutThreads);
+    mbar_init(&s.bar_hn, kOutThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -217,18 +221,23 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
   const uint32_t tmem = s.tmem_base;
   if (tid == 0) X3_TL(111);
 
-  if (warp == kLoaderWarp) {
-    // ================================= loader warp =================================
+  if (warp == kLoader1Warp || warp == kLoader2Warp) {
+    // ================================= loader warps =================================
+    // one per layer kind, so that a first-layer block (its slot frees as soon as the first layer two chunks back has
+    // completed) is never queued behind a second-layer block (whose slot frees much later)
+    const bool second = warp == kLoader2Warp;
     uint32_t G = 0;  // chunk counter of this CTA: slot G & 1, use G >> 1
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
       for (int g = 0; g < 16; ++g, ++G) {
         const uint32_t slot = G & 1u, use = G >> 1;
         const uint8_t* blk = a.wsec + (size_t)g * kBlockStride;
-        if (use >= 1u) mbar_wait(&s.bar_w1free[slot], (use - 1u) & 1u);
-        if (elect_one()) tma_load(s.w1[slot], blk, kW1Bytes, &s.bar_w1full[slot]);
-        __syncwarp();
-        if (use >= 1u) mbar_wait(&s.bar_w2free[slot], (use - 1u) & 1u);
-        if (elect_one()) tma_load(s.w2[slot], blk + kSlot, 3u * n2_of(g >> 2) * 160u, &s.bar_w2full[slot]);
+        if (!second) {
+          if (use >= 1u) mbar_wait(&s.bar_w1free[slot], (use - 1u) & 1u);
+          if (elect_one()) tma_load(s.w1[slot], blk, kW1Bytes, &s.bar_w1full[slot]);
+        } else {
+          if (use >= 1u) mbar_wait(&s.bar_w2free[slot], (use - 1u) & 1u);
+          if (elect_one()) tma_load(s.w2[slot], blk + kSlot, 3u * n2_of(g >> 2) * 160u, &s.bar_w2full[slot]);
+        }
         __syncwarp();
       }
     }
@@ -245,16 +254,17 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
 #pragma unroll 1
       for (int g = 0; g < 16; ++g, ++G) {
-        const uint32_t slot = G & 1u, use = G >> 1;
+        const uint32_t slot = G & 1u, use = G >> 1, buf = G % 3u, bu = G / 3u;
+        X3_TL(112 + g);
         mbar_wait(&s.bar_w1full[slot], use & 1u);
-        if (use >= 1u) mbar_wait(&s.bar_w2free[slot], (use - 1u) & 1u);  // accumulator buffer no longer read
+        if (bu >= 1u) mbar_wait(&s.bar_hfree[buf], (bu - 1u) & 1u);  // accumulator buffer no longer read
         if (g == 0) mbar_wait(&s.bar_g, ph_tile);    // input tile gathered
         if (g == 4) mbar_wait(&s.bar_raw, ph_tile);  // raw latent tile written (reward head input)
         if (g == 8) mbar_wait(&s.bar_hn, ph_tile);   // normalised latent tile written (value / policy head input)
         tc_fence_after();
         X3_TL(g);
         if (elect_one()) {
-          const uint32_t D1 = tmem + 128u * slot;
+          const uint32_t D1 = tmem + 128u * buf;
           const uint32_t a_in = (g >> 2) <= 1 ? smem_u32(s.t0[0]) : smem_u32(s.t1[0]);
           const uint32_t w = smem_u32(s.w1[slot]);
           const uint64_t b01 = desc_sw128(w), b2 = desc_sw128(w + 128u * 128u);
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
           }
           umma(D1, desc_plain(ax), desc_plain(w + kW1Main), id128, 1u);
           umma(D1 + 64u, desc_plain(ax), desc_plain(w + kW1Main + plain_off(128, 0)), id64, 1u);
-          umma_commit(&s.bar_d[slot]);
+          umma_commit(&s.bar_d[buf]);
           umma_commit(&s.bar_w1free[slot]);
         }
         __syncwarp();
@@ -285,10 +295,10 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
 #pragma unroll 1
       for (int g = 0; g < 16; ++g, ++G) {
-        const uint32_t slot = G & 1u, use = G >> 1;
+        const uint32_t slot = G & 1u, use = G >> 1, buf = G % 3u, bu = G / 3u;
         const int net = g >> 2, c = g & 3;
         mbar_wait(&s.bar_w2full[slot], use & 1u);
-        mbar_wait(&s.bar_a[slot], use & 1u);
+        mbar_wait(&s.bar_a[buf], bu & 1u);
         // D2 must have been drained by the previous network's output epilogue
         if (g == 4) mbar_wait(&s.bar_raw, ph_tile);
         if (c == 0 && (net >= 2 || (net == 0 && !first_tile))) {
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
         if (elect_one()) {
           const uint32_t n2 = n2_of(net);
           const uint32_t ida = umma_idesc(2u * n2), idb = umma_idesc(n2);
-          const uint32_t D1 = tmem + 128u * slot, D2 = tmem + kColD2;
+          const uint32_t D1 = tmem + 128u * buf, D2 = tmem + kColD2;
           const uint32_t w = smem_u32(s.w2[slot]);
           const uint64_t b01 = desc_sw128(w), b2 = desc_sw128(w + 2u * n2 * 128u);
           if (c == 0) {  // bias step clears D2
@@ -317,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
           }
           if (c == 3) umma_commit(&s.bar_o);
           umma_commit(&s.bar_w2free[slot]);
+          umma_commit(&s.bar_hfree[buf]);
         }
         __syncwarp();
         X3_TL(48 + g);
@@ -325,123 +336,139 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
       first_tile = false;
       tl_on = false;
     }
-  } else {
-    // ================================= epilogue warps =================================
+  } else if (warp < kOutWarp0) {
+    // ================================= hidden-epilogue warps =================================
     const int quarter = warp & 3, half = warp >> 2;
-    const int row = quarter * 32 + (tid & 31);
-    const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
-    const uint32_t T = tmem + lane_bits;
-    uint32_t G = 0, ph_o = 0;
+    const uint32_t T = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint32_t G = 0;
     tl_on = tl_on && tid == 0;
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
+#pragma unroll 1
+      for (int g = 0; g < 16; ++g, ++G) {
+        const uint32_t buf = G % 3u, bu = G / 3u;
+        mbar_wait(&s.bar_d[buf], bu & 1u);
+        tc_fence_after();
+        X3_TL(64 + g);
+        hidden_epilogue(T + 128u * buf, half);
+        tc_fence_before();
+        mbar_arrive(&s.bar_a[buf]);
+        X3_TL(80 + g);
+      }
+      tl_on = false;
+    }
+  } else {
+    // ================================= output warps =================================
+    // Four warps, thread = row: the gather of a tile's input, the new latent (raw -> reward head, normalised -> value /
+    // policy heads and HBM) and the heads' outputs — apart from the eight hidden-epilogue warps, so that the chunk
+    // epilogues of the next network never wait behind an output epilogue.  The NEXT tile's input is gathered right
+    // after the reward head (the last reader of the raw-latent tile) while the value / policy heads still run.
+    const int otid = tid - kOutWarp0 * 32;
+    const int row = otid;  // = TMEM lane: warp & 3 is the lane quarter
+    const uint32_t D2 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + kColD2;
+    uint32_t ph_o = 0;
+    tl_on = tl_on && otid == 0;
+    // parent latents -> the three part tiles; 8 consecutive lanes fetch the 8 chunks of one row (16 rows per step)
+    auto gather = [&](int tile) {
       const int64_t row0 = (int64_t)tile * kM;
-      const int64_t item = row0 + row;
-      X3_TL(104);
-      {  // parent latents -> the three part tiles; 8 consecutive lanes fetch the 8 chunks of one row
-        const int chunk = tid & 7;
-        float x[4][8];
+      const int chunk = otid & 7;
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int grow = (otid >> 3) + 16 * i;
+        const int64_t it = (row0 + grow) < n ? (row0 + grow) : n - 1;
+        const int64_t irow = it * a.in_rows_per_item + (a.in_row ? (int64_t)a.in_row[it] : 0);
+        float x[8];
+        if (a.latent_dtype == HMZ_LATENT_F32) {
+          const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.lat_in) + irow * kLatent + chunk * 8);
+          const float4 u0 = __ldcs(src), u1 = __ldcs(src + 1);
+          x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
+          x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
+        } else {
+          const uint4 q = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.lat_in) + irow * kLatent + chunk * 8));
+          const uint32_t pk[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int grow = (tid >> 3) + 32 * i;
-          const int64_t it = (row0 + grow) < n ? (row0 + grow) : n - 1;
-          const int64_t irow = it * a.in_rows_per_item + (a.in_row ? (int64_t)a.in_row[it] : 0);
-          if (a.latent_dtype == HMZ_LATENT_F32) {
-            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.lat_in) + irow * kLatent + chunk * 8);
-            const float4 u0 = __ldcs(src), u1 = __ldcs(src + 1);
-            x[i][0] = u0.x; x[i][1] = u0.y; x[i][2] = u0.z; x[i][3] = u0.w;
-            x[i][4] = u1.x; x[i][5] = u1.y; x[i][6] = u1.z; x[i][7] = u1.w;
-          } else {
-            const uint4 q = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.lat_in) + irow * kLatent + chunk * 8));
-            const uint32_t pk[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              x[i][2 * j] = bf_lo(pk[j]);
-              x[i][2 * j + 1] = bf_hi(pk[j]);
-            }
+          for (int j = 0; j < 4; ++j) {
+            x[2 * j] = bf_lo(pk[j]);
+            x[2 * j + 1] = bf_hi(pk[j]);
           }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) store_parts8(s.t0, (tid >> 3) + 32 * i, chunk, x[i]);
-        if (tid < kM) {  // extra A slice of row tid: one-hot(action) at k = 0..5, the constant 1 at k = 6
-          const int64_t it = (row0 + tid) < n ? (row0 + tid) : n - 1;
-          int act = (int)a.actions[it];
-          act = act < kActions ? act : kActions - 1;
-          uint32_t w[4] = {0u, 0u, 0u, 0x3F80u};
-          w[act >> 1] |= 0x3F80u << ((act & 1) * 16);
-          *reinterpret_cast<uint4*>(s.ax + plain_off(tid, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(s.ax + plain_off(tid, 1)) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        fence_proxy_async();
-        mbar_arrive(&s.bar_g);
-        X3_TL(105);
+        store_parts8(s.t0, grow, chunk, x);
       }
+      fence_proxy_async();
+    };
+    // extra A slice of this row: one-hot(action) at k = 0..5, the constant 1 at k = 6; then the tile is handed over
+    auto publish_inputs = [&](int tile) {
+      const int64_t it = ((int64_t)tile * kM + row) < n ? ((int64_t)tile * kM + row) : n - 1;
+      const uint32_t act = min((uint32_t)a.actions[it], (uint32_t)(kActions - 1));
+      const uint32_t one = 0x3F80u << ((act & 1u) * 16u);
+      const uint32_t ax = smem_u32(s.ax);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ax + plain_off(row, 0)), "r"((act >> 1) == 0u ? one : 0u),
+                   "r"((act >> 1) == 1u ? one : 0u), "r"((act >> 1) == 2u ? one : 0u), "r"(0x3F80u)
+                   : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(ax + plain_off(row, 1)), "r"(0u) : "memory");
+      fence_proxy_async();
+      mbar_arrive(&s.bar_g);
+    };
+    X3_TL(104);
+    if (cta < n_tiles) {
+      gather(cta);
+      publish_inputs(cta);
+    }
+    X3_TL(105);
+    for (int tile = cta; tile < n_tiles; tile += n_cta) {
+      const int64_t item = (int64_t)tile * kM + row;
+      const int next_tile = tile + n_cta;
 #pragma unroll 1
       for (int net = 0; net < 4; ++net) {  // dynamics, reward, value, policy
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c, ++G) {
-          const uint32_t slot = G & 1u, use = G >> 1;
-          mbar_wait(&s.bar_d[slot], use & 1u);
-          tc_fence_after();
-          X3_TL(64 + net * 4 + c);
-          hidden_epilogue(T + 128u * slot, half);
-          tc_fence_before();
-          mbar_arrive(&s.bar_a[slot]);
-          X3_TL(80 + net * 4 + c);
-        }
         mbar_wait(&s.bar_o, ph_o);
         ph_o ^= 1u;
         tc_fence_after();
         X3_TL(96 + net);
-        const uint32_t D2 = T + kColD2;
         if (net == 0) {
-          // ---- new latent: thread (row, half) owns columns [32 half, 32 half + 32)
-          float raw[32];
-          ld_sum16(D2 + 32 * half, D2 + 64 + 32 * half, *reinterpret_cast<float(*)[16]>(&raw[0]));
-          ld_sum16(D2 + 32 * half + 16, D2 + 64 + 32 * half + 16, *reinterpret_cast<float(*)[16]>(&raw[16]));
-          tc_fence_before();
-          // the raw latent feeds the reward head: publish it first so that head's first layers overlap the rest
+          // ---- new latent.  The raw latent feeds the reward head: publish it first so that head's first layers overlap
+          // the normalisation.
+          float raw[64];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) store_parts8(s.t0, row, half * 4 + c, *reinterpret_cast<float(*)[8]>(&raw[c * 8]));
+          for (int j = 0; j < 4; ++j) ld_sum16(D2 + 16 * j, D2 + 64 + 16 * j, *reinterpret_cast<float(*)[16]>(&raw[16 * j]));
+          tc_fence_before();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) store_parts8(s.t0, row, c, *reinterpret_cast<float(*)[8]>(&raw[c * 8]));
           fence_proxy_async();
           mbar_arrive(&s.bar_raw);
-          float mn = raw[0], mx = raw[0];
+          X3_TL(106);
+          float mn4[4], mx4[4];
 #pragma unroll
-          for (int i = 1; i < 32; ++i) {
-            mn = fminf(mn, raw[i]);
-            mx = fmaxf(mx, raw[i]);
+          for (int i = 0; i < 4; ++i) mn4[i] = mx4[i] = raw[i];
+#pragma unroll
+          for (int i = 4; i < 64; ++i) {
+            mn4[i & 3] = fminf(mn4[i & 3], raw[i]);
+            mx4[i & 3] = fmaxf(mx4[i & 3], raw[i]);
           }
-          s.row_minmax[half][row] = make_float2(mn, mx);
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-          const float2 m0 = s.row_minmax[0][row], m1 = s.row_minmax[1][row];
-          mn = fminf(m0.x, m1.x);
-          mx = fmaxf(m0.y, m1.y);
+          const float mn = fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3]));
+          const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
           // normalize_h_state (networks.py:191-196); the quotient as a product with the correctly rounded reciprocal
-          // (<= 1.5 ulp from the division, far inside the gate; 32 IEEE divisions per thread sat on the chain that the
-          // reward head's first chunk waits behind)
+          // (<= 1.5 ulp from the division, far inside the gate)
           const float inv = __frcp_rn(__fadd_rn(__fsub_rn(mx, mn), 1e-8f));
           const int64_t orow = item * a.out_rows_per_item + a.out_row;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 8; ++c) {
             float hn[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) hn[j] = __fmul_rn(__fsub_rn(raw[c * 8 + j], mn), inv);
-            store_parts8(s.t1, row, half * 4 + c, hn);
+            store_parts8(s.t1, row, c, hn);
             if (item < n) {
               if (a.latent_dtype == HMZ_LATENT_F32) {
-                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.lat_out) + orow * kLatent + half * 32 + c * 8);
+                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.lat_out) + orow * kLatent + c * 8);
                 __stcs(dst, make_float4(hn[0], hn[1], hn[2], hn[3]));
                 __stcs(dst + 1, make_float4(hn[4], hn[5], hn[6], hn[7]));
               } else {
-                __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.lat_out) + orow * kLatent + half * 32 + c * 8),
+                __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.lat_out) + orow * kLatent + c * 8),
                        make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7])));
               }
             }
           }
           fence_proxy_async();
           mbar_arrive(&s.bar_hn);
-        } else if (half != 0) {
-          mbar_arrive(&s.bar_out);  // the heads' outputs are one thread per row
-        } else if (net == 3) {      // F.softmax(pi_logits) (networks.py:109)
+        } else if (net == 3) {  // F.softmax(pi_logits) (networks.py:109)
           float lg[16];
           ld_sum16(D2, D2 + 16, lg);
           tc_fence_before();
@@ -458,6 +485,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
 #pragma unroll
             for (int k = 0; k < kActions; ++k) a.p_out[item * kActions + k] = __fdiv_rn(lg[k], den);
           }
+          // every tcgen05.mma of the tile has completed: the extra A slice may change hands
+          if (next_tile < n_tiles) publish_inputs(next_tile);
         } else {  // support transform (networks.py:152-189) of the 33 logits
           float lg[48];
 #pragma unroll
@@ -466,6 +495,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
           mbar_arrive(&s.bar_out);
           const float x = support_to_scalar([&](int i) { return lg[i]; });
           if (item < n) (net == 1 ? a.r_out : a.v_out)[item] = x;
+          // the reward head's first layers were the last readers of the raw-latent tile: gather the next tile into it
+          if (net == 1 && next_tile < n_tiles) gather(next_tile);
         }
         X3_TL(100 + net);
       }
