@@ -5,6 +5,7 @@
 #   bash tools/gpu_round.sh envsweep       env kernels over HMZ_ENV_UNROLL x HMZ_ENV_CTAS
 #   bash tools/gpu_round.sh memcheck       compute-sanitizer --tool memcheck over smoke()
 #   bash tools/gpu_round.sh microbench     TMEM / tcgen05.mma micro-benchmarks, kernel families alone, clock64 timelines
+#   bash tools/gpu_round.sh x3             the fast parity mode's kernel: probe, timeline, bench line, ncu --set full
 #   bash tools/gpu_round.sh ncu            plain bench, ncu launch list of one step, ncu --set full of the hot kernels
 # Several stages may be given; every stage writes into gpurun_out/ (scratch) and never stops the others.
 # (At most one of ncu / compute-sanitizer per call: B200_PROFILING.md.)
@@ -114,6 +115,16 @@ for stage in "$@"; do
       for m in 64 68 72 76 80; do HMZ_SERVER_MLP=$m SCHEDULES=128 MOVES=8 timeout 200 python tools/persist_probe.py 2>&1 | sed "s/^/HMZ_SERVER_MLP=$m /" >> gpurun_out/schedules.txt; done
       timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-env --no-configs --schedule server > gpurun_out/bench_server.json 2> gpurun_out/bench_server.log
       TORCH_INIT=1 SEARCHES=17,30000,5000 timeout 120 python tools/tree_timeline.py > gpurun_out/timeline_tree.txt 2>&1
+      ;;
+    x3)
+      # the fast parity mode's kernel: launch time per batch size in all three modes, clock64 timeline of one tile, a bench
+      # line in that mode, then ncu --set full of one launch (65,536 rows)
+      timeout 120 python tools/x3_probe.py > gpurun_out/x3_probe.txt 2>&1; cat gpurun_out/x3_probe.txt
+      timeout 60 python tools/x3_timeline.py > gpurun_out/x3_timeline.txt 2>&1
+      timeout 300 python bench.py --mode fp32x3 --steps 5 --warmup 3 --no-configs --no-cpu-baseline --no-env > gpurun_out/bench_x3.json 2> gpurun_out/bench_x3.log
+      echo "bench x3 rc=$?"; tail -n 3 gpurun_out/bench_x3.log
+      ROWS=65536 MODES=x3 timeout 200 ncu --set full --clock-control none --import-source on -k regex:net_x3 -s 5 -c 1 -o gpurun_out/prof_x3 -f python tools/x3_probe.py > gpurun_out/ncu_x3.log 2>&1
+      echo "ncu x3 rc=$?"
       ;;
     groupsweep)
       : > gpurun_out/group_sweep.txt

@@ -26,7 +26,8 @@ def to_us(val, unit):
 
 summary, traffic = {}, {"source": f"ncu --set full --clock-control none, profiles/{R}_ncu_*.raw.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch; "
                                  "tree / MLP kernels captured with --schedule 1 = one launch per 65,536 searches, N = 5, S = 100)"}
-for tag, key in (("tree", "backup_select"), ("net", "net_recurrent"), ("persist", "search_persistent"), ("env", "env_step")):
+for tag, key in (("tree", "backup_select"), ("net", "net_recurrent"), ("persist", "search_persistent"), ("env", "env_step"),
+                 ("x3", "net_x3_recurrent")):
     rep = os.path.join(SRC, f"prof_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -88,7 +89,8 @@ for src, dst in (("bench_default.json", "bench_default_line.json"), ("bench_refe
                  ("timeline_net_tc.txt", "timeline_net_tc.txt"), ("timeline_tree.txt", "timeline_tree.txt"),
                  ("gantt_4groups.txt", "gantt_4groups.txt"), ("gantt_server.txt", "gantt_server.txt"),
                  ("timeline_net_tc_server.txt", "timeline_net_tc_server.txt"), ("schedules.txt", "schedules.txt"),
-                 ("bench_server.json", "bench_server_line.json")):
+                 ("bench_server.json", "bench_server_line.json"), ("x3_probe.txt", "x3_probe.txt"), ("x3_timeline.txt", "x3_timeline.txt"),
+                 ("bench_x3.json", "bench_fp32x3_line.json")):
     if os.path.exists(os.path.join(SRC, src)):
         shutil.copyfile(os.path.join(SRC, src), os.path.join(DST, f"{R}_{dst}"))
 tm = os.path.join(SRC, "test_metrics.jsonl")

@@ -12,9 +12,11 @@ B, S, n = int(os.environ.get("B", 65536)), int(os.environ.get("S", 100)), int(os
 moves = int(os.environ.get("MOVES", 12))
 lib = _lib.load()
 torch.manual_seed(0)
-w = PackedWeights(MuZeroNet(3 * n, 6, 0.002, "cpu", TD_return=True).state_dict(), n, _lib.MODE_BF16)
+MODE = int(os.environ.get("MODE", _lib.MODE_BF16))  # 0: float32 FFMA, 1: bf16 tcgen05, 2: float32 accuracy on tcgen05
+LDT = _lib.LATENT_BF16 if MODE == _lib.MODE_BF16 else _lib.LATENT_F32
+w = PackedWeights(MuZeroNet(3 * n, 6, 0.002, "cpu", TD_return=True).state_dict(), n, MODE)
 for sched in [int(x) for x in os.environ.get("SCHEDULES", "64").split(",")]:
-    sp = SelfPlay(n, 200, B, S, w, seed=1, ring_slots=4, latent_dtype=_lib.LATENT_BF16)
+    sp = SelfPlay(n, 200, B, S, w, seed=1, ring_slots=4, latent_dtype=LDT)
     sp.mcts.store.set_schedule(sched)
     for _ in range(4):
         sp.move()
@@ -28,7 +30,7 @@ for sched in [int(x) for x in os.environ.get("SCHEDULES", "64").split(",")]:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / moves
-    line = f"B={B} S={S} schedule={sched} HMZ_PERSIST_MLP={os.environ.get('HMZ_PERSIST_MLP', '-')}: {ms:.3f} ms/move, {B * S / ms / 1e6:.1f} M sims/s, {ms / S * 1e3:.2f} us/round"
+    line = f"B={B} S={S} mode={MODE} schedule={sched} HMZ_PERSIST_MLP={os.environ.get('HMZ_PERSIST_MLP', '-')}: {ms:.3f} ms/move, {B * S / ms / 1e6:.1f} M sims/s, {ms / S * 1e3:.2f} us/round"
     if sched == 64 and os.environ.get("HMZ_PERSIST_STATS"):
         buf = (C.c_ulonglong * 16)()
         _lib.check(lib.hmz_debug_persist_stats(buf))
