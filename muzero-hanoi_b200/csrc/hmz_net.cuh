@@ -48,6 +48,7 @@ int tc_debug_read_timeline(unsigned long long* host_out);
 void tc_pack(const float* const* tensors, int n_disks, void* out);
 int tc_net_initial(const void* weights, int n_disks, const uint32_t* words, void* lat_out, int64_t out_rows_per_item,
                    int latent_dtype, float* p0, float* v0, int64_t n, cudaStream_t stream);
+int tc_head_split_allowed();
 void tc_allow_head_split(int allow);  // per host thread; hmz_search_run clears it while several stream groups are in flight
 int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
                      const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row,

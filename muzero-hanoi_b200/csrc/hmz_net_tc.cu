@@ -162,6 +162,7 @@ static unsigned tc_grid(int64_t n, int* n_pairs, int passes = 1) {
 // hmz_search_run with several stream groups: the launches of the other groups want the idle SMs — no head split then
 static thread_local int tl_split_allowed = 1;
 void tc_allow_head_split(int allow) { tl_split_allowed = allow; }
+int tc_head_split_allowed() { return tl_split_allowed; }
 
 int tc_net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
                      const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row,

@@ -75,6 +75,9 @@ struct Args {
   float *r_out, *p_out, *v_out;
   int64_t n;
   int n_tiles;
+  int head_split;  // 3: small batches (3 x tiles <= SMs) — CTAs 3 t, 3 t + 1, 3 t + 2 all run the dynamics network of tile t and
+                   // then ONE head each (reward + the latent rows / value / policy), as in the bf16 kernel: the dependent chain
+                   // of a launch shrinks from sixteen chunks to eight while idle SMs do the redundant work; else 1
   int timeline;  // tooling (HMZ_X3_TIMELINE=1): CTA 0 records clock64() at the phase boundaries of its first tile
 };
 
@@ -185,10 +188,15 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
   extern __shared__ uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int cta = (int)blockIdx.x, n_cta = (int)gridDim.x;
+  const int split = a.head_split == 3 ? 3 : 1;
+  const int role = split == 3 ? (int)blockIdx.x % 3 : -1;  // -1: every network
+  const int cta = (int)blockIdx.x / split, n_cta = (int)gridDim.x / split;
+  const int n_steps = split == 3 ? 8 : 16;  // chunks per tile in this CTA
+  // chunk gi of this CTA -> chunk g = 4 network + c of the pass order dynamics, reward, value, policy
+  auto chunk_of = [&](int gi) { return (split == 1 || gi < 4) ? gi : (role + 1) * 4 + (gi - 4); };
   const int n_tiles = a.n_tiles;
   const int64_t n = a.n;
-  bool tl_on = a.timeline != 0 && cta == 0 && (tid & 31) == 0;  // (switched off after the first tile)
+  bool tl_on = a.timeline != 0 && blockIdx.x == 0 && (tid & 31) == 0;  // (switched off after the first tile)
   if (tid == 0) X3_TL(110);
 
   if (tid == 32) {
@@ -228,7 +236,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     const bool second = warp == kLoader2Warp;
     uint32_t G = 0;  // chunk counter of this CTA: slot G & 1, use G >> 1
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
-      for (int g = 0; g < 16; ++g, ++G) {
+      for (int gi = 0; gi < n_steps; ++gi, ++G) {
+        const int g = chunk_of(gi);
         const uint32_t slot = G & 1u, use = G >> 1;
         const uint8_t* blk = a.wsec + (size_t)g * kBlockStride;
         if (!second) {
@@ -253,14 +262,15 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     uint32_t G = 0, ph_tile = 0;
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
 #pragma unroll 1
-      for (int g = 0; g < 16; ++g, ++G) {
+      for (int gi = 0; gi < n_steps; ++gi, ++G) {
+        const int g = chunk_of(gi);
         const uint32_t slot = G & 1u, use = G >> 1, buf = G % 3u, bu = G / 3u;
         X3_TL(112 + g);
         mbar_wait(&s.bar_w1full[slot], use & 1u);
         if (bu >= 1u) mbar_wait(&s.bar_hfree[buf], (bu - 1u) & 1u);  // accumulator buffer no longer read
         if (g == 0) mbar_wait(&s.bar_g, ph_tile);    // input tile gathered
         if (g == 4) mbar_wait(&s.bar_raw, ph_tile);  // raw latent tile written (reward head input)
-        if (g == 8) mbar_wait(&s.bar_hn, ph_tile);   // normalised latent tile written (value / policy head input)
+        if (g >= 8 && (g & 3) == 0) mbar_wait(&s.bar_hn, ph_tile);  // normalised latent tile written (value / policy head input)
         tc_fence_after();
         X3_TL(g);
         if (elect_one()) {
@@ -294,14 +304,16 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     bool first_tile = true;
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
 #pragma unroll 1
-      for (int g = 0; g < 16; ++g, ++G) {
+      for (int gi = 0; gi < n_steps; ++gi, ++G) {
+        const int g = chunk_of(gi);
         const uint32_t slot = G & 1u, use = G >> 1, buf = G % 3u, bu = G / 3u;
         const int net = g >> 2, c = g & 3;
         mbar_wait(&s.bar_w2full[slot], use & 1u);
         mbar_wait(&s.bar_a[buf], bu & 1u);
-        // D2 must have been drained by the previous network's output epilogue
-        if (g == 4) mbar_wait(&s.bar_raw, ph_tile);
-        if (c == 0 && (net >= 2 || (net == 0 && !first_tile))) {
+        // D2 must have been drained by the output epilogue of the network this CTA ran before: the dynamics network's
+        // (bar_raw) for the network that follows it, a head's (bar_out) otherwise
+        if (gi == 4) mbar_wait(&s.bar_raw, ph_tile);
+        if (c == 0 && gi != 4 && (gi != 0 || !first_tile)) {
           mbar_wait(&s.bar_out, ph_out);
           ph_out ^= 1u;
         }
@@ -344,7 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     tl_on = tl_on && tid == 0;
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
 #pragma unroll 1
-      for (int g = 0; g < 16; ++g, ++G) {
+      for (int gi = 0; gi < n_steps; ++gi, ++G) {
+        const int g = chunk_of(gi);
         const uint32_t buf = G % 3u, bu = G / 3u;
         mbar_wait(&s.bar_d[buf], bu & 1u);
         tc_fence_after();
@@ -419,6 +432,9 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
       const int next_tile = tile + n_cta;
 #pragma unroll 1
       for (int net = 0; net < 4; ++net) {  // dynamics, reward, value, policy
+        if (split == 3 && net != 0 && net != role + 1) continue;
+        const bool last_net = split == 3 ? net != 0 : net == 3;
+        const bool raw_tile_free = split == 3 ? net != 0 : net == 1;  // the raw-latent tile has no reader left in this CTA
         mbar_wait(&s.bar_o, ph_o);
         ph_o ^= 1u;
         tc_fence_after();
@@ -455,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
 #pragma unroll
             for (int j = 0; j < 8; ++j) hn[j] = __fmul_rn(__fsub_rn(raw[c * 8 + j], mn), inv);
             store_parts8(s.t1, row, c, hn);
-            if (item < n) {
+            if (item < n && role <= 0) {  // (head split: the reward CTA stores the rows)
               if (a.latent_dtype == HMZ_LATENT_F32) {
                 float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.lat_out) + orow * kLatent + c * 8);
                 __stcs(dst, make_float4(hn[0], hn[1], hn[2], hn[3]));
@@ -485,8 +501,6 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
 #pragma unroll
             for (int k = 0; k < kActions; ++k) a.p_out[item * kActions + k] = __fdiv_rn(lg[k], den);
           }
-          // every tcgen05.mma of the tile has completed: the extra A slice may change hands
-          if (next_tile < n_tiles) publish_inputs(next_tile);
         } else {  // support transform (networks.py:152-189) of the 33 logits
           float lg[48];
 #pragma unroll
@@ -495,8 +509,12 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
           mbar_arrive(&s.bar_out);
           const float x = support_to_scalar([&](int i) { return lg[i]; });
           if (item < n) (net == 1 ? a.r_out : a.v_out)[item] = x;
-          // the reward head's first layers were the last readers of the raw-latent tile: gather the next tile into it
-          if (net == 1 && next_tile < n_tiles) gather(next_tile);
+        }
+        if (next_tile < n_tiles) {
+          // the reward head's first layers were the last readers of the raw-latent tile: gather the next tile into it;
+          // after the last network every tcgen05.mma of the tile has completed and the extra A slice may change hands
+          if (raw_tile_free) gather(next_tile);
+          if (last_net) publish_inputs(next_tile);
         }
         X3_TL(100 + net);
       }
@@ -608,10 +626,14 @@ int net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_i
   a.v_out = v;
   a.n = n;
   a.n_tiles = (int)((n + kM - 1) / kM);
+  const int sms = sm_count();
+  // small batches: three CTAs per tile, one head each (HMZ_TC_SPLIT=0 switches it off; hmz_search_run clears the permission
+  // while several stream groups share the machine)
+  static const int split_on = getenv("HMZ_TC_SPLIT") ? atoi(getenv("HMZ_TC_SPLIT")) : 1;
+  a.head_split = (split_on && tc_head_split_allowed() && 3 * a.n_tiles <= sms) ? 3 : 1;
   static const int tl = getenv("HMZ_X3_TIMELINE") ? atoi(getenv("HMZ_X3_TIMELINE")) : 0;
   a.timeline = tl;
-  const int sms = sm_count();
-  const unsigned grid = (unsigned)(a.n_tiles < sms ? a.n_tiles : sms);
+  const unsigned grid = a.head_split == 3 ? 3u * (unsigned)a.n_tiles : (unsigned)(a.n_tiles < sms ? a.n_tiles : sms);
   net_x3_recurrent<<<grid, kThreads, (size_t)smem, stream>>>(a);
   return check_launch("net_x3_recurrent");
 }
