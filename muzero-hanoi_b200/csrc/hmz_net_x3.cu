@@ -10,14 +10,16 @@
 // accumulator's rounding acts on them at their own scale.
 //
 // One CTA = one tile of 128 rows (UMMA M = 128), persistent over tiles.  A network is processed in four CHUNKS
-// of 64 hidden units: first layer of chunk c -> TMEM accumulator (128 columns, double-buffered) -> the epilogue
+// of 64 hidden units: first layer of chunk c -> TMEM accumulator (128 columns, three buffers) -> the hidden-epilogue
 // warps add the blocks, apply relu, split into three bf16 parts and write them back IN PLACE -> the second layer
-// accumulates the chunk's K = 64 slice with its A operand taken from TMEM (the .ts form).  The first layer of
-// chunk c + 1 is issued before the second layer of chunk c, so the tensor core works while a chunk is drained.
-// Bias and the one-hot action columns of dynamic_net.0 ride in an extra K = 16 step as in the bf16 kernel
-// (hmz_net_tc.cuh).  Weights stream from L2 per chunk with 1-D TMA bulk copies into double-buffered slots.
-// Epilogue math (normalize_h_state :191-196, support transform :152-189, softmax) is the float32 code of the
-// FFMA kernel (hmz_net.cu).
+// accumulates the chunk's K = 64 slice with its A operand taken from TMEM (the .ts form).  One issuing warp per layer
+// kind (issuing a tcgen05.mma blocks for about its execution time), so first layers run ahead of second layers and the
+// tensor core works while a chunk is drained; four output warps (thread = row) own the new latent, the heads' outputs
+// and the gather of the next tile.  Bias and the one-hot action columns of dynamic_net.0 ride in an extra K = 16 step
+// as in the bf16 kernel (hmz_net_tc.cuh).  Weights stream from L2 per chunk with 1-D TMA bulk copies into
+// double-buffered slots (one loader warp per layer kind).  Small batches (3 x tiles <= SMs): three CTAs per tile run
+// the dynamics network and ONE head each.  Epilogue math (normalize_h_state :191-196, support transform :152-189,
+// softmax) is the float32 code of the FFMA kernel (hmz_net.cu).  DESIGN.md §4 has the measurements.
 #include <cstdlib>
 #include <cstring>
 
@@ -255,8 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     // Two issuing warps, one per layer kind: issuing a tcgen05.mma blocks for about its execution time, so a single warp
     // would serialise the second layer of chunk g behind the issue of the first layer of chunk g + 1 (and behind its own
     // waits); the tensor core takes the two streams in arrival order.  The write-after-read hazard on an accumulator
-    // buffer — the first layer of chunk G + 2 overwrites what the second layer of chunk G reads as its A operand —
-    // is then ordered by an mbarrier (bar_w2free: second layer of chunk G complete) instead of by issue order.
+    // buffer — the first layer of chunk G + 3 overwrites what the second layer of chunk G reads as its A operand —
+    // is then ordered by an mbarrier (bar_hfree: second layer of chunk G complete) instead of by issue order.
     const uint32_t id128 = umma_idesc(128), id64 = umma_idesc(64);
     const uint32_t ax = smem_u32(s.ax);
     uint32_t G = 0, ph_tile = 0;
