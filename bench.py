@@ -542,7 +542,10 @@ def run_ours(args):
                 return {"kernel": "net_tc<recurrent> (fused g + reward/policy/value heads, tcgen05)" if args.mode == "bf16" else ("net_recurrent_fp32 (FFMA)" if args.mode == "fp32" else "net_x3_recurrent (tcgen05, three bf16 parts per float32 operand)"),
                         "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": tr, "traffic_source": src,
-                        "peak_source": peaks["source"] + ", sustained bf16", "algorithmic": f"{FLOP_PER_SIM} FLOP/sim x {B} sims per launch"}
+                        "peak_source": peaks["source"] + ", sustained bf16", "algorithmic": f"{FLOP_PER_SIM} FLOP/sim x {B} sims per launch",
+                        **({"executed_bf16": 7 * ach, "executed_frac": 7 * ach / peaks["bf16_tflops_sustained"],
+                            "executed_note": "float32 accuracy from seven exact bf16 x bf16 products per multiply: the tensor cores execute 7 x the algorithmic FLOPs"}
+                           if args.mode == "fp32x3" else {})}
             tb = 156.0 * depth + 160.0
             return {"kernel": "search_backup_select (expand + backup + next select)", "bound": "hbm", "achieved": tb * B / per_launch_s / 1e9,
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tb * B / per_launch_s / 1e9 / peaks["hbm_gbs"], "traffic": tr,

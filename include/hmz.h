@@ -250,9 +250,10 @@ int hmz_search_root_policy(const hmz_search_t* s, int n_simulations, double temp
  */
 #define HMZ_MODE_FP32 0 /* FFMA, fp32 accumulate: parity mode (<= 1e-5 vs reference)      */
 #define HMZ_MODE_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 in TMEM: throughput mode (<= 2e-2) */
-#define HMZ_MODE_FP32X3 2 /* fast parity mode: recurrent_inference on tcgen05 with every float32 operand split into three
+#define HMZ_MODE_FP32X3 2 /* fast parity mode: the network on tcgen05 with every float32 operand split into three
                            * bf16 parts (7 exact bf16 products per multiply, fp32 accumulate; <= 1e-5 vs reference, same gate
-                           * as HMZ_MODE_FP32); the root inference runs the FFMA kernel on an embedded float32 copy */
+                           * as HMZ_MODE_FP32), for both inferences from packed env words; float observations (hmz_net_initial with obs) run the
+                           * FFMA kernel on an embedded float32 copy */
 
 int64_t hmz_weights_packed_bytes(int n_disks, int mode);
 /* host_tensors: 20 HOST pointers to contiguous float32 tensors; host_out: HOST buffer of

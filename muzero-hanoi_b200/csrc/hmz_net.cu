@@ -375,6 +375,8 @@ int hmz_net_initial(const void* weights, int mode, int n_disks, const uint32_t* 
   // float observations (drop-in B = 1 views, arbitrary input vectors) keep the float32 kernel below
   if (mode == HMZ_MODE_BF16 && words != nullptr)
     return tc_net_initial(weights, n_disks, words, latents_out, out_rows_per_item, latent_dtype, p0, v0, n, (cudaStream_t)stream);
+  if (mode == HMZ_MODE_FP32X3 && words != nullptr)  // float32 accuracy on tcgen05, like the recurrent inference of this mode
+    return x3::net_initial(weights, n_disks, words, latents_out, out_rows_per_item, latent_dtype, p0, v0, n, (cudaStream_t)stream);
   if (int rc = ensure_smem_optin()) return rc;
   const unsigned grid = (unsigned)((n + kRows - 1) / kRows);
   const int64_t w32_off = mode == HMZ_MODE_BF16 ? tc_fp32_offset_bytes() : (mode == HMZ_MODE_FP32X3 ? x3::fp32_offset_bytes() : 0);

@@ -62,6 +62,8 @@ void pack(const float* const* tensors, int n_disks, void* out);
 int net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
                   const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row, int latent_dtype,
                   float* r, float* p, float* v, int64_t n, cudaStream_t stream);
+int net_initial(const void* weights, int n_disks, const uint32_t* words, void* lat_out, int64_t out_rows_per_item,
+                int latent_dtype, float* p0, float* v0, int64_t n, cudaStream_t stream);
 int debug_read_timeline(unsigned long long* host_out);
 }  // namespace x3
 

@@ -1,5 +1,5 @@
-// MuZeroNet recurrent_inference (networks.py:96-116) at float32 accuracy ON THE TENSOR CORES (HMZ_MODE_FP32X3):
-// the fast parity mode.  Every float32 operand is split into three bf16 parts, x = x0 + x1 + x2 with
+// MuZeroNet recurrent_inference (networks.py:96-116) and initial_inference (:71-94) at float32 accuracy ON THE TENSOR
+// CORES (HMZ_MODE_FP32X3): the fast parity mode.  Every float32 operand is split into three bf16 parts, x = x0 + x1 + x2 with
 // x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1) (the residuals are exact in float32), and a product
 // x w is evaluated as the seven bf16 x bf16 products x0 w0, x1 w0, x2 w0, x0 w1, x1 w1, x2 w1, x0 w2 — each
 // exact in the float32 accumulator; the dropped x1 w2, x2 w2 are <= 2^-25 |x w|.  Per Linear layer that is
@@ -42,7 +42,8 @@ constexpr uint32_t kW1Main = 192 * 128;            // [w0; w1; w2] rows of a 64-
 constexpr uint32_t kW1Bytes = 192 * 160;           // + the extra K = 16 slice
 constexpr uint32_t kSlot = 30720;                  // both layer kinds: 192 x 160 >= 3 n2 x 160
 constexpr uint32_t kBlockStride = 2 * kSlot;       // one (network, chunk) block of the weight section
-constexpr uint32_t kSectionBytes = 16 * kBlockStride;
+constexpr uint32_t kRepBlock0 = 16;                // blocks 16..19: representation_net (root inference)
+constexpr uint32_t kSectionBytes = 20 * kBlockStride;
 constexpr uint32_t kColD2 = 384;                   // TMEM: D1[3] at columns 0 / 128 / 256, D2 at 384 (all 512 columns)
 // second-layer width per network in pass order dynamics, reward, value, policy (33 support logits -> 48, 6 -> 16)
 __host__ __device__ constexpr uint32_t n2_of(int net) { return net == 0 ? 64u : (net == 3 ? 16u : 48u); }
@@ -71,6 +72,8 @@ struct Args {
   int64_t in_rows_per_item;
   const uint16_t* in_row;
   const uint8_t* actions;
+  const uint32_t* words;  // env words (initial inference)
+  int n_disks;
   void* lat_out;
   int64_t out_rows_per_item, out_row;
   int latent_dtype;
@@ -186,16 +189,23 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t D, int half) {
   tmem_st_wait();
 }
 
-__global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_constant__ Args a) {
+// kInitial = false: recurrent_inference — networks dynamics, reward, value, policy; input = gathered latents.
+// kInitial = true : initial_inference  — networks representation (in the dynamics network's place), value, policy;
+//                   input = utils.oneHot_encoding (utils.py:9-25) of the env words (exact in bf16: only part 0 is non-zero).
+template <bool kInitial>
+__global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Args a) {
   extern __shared__ uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int split = a.head_split == 3 ? 3 : 1;
+  const int split = (!kInitial && a.head_split == 3) ? 3 : 1;
   const int role = split == 3 ? (int)blockIdx.x % 3 : -1;  // -1: every network
   const int cta = (int)blockIdx.x / split, n_cta = (int)gridDim.x / split;
-  const int n_steps = split == 3 ? 8 : 16;  // chunks per tile in this CTA
+  const int n_steps = kInitial ? 12 : (split == 3 ? 8 : 16);  // chunks per tile in this CTA
   // chunk gi of this CTA -> chunk g = 4 network + c of the pass order dynamics, reward, value, policy
-  auto chunk_of = [&](int gi) { return (split == 1 || gi < 4) ? gi : (role + 1) * 4 + (gi - 4); };
+  auto chunk_of = [&](int gi) {
+    if (kInitial) return gi < 4 ? gi : gi + 4;  // no reward head at the root
+    return (split == 1 || gi < 4) ? gi : (role + 1) * 4 + (gi - 4);
+  };
   const int n_tiles = a.n_tiles;
   const int64_t n = a.n;
   bool tl_on = a.timeline != 0 && blockIdx.x == 0 && (tid & 31) == 0;  // (switched off after the first tile)
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
       for (int gi = 0; gi < n_steps; ++gi, ++G) {
         const int g = chunk_of(gi);
         const uint32_t slot = G & 1u, use = G >> 1;
-        const uint8_t* blk = a.wsec + (size_t)g * kBlockStride;
+        const uint8_t* blk = a.wsec + (size_t)((kInitial && g < 4) ? kRepBlock0 + g : g) * kBlockStride;
         if (!second) {
           if (use >= 1u) mbar_wait(&s.bar_w1free[slot], (use - 1u) & 1u);
           if (elect_one()) tma_load(s.w1[slot], blk, kW1Bytes, &s.bar_w1full[slot]);
@@ -390,8 +400,18 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
       for (int i = 0; i < 8; ++i) {
         const int grow = (otid >> 3) + 16 * i;
         const int64_t it = (row0 + grow) < n ? (row0 + grow) : n - 1;
-        const int64_t irow = it * a.in_rows_per_item + (a.in_row ? (int64_t)a.in_row[it] : 0);
         float x[8];
+        if (kInitial) {  // one-hot observation: column 3 d + peg(d), columns 8 chunk .. 8 chunk + 7 of this row
+          const uint32_t w = a.words[it];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = chunk * 8 + j, d = col / 3;
+            x[j] = (col < 3 * a.n_disks && ((w >> (2 * d)) & 3u) == (uint32_t)(col - 3 * d)) ? 1.f : 0.f;
+          }
+          store_parts8(s.t0, grow, chunk, x);
+          continue;
+        }
+        const int64_t irow = it * a.in_rows_per_item + (a.in_row ? (int64_t)a.in_row[it] : 0);
         if (a.latent_dtype == HMZ_LATENT_F32) {
           const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.lat_in) + irow * kLatent + chunk * 8);
           const float4 u0 = __ldcs(src), u1 = __ldcs(src + 1);
@@ -413,8 +433,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
     // extra A slice of this row: one-hot(action) at k = 0..5, the constant 1 at k = 6; then the tile is handed over
     auto publish_inputs = [&](int tile) {
       const int64_t it = ((int64_t)tile * kM + row) < n ? ((int64_t)tile * kM + row) : n - 1;
-      const uint32_t act = min((uint32_t)a.actions[it], (uint32_t)(kActions - 1));
-      const uint32_t one = 0x3F80u << ((act & 1u) * 16u);
+      const uint32_t act = kInitial ? 0u : min((uint32_t)a.actions[it], (uint32_t)(kActions - 1));
+      const uint32_t one = kInitial ? 0u : 0x3F80u << ((act & 1u) * 16u);
       const uint32_t ax = smem_u32(s.ax);
       asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ax + plain_off(row, 0)), "r"((act >> 1) == 0u ? one : 0u),
                    "r"((act >> 1) == 1u ? one : 0u), "r"((act >> 1) == 2u ? one : 0u), "r"(0x3F80u)
@@ -435,8 +455,10 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
 #pragma unroll 1
       for (int net = 0; net < 4; ++net) {  // dynamics, reward, value, policy
         if (split == 3 && net != 0 && net != role + 1) continue;
+        if (kInitial && net == 1) continue;
         const bool last_net = split == 3 ? net != 0 : net == 3;
-        const bool raw_tile_free = split == 3 ? net != 0 : net == 1;  // the raw-latent tile has no reader left in this CTA
+        // the raw-latent tile has no reader left in this CTA
+        const bool raw_tile_free = kInitial ? net == 0 : (split == 3 ? net != 0 : net == 1);
         mbar_wait(&s.bar_o, ph_o);
         ph_o ^= 1u;
         tc_fence_after();
@@ -448,9 +470,11 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3_recurrent(const __grid_con
 #pragma unroll
           for (int j = 0; j < 4; ++j) ld_sum16(D2 + 16 * j, D2 + 64 + 16 * j, *reinterpret_cast<float(*)[16]>(&raw[16 * j]));
           tc_fence_before();
+          if (!kInitial) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) store_parts8(s.t0, row, c, *reinterpret_cast<float(*)[8]>(&raw[c * 8]));
-          fence_proxy_async();
+            for (int c = 0; c < 8; ++c) store_parts8(s.t0, row, c, *reinterpret_cast<float(*)[8]>(&raw[c * 8]));
+            fence_proxy_async();
+          }
           mbar_arrive(&s.bar_raw);
           X3_TL(106);
           float mn4[4], mx4[4];
@@ -573,7 +597,7 @@ int64_t packed_bytes(int n_disks) { return fp32_offset_bytes() + (int64_t)Fp32La
 
 void pack(const float* const* t, int n_disks, void* out) {
   std::memset(out, 0, (size_t)packed_bytes(n_disks));
-  // the root inference (1/S of the work) runs on the float32 copy behind the section (FFMA kernel)
+  // float observations (drop-in B = 1 views, arbitrary input vectors) run the FFMA kernel on the float32 copy behind the section
   pack_fp32(t, n_disks, (float*)((uint8_t*)out + fp32_offset_bytes()));
   uint8_t* sec = (uint8_t*)out;
   // state_dict order: rep(0-3) dyn(4-7) rwd(8-11) pol(12-15) val(16-19), each {w1, b1, w2, b2}; pass order dyn, rwd, val, pol
@@ -599,20 +623,41 @@ void pack(const float* const* t, int n_disks, void* out) {
       });
     }
   }
+  // representation_net (root inference): Linear(3N, 256) on the one-hot observation padded to K = 64, Linear(256, 64)
+  const int d_in = 3 * n_disks;
+  for (int c = 0; c < 4; ++c) {
+    uint8_t* blk = sec + (size_t)(kRepBlock0 + c) * kBlockStride;
+    pack_block(blk, 64, [&](int r, int k) -> float {
+      const int unit = 64 * c + r;
+      if (k < 64) return k < d_in ? t[0][(size_t)unit * d_in + k] : 0.f;
+      return k - 64 == kBiasK ? t[1][unit] : 0.f;
+    });
+    pack_block(blk + kSlot, 64, [&](int r, int k) -> float {
+      if (k < 64) return t[2][(size_t)r * kHidden + 64 * c + k];
+      return (c == 0 && k - 64 == kBiasK) ? t[3][r] : 0.f;
+    });
+  }
+}
+
+static int prepare(int* smem_bytes) {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)");
+  *smem_bytes = (int)sizeof(Smem) + 1024;
+  if (done_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(net_x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(net_x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem_bytes);
+    if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaFuncSetAttribute(net_x3): %s", cudaGetErrorString(e));
+    done_dev = dev;
+  }
+  return HMZ_OK;
 }
 
 int net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_item, const uint16_t* in_row,
                   const uint8_t* actions, void* lat_out, int64_t out_rows_per_item, int64_t out_row, int latent_dtype,
                   float* r, float* p, float* v, int64_t n, cudaStream_t stream) {
-  static thread_local int done_dev = -1;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)");
-  const int smem = (int)sizeof(Smem) + 1024;
-  if (done_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(net_x3_recurrent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(HMZ_ERR_CUDA, "cudaFuncSetAttribute(net_x3_recurrent): %s", cudaGetErrorString(e));
-    done_dev = dev;
-  }
+  int smem = 0;
+  if (int rc = prepare(&smem)) return rc;
   Args a{};
   a.wsec = (const uint8_t*)weights;
   a.lat_in = lat_in;
@@ -636,8 +681,31 @@ int net_recurrent(const void* weights, const void* lat_in, int64_t in_rows_per_i
   static const int tl = getenv("HMZ_X3_TIMELINE") ? atoi(getenv("HMZ_X3_TIMELINE")) : 0;
   a.timeline = tl;
   const unsigned grid = a.head_split == 3 ? 3u * (unsigned)a.n_tiles : (unsigned)(a.n_tiles < sms ? a.n_tiles : sms);
-  net_x3_recurrent<<<grid, kThreads, (size_t)smem, stream>>>(a);
-  return check_launch("net_x3_recurrent");
+  net_x3<false><<<grid, kThreads, (size_t)smem, stream>>>(a);
+  return check_launch("net_x3<recurrent>");
+}
+
+int net_initial(const void* weights, int n_disks, const uint32_t* words, void* lat_out, int64_t out_rows_per_item,
+                int latent_dtype, float* p0, float* v0, int64_t n, cudaStream_t stream) {
+  int smem = 0;
+  if (int rc = prepare(&smem)) return rc;
+  Args a{};
+  a.wsec = (const uint8_t*)weights;
+  a.in_rows_per_item = 1;
+  a.words = words;
+  a.n_disks = n_disks;
+  a.lat_out = lat_out;
+  a.out_rows_per_item = out_rows_per_item;
+  a.out_row = 0;
+  a.latent_dtype = latent_dtype;
+  a.p_out = p0;
+  a.v_out = v0;
+  a.n = n;
+  a.n_tiles = (int)((n + kM - 1) / kM);
+  a.head_split = 1;
+  const int sms = sm_count();
+  net_x3<true><<<(unsigned)(a.n_tiles < sms ? a.n_tiles : sms), kThreads, (size_t)smem, stream>>>(a);
+  return check_launch("net_x3<initial>");
 }
 
 int debug_read_timeline(unsigned long long* host_out) {

@@ -11,8 +11,9 @@ import numpy as np
 from oracle import port
 
 SLOT, STRIDE = 30720, 61440
-FIRST = {0: "dynamic_net", 1: "rwd_net", 2: "value_net", 3: "policy_net"}  # pass order of the kernel
-N2 = {0: 64, 1: 48, 2: 48, 3: 16}
+FIRST = {0: "dynamic_net", 1: "rwd_net", 2: "value_net", 3: "policy_net",  # pass order of the kernel
+         4: "representation_net"}  # blocks 16..19: the root inference
+N2 = {0: 64, 1: 48, 2: 48, 3: 16, 4: 64}
 
 
 def _bf16_to_f32(u16):
@@ -55,7 +56,7 @@ def _pack(lib, sd, n):
 
     arrays = [np.ascontiguousarray(sd[k], dtype=np.float32) for k in STATE_DICT_ORDER]
     nbytes = int(lib.hmz_weights_packed_bytes(n, 2))
-    assert nbytes > 16 * STRIDE
+    assert nbytes > 20 * STRIDE
     host = np.zeros(nbytes, np.uint8)
     table = (C.c_void_p * 20)(*[a.ctypes.data for a in arrays])
     assert lib.hmz_weights_pack(table, n, 2, host.ctypes.data) == 0
@@ -65,7 +66,7 @@ def _pack(lib, sd, n):
 def _layers(host):
     """Decoded parts per network: W1 [3][256][64], X1 [3][256][16], W2 [3][n2][256], X2 [3][n2][16]."""
     out = {}
-    for net in range(4):
+    for net in range(5):
         n2 = N2[net]
         w1 = np.zeros((3, 256, 64), np.float32)
         x1 = np.zeros((3, 256, 16), np.float32)
@@ -91,7 +92,8 @@ def test_section_reproduces_every_weight_exactly(lib):
     for net, name in FIRST.items():
         w1, x1, w2, x2 = L[net]
         W1, B1, W2, B2 = (sd[f"{name}.{k}"] for k in ("0.weight", "0.bias", "2.weight", "2.bias"))
-        assert np.array_equal(w1.astype(np.float64).sum(0), W1[:, :64].astype(np.float64))
+        k_in = min(64, W1.shape[1])  # representation_net: 3N input columns, zero-padded to K = 64
+        assert np.array_equal(w1.astype(np.float64).sum(0)[:, :k_in], W1[:, :k_in].astype(np.float64)) and not w1[:, :, k_in:].any()
         assert np.array_equal(x1.astype(np.float64).sum(0)[:, 6], B1.astype(np.float64))
         if net == 0:
             assert np.array_equal(x1.astype(np.float64).sum(0)[:, :6], W1[:, 64:70].astype(np.float64))
@@ -102,8 +104,8 @@ def test_section_reproduces_every_weight_exactly(lib):
         assert np.array_equal(w2.astype(np.float64).sum(0)[:out], W2.astype(np.float64)) and not w2[:, out:].any()
         assert np.array_equal(x2.astype(np.float64).sum(0)[:out, 6], B2.astype(np.float64))
         # the parts are what the device-side split produces: bf16(w), bf16(w - w0), bf16(w - w0 - w1)
-        for got, want in zip(w1, _split3(W1[:, :64])):
-            assert np.array_equal(got, want)
+        for got, want in zip(w1, _split3(W1[:, :k_in])):
+            assert np.array_equal(got[:, :k_in], want)
 
 
 def _linear7(xparts, wparts, ax, xw):
