@@ -396,37 +396,63 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
     auto gather = [&](int tile) {
       const int64_t row0 = (int64_t)tile * kM;
       const int chunk = otid & 7;
-#pragma unroll 2
-      for (int i = 0; i < 8; ++i) {
-        const int grow = (otid >> 3) + 16 * i;
-        const int64_t it = (row0 + grow) < n ? (row0 + grow) : n - 1;
-        float x[8];
-        if (kInitial) {  // one-hot observation: column 3 d + peg(d), columns 8 chunk .. 8 chunk + 7 of this row
-          const uint32_t w = a.words[it];
+      if (kInitial) {  // one-hot observation: column 3 d + peg(d), columns 8 chunk .. 8 chunk + 7 of each row
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = row0 + (otid >> 3) + 16 * i;
+          w[i] = a.words[r < n ? r : n - 1];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int col = chunk * 8 + j, d = col / 3;
-            x[j] = (col < 3 * a.n_disks && ((w >> (2 * d)) & 3u) == (uint32_t)(col - 3 * d)) ? 1.f : 0.f;
+            x[j] = (col < 3 * a.n_disks && ((w[i] >> (2 * d)) & 3u) == (uint32_t)(col - 3 * d)) ? 1.f : 0.f;
           }
-          store_parts8(s.t0, grow, chunk, x);
-          continue;
+          store_parts8(s.t0, (otid >> 3) + 16 * i, chunk, x);
         }
-        const int64_t irow = it * a.in_rows_per_item + (a.in_row ? (int64_t)a.in_row[it] : 0);
-        if (a.latent_dtype == HMZ_LATENT_F32) {
-          const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.lat_in) + irow * kLatent + chunk * 8);
-          const float4 u0 = __ldcs(src), u1 = __ldcs(src + 1);
-          x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
-          x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
-        } else {
-          const uint4 q = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.lat_in) + irow * kLatent + chunk * 8));
-          const uint32_t pk[4] = {q.x, q.y, q.z, q.w};
+      } else {
+        // all eight rows' loads are in flight before the first split: the first tile's gather sits on the launch's
+        // critical path (two dependent round trips: leaf parent, then the latent row)
+        int64_t irow[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            x[2 * j] = bf_lo(pk[j]);
-            x[2 * j + 1] = bf_hi(pk[j]);
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = row0 + (otid >> 3) + 16 * i;
+          const int64_t it = r < n ? r : n - 1;
+          irow[i] = it * a.in_rows_per_item + (a.in_row ? (int64_t)a.in_row[it] : 0);
+        }
+        if (a.latent_dtype == HMZ_LATENT_F32) {
+          float4 u[8][2];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.lat_in) + irow[i] * kLatent + chunk * 8);
+            u[i][0] = __ldcs(src);
+            u[i][1] = __ldcs(src + 1);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x[8] = {u[i][0].x, u[i][0].y, u[i][0].z, u[i][0].w, u[i][1].x, u[i][1].y, u[i][1].z, u[i][1].w};
+            store_parts8(s.t0, (otid >> 3) + 16 * i, chunk, x);
+          }
+        } else {
+          uint4 q[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            q[i] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.lat_in) + irow[i] * kLatent + chunk * 8));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t pk[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              x[2 * j] = bf_lo(pk[j]);
+              x[2 * j + 1] = bf_hi(pk[j]);
+            }
+            store_parts8(s.t0, (otid >> 3) + 16 * i, chunk, x);
           }
         }
-        store_parts8(s.t0, grow, chunk, x);
       }
       fence_proxy_async();
     };
