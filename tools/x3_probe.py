@@ -9,10 +9,11 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from muzero_hanoi_b200 import _lib  # noqa: E402
 from muzero_hanoi_b200.engine import PackedWeights  # noqa: E402
-from oracle import port  # noqa: E402  (synthetic weights only)
+from muzero_hanoi_b200.networks import MuZeroNet  # noqa: E402
 
 FLOP = 203776
-sd = port.make_weights(5, 3)
+torch.manual_seed(0)
+sd = MuZeroNet(15, 6, 0.002, "cpu", TD_return=True).state_dict()
 dev = torch.device("cuda")
 ROWS = [int(x) for x in os.environ["ROWS"].split(",")] if os.environ.get("ROWS") else [1024, 4096, 8192, 16384, 18944, 32768, 65536, 131072]
 MODES = os.environ.get("MODES", "ffma,x3,bf16").split(",")

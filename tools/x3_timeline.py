@@ -11,10 +11,11 @@ import torch  # noqa: E402
 
 from muzero_hanoi_b200 import _lib  # noqa: E402
 from muzero_hanoi_b200.engine import PackedWeights  # noqa: E402
-from oracle import port  # noqa: E402  (synthetic weights only)
+from muzero_hanoi_b200.networks import MuZeroNet  # noqa: E402
 
 n = int(os.environ.get("N", 65536))
-w = PackedWeights(port.make_weights(5, 3), 5, _lib.MODE_FP32X3)
+torch.manual_seed(0)
+w = PackedWeights(MuZeroNet(15, 6, 0.002, "cpu", TD_return=True).state_dict(), 5, _lib.MODE_FP32X3)
 h_in = torch.rand(n, 64, device="cuda")
 acts = torch.randint(0, 6, (n,), dtype=torch.uint8, device="cuda")
 h = torch.empty(n, 64, device="cuda")
