@@ -286,9 +286,10 @@ int hmz_search_run(const hmz_search_t* s, const void* weights, int mode, int n_s
 /* Tooling only: with HMZ_TC_TIMELINE=1 in the environment, CTA 0 of the tensor-core kernel records
  * clock64() at its phase boundaries; this copies the 96 marks of the last launch to the host. */
 int hmz_debug_tc_timeline(unsigned long long* host_out);
-/* Tooling only: the same for the HMZ_MODE_FP32X3 kernel (HMZ_X3_TIMELINE=1): 128 marks of CTA 0's first tile — [g] / [16 + g]
+/* Tooling only: the same for the HMZ_MODE_FP32X3 kernel (HMZ_X3_TIMELINE=1): 160 marks of CTA 0's first tile — [g] / [16 + g]
  * first layer of chunk g issued from / to, [32 + g] / [48 + g] second layer, [64 + g] / [80 + g] hidden epilogue of chunk g
- * (epilogue thread 0), [96 + net] / [100 + net] output epilogue of a network, [106] raw latent tile published, [104] / [105] gather, [110] / [111] prologue. */
+ * (epilogue thread 0), [96 + net] / [100 + net] output epilogue of a network, [106] raw latent tile published, [104] / [105] gather, [110] / [111] prologue,
+ * [112 + g] first-layer warp at its loop top, [128 + g] first-layer weight block's TMA issued, [144 + g] seen landed. */
 int hmz_debug_x3_timeline(unsigned long long* host_out);
 /* Tooling only: key = search | (simulation << 32) >= 0 switches hmz_search_run to the instrumented fused
  * backup + select kernel, whose lane pair `search` records clock64() at its phase boundaries in that

@@ -12,12 +12,12 @@
 // One CTA = one tile of 128 rows (UMMA M = 128), persistent over tiles.  A network is processed in four CHUNKS
 // of 64 hidden units: first layer of chunk c -> TMEM accumulator (128 columns, three buffers) -> the hidden-epilogue
 // warps add the blocks, apply relu, split into three bf16 parts and write them back IN PLACE -> the second layer
-// accumulates the chunk's K = 64 slice with its A operand taken from TMEM (the .ts form).  One issuing warp per layer
-// kind (issuing a tcgen05.mma blocks for about its execution time), so first layers run ahead of second layers and the
-// tensor core works while a chunk is drained; four output warps (thread = row) own the new latent, the heads' outputs
-// and the gather of the next tile.  Bias and the one-hot action columns of dynamic_net.0 ride in an extra K = 16 step
+// accumulates the chunk's K = 64 slice with its A operand taken from TMEM (the .ts form).  Separate issuing warps for
+// the layer kinds (two alternating on the first layers, one for the second: issuing a tcgen05.mma blocks for about its
+// execution time), so first layers run ahead of second layers and the tensor core works while a chunk is drained; four
+// output warps (thread = row) own the new latent, the heads' outputs and the gather of the next tile.  Bias and the one-hot action columns of dynamic_net.0 ride in an extra K = 16 step
 // as in the bf16 kernel (hmz_net_tc.cuh).  Weights stream from L2 per chunk with 1-D TMA bulk copies into
-// double-buffered slots (one loader warp per layer kind).  Small batches (3 x tiles <= SMs): three CTAs per tile run
+// double-buffered slots.  Small batches (3 x tiles <= SMs): three CTAs per tile run
 // the dynamics network and ONE head each.  Epilogue math (normalize_h_state :191-196, support transform :152-189,
 // softmax) is the float32 code of the FFMA kernel (hmz_net.cu).  DESIGN.md §4 has the measurements.
 #include <cstdlib>
@@ -36,7 +36,7 @@ using tc::v4::umma_ts;
 
 constexpr int kEpiThreads = 256;  // 8 hidden-epilogue warps: warp -> TMEM lane quarter (w & 3), column half (w >> 2)
 constexpr int kOutThreads = 128;  // 4 output warps: thread = row
-constexpr int kOutWarp0 = 8, kMma1Warp = 12, kMma2Warp = 13, kLoader1Warp = 14, kLoader2Warp = 15;
+constexpr int kOutWarp0 = 8, kMma1Warp = 12, kMma1bWarp = 13, kMma2Warp = 14, kLoaderWarp = 15;
 constexpr int kThreads = 16 * 32;
 constexpr uint32_t kW1Main = 192 * 128;            // [w0; w1; w2] rows of a 64-unit chunk, K = 64
 constexpr uint32_t kW1Bytes = 192 * 160;           // + the extra K = 16 slice
@@ -86,7 +86,7 @@ struct Args {
   int timeline;  // tooling (HMZ_X3_TIMELINE=1): CTA 0 records clock64() at the phase boundaries of its first tile
 };
 
-static __device__ unsigned long long g_x3_timeline[128];
+static __device__ unsigned long long g_x3_timeline[160];
 #define X3_TL(slot)                                                   \
   do {                                                                \
     if (tl_on) {                                                      \
@@ -241,29 +241,36 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
   const uint32_t tmem = s.tmem_base;
   if (tid == 0) X3_TL(111);
 
-  if (warp == kLoader1Warp || warp == kLoader2Warp) {
-    // ================================= loader warps =================================
-    // one per layer kind, so that a first-layer block (its slot frees as soon as the first layer two chunks back has
-    // completed) is never queued behind a second-layer block (whose slot frees much later)
-    const bool second = warp == kLoader2Warp;
-    uint32_t G = 0;  // chunk counter of this CTA: slot G & 1, use G >> 1
-    for (int tile = cta; tile < n_tiles; tile += n_cta) {
-      for (int gi = 0; gi < n_steps; ++gi, ++G) {
-        const int g = chunk_of(gi);
-        const uint32_t slot = G & 1u, use = G >> 1;
-        const uint8_t* blk = a.wsec + (size_t)((kInitial && g < 4) ? kRepBlock0 + g : g) * kBlockStride;
-        if (!second) {
-          if (use >= 1u) mbar_wait(&s.bar_w1free[slot], (use - 1u) & 1u);
-          if (elect_one()) tma_load(s.w1[slot], blk, kW1Bytes, &s.bar_w1full[slot]);
-        } else {
-          if (use >= 1u) mbar_wait(&s.bar_w2free[slot], (use - 1u) & 1u);
-          if (elect_one()) tma_load(s.w2[slot], blk + kSlot, 3u * n2_of(g >> 2) * 160u, &s.bar_w2full[slot]);
-        }
-        __syncwarp();
+  if (warp == kLoaderWarp) {
+    // ================================= loader warp =================================
+    // First-layer blocks run one chunk ahead of second-layer blocks (W1(0), W1(1), W2(0), W1(2), W2(1), ...): a first-layer
+    // slot frees as soon as the first layer two chunks back has completed, a second-layer slot only when that chunk's
+    // second layer has — queued strictly in chunk order, the next first-layer block would sit behind that later event.
+    const uint32_t total = cta < n_tiles ? (uint32_t)((n_tiles - cta + n_cta - 1) / n_cta) * (uint32_t)n_steps : 0u;
+    auto load = [&](uint32_t G, bool second) {  // chunk counter of this CTA: slot G & 1, use G >> 1
+      const int g = chunk_of((int)(G % (uint32_t)n_steps));
+      const uint32_t slot = G & 1u, use = G >> 1;
+      const uint8_t* blk = a.wsec + (size_t)((kInitial && g < 4) ? kRepBlock0 + g : g) * kBlockStride;
+      if (!second) {
+        if (use >= 1u) mbar_wait(&s.bar_w1free[slot], (use - 1u) & 1u);
+        if (G < 16u) X3_TL(128 + g);
+        if (elect_one()) tma_load(s.w1[slot], blk, kW1Bytes, &s.bar_w1full[slot]);
+      } else {
+        if (use >= 1u) mbar_wait(&s.bar_w2free[slot], (use - 1u) & 1u);
+        if (elect_one()) tma_load(s.w2[slot], blk + kSlot, 3u * n2_of(g >> 2) * 160u, &s.bar_w2full[slot]);
       }
+      __syncwarp();
+    };
+    for (uint32_t j = 0; j <= total; ++j) {
+      if (j < total) load(j, false);
+      if (j >= 1u) load(j - 1u, true);
     }
-  } else if (warp == kMma1Warp) {
-    // ========================= first-layer issuing warp =========================
+  } else if (warp == kMma1Warp || warp == kMma1bWarp) {
+    // ========================= first-layer issuing warps =========================
+    // (two of them, one for the even and one for the odd chunks of the CTA's chunk sequence — each always uses the same
+    // weight slot: between two chunks a warp spends ~800 clk in its barrier waits and fences, which the other warp's
+    // issue now covers; the timeline showed the single first-layer warp's loop, not the tensor pipe, pacing the kernel)
+    const uint32_t my_parity = warp == kMma1Warp ? 0u : 1u;
     // Two issuing warps, one per layer kind: issuing a tcgen05.mma blocks for about its execution time, so a single warp
     // would serialise the second layer of chunk g behind the issue of the first layer of chunk g + 1 (and behind its own
     // waits); the tensor core takes the two streams in arrival order.  The write-after-read hazard on an accumulator
@@ -275,14 +282,17 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
 #pragma unroll 1
       for (int gi = 0; gi < n_steps; ++gi, ++G) {
+        if ((G & 1u) != my_parity) continue;
         const int g = chunk_of(gi);
         const uint32_t slot = G & 1u, use = G >> 1, buf = G % 3u, bu = G / 3u;
         X3_TL(112 + g);
         mbar_wait(&s.bar_w1full[slot], use & 1u);
+        X3_TL(144 + g);
         if (bu >= 1u) mbar_wait(&s.bar_hfree[buf], (bu - 1u) & 1u);  // accumulator buffer no longer read
-        if (g == 0) mbar_wait(&s.bar_g, ph_tile);    // input tile gathered
-        if (g == 4) mbar_wait(&s.bar_raw, ph_tile);  // raw latent tile written (reward head input)
-        if (g >= 8 && (g & 3) == 0) mbar_wait(&s.bar_hn, ph_tile);  // normalised latent tile written (value / policy head input)
+        // this chunk's A tile (each issuing warp checks for itself: the other one may have done the network's first chunk)
+        if (g < 4) mbar_wait(&s.bar_g, ph_tile);         // input tile gathered
+        else if (g < 8) mbar_wait(&s.bar_raw, ph_tile);  // raw latent tile written (reward head input)
+        else mbar_wait(&s.bar_hn, ph_tile);              // normalised latent tile written (value / policy head input)
         tc_fence_after();
         X3_TL(g);
         if (elect_one()) {

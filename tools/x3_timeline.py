@@ -24,15 +24,15 @@ for _ in range(3):
     w.recurrent(n, latents_in=h_in, in_rows_per_item=1, in_row=None, actions=acts, latents_out=h, out_rows_per_item=1, out_row=0,
                 latent_dtype=0, r=r, p=p, v=v)
 torch.cuda.synchronize()
-buf = (C.c_ulonglong * 128)()
+buf = (C.c_ulonglong * 160)()
 _lib.check(_lib.load().hmz_debug_x3_timeline(buf))
 m = np.array(list(buf), dtype=np.int64)
 t0 = m[110]
 rel = lambda i: int(m[i] - t0)
 print(f"rows {n}: prologue done {rel(111)}, gather {rel(104)} -> {rel(105)}")
-print(" g net c | L1 loop top, issue from   to |  epilogue from    to |  L2 issue from    to")
+print(" g net c | W1 TMA issued, landed | L1 loop top, issue from   to |  epilogue from    to |  L2 issue from    to")
 for g in range(16):
-    print(f"{g:2d}  {'grvp'[g >> 2]}  {g & 3} | {rel(112 + g):8d} {rel(g):8d} {rel(16 + g):8d} | {rel(64 + g):8d} {rel(80 + g):8d} | {rel(32 + g):8d} {rel(48 + g):8d}")
+    print(f"{g:2d}  {'grvp'[g >> 2]}  {g & 3} | {rel(128 + g):8d} {rel(144 + g):8d} | {rel(112 + g):8d} {rel(g):8d} {rel(16 + g):8d} | {rel(64 + g):8d} {rel(80 + g):8d} | {rel(32 + g):8d} {rel(48 + g):8d}")
     if (g & 3) == 3:
         print(f"      output epilogue of network {'grvp'[g >> 2]}: {rel(96 + (g >> 2))} -> {rel(100 + (g >> 2))}"
               + (f" (raw latent tile published {rel(106)})" if g == 3 else ""))
