@@ -536,7 +536,8 @@ def run_ours(args):
     else:
         def roofline_of(name):
             per_launch_s = kern[name]["us_per_launch"] * 1e-6
-            tr, src = traffic_of(name, B)
+            # (the ncu captures are of the bf16 network kernel and of net_x3; the FFMA kernel has none)
+            tr, src = traffic_of({"fp32x3": "net_x3_recurrent", "fp32": "net_recurrent_fp32"}.get(args.mode, name) if name == "net_recurrent" else name, B)
             if name == "net_recurrent":
                 ach = FLOP_PER_SIM * B / per_launch_s / 1e12
                 return {"kernel": "net_tc<recurrent> (fused g + reward/policy/value heads, tcgen05)" if args.mode == "bf16" else ("net_recurrent_fp32 (FFMA)" if args.mode == "fp32" else "net_x3_recurrent (tcgen05, three bf16 parts per float32 operand)"),

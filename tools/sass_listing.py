@@ -29,7 +29,7 @@ def demangle(name):
 
 plain = {"tree_search_backup_select": "search_backup_selectILb0ELb1", "tree_search_select": "search_selectE",
          "env_step_vec4": "env_step_vec4ILb0ELi1", "env_step_random_vec4": "env_step_random_vec4ILi1"}
-zipped = {"net_tc_recurrent": "net_tcILb0", "search_persistent": "search_persistent", "net_x3_recurrent": "net_x3_recurrent"}
+zipped = {"net_tc_recurrent": "net_tcILb0", "search_persistent": "search_persistent", "net_x3_recurrent": "net_x3ILb0"}
 for name, key in plain.items():
     with open(os.path.join(OUT, f"{R}_{name}.sass"), "w") as f:
         f.write("\n".join(funcs[find(key)]) + "\n")
@@ -39,7 +39,7 @@ for name, key in zipped.items():
 proof = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR", "LDG.E.ENL2.256", "STG.E.ENL2.256", "LDG.E.128", "STG.E.EF.128", "CCTL.IVALL",
          "MEMBAR.ALL.GPU", "REDG.E.ADD.STRONG.GPU", "ATOMG.E.ADD.STRONG.GPU", "DFMA", "BSSY"]
 with open(os.path.join(OUT, f"{R}_summary.txt"), "w") as f:
-    for key in ("search_backup_selectILb0ELb1", "env_step_vec4ILb0ELi1", "env_step_random_vec4ILi1", "net_tcILb0", "search_persistent", "net_x3_recurrent"):
+    for key in ("search_backup_selectILb0ELb1", "env_step_vec4ILb0ELi1", "env_step_random_vec4ILi1", "net_tcILb0", "search_persistent", "net_x3ILb0"):
         k = find(key)
         ins = [l for l in funcs[k] if re.match(r"\s*/\*[0-9a-f]+\*/", l)]
         ops = collections.Counter()
