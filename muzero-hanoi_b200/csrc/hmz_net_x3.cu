@@ -97,7 +97,7 @@ static __device__ unsigned long long g_x3_timeline[160];
   } while (0)
 
 // Every wait of this kernel is time-bounded (2 s: a launch lasts well under a millisecond): a protocol failure traps —
-// the launch fails with an error — instead of hanging the GPU.  (Registers are plentiful here: 320 threads per SM.)
+// the launch fails with an error — instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t spins = 0;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
       const uint8_t* blk = a.wsec + (size_t)((kInitial && g < 4) ? kRepBlock0 + g : g) * kBlockStride;
       if (!second) {
         if (use >= 1u) mbar_wait(&s.bar_w1free[slot], (use - 1u) & 1u);
-        if (G < 16u) X3_TL(128 + g);
+        if (G < (uint32_t)n_steps) X3_TL(128 + g);
         if (elect_one()) tma_load(s.w1[slot], blk, kW1Bytes, &s.bar_w1full[slot]);
       } else {
         if (use >= 1u) mbar_wait(&s.bar_w2free[slot], (use - 1u) & 1u);
