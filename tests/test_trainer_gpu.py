@@ -8,14 +8,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_batched_training_loop_learns_three_disk_hanoi():
+@pytest.mark.parametrize("acting_mode", [0, 2])  # acting on the FFMA kernel / on the tensor cores (HMZ_MODE_FP32X3)
+def test_batched_training_loop_learns_three_disk_hanoi(acting_mode):
     from muzero_hanoi_b200.networks import MuZeroNet
     from muzero_hanoi_b200.trainer import BatchedMuzero
 
     torch.manual_seed(1)
     np.random.seed(1)
     net = MuZeroNet(9, 6, 0.002, "cpu", TD_return=True)
-    mz = BatchedMuzero(net.state_dict(), 3, 200, 512, n_mcts_simulations=25, n_update_x_loop=8, seed=1)
+    mz = BatchedMuzero(net.state_dict(), 3, 200, 512, n_mcts_simulations=25, n_update_x_loop=8, acting_mode=acting_mode, seed=1)
     hist = mz.training_loop(160, min_replay_size=5000)
     lens = [h[1] for h in hist if h[1] == h[1]]
     early, late = float(np.mean(lens[:15])), float(np.mean(lens[-15:]))
