@@ -86,9 +86,13 @@ def _layers(host):
     return out
 
 
-def test_section_reproduces_every_weight_exactly(lib):
-    sd = port.make_weights(5, 11)
-    L = _layers(_pack(lib, sd, 5))
+import pytest
+
+
+@pytest.mark.parametrize("n", [1, 5, 12])  # 3N = 3 .. 36 observation columns, zero-padded to K = 64
+def test_section_reproduces_every_weight_exactly(lib, n):
+    sd = port.make_weights(n, 11)
+    L = _layers(_pack(lib, sd, n))
     for net, name in FIRST.items():
         w1, x1, w2, x2 = L[net]
         W1, B1, W2, B2 = (sd[f"{name}.{k}"] for k in ("0.weight", "0.bias", "2.weight", "2.bias"))
