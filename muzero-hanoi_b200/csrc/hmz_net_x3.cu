@@ -44,24 +44,25 @@ constexpr uint32_t kSlot = 30720;                  // both layer kinds: 192 x 16
 constexpr uint32_t kBlockStride = 2 * kSlot;       // one (network, chunk) block of the weight section
 constexpr uint32_t kRepBlock0 = 16;                // blocks 16..19: representation_net (root inference)
 constexpr uint32_t kSectionBytes = 20 * kBlockStride;
-constexpr uint32_t kColD2 = 384;                   // TMEM: D1[3] at columns 0 / 128 / 256, D2 at 384 (all 512 columns)
+constexpr uint32_t kBufs = 2;                      // first-layer accumulator buffers
+constexpr uint32_t kColD2 = 128 * kBufs;           // TMEM: D1[2] at columns 0 / 128, D2 at 256,
+constexpr uint32_t kColHn = kColD2 + 128;          //       the normalised latent's three bf16 parts at 384 + 32 part (96 columns)
 // second-layer width per network in pass order dynamics, reward, value, policy (33 support logits -> 48, 6 -> 16)
 __host__ __device__ constexpr uint32_t n2_of(int net) { return net == 0 ? 64u : (net == 3 ? 16u : 48u); }
 
 struct __align__(1024) Smem {
   uint8_t t0[3][kAtomA];  // parts of the input latent tile, later of the raw new latent (reward head input)
-  uint8_t t1[3][kAtomA];  // parts of the normalised new latent (value / policy head input)
   uint8_t w1[2][kSlot];   // first-layer chunk blocks, slot = chunk counter & 1
   uint8_t w2[2][kSlot];   // second-layer chunk blocks
   uint8_t ax[kM * 32];    // extra A slice [onehot(action) (6), 1, 0 x 9] per row (exact in bf16: one part)
   uint64_t bar_w1full[2], bar_w1free[2], bar_w2full[2], bar_w2free[2];
   uint64_t bar_g;         // input tile + extra slice written (128 arrivals: the output warps)
-  uint64_t bar_d[3];      // first-layer accumulator of the buffer complete
-  uint64_t bar_a[3];      // hidden parts written back (256 arrivals)
-  uint64_t bar_hfree[3];  // the second layer that read the buffer's hidden parts has completed
+  uint64_t bar_d[kBufs];      // first-layer accumulator of the buffer complete
+  uint64_t bar_a[kBufs];      // hidden parts written back (256 arrivals)
+  uint64_t bar_hfree[kBufs];  // the second layer that read the buffer's hidden parts has completed
   uint64_t bar_o;         // second layer of a network complete
   uint64_t bar_raw;       // dynamics output: D2 drained and the raw latent tile written (128 arrivals)
-  uint64_t bar_hn;        // dynamics output: normalised latent tile written (128 arrivals)
+  uint64_t bar_hn;        // dynamics output: normalised latent parts written to TMEM (128 arrivals)
   uint64_t bar_out;       // a head's output: D2 drained (128 arrivals)
   uint32_t tmem_base;
 };
@@ -157,6 +158,10 @@ __device__ __forceinline__ void ld_sum16(uint32_t t0, uint32_t t1, float (&out)[
   for (int j = 0; j < 16; ++j) out[j] = __fadd_rn(__uint_as_float(a[j]), __uint_as_float(b[j]));
 }
 
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
 // Hidden epilogue of one chunk for this thread's row and column half: units 32 half .. 32 half + 31 of the chunk.
 // Batch b (16 units) reads columns [16b, 16b + 16) of both blocks and leaves h0 in [16b, 16b + 8), h1 in
 // [16b + 8, 16b + 16) and h2 in [64 + 16b, 64 + 16b + 8): always inside the columns it has just read.
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
       mbar_init(&s.bar_w2full[j], 1);
       mbar_init(&s.bar_w2free[j], 1);
     }
-    for (int j = 0; j < 3; ++j) {
+    for (int j = 0; j < (int)kBufs; ++j) {
       mbar_init(&s.bar_d[j], 1);
       mbar_init(&s.bar_a[j], kEpiThreads);
       mbar_init(&s.bar_hfree[j], 1);
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
       for (int gi = 0; gi < n_steps; ++gi, ++G) {
         if ((G & 1u) != my_parity) continue;
         const int g = chunk_of(gi);
-        const uint32_t slot = G & 1u, use = G >> 1, buf = G % 3u, bu = G / 3u;
+        const uint32_t slot = G & 1u, use = G >> 1, buf = G % kBufs, bu = G / kBufs;
         X3_TL(112 + g);
         mbar_wait(&s.bar_w1full[slot], use & 1u);
         X3_TL(144 + g);
@@ -297,15 +302,27 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
         X3_TL(g);
         if (elect_one()) {
           const uint32_t D1 = tmem + 128u * buf;
-          const uint32_t a_in = (g >> 2) <= 1 ? smem_u32(s.t0[0]) : smem_u32(s.t1[0]);
           const uint32_t w = smem_u32(s.w1[slot]);
           const uint64_t b01 = desc_sw128(w), b2 = desc_sw128(w + 128u * 128u);
+          if ((g >> 2) <= 1) {  // dynamics / representation (input tile), reward head (raw latent tile): A from shared memory
+            const uint32_t a_in = smem_u32(s.t0[0]);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-              umma(D1, desc_sw128(a_in + (uint32_t)i * kAtomA) + (uint64_t)(kk * 2), b01 + (uint64_t)(kk * 2), id128, (kk | i) ? 1u : 0u);
-            umma(D1 + 64u, desc_sw128(a_in) + (uint64_t)(kk * 2), b2 + (uint64_t)(kk * 2), id64, 1u);
+              for (int i = 0; i < 3; ++i)
+                umma(D1, desc_sw128(a_in + (uint32_t)i * kAtomA) + (uint64_t)(kk * 2), b01 + (uint64_t)(kk * 2), id128, (kk | i) ? 1u : 0u);
+              umma(D1 + 64u, desc_sw128(a_in) + (uint64_t)(kk * 2), b2 + (uint64_t)(kk * 2), id64, 1u);
+            }
+          } else {  // value / policy heads: the normalised latent's parts are a TMEM operand (no shared-memory reads for A:
+                    // a first layer with both operands in shared memory runs at the port's 128 B/clk)
+            const uint32_t hn = tmem + kColHn;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+                umma_ts(D1, hn + 32u * (uint32_t)i + 8u * (uint32_t)kk, b01 + (uint64_t)(kk * 2), id128, (kk | i) ? 1u : 0u);
+              umma_ts(D1 + 64u, hn + 8u * (uint32_t)kk, b2 + (uint64_t)(kk * 2), id64, 1u);
+            }
           }
           umma(D1, desc_plain(ax), desc_plain(w + kW1Main), id128, 1u);
           umma(D1 + 64u, desc_plain(ax), desc_plain(w + kW1Main + plain_off(128, 0)), id64, 1u);
@@ -328,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
 #pragma unroll 1
       for (int gi = 0; gi < n_steps; ++gi, ++G) {
         const int g = chunk_of(gi);
-        const uint32_t slot = G & 1u, use = G >> 1, buf = G % 3u, bu = G / 3u;
+        const uint32_t slot = G & 1u, use = G >> 1, buf = G % kBufs, bu = G / kBufs;
         const int net = g >> 2, c = g & 3;
         mbar_wait(&s.bar_w2full[slot], use & 1u);
         mbar_wait(&s.bar_a[buf], bu & 1u);
@@ -380,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
 #pragma unroll 1
       for (int gi = 0; gi < n_steps; ++gi, ++G) {
         const int g = chunk_of(gi);
-        const uint32_t buf = G % 3u, bu = G / 3u;
+        const uint32_t buf = G % kBufs, bu = G / kBufs;
         mbar_wait(&s.bar_d[buf], bu & 1u);
         tc_fence_after();
         X3_TL(64 + g);
@@ -532,7 +549,13 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
             float hn[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) hn[j] = __fmul_rn(__fsub_rn(raw[c * 8 + j], mn), inv);
-            store_parts8(s.t1, row, c, hn);
+            {  // three bf16 parts of the eight values -> four packed columns per part (lane = row, one column = two k)
+              uint32_t pp[3][4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) split3(hn[2 * j], hn[2 * j + 1], pp[0][j], pp[1][j], pp[2][j]);
+#pragma unroll
+              for (int i = 0; i < 3; ++i) tmem_st4(D2 - kColD2 + kColHn + 32u * (uint32_t)i + 4u * (uint32_t)c, pp[i]);
+            }
             if (item < n && role <= 0) {  // (head split: the reward CTA stores the rows)
               if (a.latent_dtype == HMZ_LATENT_F32) {
                 float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.lat_out) + orow * kLatent + c * 8);
@@ -544,7 +567,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
               }
             }
           }
-          fence_proxy_async();
+          tmem_st_wait();
+          tc_fence_before();
           mbar_arrive(&s.bar_hn);
         } else if (net == 3) {  // F.softmax(pi_logits) (networks.py:109)
           float lg[16];
