@@ -10,7 +10,7 @@
 // accumulator's rounding acts on them at their own scale.
 //
 // One CTA = one tile of 128 rows (UMMA M = 128), persistent over tiles.  A network is processed in four CHUNKS
-// of 64 hidden units: first layer of chunk c -> TMEM accumulator (128 columns, three buffers) -> the hidden-epilogue
+// of 64 hidden units: first layer of chunk c -> TMEM accumulator (128 columns, two buffers) -> the hidden-epilogue
 // warps add the blocks, apply relu, split into three bf16 parts and write them back IN PLACE -> the second layer
 // accumulates the chunk's K = 64 slice with its A operand taken from TMEM (the .ts form).  Separate issuing warps for
 // the layer kinds (two alternating on the first layers, one for the second: issuing a tcgen05.mma blocks for about its
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
     // Two issuing warps, one per layer kind: issuing a tcgen05.mma blocks for about its execution time, so a single warp
     // would serialise the second layer of chunk g behind the issue of the first layer of chunk g + 1 (and behind its own
     // waits); the tensor core takes the two streams in arrival order.  The write-after-read hazard on an accumulator
-    // buffer — the first layer of chunk G + 3 overwrites what the second layer of chunk G reads as its A operand —
+    // buffer — the first layer of chunk G + 2 overwrites what the second layer of chunk G reads as its A operand —
     // is then ordered by an mbarrier (bar_hfree: second layer of chunk G complete) instead of by issue order.
     const uint32_t id128 = umma_idesc(128), id64 = umma_idesc(64);
     const uint32_t ax = smem_u32(s.ax);
