@@ -57,6 +57,7 @@ struct __align__(1024) Smem {
   uint8_t ax[kM * 32];    // extra A slice [onehot(action) (6), 1, 0 x 9] per row (exact in bf16: one part)
   uint64_t bar_w1full[2], bar_w1free[2], bar_w2full[2], bar_w2free[2];
   uint64_t bar_g;         // input tile + extra slice written (128 arrivals: the output warps)
+  uint64_t bar_g0;        // the same for the CTA's FIRST tile, which the idle hidden-epilogue warps gather (256 + 128 arrivals)
   uint64_t bar_d[kBufs];      // first-layer accumulator of the buffer complete
   uint64_t bar_a[kBufs];      // hidden parts written back (256 arrivals)
   uint64_t bar_hfree[kBufs];  // the second layer that read the buffer's hidden parts has completed
@@ -194,6 +195,74 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t D, int half) {
   tmem_st_wait();
 }
 
+// Parent latents (or the one-hot observation of the env words) of a tile -> the three part tiles; 8 consecutive threads
+// fetch the 8 chunks of one row, kSteps row steps per thread (128 threads: 8 steps of 16 rows, 256 threads: 4 of 32).
+// All rows' loads are in flight before the first split: the first tile's gather sits on the launch's critical path (two
+// dependent round trips: leaf parent, then the latent row).
+template <bool kInitial, int kSteps>
+__device__ __forceinline__ void gather_tile(const Args& a, uint8_t (*t0)[kAtomA], int tile, int gtid) {
+  constexpr int kRowStep = kM / kSteps;
+  const int64_t row0 = (int64_t)tile * kM, n = a.n;
+  const int chunk = gtid & 7, r0 = gtid >> 3;
+  if (kInitial) {  // one-hot observation: column 3 d + peg(d), columns 8 chunk .. 8 chunk + 7 of each row
+    uint32_t w[kSteps];
+#pragma unroll
+    for (int i = 0; i < kSteps; ++i) {
+      const int64_t r = row0 + r0 + kRowStep * i;
+      w[i] = a.words[r < n ? r : n - 1];
+    }
+#pragma unroll
+    for (int i = 0; i < kSteps; ++i) {
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = chunk * 8 + j, d = col / 3;
+        x[j] = (col < 3 * a.n_disks && ((w[i] >> (2 * d)) & 3u) == (uint32_t)(col - 3 * d)) ? 1.f : 0.f;
+      }
+      store_parts8(t0, r0 + kRowStep * i, chunk, x);
+    }
+  } else {
+    int64_t irow[kSteps];
+#pragma unroll
+    for (int i = 0; i < kSteps; ++i) {
+      const int64_t r = row0 + r0 + kRowStep * i;
+      const int64_t it = r < n ? r : n - 1;
+      irow[i] = it * a.in_rows_per_item + (a.in_row ? (int64_t)a.in_row[it] : 0);
+    }
+    if (a.latent_dtype == HMZ_LATENT_F32) {
+      float4 u[kSteps][2];
+#pragma unroll
+      for (int i = 0; i < kSteps; ++i) {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.lat_in) + irow[i] * kLatent + chunk * 8);
+        u[i][0] = __ldcs(src);
+        u[i][1] = __ldcs(src + 1);
+      }
+#pragma unroll
+      for (int i = 0; i < kSteps; ++i) {
+        const float x[8] = {u[i][0].x, u[i][0].y, u[i][0].z, u[i][0].w, u[i][1].x, u[i][1].y, u[i][1].z, u[i][1].w};
+        store_parts8(t0, r0 + kRowStep * i, chunk, x);
+      }
+    } else {
+      uint4 q[kSteps];
+#pragma unroll
+      for (int i = 0; i < kSteps; ++i)
+        q[i] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.lat_in) + irow[i] * kLatent + chunk * 8));
+#pragma unroll
+      for (int i = 0; i < kSteps; ++i) {
+        const uint32_t pk[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          x[2 * j] = bf_lo(pk[j]);
+          x[2 * j + 1] = bf_hi(pk[j]);
+        }
+        store_parts8(t0, r0 + kRowStep * i, chunk, x);
+      }
+    }
+  }
+  fence_proxy_async();
+}
+
 // kInitial = false: recurrent_inference — networks dynamics, reward, value, policy; input = gathered latents.
 // kInitial = true : initial_inference  — networks representation (in the dynamics network's place), value, policy;
 //                   input = utils.oneHot_encoding (utils.py:9-25) of the env words (exact in bf16: only part 0 is non-zero).
@@ -229,6 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
       mbar_init(&s.bar_hfree[j], 1);
     }
     mbar_init(&s.bar_g, kOutThreads);
+    mbar_init(&s.bar_g0, kEpiThreads + kOutThreads);
     mbar_init(&s.bar_o, 1);
     mbar_init(&s.bar_out, kOutThreads);
     mbar_init(&s.bar_raw, kOutThreads);
@@ -295,7 +365,10 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
         X3_TL(144 + g);
         if (bu >= 1u) mbar_wait(&s.bar_hfree[buf], (bu - 1u) & 1u);  // accumulator buffer no longer read
         // this chunk's A tile (each issuing warp checks for itself: the other one may have done the network's first chunk)
-        if (g < 4) mbar_wait(&s.bar_g, ph_tile);         // input tile gathered
+        if (g < 4) {                                     // input tile gathered
+          if (tile == cta) mbar_wait(&s.bar_g0, 0u);
+          else mbar_wait(&s.bar_g, ph_tile ^ 1u);        // (bar_g's first phase belongs to the CTA's second tile)
+        }
         else if (g < 8) mbar_wait(&s.bar_raw, ph_tile);  // raw latent tile written (reward head input)
         else mbar_wait(&s.bar_hn, ph_tile);              // normalised latent tile written (value / policy head input)
         tc_fence_after();
@@ -393,6 +466,12 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
     const uint32_t T = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t G = 0;
     tl_on = tl_on && tid == 0;
+    if (cta < n_tiles) {  // these warps have nothing to do until the first chunk's accumulator: they gather the first tile
+      X3_TL(104);
+      gather_tile<kInitial, 4>(a, s.t0, cta, tid);
+      mbar_arrive(&s.bar_g0);
+      X3_TL(105);
+    }
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
 #pragma unroll 1
       for (int gi = 0; gi < n_steps; ++gi, ++G) {
@@ -419,72 +498,9 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
     const uint32_t D2 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + kColD2;
     uint32_t ph_o = 0;
     tl_on = tl_on && otid == 0;
-    // parent latents -> the three part tiles; 8 consecutive lanes fetch the 8 chunks of one row (16 rows per step)
-    auto gather = [&](int tile) {
-      const int64_t row0 = (int64_t)tile * kM;
-      const int chunk = otid & 7;
-      if (kInitial) {  // one-hot observation: column 3 d + peg(d), columns 8 chunk .. 8 chunk + 7 of each row
-        uint32_t w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t r = row0 + (otid >> 3) + 16 * i;
-          w[i] = a.words[r < n ? r : n - 1];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float x[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = chunk * 8 + j, d = col / 3;
-            x[j] = (col < 3 * a.n_disks && ((w[i] >> (2 * d)) & 3u) == (uint32_t)(col - 3 * d)) ? 1.f : 0.f;
-          }
-          store_parts8(s.t0, (otid >> 3) + 16 * i, chunk, x);
-        }
-      } else {
-        // all eight rows' loads are in flight before the first split: the first tile's gather sits on the launch's
-        // critical path (two dependent round trips: leaf parent, then the latent row)
-        int64_t irow[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t r = row0 + (otid >> 3) + 16 * i;
-          const int64_t it = r < n ? r : n - 1;
-          irow[i] = it * a.in_rows_per_item + (a.in_row ? (int64_t)a.in_row[it] : 0);
-        }
-        if (a.latent_dtype == HMZ_LATENT_F32) {
-          float4 u[8][2];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.lat_in) + irow[i] * kLatent + chunk * 8);
-            u[i][0] = __ldcs(src);
-            u[i][1] = __ldcs(src + 1);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x[8] = {u[i][0].x, u[i][0].y, u[i][0].z, u[i][0].w, u[i][1].x, u[i][1].y, u[i][1].z, u[i][1].w};
-            store_parts8(s.t0, (otid >> 3) + 16 * i, chunk, x);
-          }
-        } else {
-          uint4 q[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            q[i] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.lat_in) + irow[i] * kLatent + chunk * 8));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t pk[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
-            float x[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              x[2 * j] = bf_lo(pk[j]);
-              x[2 * j + 1] = bf_hi(pk[j]);
-            }
-            store_parts8(s.t0, (otid >> 3) + 16 * i, chunk, x);
-          }
-        }
-      }
-      fence_proxy_async();
-    };
+    auto gather = [&](int tile) { gather_tile<kInitial, 8>(a, s.t0, tile, otid); };
     // extra A slice of this row: one-hot(action) at k = 0..5, the constant 1 at k = 6; then the tile is handed over
-    auto publish_inputs = [&](int tile) {
+    auto publish_inputs = [&](int tile, uint64_t* bar) {
       const int64_t it = ((int64_t)tile * kM + row) < n ? ((int64_t)tile * kM + row) : n - 1;
       const uint32_t act = kInitial ? 0u : min((uint32_t)a.actions[it], (uint32_t)(kActions - 1));
       const uint32_t one = kInitial ? 0u : 0x3F80u << ((act & 1u) * 16u);
@@ -494,14 +510,9 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
                    : "memory");
       asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(ax + plain_off(row, 1)), "r"(0u) : "memory");
       fence_proxy_async();
-      mbar_arrive(&s.bar_g);
+      mbar_arrive(bar);
     };
-    X3_TL(104);
-    if (cta < n_tiles) {
-      gather(cta);
-      publish_inputs(cta);
-    }
-    X3_TL(105);
+    if (cta < n_tiles) publish_inputs(cta, &s.bar_g0);
     for (int tile = cta; tile < n_tiles; tile += n_cta) {
       const int64_t item = (int64_t)tile * kM + row;
       const int next_tile = tile + n_cta;
@@ -600,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_x3(const __grid_constant__ Ar
           // the reward head's first layers were the last readers of the raw-latent tile: gather the next tile into it;
           // after the last network every tcgen05.mma of the tile has completed and the extra A slice may change hands
           if (raw_tile_free) gather(next_tile);
-          if (last_net) publish_inputs(next_tile);
+          if (last_net) publish_inputs(next_tile, &s.bar_g);
         }
         X3_TL(100 + net);
       }
